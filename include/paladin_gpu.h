@@ -1,0 +1,149 @@
+/*
+ * paladin_gpu.h -- C-ABI of libpaladin_gpu.so, the B200 (sm_100a) replacement for the one numerical
+ * call on paladin's hot path.
+ *
+ * What it replaces in the reference (/root/reference):
+ *   - extern "C" dgeev_(...)                         src/lapack-wrapper.hpp:47-60
+ *     called twice per matrix (lwork=-1 query, solve) src/paladin.hpp:248-249, :253-254
+ *   - the dense scatter inside SquareMatrix::read_matrix (mat_[(i-1)+n*(j-1)] = v, file order,
+ *     later entries overwrite earlier ones)           src/square-matrix.hpp:101-117 (store at :115)
+ *     over the zero fill of the SquareMatrix ctor      src/square-matrix.hpp:70-71
+ *
+ * Plain C types only. All matrices are column-major, indices in COO input are 1-based exactly as
+ * they appear in the MatrixMarket file. Eigenvalues/eigenvectors come back in LAPACK dgeev's layout
+ * (conjugate pairs consecutive, positive imaginary part first, wi[k+1] == -wi[k] exactly, vectors
+ * real-packed) because the reference's unpack loop (src/paladin.hpp:256-333) consumes that layout.
+ *
+ * There is NO CPU fallback: every compute entry fails with PALADIN_GPU_ENODEVICE when no sm_100
+ * device is usable.
+ *
+ * Thread model: one host thread per device may call concurrently; calls that name the same device
+ * are serialised inside the library.
+ */
+#ifndef PALADIN_GPU_H_
+#define PALADIN_GPU_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes (return value of every int-returning entry; 0 = success) -------------------- */
+#define PALADIN_GPU_OK 0
+#define PALADIN_GPU_EINVAL 1     /* bad argument (null pointer, negative size, bad job character) */
+#define PALADIN_GPU_ENODEVICE 2  /* no usable CUDA device / device index out of range / not sm_100 */
+#define PALADIN_GPU_ECUDA 3      /* a CUDA runtime call or kernel failed; see paladin_gpu_last_error */
+#define PALADIN_GPU_ENOMEM 4     /* device or pinned-host allocation failed */
+#define PALADIN_GPU_ENOTSUP 5    /* valid request that this build does not implement */
+
+/* per-matrix info values (LAPACK dgeev convention, extended):
+ *    0      success
+ *    i > 0  the QR iteration failed to converge; wr/wi[i..n) hold converged eigenvalues, no vectors
+ *   -4      the matrix holds a non-finite entry (argument 4 of dgeev); nothing was computed
+ *   -101    a COO index is outside [1, n] (the reference would write out of bounds; we refuse) */
+#define PALADIN_GPU_INFO_NONFINITE (-4)
+#define PALADIN_GPU_INFO_BAD_INDEX (-101)
+
+/* stage indices for paladin_gpu_batch_stage_ms */
+#define PALADIN_GPU_STAGE_SCATTER 0    /* COO -> dense */
+#define PALADIN_GPU_STAGE_BALANCE 1    /* scale check + balancing (0 when fused into a later stage) */
+#define PALADIN_GPU_STAGE_HESSENBERG 2 /* reduction to Hessenberg form (+ explicit Q when vectors) */
+#define PALADIN_GPU_STAGE_QR 3         /* QR iteration to (quasi-)triangular form */
+#define PALADIN_GPU_STAGE_VECTORS 4    /* eigenvectors of T, back-transform, un-balance, normalise */
+#define PALADIN_GPU_STAGE_SMALL 5      /* fused warp-per-matrix path for n <= 64 (all stages in one kernel) */
+#define PALADIN_GPU_STAGE_GENERIC 6    /* fused CTA-per-matrix path in global memory (all stages) */
+#define PALADIN_GPU_NUM_STAGES 8
+
+/* ---- lifecycle ------------------------------------------------------------------------------- */
+
+/* Number of usable devices (compute capability 10.x). 0 when there is none. Never fails. */
+int paladin_gpu_device_count( void );
+
+/* Creates the per-device context (stream, events). Idempotent. */
+int paladin_gpu_init( int device );
+
+/* Releases everything the library holds on `device` (open batches must be destroyed first). */
+int paladin_gpu_shutdown( int device );
+
+/* Human-readable description of the last failure on the calling thread ("" if none). */
+const char* paladin_gpu_last_error( void );
+
+/* Library version string, e.g. "paladin_gpu 0.1 sm_100a". */
+const char* paladin_gpu_version( void );
+
+/* Page-locked host memory so that uploads/downloads run as asynchronous DMA. */
+int paladin_gpu_host_alloc( void** ptr, size_t bytes );
+int paladin_gpu_host_free( void* ptr );
+
+/* Device-side stopwatch on the library's own stream of `device` (CUDA events): start records an
+ * event, stop records a second one, waits for it and returns the elapsed milliseconds. Used by
+ * bench.py so that timings are taken on the stream the kernels are launched on. */
+int paladin_gpu_timer_start( int device );
+int paladin_gpu_timer_stop( int device, float* ms );
+
+/* ---- one-shot batched entry (host buffers in, host buffers out) -------------------------------
+ * Replaces, for `count` matrices at once, the reference's scatter (src/square-matrix.hpp:115) and
+ * its two dgeev_ calls (src/paladin.hpp:248-254).
+ *   n[k]                 order of matrix k (0 allowed)
+ *   nnz_offsets[k..k+1]  range of matrix k's entries in coo_i/coo_j/coo_v (count+1 values)
+ *   coo_i, coo_j         1-based row / column, file order; duplicates resolve to the LAST entry
+ *   jobvl, jobvr         'N' or 'V'
+ *   wr[k], wi[k]         n[k] doubles each (caller-owned)
+ *   vl[k], vr[k]         n[k]*n[k] doubles each, ld = n[k]; may be NULL when the job is 'N'
+ *   info[k]              per-matrix status, see above
+ */
+int paladin_gpu_geev_batch( int device, int count, const int* n, const int64_t* nnz_offsets, const int* coo_i,
+                            const int* coo_j, const double* coo_v, char jobvl, char jobvr, double* const* wr,
+                            double* const* wi, double* const* vl, double* const* vr, int* info );
+
+/* ---- staged entry: the same work with the phases separated, so that a caller (or a benchmark)
+ * can keep inputs resident in device memory, overlap phases of different batches, and read the
+ * dense matrices for parity checks. ------------------------------------------------------------ */
+typedef struct paladin_gpu_batch paladin_gpu_batch;
+
+/* Allocates device storage for `count` matrices of the given orders and entry counts. */
+int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t* nnz_offsets, char jobvl, char jobvr,
+                              paladin_gpu_batch** out );
+
+/* Host -> device copy of the COO triplets (asynchronous when the buffers are pinned; the call
+ * returns after the copies completed). */
+int paladin_gpu_batch_upload( paladin_gpu_batch* b, const int* coo_i, const int* coo_j, const double* coo_v );
+
+/* COO -> dense on the device. */
+int paladin_gpu_batch_scatter( paladin_gpu_batch* b );
+
+/* Alternative to upload+scatter: dense column-major matrices, concatenated (sum n[k]^2 doubles). */
+int paladin_gpu_batch_upload_dense( paladin_gpu_batch* b, const double* dense );
+
+/* Parity/debug: copies the dense matrix k (n[k]^2 doubles, column-major) as the scatter left it.
+ * Only meaningful between scatter and solve (solve destroys the matrices). */
+int paladin_gpu_batch_get_dense( paladin_gpu_batch* b, int k, double* out );
+
+/* Eigen-solve of every matrix of the batch on the device; returns when it finished. */
+int paladin_gpu_batch_solve( paladin_gpu_batch* b );
+
+/* Device -> host copy of the results into caller-owned buffers laid out as concatenations:
+ * wr/wi: sum n[k] doubles; vl/vr: sum n[k]^2 doubles (NULL when not computed); info: count ints. */
+int paladin_gpu_batch_download( paladin_gpu_batch* b, double* wr, double* wi, double* vl, double* vr, int* info );
+
+/* Device time of each stage of the most recent scatter/solve, in milliseconds, measured with CUDA
+ * events on the library's own stream. ms must hold PALADIN_GPU_NUM_STAGES floats. launches (may be
+ * NULL) receives the number of kernel launches of each stage. */
+int paladin_gpu_batch_stage_ms( paladin_gpu_batch* b, float* ms, int* launches );
+
+int paladin_gpu_batch_destroy( paladin_gpu_batch* b );
+
+/* ---- single-matrix shim with the exact Fortran signature the reference declares ---------------
+ * (src/lapack-wrapper.hpp:47-60). Exported as paladin_gpu_dgeev_ so that it can coexist with a real
+ * LAPACK in one process; link with -Ddgeev_=paladin_gpu_dgeev_ (or the alias library) to make the
+ * unmodified reference call it. lwork == -1 answers the workspace query with work[0] = 1 and
+ * touches nothing else. Uses device 0 unless PALADIN_GPU_DEVICE is set in the environment. */
+void paladin_gpu_dgeev_( const char* jobvl, const char* jobvr, int* n, double* a, int* lda, double* wr, double* wi,
+                         double* vl, int* ldvl, double* vr, int* ldvr, double* work, int* lwork, int* info );
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* PALADIN_GPU_H_ */

@@ -1,0 +1,243 @@
+"""
+ctypes bindings of include/paladin_gpu.h. Nothing here computes: every numerical entry forwards to
+libpaladin_gpu.so and raises PaladinGpuError when the library reports a failure (no CPU fallback).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+NUM_STAGES = 8
+STAGE_NAMES = ("scatter", "balance", "hessenberg", "qr", "vectors", "small", "generic", "reserved")
+
+_c_int_p = ctypes.POINTER(ctypes.c_int)
+_c_i64_p = ctypes.POINTER(ctypes.c_int64)
+_c_dbl_p = ctypes.POINTER(ctypes.c_double)
+_c_flt_p = ctypes.POINTER(ctypes.c_float)
+
+
+class PaladinGpuError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("paladin_gpu error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib_path():
+    return os.path.join(_HERE, "lib", "libpaladin_gpu.so")
+
+
+def lib():
+    """Loads libpaladin_gpu.so (built by __graft_entry__.build() / paladin_b200/csrc/Makefile)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    p = lib_path()
+    if not os.path.exists(p):
+        raise PaladinGpuError(-1, "%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                  "(there is no CPU fallback)" % p)
+    L = ctypes.CDLL(p)
+    L.paladin_gpu_device_count.restype = ctypes.c_int
+    L.paladin_gpu_init.argtypes = [ctypes.c_int]
+    L.paladin_gpu_shutdown.argtypes = [ctypes.c_int]
+    L.paladin_gpu_last_error.restype = ctypes.c_char_p
+    L.paladin_gpu_version.restype = ctypes.c_char_p
+    L.paladin_gpu_host_alloc.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_size_t]
+    L.paladin_gpu_host_free.argtypes = [ctypes.c_void_p]
+    L.paladin_gpu_geev_batch.argtypes = [ctypes.c_int, ctypes.c_int, _c_int_p, _c_i64_p, _c_int_p, _c_int_p, _c_dbl_p,
+                                         ctypes.c_char, ctypes.c_char, ctypes.POINTER(_c_dbl_p),
+                                         ctypes.POINTER(_c_dbl_p), ctypes.POINTER(_c_dbl_p), ctypes.POINTER(_c_dbl_p),
+                                         _c_int_p]
+    L.paladin_gpu_batch_create.argtypes = [ctypes.c_int, ctypes.c_int, _c_int_p, _c_i64_p, ctypes.c_char,
+                                           ctypes.c_char, ctypes.POINTER(ctypes.c_void_p)]
+    L.paladin_gpu_batch_upload.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.paladin_gpu_batch_scatter.argtypes = [ctypes.c_void_p]
+    L.paladin_gpu_batch_upload_dense.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.paladin_gpu_batch_get_dense.argtypes = [ctypes.c_void_p, ctypes.c_int, _c_dbl_p]
+    L.paladin_gpu_batch_solve.argtypes = [ctypes.c_void_p]
+    L.paladin_gpu_batch_download.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                             ctypes.c_void_p, ctypes.c_void_p]
+    L.paladin_gpu_batch_stage_ms.argtypes = [ctypes.c_void_p, _c_flt_p, _c_int_p]
+    L.paladin_gpu_batch_destroy.argtypes = [ctypes.c_void_p]
+    L.paladin_gpu_timer_start.argtypes = [ctypes.c_int]
+    L.paladin_gpu_timer_stop.argtypes = [ctypes.c_int, _c_flt_p]
+    L.paladin_gpu_dgeev_.restype = None
+    L.paladin_gpu_dgeev_.argtypes = [ctypes.c_char_p, ctypes.c_char_p, _c_int_p, _c_dbl_p, _c_int_p, _c_dbl_p, _c_dbl_p,
+                                     _c_dbl_p, _c_int_p, _c_dbl_p, _c_int_p, _c_dbl_p, _c_int_p, _c_int_p]
+    _LIB = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise PaladinGpuError(rc, lib().paladin_gpu_last_error().decode())
+
+
+def version():
+    return lib().paladin_gpu_version().decode()
+
+
+def device_count():
+    return lib().paladin_gpu_device_count()
+
+
+def timer_start(device=0):
+    _check(lib().paladin_gpu_timer_start(device))
+
+
+def timer_stop(device=0):
+    ms = ctypes.c_float()
+    _check(lib().paladin_gpu_timer_stop(device, ctypes.byref(ms)))
+    return float(ms.value)
+
+
+def _ptr(a):
+    return ctypes.c_void_p(a.ctypes.data) if a is not None else None
+
+
+class PinnedArray:
+    """numpy view over page-locked host memory from paladin_gpu_host_alloc."""
+
+    def __init__(self, shape, dtype):
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(shape)) * self.dtype.itemsize
+        p = ctypes.c_void_p()
+        _check(lib().paladin_gpu_host_alloc(ctypes.byref(p), self.nbytes))
+        self._p = p
+        buf = (ctypes.c_char * max(self.nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._p is not None:
+            self.array = None
+            lib().paladin_gpu_host_free(self._p)
+            self._p = None
+
+
+class Batch:
+    """Staged API: create -> upload -> scatter -> solve -> download (include/paladin_gpu.h)."""
+
+    def __init__(self, n, nnz_offsets, jobvl="N", jobvr="N", device=0):
+        self.n = np.ascontiguousarray(n, dtype=np.int32)
+        self.nnz_offsets = np.ascontiguousarray(nnz_offsets, dtype=np.int64)
+        assert len(self.nnz_offsets) == len(self.n) + 1
+        self.count = len(self.n)
+        self.jobvr = jobvr
+        self.jobvl = jobvl
+        self.total_n = int(self.n.astype(np.int64).sum())
+        self.total_nn = int((self.n.astype(np.int64) ** 2).sum())
+        h = ctypes.c_void_p()
+        _check(lib().paladin_gpu_batch_create(device, self.count, self.n.ctypes.data_as(_c_int_p),
+                                              self.nnz_offsets.ctypes.data_as(_c_i64_p), jobvl.encode(), jobvr.encode(),
+                                              ctypes.byref(h)))
+        self._h = h
+
+    def upload(self, coo_i, coo_j, coo_v):
+        assert coo_i.dtype == np.int32 and coo_j.dtype == np.int32 and coo_v.dtype == np.float64
+        _check(lib().paladin_gpu_batch_upload(self._h, _ptr(coo_i), _ptr(coo_j), _ptr(coo_v)))
+
+    def scatter(self):
+        _check(lib().paladin_gpu_batch_scatter(self._h))
+
+    def upload_dense(self, dense):
+        dense = np.ascontiguousarray(dense, dtype=np.float64)
+        _check(lib().paladin_gpu_batch_upload_dense(self._h, _ptr(dense)))
+
+    def get_dense(self, k):
+        out = np.empty(int(self.n[k]) ** 2, dtype=np.float64)
+        _check(lib().paladin_gpu_batch_get_dense(self._h, k, out.ctypes.data_as(_c_dbl_p)))
+        return out
+
+    def solve(self):
+        _check(lib().paladin_gpu_batch_solve(self._h))
+
+    def download(self, wr=None, wi=None, vr=None, info=None):
+        wr = np.empty(self.total_n) if wr is None else wr
+        wi = np.empty(self.total_n) if wi is None else wi
+        info = np.empty(self.count, dtype=np.int32) if info is None else info
+        if self.jobvr == "V" and vr is None:
+            vr = np.empty(self.total_nn)
+        _check(lib().paladin_gpu_batch_download(self._h, _ptr(wr), _ptr(wi), None, _ptr(vr) if self.jobvr == "V" else None,
+                                                _ptr(info)))
+        return wr, wi, vr, info
+
+    def stage_ms(self):
+        ms = (ctypes.c_float * NUM_STAGES)()
+        ln = (ctypes.c_int * NUM_STAGES)()
+        _check(lib().paladin_gpu_batch_stage_ms(self._h, ms, ln))
+        return {STAGE_NAMES[i]: (float(ms[i]), int(ln[i])) for i in range(NUM_STAGES)}
+
+    def destroy(self):
+        if self._h is not None:
+            lib().paladin_gpu_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def split_results(n, wr, wi, vr):
+    """Concatenated outputs -> per-matrix (wr, wi, VR[n,n] Fortran-ordered or None)."""
+    out = []
+    o1 = 0
+    o2 = 0
+    for nk in n:
+        nk = int(nk)
+        V = None
+        if vr is not None:
+            V = vr[o2:o2 + nk * nk].reshape((nk, nk), order="F")
+        out.append((wr[o1:o1 + nk], wi[o1:o1 + nk], V))
+        o1 += nk
+        o2 += nk * nk
+    return out
+
+
+def geev_batch(n, nnz_offsets, coo_i, coo_j, coo_v, jobvr="N", device=0):
+    """One-shot entry paladin_gpu_geev_batch with host buffers. Returns (list of (wr, wi, VR), info)."""
+    n = np.ascontiguousarray(n, dtype=np.int32)
+    off = np.ascontiguousarray(nnz_offsets, dtype=np.int64)
+    coo_i = np.ascontiguousarray(coo_i, dtype=np.int32)
+    coo_j = np.ascontiguousarray(coo_j, dtype=np.int32)
+    coo_v = np.ascontiguousarray(coo_v, dtype=np.float64)
+    count = len(n)
+    wr = [np.zeros(int(k)) for k in n]
+    wi = [np.zeros(int(k)) for k in n]
+    vr = [np.zeros((int(k), int(k)), order="F") if jobvr == "V" else None for k in n]
+    info = np.zeros(max(count, 1), dtype=np.int32)
+    PP = _c_dbl_p * max(count, 1)
+    pwr = PP(*[a.ctypes.data_as(_c_dbl_p) for a in wr])
+    pwi = PP(*[a.ctypes.data_as(_c_dbl_p) for a in wi])
+    pvr = PP(*[(a.ctypes.data_as(_c_dbl_p) if a is not None else None) for a in vr])
+    _check(lib().paladin_gpu_geev_batch(device, count, n.ctypes.data_as(_c_int_p), off.ctypes.data_as(_c_i64_p),
+                                        coo_i.ctypes.data_as(_c_int_p), coo_j.ctypes.data_as(_c_int_p),
+                                        coo_v.ctypes.data_as(_c_dbl_p), b"N", jobvr.encode(), pwr, pwi, None,
+                                        pvr if jobvr == "V" else None, info.ctypes.data_as(_c_int_p)))
+    return list(zip(wr, wi, vr)), info[:count]
+
+
+def dgeev(A, jobvr="V"):
+    """Single dense matrix through the Fortran-signature shim paladin_gpu_dgeev_ (query + solve, exactly the
+    two calls of reference src/paladin.hpp:247-254). Returns wr, wi, VR, info."""
+    A = np.array(A, dtype=np.float64, order="F")
+    n = A.shape[0]
+    ld = max(n, 1)
+    wr, wi = np.zeros(ld), np.zeros(ld)
+    VL = np.zeros((ld, ld), order="F")
+    VR = np.zeros((ld, ld), order="F")
+    wk = np.zeros(1)
+    info = ctypes.c_int(0)
+    ci = lambda v: ctypes.byref(ctypes.c_int(v))
+    dp = lambda a: a.ctypes.data_as(_c_dbl_p)
+    f = lib().paladin_gpu_dgeev_
+    f(b"N", jobvr.encode(), ci(n), dp(A), ci(ld), dp(wr), dp(wi), dp(VL), ci(ld), dp(VR), ci(ld), dp(wk), ci(-1),
+      ctypes.byref(info))
+    lwork = max(1, int(wk[0]))
+    work = np.zeros(lwork)
+    f(b"N", jobvr.encode(), ci(n), dp(A), ci(ld), dp(wr), dp(wi), dp(VL), ci(ld), dp(VR), ci(ld), dp(work), ci(lwork),
+      ctypes.byref(info))
+    return wr[:n], wi[:n], VR[:n, :n], info.value

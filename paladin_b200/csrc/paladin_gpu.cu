@@ -1,0 +1,740 @@
+// paladin_gpu.cu -- kernels' launch code and the C-ABI declared in include/paladin_gpu.h.
+//
+// Drop-in boundary: the reference's extern "C" dgeev_ (reference src/lapack-wrapper.hpp:47-60, called
+// at src/paladin.hpp:248-254) plus the dense scatter of its MatrixMarket reader
+// (src/square-matrix.hpp:101-117). Everything here runs on the device; there is no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/paladin_gpu.h"
+#include "pb_geev.cuh"
+#include "pb_scatter.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail( int code, const std::string& msg ) {
+  g_err = msg;
+  return code;
+}
+
+#define PB_CUDA( call )                                                                           \
+  do {                                                                                            \
+    cudaError_t e__ = ( call );                                                                   \
+    if ( e__ != cudaSuccess ) {                                                                   \
+      return fail( e__ == cudaErrorMemoryAllocation ? PALADIN_GPU_ENOMEM : PALADIN_GPU_ECUDA,     \
+                   std::string( #call ) + ": " + cudaGetErrorString( e__ ) );                     \
+    }                                                                                             \
+  } while ( 0 )
+
+constexpr int kMaxDevices = 64;
+constexpr int kSmallMax = 64;       // warp-per-matrix path for n <= kSmallMax
+constexpr int kSmallBucket = 8;     // shared-memory buckets of 8 rows
+constexpr int kGenericThreads = 256;
+
+struct DeviceCtx {
+  std::mutex mu;
+  bool ready = false;
+  cudaStream_t stream = nullptr;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
+};
+
+DeviceCtx g_ctx[kMaxDevices];
+
+int usable_devices() {
+  int cnt = 0;
+  if ( cudaGetDeviceCount( &cnt ) != cudaSuccess ) {
+    cudaGetLastError();
+    return 0;
+  }
+  int ok = 0;
+  for ( int d = 0; d < cnt && d < kMaxDevices; ++d ) {
+    int major = 0;
+    if ( cudaDeviceGetAttribute( &major, cudaDevAttrComputeCapabilityMajor, d ) == cudaSuccess && major == 10 ) ok = d + 1;
+  }
+  return ok;  // devices 0..ok-1 are addressable; entries check the capability again
+}
+
+int ensure_ctx( int device ) {
+  if ( device < 0 || device >= kMaxDevices ) return fail( PALADIN_GPU_ENODEVICE, "device index out of range" );
+  int cnt = 0;
+  if ( cudaGetDeviceCount( &cnt ) != cudaSuccess || device >= cnt ) {
+    cudaGetLastError();
+    return fail( PALADIN_GPU_ENODEVICE, "no CUDA device " + std::to_string( device ) + " (there is no CPU fallback)" );
+  }
+  int major = 0;
+  PB_CUDA( cudaDeviceGetAttribute( &major, cudaDevAttrComputeCapabilityMajor, device ) );
+  if ( major != 10 )
+    return fail( PALADIN_GPU_ENODEVICE, "device is not compute capability 10.x (library is built for sm_100a only)" );
+  DeviceCtx& c = g_ctx[device];
+  std::lock_guard<std::mutex> lk( c.mu );
+  PB_CUDA( cudaSetDevice( device ) );
+  if ( !c.ready ) {
+    PB_CUDA( cudaStreamCreateWithFlags( &c.stream, cudaStreamNonBlocking ) );
+    PB_CUDA( cudaDeviceGetAttribute( &c.sm_count, cudaDevAttrMultiProcessorCount, device ) );
+    PB_CUDA( cudaDeviceGetAttribute( &c.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device ) );
+    PB_CUDA( cudaEventCreate( &c.t0 ) );
+    PB_CUDA( cudaEventCreate( &c.t1 ) );
+    c.ready = true;
+  }
+  return PALADIN_GPU_OK;
+}
+
+// ---- device view of a batch ------------------------------------------------------------------
+struct BatchView {
+  const int* n;
+  const int64_t* a_off;  // dense offsets (doubles)
+  const int64_t* w_off;  // eigenvalue offsets (doubles)
+  double* A;
+  double* V;   // right vectors / Schur vectors (nullptr when not wanted)
+  double* wr;
+  double* wi;
+  int* info;
+  double* dwork;  // 5 doubles per eigenvalue slot (generic path)
+  int* iwork;     // 2 ints per eigenvalue slot + 2 per matrix
+  int wantvr;
+};
+
+// ---- warp-per-matrix path, n <= 64: the matrix (and Z) live in shared memory ---------------------
+// one warp per CTA; dynamic shared memory = lds*nmax doubles (x2 with vectors) + 5*nmax doubles + ints
+__global__ void __launch_bounds__( 32 ) geev_warp_kernel( BatchView bv, const int* ids, int nmax, int lds ) {
+  extern __shared__ double smem[];
+  const int id = ids[blockIdx.x];
+  const int n = bv.n[id];
+  const int lane = threadIdx.x;
+  double* As = smem;
+  double* Vs = As + (size_t)lds * nmax;
+  double* dw = bv.wantvr ? Vs + (size_t)lds * nmax : Vs;
+  int* iw = reinterpret_cast<int*>( dw + 5 * nmax );
+  const double* Ag = bv.A + bv.a_off[id];
+  const int nn = n * n;
+  for ( int q = lane; q < nn; q += 32 ) {
+    const int c = q / n, r = q - c * n;
+    As[r + c * lds] = Ag[q];
+  }
+  __syncwarp();
+  pb::WarpGroup g;
+  double* wr = bv.wr + bv.w_off[id];
+  double* wi = bv.wi + bv.w_off[id];
+  const int info = pb::geev_group( g, n, As, lds, wr, wi, bv.wantvr != 0, Vs, lds, dw, iw );
+  __syncwarp();
+  if ( bv.wantvr && info == 0 ) {
+    double* Vg = bv.V + bv.a_off[id];
+    for ( int q = lane; q < nn; q += 32 ) {
+      const int c = q / n, r = q - c * n;
+      Vg[q] = Vs[r + c * lds];
+    }
+  }
+  if ( lane == 0 ) bv.info[id] = info;
+}
+
+// ---- size-generic path: one CTA per matrix, in place in global memory ----------------------------
+__global__ void __launch_bounds__( kGenericThreads ) geev_cta_kernel( BatchView bv, const int* ids ) {
+  __shared__ double red[64];
+  const int id = ids[blockIdx.x];
+  const int n = bv.n[id];
+  pb::CtaGroup g{ red };
+  double* A = bv.A + bv.a_off[id];
+  double* V = bv.wantvr ? bv.V + bv.a_off[id] : nullptr;
+  double* wr = bv.wr + bv.w_off[id];
+  double* wi = bv.wi + bv.w_off[id];
+  double* dw = bv.dwork + 5 * bv.w_off[id];
+  int* iw = bv.iwork + 2 * bv.w_off[id] + 2 * id;
+  const int info = pb::geev_group( g, n, A, n, wr, wi, bv.wantvr != 0, V, n, dw, iw );
+  if ( threadIdx.x == 0 ) bv.info[id] = info;
+}
+
+struct StageTimer {
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  bool used = false;
+  int launches = 0;
+};
+
+}  // namespace
+
+// ---- the opaque batch ------------------------------------------------------------------------------
+struct paladin_gpu_batch {
+  int device = 0;
+  int count = 0;
+  char jobvl = 'N', jobvr = 'N';
+  std::vector<int> n;
+  std::vector<int64_t> nnz_off, a_off, w_off;
+  int64_t total_nnz = 0, total_nn = 0, total_n = 0;
+  // device
+  int* d_n = nullptr;
+  int64_t *d_nnz_off = nullptr, *d_a_off = nullptr, *d_w_off = nullptr;
+  int *d_coo_i = nullptr, *d_coo_j = nullptr;
+  double* d_coo_v = nullptr;
+  double *d_A = nullptr, *d_V = nullptr, *d_wr = nullptr, *d_wi = nullptr, *d_dwork = nullptr;
+  int *d_info = nullptr, *d_iwork = nullptr, *d_flags = nullptr, *d_ids = nullptr;
+  pb::ScatterChunk* d_chunks = nullptr;
+  int nchunks = 0;
+  // host-side plan
+  std::vector<int> flags;                    // scatter flags per matrix
+  std::vector<int> ids;                      // all ids grouped by class
+  struct Group { int first, count, nmax, kind; };  // kind 0 = warp bucket, 1 = generic
+  std::vector<Group> groups;
+  StageTimer st[PALADIN_GPU_NUM_STAGES];
+  bool scattered = false;
+};
+
+namespace {
+
+void free_batch( paladin_gpu_batch* b ) {
+  if ( !b ) return;
+  cudaSetDevice( b->device );
+  cudaFree( b->d_n ); cudaFree( b->d_nnz_off ); cudaFree( b->d_a_off ); cudaFree( b->d_w_off );
+  cudaFree( b->d_coo_i ); cudaFree( b->d_coo_j ); cudaFree( b->d_coo_v );
+  cudaFree( b->d_A ); cudaFree( b->d_V ); cudaFree( b->d_wr ); cudaFree( b->d_wi ); cudaFree( b->d_dwork );
+  cudaFree( b->d_info ); cudaFree( b->d_iwork ); cudaFree( b->d_flags ); cudaFree( b->d_ids ); cudaFree( b->d_chunks );
+  for ( auto& s : b->st ) {
+    if ( s.e0 ) cudaEventDestroy( s.e0 );
+    if ( s.e1 ) cudaEventDestroy( s.e1 );
+  }
+  delete b;
+}
+
+template <class T>
+int dev_alloc( T** p, size_t count ) {
+  *p = nullptr;
+  if ( count == 0 ) count = 1;
+  PB_CUDA( cudaMalloc( reinterpret_cast<void**>( p ), count * sizeof( T ) ) );
+  return PALADIN_GPU_OK;
+}
+
+#define PB_TRY( expr )                    \
+  do {                                    \
+    int rc__ = ( expr );                  \
+    if ( rc__ != PALADIN_GPU_OK ) return rc__; \
+  } while ( 0 )
+
+void stage_begin( paladin_gpu_batch* b, int s, cudaStream_t st ) {
+  if ( !b->st[s].used ) {
+    cudaEventRecord( b->st[s].e0, st );
+    b->st[s].used = true;
+  }
+}
+void stage_end( paladin_gpu_batch* b, int s, cudaStream_t st, int launches ) {
+  cudaEventRecord( b->st[s].e1, st );
+  b->st[s].launches += launches;
+}
+void stage_reset( paladin_gpu_batch* b, int s ) {
+  b->st[s].used = false;
+  b->st[s].launches = 0;
+}
+
+pb::ScatterArgs scatter_args( paladin_gpu_batch* b ) {
+  pb::ScatterArgs a;
+  a.chunks = b->d_chunks;
+  a.n = b->d_n;
+  a.nnz_off = b->d_nnz_off;
+  a.a_off = b->d_a_off;
+  a.coo_i = b->d_coo_i;
+  a.coo_j = b->d_coo_j;
+  a.coo_v = b->d_coo_v;
+  a.dense = b->d_A;
+  a.flags = b->d_flags;
+  return a;
+}
+
+BatchView batch_view( paladin_gpu_batch* b ) {
+  BatchView v;
+  v.n = b->d_n;
+  v.a_off = b->d_a_off;
+  v.w_off = b->d_w_off;
+  v.A = b->d_A;
+  v.V = b->d_V;
+  v.wr = b->d_wr;
+  v.wi = b->d_wi;
+  v.info = b->d_info;
+  v.dwork = b->d_dwork;
+  v.iwork = b->d_iwork;
+  v.wantvr = ( b->jobvr == 'V' ) ? 1 : 0;
+  return v;
+}
+
+size_t warp_smem_bytes( int nmax, bool wantvr ) {
+  const int lds = nmax | 1;
+  return sizeof( double ) * ( (size_t)lds * nmax * ( wantvr ? 2 : 1 ) + 5 * (size_t)nmax ) + sizeof( int ) * ( 2 * (size_t)nmax + 2 );
+}
+
+}  // namespace
+
+// =====================================================================================================
+extern "C" {
+
+int paladin_gpu_device_count( void ) { return usable_devices(); }
+
+int paladin_gpu_init( int device ) { return ensure_ctx( device ); }
+
+int paladin_gpu_shutdown( int device ) {
+  if ( device < 0 || device >= kMaxDevices ) return fail( PALADIN_GPU_ENODEVICE, "device index out of range" );
+  DeviceCtx& c = g_ctx[device];
+  std::lock_guard<std::mutex> lk( c.mu );
+  if ( c.ready ) {
+    cudaSetDevice( device );
+    cudaStreamSynchronize( c.stream );
+    cudaStreamDestroy( c.stream );
+    cudaEventDestroy( c.t0 );
+    cudaEventDestroy( c.t1 );
+    c.stream = nullptr;
+    c.ready = false;
+  }
+  return PALADIN_GPU_OK;
+}
+
+const char* paladin_gpu_last_error( void ) { return g_err.c_str(); }
+
+const char* paladin_gpu_version( void ) { return "paladin_gpu 0.1 sm_100a"; }
+
+int paladin_gpu_host_alloc( void** ptr, size_t bytes ) {
+  if ( !ptr ) return fail( PALADIN_GPU_EINVAL, "null pointer" );
+  *ptr = nullptr;
+  if ( usable_devices() == 0 ) return fail( PALADIN_GPU_ENODEVICE, "no CUDA device (there is no CPU fallback)" );
+  PB_CUDA( cudaHostAlloc( ptr, bytes ? bytes : 1, cudaHostAllocPortable ) );
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_host_free( void* ptr ) {
+  if ( ptr ) PB_CUDA( cudaFreeHost( ptr ) );
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_timer_start( int device ) {
+  PB_TRY( ensure_ctx( device ) );
+  DeviceCtx& c = g_ctx[device];
+  std::lock_guard<std::mutex> lk( c.mu );
+  PB_CUDA( cudaSetDevice( device ) );
+  PB_CUDA( cudaEventRecord( c.t0, c.stream ) );
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_timer_stop( int device, float* ms ) {
+  if ( !ms ) return fail( PALADIN_GPU_EINVAL, "null pointer" );
+  PB_TRY( ensure_ctx( device ) );
+  DeviceCtx& c = g_ctx[device];
+  std::lock_guard<std::mutex> lk( c.mu );
+  PB_CUDA( cudaSetDevice( device ) );
+  PB_CUDA( cudaEventRecord( c.t1, c.stream ) );
+  PB_CUDA( cudaEventSynchronize( c.t1 ) );
+  PB_CUDA( cudaEventElapsedTime( ms, c.t0, c.t1 ) );
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t* nnz_offsets, char jobvl, char jobvr,
+                              paladin_gpu_batch** out ) {
+  if ( !out ) return fail( PALADIN_GPU_EINVAL, "out is null" );
+  *out = nullptr;
+  if ( count < 0 || ( count > 0 && ( !n || !nnz_offsets ) ) ) return fail( PALADIN_GPU_EINVAL, "bad count / null sizes" );
+  if ( ( jobvl != 'N' && jobvl != 'V' ) || ( jobvr != 'N' && jobvr != 'V' ) )
+    return fail( PALADIN_GPU_EINVAL, "jobvl/jobvr must be 'N' or 'V'" );
+  if ( jobvl == 'V' ) return fail( PALADIN_GPU_ENOTSUP, "left eigenvectors are not implemented yet" );
+  PB_TRY( ensure_ctx( device ) );
+  DeviceCtx& c = g_ctx[device];
+  std::lock_guard<std::mutex> lk( c.mu );
+  PB_CUDA( cudaSetDevice( device ) );
+
+  paladin_gpu_batch* b = new paladin_gpu_batch;
+  b->device = device;
+  b->count = count;
+  b->jobvl = jobvl;
+  b->jobvr = jobvr;
+  b->n.assign( n, n + count );
+  b->nnz_off.assign( count + 1, 0 );
+  b->a_off.assign( count + 1, 0 );
+  b->w_off.assign( count + 1, 0 );
+  for ( int k = 0; k < count; ++k ) {
+    if ( n[k] < 0 || nnz_offsets[k + 1] < nnz_offsets[k] || nnz_offsets[k + 1] - nnz_offsets[k] > 0x7fffffffLL ) {
+      delete b;
+      return fail( PALADIN_GPU_EINVAL, "negative order or decreasing nnz_offsets at matrix " + std::to_string( k ) );
+    }
+    b->nnz_off[k] = nnz_offsets[k] - nnz_offsets[0];
+    // every dense matrix starts on a 16-byte boundary so that paired stores stay aligned
+    int64_t nn = (int64_t)n[k] * n[k];
+    b->a_off[k + 1] = b->a_off[k] + ( ( nn + 1 ) & ~1LL );
+    b->w_off[k + 1] = b->w_off[k] + n[k];
+  }
+  if ( count > 0 ) b->nnz_off[count] = nnz_offsets[count] - nnz_offsets[0];
+  b->total_nnz = b->nnz_off[count];
+  b->total_nn = b->a_off[count];
+  b->total_n = b->w_off[count];
+
+  // scatter chunk table
+  std::vector<pb::ScatterChunk> chunks;
+  for ( int k = 0; k < count; ++k ) {
+    const int nnz = (int)( b->nnz_off[k + 1] - b->nnz_off[k] );
+    const int nch = std::max( 1, ( nnz + pb::kScatterChunk - 1 ) / pb::kScatterChunk );
+    for ( int c2 = 0; c2 < nch; ++c2 ) {
+      pb::ScatterChunk ch;
+      ch.matrix = k;
+      ch.first = c2 * pb::kScatterChunk;
+      ch.count = std::max( 0, std::min( pb::kScatterChunk, nnz - ch.first ) );
+      ch.nchunks = nch;
+      chunks.push_back( ch );
+    }
+  }
+  b->nchunks = (int)chunks.size();
+
+  // solve plan: warp buckets for n <= kSmallMax (when the bucket fits in shared memory), generic otherwise
+  {
+    std::vector<std::vector<int>> bucket( kSmallMax / kSmallBucket + 1 );
+    std::vector<int> generic;
+    for ( int k = 0; k < count; ++k ) {
+      if ( n[k] == 0 ) continue;
+      if ( n[k] <= kSmallMax )
+        bucket[( n[k] + kSmallBucket - 1 ) / kSmallBucket].push_back( k );
+      else
+        generic.push_back( k );
+    }
+    std::stable_sort( generic.begin(), generic.end(), [&]( int x, int y ) { return n[x] > n[y]; } );
+    for ( size_t q = 0; q < bucket.size(); ++q ) {
+      if ( bucket[q].empty() ) continue;
+      paladin_gpu_batch::Group g{ (int)b->ids.size(), (int)bucket[q].size(), (int)q * kSmallBucket, 0 };
+      b->ids.insert( b->ids.end(), bucket[q].begin(), bucket[q].end() );
+      b->groups.push_back( g );
+    }
+    if ( !generic.empty() ) {
+      paladin_gpu_batch::Group g{ (int)b->ids.size(), (int)generic.size(), n[generic[0]], 1 };
+      b->ids.insert( b->ids.end(), generic.begin(), generic.end() );
+      b->groups.push_back( g );
+    }
+  }
+
+  int rc = PALADIN_GPU_OK;
+  auto A = [&]( int r ) { if ( rc == PALADIN_GPU_OK ) rc = r; };
+  A( dev_alloc( &b->d_n, count ) );
+  A( dev_alloc( &b->d_nnz_off, count + 1 ) );
+  A( dev_alloc( &b->d_a_off, count + 1 ) );
+  A( dev_alloc( &b->d_w_off, count + 1 ) );
+  A( dev_alloc( &b->d_coo_i, b->total_nnz + 2 ) );
+  A( dev_alloc( &b->d_coo_j, b->total_nnz + 2 ) );
+  A( dev_alloc( &b->d_coo_v, b->total_nnz + 2 ) );
+  A( dev_alloc( &b->d_A, b->total_nn ) );
+  if ( jobvr == 'V' ) A( dev_alloc( &b->d_V, b->total_nn ) );
+  A( dev_alloc( &b->d_wr, b->total_n ) );
+  A( dev_alloc( &b->d_wi, b->total_n ) );
+  A( dev_alloc( &b->d_dwork, 5 * b->total_n ) );
+  A( dev_alloc( &b->d_iwork, 2 * b->total_n + 2 * count ) );
+  A( dev_alloc( &b->d_info, count ) );
+  A( dev_alloc( &b->d_flags, count ) );
+  A( dev_alloc( &b->d_ids, b->ids.size() ) );
+  A( dev_alloc( &b->d_chunks, chunks.size() ) );
+  if ( rc != PALADIN_GPU_OK ) {
+    free_batch( b );
+    return rc;
+  }
+  for ( auto& s : b->st ) {
+    cudaEventCreate( &s.e0 );
+    cudaEventCreate( &s.e1 );
+  }
+  cudaStream_t st = c.stream;
+  auto H2D = [&]( void* d, const void* h, size_t bytes ) {
+    if ( rc == PALADIN_GPU_OK && bytes ) {
+      cudaError_t e = cudaMemcpyAsync( d, h, bytes, cudaMemcpyHostToDevice, st );
+      if ( e != cudaSuccess ) rc = fail( PALADIN_GPU_ECUDA, cudaGetErrorString( e ) );
+    }
+  };
+  H2D( b->d_n, b->n.data(), sizeof( int ) * count );
+  H2D( b->d_nnz_off, b->nnz_off.data(), sizeof( int64_t ) * ( count + 1 ) );
+  H2D( b->d_a_off, b->a_off.data(), sizeof( int64_t ) * ( count + 1 ) );
+  H2D( b->d_w_off, b->w_off.data(), sizeof( int64_t ) * ( count + 1 ) );
+  H2D( b->d_ids, b->ids.data(), sizeof( int ) * b->ids.size() );
+  H2D( b->d_chunks, chunks.data(), sizeof( pb::ScatterChunk ) * chunks.size() );
+  if ( rc == PALADIN_GPU_OK ) {
+    cudaError_t e = cudaMemsetAsync( b->d_info, 0, sizeof( int ) * std::max( count, 1 ), st );
+    if ( e == cudaSuccess ) e = cudaStreamSynchronize( st );
+    if ( e != cudaSuccess ) rc = fail( PALADIN_GPU_ECUDA, cudaGetErrorString( e ) );
+  }
+  if ( rc != PALADIN_GPU_OK ) {
+    free_batch( b );
+    return rc;
+  }
+  b->flags.assign( count, 0 );
+  *out = b;
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_batch_upload( paladin_gpu_batch* b, const int* coo_i, const int* coo_j, const double* coo_v ) {
+  if ( !b ) return fail( PALADIN_GPU_EINVAL, "null batch" );
+  if ( b->total_nnz > 0 && ( !coo_i || !coo_j || !coo_v ) ) return fail( PALADIN_GPU_EINVAL, "null COO arrays" );
+  DeviceCtx& c = g_ctx[b->device];
+  std::lock_guard<std::mutex> lk( c.mu );
+  PB_CUDA( cudaSetDevice( b->device ) );
+  if ( b->total_nnz > 0 ) {
+    PB_CUDA( cudaMemcpyAsync( b->d_coo_i, coo_i, sizeof( int ) * b->total_nnz, cudaMemcpyHostToDevice, c.stream ) );
+    PB_CUDA( cudaMemcpyAsync( b->d_coo_j, coo_j, sizeof( int ) * b->total_nnz, cudaMemcpyHostToDevice, c.stream ) );
+    PB_CUDA( cudaMemcpyAsync( b->d_coo_v, coo_v, sizeof( double ) * b->total_nnz, cudaMemcpyHostToDevice, c.stream ) );
+  }
+  PB_CUDA( cudaStreamSynchronize( c.stream ) );
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_batch_scatter( paladin_gpu_batch* b ) {
+  if ( !b ) return fail( PALADIN_GPU_EINVAL, "null batch" );
+  DeviceCtx& c = g_ctx[b->device];
+  std::lock_guard<std::mutex> lk( c.mu );
+  PB_CUDA( cudaSetDevice( b->device ) );
+  cudaStream_t st = c.stream;
+  stage_reset( b, PALADIN_GPU_STAGE_SCATTER );
+  if ( b->count == 0 ) {
+    b->scattered = true;
+    return PALADIN_GPU_OK;
+  }
+  PB_CUDA( cudaMemsetAsync( b->d_flags, 0, sizeof( int ) * b->count, st ) );
+  PB_CUDA( cudaMemsetAsync( b->d_info, 0, sizeof( int ) * b->count, st ) );
+  pb::ScatterArgs a = scatter_args( b );
+  stage_begin( b, PALADIN_GPU_STAGE_SCATTER, st );
+  pb::scatter_sorted_kernel<<<b->nchunks, pb::kScatterThreads, 0, st>>>( a );
+  stage_end( b, PALADIN_GPU_STAGE_SCATTER, st, 1 );
+  PB_CUDA( cudaGetLastError() );
+  PB_CUDA( cudaMemcpyAsync( b->flags.data(), b->d_flags, sizeof( int ) * b->count, cudaMemcpyDeviceToHost, st ) );
+  PB_CUDA( cudaStreamSynchronize( st ) );
+  bool any_unsorted = false, any_bad = false;
+  for ( int k = 0; k < b->count; ++k ) {
+    if ( b->flags[k] & pb::kFlagBadIndex ) any_bad = true;
+    else if ( b->flags[k] & pb::kFlagUnsorted ) any_unsorted = true;
+  }
+  if ( any_unsorted ) {
+    // order-exact fallback for the flagged matrices (separate launches = global barriers between passes)
+    pb::zero_flagged_kernel<<<b->nchunks, pb::kScatterThreads, 0, st>>>( a );
+    pb::scatter_fallback_kernel<0><<<b->nchunks, pb::kScatterThreads, 0, st>>>( a );
+    pb::scatter_fallback_kernel<1><<<b->nchunks, pb::kScatterThreads, 0, st>>>( a );
+    pb::scatter_fallback_kernel<2><<<b->nchunks, pb::kScatterThreads, 0, st>>>( a );
+    stage_end( b, PALADIN_GPU_STAGE_SCATTER, st, 4 );
+    PB_CUDA( cudaGetLastError() );
+    PB_CUDA( cudaStreamSynchronize( st ) );
+  }
+  if ( any_bad ) {
+    std::vector<int> info( b->count, 0 );
+    for ( int k = 0; k < b->count; ++k )
+      if ( b->flags[k] & pb::kFlagBadIndex ) info[k] = PALADIN_GPU_INFO_BAD_INDEX;
+    PB_CUDA( cudaMemcpyAsync( b->d_info, info.data(), sizeof( int ) * b->count, cudaMemcpyHostToDevice, st ) );
+    PB_CUDA( cudaStreamSynchronize( st ) );
+  }
+  b->scattered = true;
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_batch_upload_dense( paladin_gpu_batch* b, const double* dense ) {
+  if ( !b ) return fail( PALADIN_GPU_EINVAL, "null batch" );
+  if ( b->total_nn > 0 && !dense ) return fail( PALADIN_GPU_EINVAL, "null dense array" );
+  DeviceCtx& c = g_ctx[b->device];
+  std::lock_guard<std::mutex> lk( c.mu );
+  PB_CUDA( cudaSetDevice( b->device ) );
+  int64_t src = 0;
+  for ( int k = 0; k < b->count; ++k ) {
+    const int64_t nn = (int64_t)b->n[k] * b->n[k];
+    if ( nn )
+      PB_CUDA( cudaMemcpyAsync( b->d_A + b->a_off[k], dense + src, sizeof( double ) * nn, cudaMemcpyHostToDevice, c.stream ) );
+    src += nn;
+  }
+  PB_CUDA( cudaMemsetAsync( b->d_info, 0, sizeof( int ) * std::max( b->count, 1 ), c.stream ) );
+  PB_CUDA( cudaStreamSynchronize( c.stream ) );
+  std::fill( b->flags.begin(), b->flags.end(), 0 );
+  b->scattered = true;
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_batch_get_dense( paladin_gpu_batch* b, int k, double* out ) {
+  if ( !b || k < 0 || k >= b->count || !out ) return fail( PALADIN_GPU_EINVAL, "bad arguments" );
+  DeviceCtx& c = g_ctx[b->device];
+  std::lock_guard<std::mutex> lk( c.mu );
+  PB_CUDA( cudaSetDevice( b->device ) );
+  const int64_t nn = (int64_t)b->n[k] * b->n[k];
+  if ( nn ) PB_CUDA( cudaMemcpyAsync( out, b->d_A + b->a_off[k], sizeof( double ) * nn, cudaMemcpyDeviceToHost, c.stream ) );
+  PB_CUDA( cudaStreamSynchronize( c.stream ) );
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
+  if ( !b ) return fail( PALADIN_GPU_EINVAL, "null batch" );
+  if ( !b->scattered ) return fail( PALADIN_GPU_EINVAL, "solve called before scatter / upload_dense" );
+  DeviceCtx& c = g_ctx[b->device];
+  std::lock_guard<std::mutex> lk( c.mu );
+  PB_CUDA( cudaSetDevice( b->device ) );
+  cudaStream_t st = c.stream;
+  for ( int s = 1; s < PALADIN_GPU_NUM_STAGES; ++s ) stage_reset( b, s );
+  BatchView bv = batch_view( b );
+  const bool wantvr = b->jobvr == 'V';
+  bool any_bad = false;
+  for ( int k = 0; k < b->count; ++k ) any_bad = any_bad || ( b->flags[k] & pb::kFlagBadIndex );
+  std::vector<int> ids_filtered;
+  for ( const auto& g : b->groups ) {
+    const int* ids = b->d_ids + g.first;
+    int cnt = g.count;
+    if ( any_bad ) {
+      // rare: drop matrices whose scatter failed; re-upload the filtered list of this group
+      ids_filtered.clear();
+      for ( int q = 0; q < g.count; ++q )
+        if ( !( b->flags[b->ids[g.first + q]] & pb::kFlagBadIndex ) ) ids_filtered.push_back( b->ids[g.first + q] );
+      cnt = (int)ids_filtered.size();
+      if ( cnt ) PB_CUDA( cudaMemcpyAsync( b->d_ids + g.first, ids_filtered.data(), sizeof( int ) * cnt, cudaMemcpyHostToDevice, st ) );
+      PB_CUDA( cudaStreamSynchronize( st ) );
+    }
+    if ( cnt == 0 ) continue;
+    if ( g.kind == 0 ) {
+      const size_t smem = warp_smem_bytes( g.nmax, wantvr );
+      if ( smem <= (size_t)c.max_smem_optin ) {
+        PB_CUDA( cudaFuncSetAttribute( geev_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
+        stage_begin( b, PALADIN_GPU_STAGE_SMALL, st );
+        geev_warp_kernel<<<cnt, 32, smem, st>>>( bv, ids, g.nmax, g.nmax | 1 );
+        stage_end( b, PALADIN_GPU_STAGE_SMALL, st, 1 );
+        PB_CUDA( cudaGetLastError() );
+        continue;
+      }
+    }
+    stage_begin( b, PALADIN_GPU_STAGE_GENERIC, st );
+    geev_cta_kernel<<<cnt, kGenericThreads, 0, st>>>( bv, ids );
+    stage_end( b, PALADIN_GPU_STAGE_GENERIC, st, 1 );
+    PB_CUDA( cudaGetLastError() );
+  }
+  PB_CUDA( cudaStreamSynchronize( st ) );
+  if ( any_bad ) PB_CUDA( cudaMemcpy( b->d_ids, b->ids.data(), sizeof( int ) * b->ids.size(), cudaMemcpyHostToDevice ) );
+  b->scattered = false;  // the dense matrices have been destroyed
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_batch_download( paladin_gpu_batch* b, double* wr, double* wi, double* vl, double* vr, int* info ) {
+  if ( !b ) return fail( PALADIN_GPU_EINVAL, "null batch" );
+  (void)vl;
+  DeviceCtx& c = g_ctx[b->device];
+  std::lock_guard<std::mutex> lk( c.mu );
+  PB_CUDA( cudaSetDevice( b->device ) );
+  cudaStream_t st = c.stream;
+  if ( wr && b->total_n ) PB_CUDA( cudaMemcpyAsync( wr, b->d_wr, sizeof( double ) * b->total_n, cudaMemcpyDeviceToHost, st ) );
+  if ( wi && b->total_n ) PB_CUDA( cudaMemcpyAsync( wi, b->d_wi, sizeof( double ) * b->total_n, cudaMemcpyDeviceToHost, st ) );
+  if ( info && b->count ) PB_CUDA( cudaMemcpyAsync( info, b->d_info, sizeof( int ) * b->count, cudaMemcpyDeviceToHost, st ) );
+  if ( vr && b->jobvr == 'V' ) {
+    // device matrices are padded to even length; the host layout is the plain concatenation
+    bool padded = false;
+    for ( int k = 0; k < b->count; ++k ) padded = padded || ( b->n[k] & 1 );
+    if ( !padded ) {
+      if ( b->total_nn ) PB_CUDA( cudaMemcpyAsync( vr, b->d_V, sizeof( double ) * b->total_nn, cudaMemcpyDeviceToHost, st ) );
+    } else {
+      int64_t dst = 0;
+      for ( int k = 0; k < b->count; ++k ) {
+        const int64_t nn = (int64_t)b->n[k] * b->n[k];
+        if ( nn ) PB_CUDA( cudaMemcpyAsync( vr + dst, b->d_V + b->a_off[k], sizeof( double ) * nn, cudaMemcpyDeviceToHost, st ) );
+        dst += nn;
+      }
+    }
+  }
+  PB_CUDA( cudaStreamSynchronize( st ) );
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_batch_stage_ms( paladin_gpu_batch* b, float* ms, int* launches ) {
+  if ( !b || !ms ) return fail( PALADIN_GPU_EINVAL, "bad arguments" );
+  DeviceCtx& c = g_ctx[b->device];
+  std::lock_guard<std::mutex> lk( c.mu );
+  PB_CUDA( cudaSetDevice( b->device ) );
+  for ( int s = 0; s < PALADIN_GPU_NUM_STAGES; ++s ) {
+    ms[s] = 0.0f;
+    if ( launches ) launches[s] = b->st[s].launches;
+    if ( b->st[s].used ) {
+      cudaEventSynchronize( b->st[s].e1 );
+      cudaEventElapsedTime( &ms[s], b->st[s].e0, b->st[s].e1 );
+    }
+  }
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_batch_destroy( paladin_gpu_batch* b ) {
+  if ( !b ) return PALADIN_GPU_OK;
+  DeviceCtx& c = g_ctx[b->device];
+  std::lock_guard<std::mutex> lk( c.mu );
+  free_batch( b );
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_geev_batch( int device, int count, const int* n, const int64_t* nnz_offsets, const int* coo_i,
+                            const int* coo_j, const double* coo_v, char jobvl, char jobvr, double* const* wr,
+                            double* const* wi, double* const* vl, double* const* vr, int* info ) {
+  (void)vl;
+  if ( count < 0 || ( count > 0 && ( !wr || !wi || !info ) ) ) return fail( PALADIN_GPU_EINVAL, "null output arrays" );
+  if ( jobvr == 'V' && count > 0 && !vr ) return fail( PALADIN_GPU_EINVAL, "vr is null but jobvr == 'V'" );
+  paladin_gpu_batch* b = nullptr;
+  PB_TRY( paladin_gpu_batch_create( device, count, n, nnz_offsets, jobvl, jobvr, &b ) );
+  int rc = paladin_gpu_batch_upload( b, coo_i ? coo_i + nnz_offsets[0] : nullptr, coo_j ? coo_j + nnz_offsets[0] : nullptr,
+                                     coo_v ? coo_v + nnz_offsets[0] : nullptr );
+  if ( rc == PALADIN_GPU_OK ) rc = paladin_gpu_batch_scatter( b );
+  if ( rc == PALADIN_GPU_OK ) rc = paladin_gpu_batch_solve( b );
+  if ( rc == PALADIN_GPU_OK ) {
+    // results straight into the caller's per-matrix buffers
+    DeviceCtx& c = g_ctx[device];
+    std::lock_guard<std::mutex> lk( c.mu );
+    cudaSetDevice( device );
+    cudaStream_t st = c.stream;
+    cudaError_t e = cudaMemcpyAsync( info, b->d_info, sizeof( int ) * count, cudaMemcpyDeviceToHost, st );
+    for ( int k = 0; k < count && e == cudaSuccess; ++k ) {
+      const int nk = b->n[k];
+      if ( nk == 0 ) continue;
+      e = cudaMemcpyAsync( wr[k], b->d_wr + b->w_off[k], sizeof( double ) * nk, cudaMemcpyDeviceToHost, st );
+      if ( e == cudaSuccess ) e = cudaMemcpyAsync( wi[k], b->d_wi + b->w_off[k], sizeof( double ) * nk, cudaMemcpyDeviceToHost, st );
+      if ( e == cudaSuccess && jobvr == 'V' && vr[k] )
+        e = cudaMemcpyAsync( vr[k], b->d_V + b->a_off[k], sizeof( double ) * nk * nk, cudaMemcpyDeviceToHost, st );
+    }
+    if ( e == cudaSuccess ) e = cudaStreamSynchronize( st );
+    if ( e != cudaSuccess ) rc = fail( PALADIN_GPU_ECUDA, cudaGetErrorString( e ) );
+  }
+  paladin_gpu_batch_destroy( b );
+  return rc;
+}
+
+void paladin_gpu_dgeev_( const char* jobvl, const char* jobvr, int* n, double* a, int* lda, double* wr, double* wi,
+                         double* vl, int* ldvl, double* vr, int* ldvr, double* work, int* lwork, int* info ) {
+  (void)vl;
+  (void)ldvl;
+  if ( !info ) return;
+  *info = 0;
+  const char jl = jobvl ? ( *jobvl == 'v' ? 'V' : ( *jobvl == 'n' ? 'N' : *jobvl ) ) : '?';
+  const char jr = jobvr ? ( *jobvr == 'v' ? 'V' : ( *jobvr == 'n' ? 'N' : *jobvr ) ) : '?';
+  if ( jl != 'N' && jl != 'V' ) { *info = -1; return; }
+  if ( jr != 'N' && jr != 'V' ) { *info = -2; return; }
+  if ( !n || *n < 0 ) { *info = -3; return; }
+  if ( !lda || *lda < std::max( 1, *n ) ) { *info = -5; return; }
+  if ( !ldvr || *ldvr < 1 || ( jr == 'V' && *ldvr < *n ) ) { *info = -11; return; }
+  if ( lwork && *lwork == -1 ) {  // workspace query (reference src/paladin.hpp:247-249): the device path owns its workspace
+    if ( work ) work[0] = 1.0;
+    return;
+  }
+  const int N = *n;
+  if ( N == 0 ) return;
+  int device = 0;
+  if ( const char* env = std::getenv( "PALADIN_GPU_DEVICE" ) ) device = std::atoi( env );
+  const int64_t offs[2] = { 0, 0 };
+  paladin_gpu_batch* b = nullptr;
+  int rc = paladin_gpu_batch_create( device, 1, &N, offs, jl, jr, &b );
+  if ( rc != PALADIN_GPU_OK ) {
+    std::fprintf( stderr, "paladin_gpu_dgeev_: %s\n", paladin_gpu_last_error() );
+    *info = -1000 - rc;  // no CPU fallback: fail loudly
+    return;
+  }
+  std::vector<double> dense( (size_t)N * N ), w( 2 * (size_t)N ), V( jr == 'V' ? (size_t)N * N : 0 );
+  for ( int c2 = 0; c2 < N; ++c2 ) std::memcpy( &dense[(size_t)c2 * N], a + (size_t)c2 * *lda, sizeof( double ) * N );
+  rc = paladin_gpu_batch_upload_dense( b, dense.data() );
+  if ( rc == PALADIN_GPU_OK ) rc = paladin_gpu_batch_solve( b );
+  if ( rc == PALADIN_GPU_OK ) rc = paladin_gpu_batch_download( b, w.data(), w.data() + N, nullptr, jr == 'V' ? V.data() : nullptr, info );
+  paladin_gpu_batch_destroy( b );
+  if ( rc != PALADIN_GPU_OK ) {
+    std::fprintf( stderr, "paladin_gpu_dgeev_: %s\n", paladin_gpu_last_error() );
+    *info = -1000 - rc;
+    return;
+  }
+  std::memcpy( wr, w.data(), sizeof( double ) * N );
+  std::memcpy( wi, w.data() + N, sizeof( double ) * N );
+  if ( jr == 'V' && vr )
+    for ( int c2 = 0; c2 < N; ++c2 ) std::memcpy( vr + (size_t)c2 * *ldvr, &V[(size_t)c2 * N], sizeof( double ) * N );
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+// pb_geev.cuh -- the whole dgeev pipeline executed by ONE thread group (a warp for n <= 64, a CTA as
+// the size-generic path) on one matrix held in memory the group can address (shared or global).
+//
+// Restates the driver logic of LAPACK 3.12 dgeev (third party to the reference; reached through
+// reference src/lapack-wrapper.hpp:47-60 from src/paladin.hpp:248-254):
+//   scale check (dlange 'M' / dlascl) -> gebal 'B' -> Hessenberg -> [orghr] -> QR iteration ->
+//   [trevc 'R','B' -> gebak 'B','R' -> normalise] -> undo scaling of the eigenvalues.
+// Output conventions consumed by the reference unpack loop (src/paladin.hpp:256-333): conjugate
+// pairs consecutive, positive imaginary part first, wi[k+1] == -wi[k] exactly, vectors real-packed.
+#pragma once
+
+#include "pb_common.cuh"
+#include "pb_small.cuh"
+#include "pb_vec.cuh"
+
+namespace pb {
+
+// x *= cto/cfrom without intermediate over/underflow (published dlascl multiplication schedule)
+template <class G>
+PB_D void lascl( const G& g, double cfrom, double cto, int rows, int cols, double* A, int lda ) {
+  const int t = g.tid(), nt = g.size();
+  const double smlnum = kSafmin, bignum = 1.0 / smlnum;
+  double cfromc = cfrom, ctoc = cto;
+  bool done = false;
+  int guard = 0;
+  while ( !done && guard++ < 64 ) {
+    const double cfrom1 = cfromc * smlnum;
+    double mul;
+    if ( cfrom1 == cfromc ) {
+      mul = ctoc / cfromc;
+      done = true;
+    } else {
+      const double cto1 = ctoc / bignum;
+      if ( cto1 == ctoc ) {
+        mul = ctoc;
+        done = true;
+        cfromc = 1.0;
+      } else if ( fabs( cfrom1 ) > fabs( ctoc ) && ctoc != 0.0 ) {
+        mul = smlnum;
+        done = false;
+        cfromc = cfrom1;
+      } else if ( fabs( cto1 ) > fabs( cfromc ) ) {
+        mul = bignum;
+        done = false;
+        ctoc = cto1;
+      } else {
+        mul = ctoc / cfromc;
+        done = true;
+      }
+    }
+    for ( int c = 0; c < cols; ++c )
+      for ( int r = t; r < rows; r += nt ) A[r + (size_t)c * lda] *= mul;
+  }
+  g.sync();
+}
+
+// Scratch carved by the caller: dwork >= 5*n doubles, iwork >= 2*n+2 ints, visible to the group.
+// Returns the LAPACK info value (0, or i > 0 when the QR iteration failed: wr/wi[i..n) are valid).
+// On exit with wantvr, V (n x n, ldv) holds the right eigenvectors. A is destroyed.
+template <class G>
+PB_D int geev_group( const G& g, int n, double* A, int lda, double* wr, double* wi, bool wantvr, double* V, int ldv,
+                     double* dwork, int* iwork ) {
+  const int t = g.tid(), nt = g.size();
+  if ( n == 0 ) return 0;
+  double* tau = dwork;
+  double* scale = dwork + n;
+  double* cnorm = dwork + 2 * n;
+  double* xr = dwork + 3 * n;
+  double* xi = dwork + 4 * n;
+
+  // ---- scale check ----
+  double anrm = 0.0;
+  bool bad = false;
+  for ( int c = 0; c < n; ++c )
+    for ( int r = t; r < n; r += nt ) {
+      const double a = fabs( PB_A( r, c ) );
+      if ( !( a <= DBL_MAX ) ) bad = true;
+      anrm = dmax( anrm, a );
+    }
+  anrm = g.max( anrm );
+  bad = g.any( bad );
+  if ( bad ) return -4;  // non-finite input (argument 4 of dgeev), nothing is computed
+  const double smlnum0 = sqrt( kSafmin ) / kUlp;
+  const double bignum0 = 1.0 / smlnum0;
+  bool scalea = false;
+  double cscale = 1.0;
+  if ( anrm > 0.0 && anrm < smlnum0 ) {
+    scalea = true;
+    cscale = smlnum0;
+  } else if ( anrm > bignum0 ) {
+    scalea = true;
+    cscale = bignum0;
+  }
+  if ( scalea ) lascl( g, anrm, cscale, n, n, A, lda );
+
+  // ---- balance, reduce, iterate ----
+  int ilo, ihi;
+  gebal( g, n, A, lda, &ilo, &ihi, scale, iwork );
+  g.sync();
+  gehd2( g, n, ilo, ihi, A, lda, tau, cnorm );
+  if ( wantvr ) orghr( g, n, ilo, ihi, A, lda, tau, V, ldv );
+  g.sync();
+  for ( int i = t; i < n; i += nt )
+    if ( i < ilo || i > ihi ) {
+      wr[i] = PB_A( i, i );
+      wi[i] = 0.0;
+    }
+  g.sync();
+  int info = lahqr( g, wantvr, wantvr, n, ilo, ihi, A, lda, wr, wi, 0, n - 1, V, ldv );
+  g.sync();
+
+  if ( info == 0 && wantvr ) {
+    // quasi-triangular T: the reflector storage below the first subdiagonal is never read again
+    trevc_right_inplace( g, n, A, lda, V, ldv, cnorm, xr, xi );
+    gebak_right( g, n, ilo, ihi, scale, n, V, ldv );
+    g.sync();
+    normalize_vectors( g, n, wi, V, ldv );
+  }
+  if ( scalea ) {
+    // undo scaling on the converged part (and on the isolated head when the iteration failed)
+    lascl( g, cscale, anrm, n - info, 1, wr + info, n );
+    lascl( g, cscale, anrm, n - info, 1, wi + info, n );
+    if ( info > 0 ) {
+      lascl( g, cscale, anrm, ilo, 1, wr, n );
+      lascl( g, cscale, anrm, ilo, 1, wi, n );
+    }
+  }
+  g.sync();
+  return info;
+}
+
+}  // namespace pb

@@ -1,0 +1,633 @@
+// pb_small.cuh -- group-parallel dense kernels for matrices that are small enough to be worked on
+// in place by one warp or one CTA (shared or global memory, generic pointers, column-major):
+//   gebal  : permutation + diagonal scaling                 (LAPACK dgebal 'B', reached from dgeev)
+//   gehd2  : unblocked Householder Hessenberg reduction     (LAPACK dgehd2)
+//   orghr  : explicit Q from the stored reflectors          (LAPACK dorghr/dorg2r)
+//   lahqr  : Francis double-shift QR with Ahues-Tisseur deflation, exceptional shifts and dlanv2
+//            standardisation                                 (LAPACK dlahqr)
+// These restate the published LAPACK 3.12 algorithms that the reference reaches through its single
+// numerical call, dgeev_ (reference src/lapack-wrapper.hpp:47-60, src/paladin.hpp:248-254), so that
+// eigenvalue order and the conjugate-pair convention consumed at src/paladin.hpp:262-263 are kept.
+// All indices are 0-based and inclusive (ilo..ihi).
+#pragma once
+
+#include "pb_common.cuh"
+
+namespace pb {
+
+#define PB_A( i, j ) A[( i ) + (size_t)( j ) * lda]
+#define PB_H( i, j ) H[( i ) + (size_t)( j ) * ldh]
+#define PB_Z( i, j ) Z[( i ) + (size_t)( j ) * ldz]
+#define PB_Q( i, j ) Q[( i ) + (size_t)( j ) * ldq]
+
+// ------------------------------------------------------------------------------------------------
+// gebal. icnt: 2*n ints of scratch (row / column off-diagonal nonzero counts).
+// On exit scale[] holds permutation indices outside ilo..ihi (0-based) and scaling factors inside.
+// ------------------------------------------------------------------------------------------------
+template <class G>
+PB_D void gebal( const G& g, int n, double* A, int lda, int* ilo_out, int* ihi_out, double* scale,
+                 int* icnt ) {
+  const int t = g.tid(), nt = g.size();
+  int* rowcnt = icnt;
+  int* colcnt = icnt + n;
+  int k = 0, l = n - 1;
+  if ( n == 0 ) {
+    *ilo_out = 0;
+    *ihi_out = -1;
+    return;
+  }
+  // off-diagonal nonzero counts
+  for ( int r = t; r < n; r += nt ) {
+    int cnt = 0;
+    for ( int c = 0; c < n; ++c ) cnt += ( c != r && PB_A( r, c ) != 0.0 ) ? 1 : 0;
+    rowcnt[r] = cnt;
+  }
+  for ( int c = t; c < n; c += nt ) {
+    int cnt = 0;
+    for ( int r = 0; r < n; ++r ) cnt += ( c != r && PB_A( r, c ) != 0.0 ) ? 1 : 0;
+    colcnt[c] = cnt;
+  }
+  g.sync();
+
+  // ---- rows isolating an eigenvalue are pushed down ----
+  bool noconv = true;
+  bool all_isolated = false;
+  while ( noconv && !all_isolated ) {
+    noconv = false;
+    for ( int i = l; i >= 0; --i ) {
+      if ( rowcnt[i] != 0 ) continue;  // uniform: every thread reads the same shared value
+      g.sync();
+      if ( t == 0 ) scale[l] = (double)i;
+      if ( i != l ) {
+        for ( int r = t; r <= l; r += nt ) {
+          const double tmp = PB_A( r, i );
+          PB_A( r, i ) = PB_A( r, l );
+          PB_A( r, l ) = tmp;
+        }
+        g.sync();
+        for ( int c = k + t; c < n; c += nt ) {
+          const double tmp = PB_A( i, c );
+          PB_A( i, c ) = PB_A( l, c );
+          PB_A( l, c ) = tmp;
+        }
+        if ( t == 0 ) {
+          int tmp = rowcnt[i];
+          rowcnt[i] = rowcnt[l];
+          rowcnt[l] = tmp;
+          tmp = colcnt[i];
+          colcnt[i] = colcnt[l];
+          colcnt[l] = tmp;
+        }
+      }
+      g.sync();
+      noconv = true;
+      if ( l == 0 ) {
+        all_isolated = true;
+        break;
+      }
+      // column l leaves the active set
+      for ( int r = t; r < l; r += nt )
+        if ( PB_A( r, l ) != 0.0 ) rowcnt[r] -= 1;
+      l -= 1;
+      g.sync();
+    }
+  }
+  if ( all_isolated ) {
+    *ilo_out = 0;
+    *ihi_out = 0;
+    return;
+  }
+
+  // ---- columns isolating an eigenvalue are pushed left ----
+  noconv = true;
+  while ( noconv ) {
+    noconv = false;
+    const int jend = l;
+    for ( int j = k; j <= jend; ++j ) {
+      if ( j < k || colcnt[j] != 0 ) continue;
+      g.sync();
+      if ( t == 0 ) scale[k] = (double)j;
+      if ( j != k ) {
+        for ( int r = t; r <= l; r += nt ) {
+          const double tmp = PB_A( r, j );
+          PB_A( r, j ) = PB_A( r, k );
+          PB_A( r, k ) = tmp;
+        }
+        g.sync();
+        for ( int c = k + t; c < n; c += nt ) {
+          const double tmp = PB_A( j, c );
+          PB_A( j, c ) = PB_A( k, c );
+          PB_A( k, c ) = tmp;
+        }
+        if ( t == 0 ) {
+          const int tmp = colcnt[j];
+          colcnt[j] = colcnt[k];
+          colcnt[k] = tmp;
+        }
+      }
+      g.sync();
+      noconv = true;
+      // row k leaves the active set
+      for ( int c = k + 1 + t; c <= l; c += nt )
+        if ( PB_A( k, c ) != 0.0 ) colcnt[c] -= 1;
+      k += 1;
+      g.sync();
+    }
+  }
+
+  // ---- diagonal scaling of rows/columns k..l (power-of-two factors) ----
+  for ( int i = k + t; i <= l; i += nt ) scale[i] = 1.0;
+  g.sync();
+  const double sclfac = 2.0, factor = 0.95;
+  const double sfmin1 = kSafmin / kUlp, sfmax1 = 1.0 / sfmin1;
+  const double sfmin2 = sfmin1 * sclfac, sfmax2 = 1.0 / sfmin2;
+  // overflow-safe sums of squares: entries are divided by a power of two near the largest magnitude
+  double amax = 0.0;
+  for ( int c = k; c <= l; ++c )
+    for ( int r = k + t; r <= l; r += nt ) amax = dmax( amax, fabs( PB_A( r, c ) ) );
+  amax = g.max( amax );
+  if ( amax == 0.0 ) {
+    *ilo_out = k;
+    *ihi_out = l;
+    return;
+  }
+  int ex = 0;
+  (void)frexp( amax, &ex );
+  const double down = ldexp( 1.0, -ex ), up = ldexp( 1.0, ex );
+
+  noconv = true;
+  int guard = 0;
+  while ( noconv && guard++ < 200 ) {
+    noconv = false;
+    for ( int i = k; i <= l; ++i ) {
+      double cs = 0.0, rs = 0.0, ca = 0.0, ra = 0.0;
+      for ( int r = k + t; r <= l; r += nt ) {
+        const double x = PB_A( r, i ) * down;
+        cs += x * x;
+      }
+      for ( int c = k + t; c <= l; c += nt ) {
+        const double x = PB_A( i, c ) * down;
+        rs += x * x;
+      }
+      for ( int r = t; r <= l; r += nt ) ca = dmax( ca, fabs( PB_A( r, i ) ) );
+      for ( int c = k + t; c < n; c += nt ) ra = dmax( ra, fabs( PB_A( i, c ) ) );
+      double c = sqrt( g.sum( cs ) ) * up;
+      double r = sqrt( g.sum( rs ) ) * up;
+      ca = g.max( ca );
+      ra = g.max( ra );
+      if ( c == 0.0 || r == 0.0 ) continue;
+      double gg = r / sclfac;
+      double f = 1.0;
+      const double s = c + r;
+      while ( c < gg && dmax( f, dmax( c, ca ) ) < sfmax2 && dmin( r, dmin( gg, ra ) ) > sfmin2 ) {
+        f *= sclfac;
+        c *= sclfac;
+        ca *= sclfac;
+        r /= sclfac;
+        gg /= sclfac;
+        ra /= sclfac;
+      }
+      gg = c / sclfac;
+      while ( gg >= r && dmax( r, ra ) < sfmax2 && dmin( dmin( f, c ), dmin( gg, ca ) ) > sfmin2 ) {
+        f /= sclfac;
+        c /= sclfac;
+        gg /= sclfac;
+        ca /= sclfac;
+        r *= sclfac;
+        ra *= sclfac;
+      }
+      if ( ( c + r ) >= factor * s ) continue;
+      const double sci = scale[i];
+      if ( f < 1.0 && sci < 1.0 ) {
+        if ( f * sci <= sfmin1 ) continue;
+      }
+      if ( f > 1.0 && sci > 1.0 ) {
+        if ( sci >= sfmax1 / f ) continue;
+      }
+      const double ginv = 1.0 / f;
+      g.sync();
+      if ( t == 0 ) scale[i] = sci * f;
+      for ( int cc = k + t; cc < n; cc += nt ) PB_A( i, cc ) *= ginv;
+      g.sync();
+      for ( int rr = t; rr <= l; rr += nt ) PB_A( rr, i ) *= f;
+      g.sync();
+      noconv = true;
+    }
+  }
+  *ilo_out = k;
+  *ihi_out = l;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Householder generation for a column segment x = A(r0+1:r1, c), alpha = A(r0, c)  (dlarfg).
+// Leaves v (scaled x) in place, returns beta and tau; A(r0,c) is NOT modified (caller stores beta).
+// ------------------------------------------------------------------------------------------------
+template <class G>
+PB_D void larfg_col( const G& g, double* A, int lda, int r0, int r1, int c, double* beta_out,
+                     double* tau_out ) {
+  const int t = g.tid(), nt = g.size();
+  double alpha = PB_A( r0, c );
+  if ( r1 <= r0 ) {
+    *beta_out = alpha;
+    *tau_out = 0.0;
+    return;
+  }
+  double mx = 0.0;
+  for ( int r = r0 + 1 + t; r <= r1; r += nt ) mx = dmax( mx, fabs( PB_A( r, c ) ) );
+  mx = g.max( mx );
+  if ( mx == 0.0 ) {
+    *beta_out = alpha;
+    *tau_out = 0.0;
+    return;
+  }
+  double ss = 0.0;
+  for ( int r = r0 + 1 + t; r <= r1; r += nt ) {
+    const double x = PB_A( r, c ) / mx;
+    ss += x * x;
+  }
+  double xnorm = mx * sqrt( g.sum( ss ) );
+  double beta = -dsign( dlapy2( alpha, xnorm ), alpha );
+  const double safmin = kSafmin / kEps;
+  int knt = 0;
+  double pre = 1.0;
+  if ( fabs( beta ) < safmin ) {
+    const double rsafmn = 1.0 / safmin;
+    do {
+      ++knt;
+      pre *= rsafmn;
+      xnorm *= rsafmn;
+      beta *= rsafmn;
+      alpha *= rsafmn;
+    } while ( fabs( beta ) < safmin && knt < 20 );
+    beta = -dsign( dlapy2( alpha, xnorm ), alpha );
+  }
+  const double tau = ( beta - alpha ) / beta;
+  const double sc = pre / ( alpha - beta );
+  g.sync();
+  for ( int r = r0 + 1 + t; r <= r1; r += nt ) PB_A( r, c ) *= sc;
+  for ( int j = 0; j < knt; ++j ) beta *= safmin;
+  g.sync();
+  *beta_out = beta;
+  *tau_out = tau;
+}
+
+// ------------------------------------------------------------------------------------------------
+// gehd2: A(0:n,0:n) -> upper Hessenberg in rows/cols ilo..ihi, reflectors below the subdiagonal.
+// wrk: n doubles of scratch visible to the whole group.
+// ------------------------------------------------------------------------------------------------
+template <class G>
+PB_D void gehd2( const G& g, int n, int ilo, int ihi, double* A, int lda, double* tau, double* wrk ) {
+  const int t = g.tid(), nt = g.size();
+  for ( int j = ilo; j < ihi; ++j ) {
+    double beta, tj;
+    larfg_col( g, A, lda, j + 1, ihi, j, &beta, &tj );
+    if ( t == 0 ) tau[j] = tj;
+    if ( tj != 0.0 ) {
+      // v = [1; A(j+2:ihi, j)]
+      // right: A(0:ihi, j+1:ihi) -= tau * (A v) v^T
+      for ( int r = t; r <= ihi; r += nt ) {
+        double w = PB_A( r, j + 1 );
+        for ( int c = j + 2; c <= ihi; ++c ) w += PB_A( r, c ) * PB_A( c, j );
+        w *= tj;
+        PB_A( r, j + 1 ) -= w;
+        for ( int c = j + 2; c <= ihi; ++c ) PB_A( r, c ) -= w * PB_A( c, j );
+      }
+      g.sync();
+      // left: A(j+1:ihi, j+1:n) -= tau * v (v^T A)
+      for ( int c = j + 1 + t; c < n; c += nt ) {
+        double w = PB_A( j + 1, c );
+        for ( int r = j + 2; r <= ihi; ++r ) w += PB_A( r, j ) * PB_A( r, c );
+        w *= tj;
+        PB_A( j + 1, c ) -= w;
+        for ( int r = j + 2; r <= ihi; ++r ) PB_A( r, c ) -= w * PB_A( r, j );
+      }
+    }
+    g.sync();
+    if ( t == 0 ) PB_A( j + 1, j ) = beta;
+    g.sync();
+  }
+  (void)wrk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// orghr: Q (n x n, ldq) from reflectors stored below the subdiagonal of A (columns ilo..ihi-1).
+// Q = H(ilo) H(ilo+1) ... H(ihi-1); rows/cols outside ilo..ihi are identity (dorghr semantics).
+// ------------------------------------------------------------------------------------------------
+template <class G>
+PB_D void orghr( const G& g, int n, int ilo, int ihi, const double* A, int lda, const double* tau,
+                 double* Q, int ldq ) {
+  const int t = g.tid(), nt = g.size();
+  for ( int c = 0; c < n; ++c )
+    for ( int r = t; r < n; r += nt ) PB_Q( r, c ) = ( r == c ) ? 1.0 : 0.0;
+  g.sync();
+  // apply H(j) from the left to Q(j+1:ihi, j+1:ihi), j descending (backward accumulation)
+  for ( int j = ihi - 1; j >= ilo; --j ) {
+    const double tj = tau[j];
+    if ( tj == 0.0 ) continue;
+    for ( int c = j + 1 + t; c <= ihi; c += nt ) {
+      double w = PB_Q( j + 1, c );
+      for ( int r = j + 2; r <= ihi; ++r ) w += PB_A( r, j ) * PB_Q( r, c );
+      w *= tj;
+      PB_Q( j + 1, c ) -= w;
+      for ( int r = j + 2; r <= ihi; ++r ) PB_Q( r, c ) -= w * PB_A( r, j );
+    }
+    g.sync();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// lahqr. H upper Hessenberg in rows/cols ilo..ihi of an n x n array. With wantt the full Schur form
+// is produced (updates extend over 0..n-1), otherwise only eigenvalues. With wantz the same
+// transformations are accumulated into rows iloz..ihiz of Z.
+// Returns 0, or (i+1) when the QR iteration failed to converge for eigenvalue index i.
+// ------------------------------------------------------------------------------------------------
+template <class G>
+PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, double* H, int ldh,
+                double* wr, double* wi, int iloz, int ihiz, double* Z, int ldz ) {
+  const int t = g.tid(), nt = g.size();
+  if ( n == 0 || ihi < ilo ) return 0;
+  if ( ilo == ihi ) {
+    if ( t == 0 ) {
+      wr[ilo] = PB_H( ilo, ilo );
+      wi[ilo] = 0.0;
+    }
+    g.sync();
+    return 0;
+  }
+  // clear out the trash below the subdiagonal
+  for ( int j = ilo + t; j <= ihi - 3; j += nt ) {
+    PB_H( j + 2, j ) = 0.0;
+    PB_H( j + 3, j ) = 0.0;
+  }
+  if ( t == 0 && ilo <= ihi - 2 ) PB_H( ihi, ihi - 2 ) = 0.0;
+  g.sync();
+
+  const int nh = ihi - ilo + 1;
+  const double smlnum = kSafmin * ( (double)nh / kUlp );
+  const double dat1 = 0.75, dat2 = -0.4375;
+  const int kexsh = 10;
+  int i1 = 0, i2 = n - 1;
+  const int itmax = 30 * imax( 10, nh );
+  int kdefl = 0;
+
+  int i = ihi;
+  while ( i >= ilo ) {
+    int l = ilo;
+    bool converged = false;
+    for ( int its = 0; its <= itmax; ++its ) {
+      // ---- look for a single small subdiagonal element (largest k in l+1..i that qualifies) ----
+      int kfound = l;
+      for ( int k = i - t; k > l; k -= nt ) {
+        const double hkk1 = fabs( PB_H( k, k - 1 ) );
+        bool small = false;
+        if ( hkk1 <= smlnum ) {
+          small = true;
+        } else {
+          double tst = fabs( PB_H( k - 1, k - 1 ) ) + fabs( PB_H( k, k ) );
+          if ( tst == 0.0 ) {
+            if ( k - 2 >= ilo ) tst += fabs( PB_H( k - 1, k - 2 ) );
+            if ( k + 1 <= ihi ) tst += fabs( PB_H( k + 1, k ) );
+          }
+          if ( hkk1 <= kUlp * tst ) {
+            const double hk1k = fabs( PB_H( k - 1, k ) );
+            const double ab = dmax( hkk1, hk1k ), ba = dmin( hkk1, hk1k );
+            const double dd = fabs( PB_H( k - 1, k - 1 ) - PB_H( k, k ) );
+            const double aa = dmax( fabs( PB_H( k, k ) ), dd ), bb = dmin( fabs( PB_H( k, k ) ), dd );
+            const double s = aa + ab;
+            if ( ba * ( ab / s ) <= dmax( smlnum, kUlp * ( bb * ( aa / s ) ) ) ) small = true;
+          }
+        }
+        if ( small ) {
+          kfound = k;
+          break;  // this thread's k values only decrease from here
+        }
+      }
+      l = g.imax_( kfound );
+      if ( l > ilo ) {
+        if ( t == 0 ) PB_H( l, l - 1 ) = 0.0;
+      }
+      g.sync();
+      if ( l >= i - 1 ) {
+        converged = true;
+        break;
+      }
+      kdefl += 1;
+      if ( !wantt ) {
+        i1 = l;
+        i2 = i;
+      }
+      double h11, h21, h12, h22;
+      if ( kdefl % ( 2 * kexsh ) == 0 ) {
+        const double s = fabs( PB_H( i, i - 1 ) ) + fabs( PB_H( i - 1, i - 2 ) );
+        h11 = dat1 * s + PB_H( i, i );
+        h12 = dat2 * s;
+        h21 = s;
+        h22 = h11;
+      } else if ( kdefl % kexsh == 0 ) {
+        const double s = fabs( PB_H( l + 1, l ) ) + fabs( PB_H( l + 2, l + 1 ) );
+        h11 = dat1 * s + PB_H( l, l );
+        h12 = dat2 * s;
+        h21 = s;
+        h22 = h11;
+      } else {
+        h11 = PB_H( i - 1, i - 1 );
+        h21 = PB_H( i, i - 1 );
+        h12 = PB_H( i - 1, i );
+        h22 = PB_H( i, i );
+      }
+      double rt1r, rt1i, rt2r, rt2i;
+      {
+        const double s = fabs( h11 ) + fabs( h12 ) + fabs( h21 ) + fabs( h22 );
+        if ( s == 0.0 ) {
+          rt1r = rt1i = rt2r = rt2i = 0.0;
+        } else {
+          h11 /= s;
+          h21 /= s;
+          h12 /= s;
+          h22 /= s;
+          const double tr = ( h11 + h22 ) / 2.0;
+          const double det = ( h11 - tr ) * ( h22 - tr ) - h12 * h21;
+          const double rtdisc = sqrt( fabs( det ) );
+          if ( det >= 0.0 ) {
+            rt1r = tr * s;
+            rt2r = rt1r;
+            rt1i = rtdisc * s;
+            rt2i = -rt1i;
+          } else {
+            rt1r = tr + rtdisc;
+            rt2r = tr - rtdisc;
+            if ( fabs( rt1r - h22 ) <= fabs( rt2r - h22 ) ) {
+              rt1r = rt1r * s;
+              rt2r = rt1r;
+            } else {
+              rt2r = rt2r * s;
+              rt1r = rt2r;
+            }
+            rt1i = rt2i = 0.0;
+          }
+        }
+      }
+      // ---- look for two consecutive small subdiagonal elements (largest m in l..i-2) ----
+      int mfound = l;
+      for ( int m = i - 2 - t; m > l; m -= nt ) {
+        double h21s = fabs( PB_H( m + 1, m ) );
+        double s = fabs( PB_H( m, m ) - rt2r ) + fabs( rt2i ) + h21s;
+        h21s = PB_H( m + 1, m ) / s;
+        double v0 = h21s * PB_H( m, m + 1 ) + ( PB_H( m, m ) - rt1r ) * ( ( PB_H( m, m ) - rt2r ) / s ) -
+                    rt1i * ( rt2i / s );
+        double v1 = h21s * ( PB_H( m, m ) + PB_H( m + 1, m + 1 ) - rt1r - rt2r );
+        double v2 = h21s * PB_H( m + 2, m + 1 );
+        s = fabs( v0 ) + fabs( v1 ) + fabs( v2 );
+        v0 /= s;
+        v1 /= s;
+        v2 /= s;
+        const double h00 = fabs( PB_H( m - 1, m - 1 ) ), h11a = fabs( PB_H( m, m ) ),
+                     h22a = fabs( PB_H( m + 1, m + 1 ) );
+        if ( fabs( PB_H( m, m - 1 ) ) * ( fabs( v1 ) + fabs( v2 ) ) <= kUlp * fabs( v0 ) * ( h00 + h11a + h22a ) ) {
+          mfound = m;
+          break;
+        }
+      }
+      const int m = g.imax_( mfound );
+      double v0, v1, v2;
+      {
+        double h21s = fabs( PB_H( m + 1, m ) );
+        double s = fabs( PB_H( m, m ) - rt2r ) + fabs( rt2i ) + h21s;
+        h21s = PB_H( m + 1, m ) / s;
+        v0 = h21s * PB_H( m, m + 1 ) + ( PB_H( m, m ) - rt1r ) * ( ( PB_H( m, m ) - rt2r ) / s ) -
+             rt1i * ( rt2i / s );
+        v1 = h21s * ( PB_H( m, m ) + PB_H( m + 1, m + 1 ) - rt1r - rt2r );
+        v2 = h21s * PB_H( m + 2, m + 1 );
+        s = fabs( v0 ) + fabs( v1 ) + fabs( v2 );
+        v0 /= s;
+        v1 /= s;
+        v2 /= s;
+      }
+      g.sync();  // every thread has finished reading H for the shift vector before the sweep writes
+      // ---- double-shift QR sweep ----
+      for ( int k = m; k <= i - 1; ++k ) {
+        const int nr = imin( 3, i - k + 1 );
+        double a0, a1, a2 = 0.0, t1;
+        if ( k > m ) {
+          a0 = PB_H( k, k - 1 );
+          a1 = PB_H( k + 1, k - 1 );
+          if ( nr == 3 ) a2 = PB_H( k + 2, k - 1 );
+        } else {
+          a0 = v0;
+          a1 = v1;
+          a2 = v2;
+        }
+        dlarfg3( nr, a0, a1, a2, t1 );
+        const double w2 = a1, t2 = t1 * w2;
+        // column k-1 is rewritten by thread 0 only after the barrier that follows the left
+        // application, i.e. once every thread has read it
+#define PB_FIX_BULGE_COLUMN()                                \
+  if ( t == 0 ) {                                            \
+    if ( k > m ) {                                           \
+      PB_H( k, k - 1 ) = a0;                                 \
+      PB_H( k + 1, k - 1 ) = 0.0;                            \
+      if ( k < i - 1 ) PB_H( k + 2, k - 1 ) = 0.0;           \
+    } else if ( m > l ) {                                    \
+      PB_H( k, k - 1 ) = PB_H( k, k - 1 ) * ( 1.0 - t1 );    \
+    }                                                        \
+  }
+        if ( nr == 3 ) {
+          const double w3 = a2, t3 = t1 * w3;
+          for ( int j = k + t; j <= i2; j += nt ) {
+            const double sum = PB_H( k, j ) + w2 * PB_H( k + 1, j ) + w3 * PB_H( k + 2, j );
+            PB_H( k, j ) -= sum * t1;
+            PB_H( k + 1, j ) -= sum * t2;
+            PB_H( k + 2, j ) -= sum * t3;
+          }
+          g.sync();
+          PB_FIX_BULGE_COLUMN();
+          const int jend = imin( k + 3, i );
+          for ( int j = i1 + t; j <= jend; j += nt ) {
+            const double sum = PB_H( j, k ) + w2 * PB_H( j, k + 1 ) + w3 * PB_H( j, k + 2 );
+            PB_H( j, k ) -= sum * t1;
+            PB_H( j, k + 1 ) -= sum * t2;
+            PB_H( j, k + 2 ) -= sum * t3;
+          }
+          if ( wantz ) {
+            for ( int j = iloz + t; j <= ihiz; j += nt ) {
+              const double sum = PB_Z( j, k ) + w2 * PB_Z( j, k + 1 ) + w3 * PB_Z( j, k + 2 );
+              PB_Z( j, k ) -= sum * t1;
+              PB_Z( j, k + 1 ) -= sum * t2;
+              PB_Z( j, k + 2 ) -= sum * t3;
+            }
+          }
+        } else if ( nr == 2 ) {
+          for ( int j = k + t; j <= i2; j += nt ) {
+            const double sum = PB_H( k, j ) + w2 * PB_H( k + 1, j );
+            PB_H( k, j ) -= sum * t1;
+            PB_H( k + 1, j ) -= sum * t2;
+          }
+          g.sync();
+          PB_FIX_BULGE_COLUMN();
+          for ( int j = i1 + t; j <= i; j += nt ) {
+            const double sum = PB_H( j, k ) + w2 * PB_H( j, k + 1 );
+            PB_H( j, k ) -= sum * t1;
+            PB_H( j, k + 1 ) -= sum * t2;
+          }
+          if ( wantz ) {
+            for ( int j = iloz + t; j <= ihiz; j += nt ) {
+              const double sum = PB_Z( j, k ) + w2 * PB_Z( j, k + 1 );
+              PB_Z( j, k ) -= sum * t1;
+              PB_Z( j, k + 1 ) -= sum * t2;
+            }
+          }
+        }
+        g.sync();
+#undef PB_FIX_BULGE_COLUMN
+      }
+    }
+    if ( !converged ) return i + 1;
+
+    if ( l == i ) {
+      if ( t == 0 ) {
+        wr[i] = PB_H( i, i );
+        wi[i] = 0.0;
+      }
+    } else if ( l == i - 1 ) {
+      double a = PB_H( i - 1, i - 1 ), b = PB_H( i - 1, i ), c = PB_H( i, i - 1 ), d = PB_H( i, i );
+      double r1r, r1i, r2r, r2i, cs, sn;
+      dlanv2( a, b, c, d, r1r, r1i, r2r, r2i, cs, sn );
+      g.sync();
+      if ( t == 0 ) {
+        PB_H( i - 1, i - 1 ) = a;
+        PB_H( i - 1, i ) = b;
+        PB_H( i, i - 1 ) = c;
+        PB_H( i, i ) = d;
+        wr[i - 1] = r1r;
+        wi[i - 1] = r1i;
+        wr[i] = r2r;
+        wi[i] = r2i;
+      }
+      if ( wantt ) {
+        for ( int j = i + 1 + t; j <= i2; j += nt ) {
+          const double x = PB_H( i - 1, j ), y = PB_H( i, j );
+          PB_H( i - 1, j ) = cs * x + sn * y;
+          PB_H( i, j ) = cs * y - sn * x;
+        }
+        for ( int j = i1 + t; j < i - 1; j += nt ) {
+          const double x = PB_H( j, i - 1 ), y = PB_H( j, i );
+          PB_H( j, i - 1 ) = cs * x + sn * y;
+          PB_H( j, i ) = cs * y - sn * x;
+        }
+      }
+      if ( wantz ) {
+        for ( int j = iloz + t; j <= ihiz; j += nt ) {
+          const double x = PB_Z( j, i - 1 ), y = PB_Z( j, i );
+          PB_Z( j, i - 1 ) = cs * x + sn * y;
+          PB_Z( j, i ) = cs * y - sn * x;
+        }
+      }
+    }
+    g.sync();
+    kdefl = 0;
+    i = l - 1;
+  }
+  return 0;
+}
+
+}  // namespace pb

@@ -1,0 +1,283 @@
+"""
+GPU parity tests (run with -m gpu on a B200). Everything goes through the C-ABI of
+libpaladin_gpu.so (include/paladin_gpu.h) and is checked against the CPU oracle (oracle/), which
+is pinned to the reference's golden files by tests/test_oracle_golden.py.
+
+Tolerances (BASELINE.json north_star): scatter and partition bit-exact; eigenvalues paired after
+conjugate-aware matching with error <= 1e-9 * max(1, ||A||); with vectors
+||A V - V L|| / (n ||A|| eps) <= 100.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import paladin_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+EIG_TOL = 1e-9
+BACKWARD_TOL = 100.0
+
+
+@pytest.fixture(scope="module")
+def pg():
+    import paladin_b200 as pg
+    assert pg.device_count() >= 1, "no B200 visible"
+    return pg
+
+
+def _concat(mats):
+    """mats: list of (n, ii, jj, vv) -> n[], offsets[], i[], j[], v[]"""
+    n = np.array([m[0] for m in mats], dtype=np.int32)
+    off = np.zeros(len(mats) + 1, dtype=np.int64)
+    for k, m in enumerate(mats):
+        off[k + 1] = off[k] + len(m[3])
+    cat = lambda idx, dt: (np.concatenate([np.asarray(m[idx], dtype=dt) for m in mats]) if mats else np.zeros(0, dt))
+    return n, off, cat(1, np.int32), cat(2, np.int32), cat(3, np.float64)
+
+
+def _scatter_on_gpu(pg, mats):
+    n, off, ii, jj, vv = _concat(mats)
+    b = pg.Batch(n, off, jobvr="N")
+    b.upload(ii, jj, vv)
+    b.scatter()
+    out = [b.get_dense(k) for k in range(len(mats))]
+    b.destroy()
+    return out
+
+
+def _check_eigs(A, wr, wi, VR, info, want_vectors):
+    n = A.shape[0]
+    assert info == 0
+    wr0, wi0, _, VR0, info0 = po.dgeev(A, right=want_vectors)
+    assert info0 == 0
+    nrm = max(1.0, np.linalg.norm(A, 2)) if n else 1.0
+    err = po.match_eigenvalues(po.eigenvalues(wr, wi), po.eigenvalues(wr0, wi0))
+    assert err <= EIG_TOL * nrm, "eigenvalue error %.3e (||A||=%.3e)" % (err, nrm)
+    # pair convention consumed by the reference unpack loop (src/paladin.hpp:262-263)
+    k = 0
+    while k < n:
+        if wi[k] != 0.0:
+            assert k + 1 < n and wi[k] > 0 and wi[k + 1] == -wi[k] and wr[k + 1] == wr[k]
+            k += 2
+        else:
+            k += 1
+    if want_vectors and n:
+        be = po.backward_error(A, wr, wi, VR)
+        assert be <= BACKWARD_TOL, "backward error %.2f" % be
+        vecs = np.array(po.unpack(wr, wi, VR))
+        assert np.allclose(np.linalg.norm(vecs, axis=1), 1.0, atol=1e-12)
+
+
+# ---------------------------------------------------------------------------------------------------
+# (a) scatter: bit-exact
+# ---------------------------------------------------------------------------------------------------
+def test_scatter_golden_fixtures_bit_exact(pg):
+    paths = sorted(glob.glob(os.path.join(GOLD, "ref_run", "*.matrix")) +
+                   glob.glob(os.path.join(GOLD, "ref_parser", "*.matrix")) +
+                   glob.glob(os.path.join(GOLD, "ref_ctest", "*", "*.matrix")))
+    mats = []
+    for p in paths:
+        n, nnz, ii, jj, vv = po.read_mm(p)
+        mats.append((n, ii, jj, vv))
+    got = _scatter_on_gpu(pg, mats)
+    for p, m, g in zip(paths, mats, got):
+        want = po.scatter_dense(*m)
+        assert g.tobytes() == want.tobytes(), p
+        if os.path.exists(p + ".dense.npy"):
+            assert g.tobytes() == np.load(p + ".dense.npy").tobytes(), p
+
+
+def test_scatter_random_shapes_bit_exact(pg):
+    rng = np.random.default_rng(11)
+    mats = []
+    for n in (1, 2, 3, 7, 31, 32, 33, 64, 65, 127, 200, 513):
+        mats.append((n,) + po.random_dense_coo(n, [1, n]))            # sorted, dense
+        mats.append((n,) + po.random_sparse_coo(n, 0.3, [2, n]))      # shuffled, sparse
+        ii, jj, vv = po.random_sparse_coo(n, 0.1, [3, n])             # sorted, sparse
+        o = np.argsort((jj.astype(np.int64) - 1) * n + ii - 1, kind="stable")
+        mats.append((n, ii[o], jj[o], vv[o]))
+    # duplicates: last entry wins, also -0.0 / denormal / nan payload values survive bit-exactly
+    n = 40
+    ii = rng.integers(1, n + 1, size=5000).astype(np.int32)
+    jj = rng.integers(1, n + 1, size=5000).astype(np.int32)
+    vv = rng.standard_normal(5000)
+    vv[::7] = -0.0
+    vv[1::11] = 5e-324
+    mats.append((n, ii, jj, vv))
+    # sorted with duplicates (not strictly increasing -> fallback)
+    ii2 = np.repeat(np.arange(1, 6, dtype=np.int32), 2)
+    jj2 = np.ones(10, dtype=np.int32)
+    mats.append((5, ii2, jj2, np.arange(10, dtype=np.float64)))
+    # empty matrices
+    mats.append((9, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0)))
+    mats.append((0, np.zeros(0, np.int32), np.zeros(0, np.int32), np.zeros(0)))
+    got = _scatter_on_gpu(pg, mats)
+    for k, (m, g) in enumerate(zip(mats, got)):
+        want = po.scatter_dense(*m)
+        assert g.tobytes() == want.tobytes(), "matrix %d n=%d" % (k, m[0])
+
+
+def test_scatter_large_sorted_sparse_gaps(pg):
+    # long zero gaps exercise the warp-cooperative fill
+    n = 1500
+    ii, jj, vv = po.random_sparse_coo(n, 0.002, [9, 9])
+    o = np.argsort((jj.astype(np.int64) - 1) * n + ii - 1, kind="stable")
+    m = (n, ii[o], jj[o], vv[o])
+    got = _scatter_on_gpu(pg, [m])[0]
+    assert got.tobytes() == po.scatter_dense(*m).tobytes()
+
+
+def test_scatter_bad_index_reported(pg):
+    n = 6
+    ii, jj, vv = po.random_dense_coo(n, 5)
+    ii = ii.copy()
+    ii[7] = n + 1
+    good = (4,) + po.random_dense_coo(4, 6)
+    res, info = pg.geev_batch(*_concat([(n, ii, jj, vv), good]), jobvr="N")
+    assert info[0] == -101 and info[1] == 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# (b) eigenvalues / eigenvectors vs the oracle's dgeev
+# ---------------------------------------------------------------------------------------------------
+def _random_mats(sizes, seed, kind="dense"):
+    mats = []
+    for q, n in enumerate(sizes):
+        if kind == "dense":
+            mats.append((n,) + po.random_dense_coo(n, [seed, q]))
+        else:
+            mats.append((n,) + po.random_sparse_coo(n, 0.15 if n > 8 else 0.6, [seed, q]))
+    return mats
+
+
+@pytest.mark.parametrize("jobvr", ["N", "V"])
+@pytest.mark.parametrize("kind", ["dense", "sparse"])
+def test_small_path_matches_oracle(pg, jobvr, kind):
+    sizes = list(range(1, 65)) + [64] * 8 + [2, 2, 3]
+    mats = _random_mats(sizes, 21, kind)
+    res, info = pg.geev_batch(*_concat(mats), jobvr=jobvr)
+    for m, (wr, wi, VR), inf in zip(mats, res, info):
+        A = po.dense_matrix(*m)
+        _check_eigs(A, wr, wi, VR, inf, jobvr == "V")
+
+
+@pytest.mark.parametrize("jobvr", ["N", "V"])
+def test_generic_path_matches_oracle(pg, jobvr):
+    sizes = [65, 66, 80, 100, 129, 200, 257]
+    mats = _random_mats(sizes, 22)
+    res, info = pg.geev_batch(*_concat(mats), jobvr=jobvr)
+    for m, (wr, wi, VR), inf in zip(mats, res, info):
+        _check_eigs(po.dense_matrix(*m), wr, wi, VR, inf, jobvr == "V")
+
+
+def test_n512_full_decomposition(pg):
+    mats = _random_mats([512, 512], 3)
+    res, info = pg.geev_batch(*_concat(mats), jobvr="V")
+    for m, (wr, wi, VR), inf in zip(mats, res, info):
+        _check_eigs(po.dense_matrix(*m), wr, wi, VR, inf, True)
+
+
+def test_badly_scaled_and_structured(pg):
+    rng = np.random.default_rng(4)
+    cases = []
+    A = rng.standard_normal((30, 30))
+    A[:, 3] *= 1e8
+    A[5, :] *= 1e-7
+    cases.append(A)
+    cases.append(rng.standard_normal((20, 20)) * 1e-200)       # dgeev scales up
+    cases.append(rng.standard_normal((20, 20)) * 1e200)        # dgeev scales down
+    cases.append(np.triu(rng.standard_normal((25, 25))))       # already triangular: all isolated by balancing
+    cases.append(np.eye(10))
+    cases.append(np.zeros((6, 6)))
+    S = rng.standard_normal((40, 40))
+    cases.append(S + S.T)                                      # symmetric: all real
+    cases.append(S - S.T)                                      # skew: all imaginary pairs
+    P = np.zeros((12, 12))
+    P[np.arange(12), (np.arange(12) + 1) % 12] = 1.0          # cyclic permutation: roots of unity
+    cases.append(P)
+    J = np.diag(np.ones(15), 1)[:15, :15] + 2.0 * np.eye(15)   # Jordan-like (defective)
+    cases.append(J)
+    for n in (70, 90):
+        B = rng.standard_normal((n, n))
+        B[rng.random((n, n)) < 0.9] = 0.0
+        cases.append(B)
+    mats = []
+    for A in cases:
+        n = A.shape[0]
+        jj, ii = np.meshgrid(np.arange(1, n + 1, dtype=np.int32), np.arange(1, n + 1, dtype=np.int32))
+        mats.append((n, ii.T.reshape(-1).copy(), jj.T.reshape(-1).copy(), np.ascontiguousarray(A.T).reshape(-1)))
+    res, info = pg.geev_batch(*_concat(mats), jobvr="V")
+    for k, (A, (wr, wi, VR), inf) in enumerate(zip(cases, res, info)):
+        assert inf == 0, k
+        wr0, wi0, _, VR0, _ = po.dgeev(A, right=True)
+        nrm = max(1.0, np.linalg.norm(A, 2))
+        err = po.match_eigenvalues(po.eigenvalues(wr, wi), po.eigenvalues(wr0, wi0))
+        # defective / ill-conditioned cases: compare with what LAPACK itself achieves
+        cond_slack = 1e-9 * nrm if k != 9 else 1e-6
+        assert err <= cond_slack, (k, err)
+        be = po.backward_error(A, wr, wi, VR)
+        assert be <= BACKWARD_TOL, (k, be)
+
+
+def test_nonfinite_input_flagged(pg):
+    A = np.ones((5, 5))
+    A[2, 2] = np.nan
+    wr, wi, VR, info = pg.dgeev(A)
+    assert info == -4
+
+
+# ---------------------------------------------------------------------------------------------------
+# (c) the reference's own golden files through the GPU path
+# ---------------------------------------------------------------------------------------------------
+CTEST = sorted(glob.glob(os.path.join(GOLD, "ref_ctest", "*", "*.matrix")))
+RUNS = sorted(glob.glob(os.path.join(GOLD, "ref_run", "*.matrix")))
+
+
+def test_reference_golden_files_through_gpu(pg):
+    mats = []
+    for p in CTEST + RUNS:
+        n, nnz, ii, jj, vv = po.read_mm(p)
+        mats.append((n, ii, jj, vv))
+    res, info = pg.geev_batch(*_concat(mats), jobvr="V")
+    assert not info.any()
+    for p, (wr, wi, VR) in zip(CTEST + RUNS, res):
+        if p in CTEST:
+            # the reference's ctest goldens: byte-identical spectrum and right-vector files
+            assert po.format_spectrum(wr, wi) == open(p + ".spectrum.exact", "rb").read(), p
+            assert po.format_vectors(po.unpack_parts(wr, wi, VR)) == open(p + ".rightvecs.exact", "rb").read(), p
+        else:
+            # reference-run vectors of random matrices: 6 printed digits can flip in the last place,
+            # so compare numerically at the precision the file carries
+            want = np.loadtxt(p + ".spectrum.exact", ndmin=2)
+            got = np.stack([wr, wi], axis=1)
+            assert np.allclose(got, want, rtol=2e-5, atol=2e-5), p
+
+
+def test_dgeev_shim_signature(pg):
+    rng = np.random.default_rng(8)
+    A = rng.standard_normal((37, 37))
+    wr, wi, VR, info = pg.dgeev(A, jobvr="V")
+    _check_eigs(A, wr, wi, VR, info, True)
+    wr, wi, VR, info = pg.dgeev(A, jobvr="N")
+    _check_eigs(A, wr, wi, None, info, False)
+
+
+def test_staged_api_and_stage_timers(pg):
+    mats = _random_mats([64] * 32 + [100] * 4, 33)
+    n, off, ii, jj, vv = _concat(mats)
+    b = pg.Batch(n, off, jobvr="V")
+    b.upload(ii, jj, vv)
+    b.scatter()
+    b.solve()
+    wr, wi, vr, info = b.download()
+    ms = b.stage_ms()
+    b.destroy()
+    assert not info.any()
+    assert ms["scatter"][0] > 0 and ms["small"][0] > 0 and ms["generic"][0] > 0
+    from paladin_b200.api import split_results
+    for m, (w1, w2, V) in zip(mats, split_results(n, wr, wi, vr)):
+        _check_eigs(po.dense_matrix(*m), w1, w2, V, 0, True)

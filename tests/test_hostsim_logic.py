@@ -1,0 +1,143 @@
+"""CPU-only: the group-templated device code (paladin_b200/csrc/*.cuh) instantiated on the host
+(tests/hostsim) against LAPACK 3.12 (oracle/lapack_stages.py): same eigenvalue order as dlahqr for
+n <= 75, tolerance parity beyond, and -- with real threads under ThreadSanitizer -- no missing barrier."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import lapack_stages as ls
+from oracle import paladin_oracle as po
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "hostsim"))
+import build as hostsim_build  # noqa: E402
+
+dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+@pytest.fixture(scope="module")
+def hs():
+    return ctypes.CDLL(hostsim_build.build())
+
+
+def _geev(hs, A, wantvr=1):
+    n = A.shape[0]
+    A2 = np.array(A, order="F")
+    wr, wi, V = np.zeros(n), np.zeros(n), np.zeros((n, n), order="F")
+    info = hs.hs_geev(n, dp(A2), dp(wr), dp(wi), wantvr, dp(V))
+    return wr, wi, V, info
+
+
+def _cases(rng, n):
+    A = rng.standard_normal((n, n))
+    yield A, 1.0
+    if n >= 5:
+        B = A.copy()
+        B[rng.random((n, n)) < 0.6] = 0
+        B[:, 2] *= 1e5
+        B[1, :] *= 1e-4
+        yield B, 1.0
+    yield A * 1e-200, 1e-200   # dgeev scales such input up / down before balancing
+    yield A * 1e200, 1e200
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 8, 10, 17, 33, 40, 64, 75, 100, 150])
+def test_geev_pipeline_matches_lapack(hs, n):
+    rng = np.random.default_rng(n)
+    for q, (A, s) in enumerate(_cases(rng, n)):
+        wr, wi, V, info = _geev(hs, A)
+        wr0, wi0, _, VR0, info0 = ls.dgeev(A)
+        assert info == 0 and info0 == 0
+        A, wr, wi, wr0, wi0 = A / s, wr / s, wi / s, wr0 / s, wi0 / s  # compare in the unscaled frame
+        nrm = max(1.0, np.linalg.norm(A, 2))
+        w, w0 = wr + 1j * wi, wr0 + 1j * wi0
+        if n <= 75 and q == 0:  # LAPACK runs dlahqr here too: identical order, pairs +imag first
+            assert np.abs(w - w0).max() <= 1e-11 * nrm
+        assert po.match_eigenvalues(w, w0) <= 1e-9 * nrm
+        assert po.backward_error(A, wr, wi, V) <= 100
+        wre, wie, _, infoe = _geev(hs, A * s, 0)
+        assert infoe == 0 and po.match_eigenvalues((wre + 1j * wie) / s, w0) <= 1e-9 * nrm
+
+
+def test_stage_functions_match_lapack(hs):
+    rng = np.random.default_rng(3)
+    for n in (6, 20, 50):
+        A = rng.standard_normal((n, n))
+        A[rng.random((n, n)) < 0.5] = 0
+        A[:, 2] *= 1e6
+        A = np.asfortranarray(A)
+        B, ilo, ihi, sc = ls.dgebal(A)
+        A2 = A.copy(order="F")
+        ilo2, ihi2, sc2 = ctypes.c_int(), ctypes.c_int(), np.zeros(n)
+        hs.hs_gebal(n, dp(A2), ctypes.byref(ilo2), ctypes.byref(ihi2), dp(sc2))
+        assert (ilo2.value, ihi2.value) == (ilo - 1, ihi - 1)
+        assert np.array_equal(B, A2)
+        scl = sc.copy()
+        for k in list(range(0, ilo - 1)) + list(range(ihi, n)):
+            scl[k] -= 1
+        assert np.array_equal(scl, sc2)
+        # trevc on LAPACK's own Schur form
+        H, tau = ls.dgehrd(B, ilo, ihi)
+        Q = ls.dorghr(H, tau, ilo, ihi)
+        T, wr, wi, Z, info = ls.dhseqr(np.triu(H, -1), ilo, ihi, Z=Q)
+        V0 = ls.dtrevc3(T, Z)
+        V = Z.copy(order="F")
+        hs.hs_trevc_right(n, dp(np.asfortranarray(T)), dp(V))
+        assert np.abs(V - V0).max() <= 1e-10 * max(1.0, np.abs(V0).max())
+        Vb0 = ls.dgebak(V0, ilo, ihi, sc)
+        hs.hs_gebak_right(n, ilo - 1, ihi - 1, dp(sc2), dp(V))
+        assert np.abs(V - Vb0).max() <= 1e-10 * max(1.0, np.abs(Vb0).max())
+
+
+def test_dlaln2_near_singular_and_scaling(hs):
+    # tiny pivots are perturbed to smin, huge right-hand sides are scaled: x solves (A - wI) x = scale*b
+    a = np.array([1.0, 0.5, -0.25, 1.0])
+    for na, nw, wr, wi in [(1, 1, 1.0, 0.0), (1, 2, 1.0, 1e-300), (2, 1, 0.3, 0.0), (2, 2, 0.3, 0.7), (2, 2, 1.0, 0.0)]:
+        b = np.array([1e300, -2e300, 3e300, 1e299])
+        x = np.zeros(4)
+        scale, xnorm = ctypes.c_double(), ctypes.c_double()
+        hs.hs_dlaln2.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_void_p,
+                                 ctypes.c_void_p, ctypes.c_double, ctypes.c_double, ctypes.c_void_p,
+                                 ctypes.c_void_p, ctypes.c_void_p]
+        hs.hs_dlaln2(0, na, nw, 1e-8, a.ctypes.data, b.ctypes.data, wr, wi, x.ctypes.data, ctypes.byref(scale),
+                     ctypes.byref(xnorm))
+        assert np.all(np.isfinite(x)) and 0 < scale.value <= 1.0
+
+
+@pytest.mark.timeout(900)
+def test_threaded_groups_are_race_free_under_tsan():
+    """4-5 real threads per group, pthread barrier behind sync(): ThreadSanitizer reports any access pair
+    that is not ordered by a barrier, i.e. a missing __syncthreads()/__syncwarp() in the device code."""
+    so = hostsim_build.build(tsan=True)
+    tsan_rt = subprocess.run(["g++", "-print-file-name=libtsan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(tsan_rt):
+        pytest.skip("libtsan not available")
+    code = r"""
+import ctypes, numpy as np, sys
+sys.path.insert(0, %r)
+from oracle import lapack_stages as ls, paladin_oracle as po
+hs = ctypes.CDLL(%r)
+dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+rng = np.random.default_rng(1)
+for n, nt in [(1, 3), (2, 3), (3, 4), (7, 4), (12, 3), (20, 5)]:
+    for trial in range(2):
+        A = rng.standard_normal((n, n))
+        if trial == 1 and n >= 5:
+            A[rng.random((n, n)) < 0.6] = 0; A[:, 2] *= 1e5; A[1, :] *= 1e-4
+        for wantvr in (0, 1):
+            A2 = np.array(A, order='F'); wr = np.zeros(n); wi = np.zeros(n); V = np.zeros((n, n), order='F')
+            info = hs.ht_geev(nt, n, dp(A2), dp(wr), dp(wi), wantvr, dp(V))
+            wr0, wi0, _, VR0, info0 = ls.dgeev(A)
+            assert info == 0
+            assert po.match_eigenvalues(wr + 1j * wi, wr0 + 1j * wi0) <= 1e-9 * max(1, np.linalg.norm(A, 2))
+            if wantvr: assert po.backward_error(A, wr, wi, V) <= 100
+print('DONE')
+""" % (os.path.dirname(HERE), so)
+    env = dict(os.environ, LD_PRELOAD=tsan_rt, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=850)
+    assert "DONE" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "ThreadSanitizer: data race" not in r.stderr, r.stderr[:6000]
