@@ -292,6 +292,10 @@ def ours(args):
     d2h = B * (2 * n * 8 + 4) + (B * nn * 8 if job == "V" else 0)
 
     if rank == 0:
+        cyc = batch.phase_cycles()
+        top = ("balance", "hessenberg", "form_q", "qr_total", "trevc", "bak_normalise")
+        tot = float(sum(cyc[k] for k in top)) or 1.0
+        phase_share = {k: round(v / tot, 4) for k, v in cyc.items() if v}
         peaks, peak_kind = measured_peaks()
         flops = (FLOPS_PER_N3_VEC if job == "V" else FLOPS_PER_N3_VAL) * n ** 3
         # dominant kernel: the eigen-solve (everything but the scatter)
@@ -332,6 +336,7 @@ def ours(args):
             "gpu_launches": launches,
             "roofline": roofline, "scatter_roofline": scatter, "cpu_baseline": cpu,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items() if v > 0},
+            "phase_cycle_share": phase_share,
             "wall_ms_per_step": wall_ms / args.steps,
         }
         print(json.dumps(line), flush=True)

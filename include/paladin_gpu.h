@@ -52,7 +52,8 @@ extern "C" {
 #define PALADIN_GPU_STAGE_QR 3         /* QR iteration to (quasi-)triangular form */
 #define PALADIN_GPU_STAGE_VECTORS 4    /* eigenvectors of T, back-transform, un-balance, normalise */
 #define PALADIN_GPU_STAGE_SMALL 5      /* fused warp-per-matrix path for n <= 64 (all stages in one kernel) */
-#define PALADIN_GPU_STAGE_GENERIC 6    /* fused CTA-per-matrix path in global memory (all stages) */
+#define PALADIN_GPU_STAGE_GENERIC 6    /* fused CTA-per-matrix path in global memory (all stages; debug fallback) */
+#define PALADIN_GPU_STAGE_MID 7        /* CTA-per-matrix path for n > 64: windowed multishift QR (all stages in one kernel) */
 #define PALADIN_GPU_NUM_STAGES 8
 
 /* ---- lifecycle ------------------------------------------------------------------------------- */
@@ -131,6 +132,12 @@ int paladin_gpu_batch_download( paladin_gpu_batch* b, double* wr, double* wi, do
  * events on the library's own stream. ms must hold PALADIN_GPU_NUM_STAGES floats. launches (may be
  * NULL) receives the number of kernel launches of each stage. */
 int paladin_gpu_batch_stage_ms( paladin_gpu_batch* b, float* ms, int* launches );
+
+/* Phase profile of the most recent CTA-per-matrix solve: SM cycles summed over all CTAs, 16 slots
+ * (0 balance, 1 Hessenberg, 2 form Q, 3 QR total, 4 eigenvectors of T, 5 un-balance + normalise,
+ *  8 deflation scans, 9 shift computation, 10 in-window bulge chasing, 11 strip updates by recorded
+ *  reflectors, 12 small-block solves, 13 strip updates by small U). Diagnostic only. */
+int paladin_gpu_batch_phase_cycles( paladin_gpu_batch* b, long long* cycles );
 
 int paladin_gpu_batch_destroy( paladin_gpu_batch* b );
 

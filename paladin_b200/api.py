@@ -11,7 +11,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
 NUM_STAGES = 8
-STAGE_NAMES = ("scatter", "balance", "hessenberg", "qr", "vectors", "small", "generic", "reserved")
+STAGE_NAMES = ("scatter", "balance", "hessenberg", "qr", "vectors", "small", "generic", "mid")
+PHASE_NAMES = ("balance", "hessenberg", "form_q", "qr_total", "trevc", "bak_normalise", "", "", "ms_scan", "ms_shifts",
+               "ms_chase", "ms_strips", "ms_small", "ms_small_u", "", "")
 
 _c_int_p = ctypes.POINTER(ctypes.c_int)
 _c_i64_p = ctypes.POINTER(ctypes.c_int64)
@@ -61,6 +63,7 @@ def lib():
                                              ctypes.c_void_p, ctypes.c_void_p]
     L.paladin_gpu_batch_stage_ms.argtypes = [ctypes.c_void_p, _c_flt_p, _c_int_p]
     L.paladin_gpu_batch_destroy.argtypes = [ctypes.c_void_p]
+    L.paladin_gpu_batch_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]
     L.paladin_gpu_timer_start.argtypes = [ctypes.c_int]
     L.paladin_gpu_timer_stop.argtypes = [ctypes.c_int, _c_flt_p]
     L.paladin_gpu_dgeev_.restype = None
@@ -168,6 +171,11 @@ class Batch:
         ln = (ctypes.c_int * NUM_STAGES)()
         _check(lib().paladin_gpu_batch_stage_ms(self._h, ms, ln))
         return {STAGE_NAMES[i]: (float(ms[i]), int(ln[i])) for i in range(NUM_STAGES)}
+
+    def phase_cycles(self):
+        cyc = (ctypes.c_longlong * 16)()
+        _check(lib().paladin_gpu_batch_phase_cycles(self._h, cyc))
+        return {PHASE_NAMES[i]: int(cyc[i]) for i in range(16) if PHASE_NAMES[i]}
 
     def destroy(self):
         if self._h is not None:

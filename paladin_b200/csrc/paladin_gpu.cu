@@ -154,6 +154,58 @@ __global__ void __launch_bounds__( kGenericThreads ) geev_cta_kernel( BatchView 
   if ( threadIdx.x == 0 ) bv.info[id] = info;
 }
 
+// ---- mid-size path: one CTA per matrix, matrix in global memory, QR by windowed multishift sweeps ----
+constexpr int kMidThreads = 256;
+constexpr int kNumTicks = 16;
+
+__host__ __device__ inline pb::MsqrCfg mid_cfg() { return pb::MsqrCfg{ 8, 49, 48, 256, 2 }; }
+
+inline size_t mid_smem_bytes() {
+  const pb::MsqrCfg c = mid_cfg();
+  return sizeof( double ) * pb::msqr_work_doubles( c, c.W | 1, c.tl | 1 ) + sizeof( int ) * ( 3 * pb::kMsMaxBulges + 8 ) +
+         sizeof( long long ) * kNumTicks;
+}
+
+__global__ void __launch_bounds__( kMidThreads ) geev_mid_kernel( BatchView bv, const int* ids, long long* stats ) {
+  extern __shared__ double smem[];
+  __shared__ double red[64];
+  const pb::MsqrCfg c = mid_cfg();
+  const int ldw = c.W | 1, ldt = c.tl | 1;
+  pb::MsqrWork wk;
+  double* p = smem;
+  wk.Hw = p; p += (size_t)c.W * ldw;
+  wk.U = p; p += (size_t)c.W * ldw;
+  wk.tile = p; p += (size_t)c.W * ldt;
+  wk.refl = p; p += (size_t)c.nb * c.W * pb::kReflStride;
+  wk.sr = p; p += 2 * c.nb * c.nchains;
+  wk.si = p; p += 2 * c.nb * c.nchains;
+  long long* lstats = reinterpret_cast<long long*>( p );
+  wk.ibuf = reinterpret_cast<int*>( lstats + kNumTicks );
+  wk.ldw = ldw;
+  wk.ldt = ldt;
+  if ( threadIdx.x < kNumTicks ) lstats[threadIdx.x] = 0;
+  if ( threadIdx.x < 3 * pb::kMsMaxBulges + 8 ) wk.ibuf[threadIdx.x] = 0;
+  __syncthreads();
+
+  const int id = ids[blockIdx.x];
+  const int n = bv.n[id];
+  pb::CtaGroup g{ red };
+  if ( stats != nullptr ) {
+    g.stats = lstats;
+    g.last = clock64();
+  }
+  double* A = bv.A + bv.a_off[id];
+  double* V = bv.wantvr ? bv.V + bv.a_off[id] : nullptr;
+  double* wr = bv.wr + bv.w_off[id];
+  double* wi = bv.wi + bv.w_off[id];
+  double* dw = bv.dwork + 5 * bv.w_off[id];
+  int* iw = bv.iwork + 2 * bv.w_off[id] + 2 * id;
+  const int info = pb::geev_group( g, n, A, n, wr, wi, bv.wantvr != 0, V, n, dw, iw, pb::QrMultishift{ c, wk } );
+  if ( threadIdx.x == 0 ) bv.info[id] = info;
+  __syncthreads();
+  if ( stats != nullptr && threadIdx.x < kNumTicks ) atomicAdd( reinterpret_cast<unsigned long long*>( stats ) + threadIdx.x, (unsigned long long)lstats[threadIdx.x] );
+}
+
 struct StageTimer {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   bool used = false;
@@ -182,7 +234,8 @@ struct paladin_gpu_batch {
   // host-side plan
   std::vector<int> flags;                    // scatter flags per matrix
   std::vector<int> ids;                      // all ids grouped by class
-  struct Group { int first, count, nmax, kind; };  // kind 0 = warp bucket, 1 = generic
+  struct Group { int first, count, nmax, kind; };  // kind 0 = warp bucket, 1 = CTA per matrix
+  long long* d_stats = nullptr;              // phase profile of the CTA-per-matrix kernel (cycles)
   std::vector<Group> groups;
   StageTimer st[PALADIN_GPU_NUM_STAGES];
   bool scattered = false;
@@ -196,6 +249,7 @@ void free_batch( paladin_gpu_batch* b ) {
   cudaFree( b->d_n ); cudaFree( b->d_nnz_off ); cudaFree( b->d_a_off ); cudaFree( b->d_w_off );
   cudaFree( b->d_coo_i ); cudaFree( b->d_coo_j ); cudaFree( b->d_coo_v );
   cudaFree( b->d_A ); cudaFree( b->d_V ); cudaFree( b->d_wr ); cudaFree( b->d_wi ); cudaFree( b->d_dwork );
+  cudaFree( b->d_stats );
   cudaFree( b->d_info ); cudaFree( b->d_iwork ); cudaFree( b->d_flags ); cudaFree( b->d_ids ); cudaFree( b->d_chunks );
   for ( auto& s : b->st ) {
     if ( s.e0 ) cudaEventDestroy( s.e0 );
@@ -429,6 +483,7 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
   A( dev_alloc( &b->d_flags, count ) );
   A( dev_alloc( &b->d_ids, b->ids.size() ) );
   A( dev_alloc( &b->d_chunks, chunks.size() ) );
+  A( dev_alloc( &b->d_stats, kNumTicks ) );
   if ( rc != PALADIN_GPU_OK ) {
     free_batch( b );
     return rc;
@@ -593,6 +648,16 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
         continue;
       }
     }
+    static const bool force_generic = std::getenv( "PALADIN_GPU_FORCE_GENERIC" ) != nullptr;
+    if ( g.kind == 1 && !force_generic && mid_smem_bytes() <= (size_t)c.max_smem_optin ) {
+      PB_CUDA( cudaFuncSetAttribute( geev_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_smem_bytes() ) );
+      PB_CUDA( cudaMemsetAsync( b->d_stats, 0, sizeof( long long ) * kNumTicks, st ) );
+      stage_begin( b, PALADIN_GPU_STAGE_MID, st );
+      geev_mid_kernel<<<cnt, kMidThreads, mid_smem_bytes(), st>>>( bv, ids, b->d_stats );
+      stage_end( b, PALADIN_GPU_STAGE_MID, st, 1 );
+      PB_CUDA( cudaGetLastError() );
+      continue;
+    }
     stage_begin( b, PALADIN_GPU_STAGE_GENERIC, st );
     geev_cta_kernel<<<cnt, kGenericThreads, 0, st>>>( bv, ids );
     stage_end( b, PALADIN_GPU_STAGE_GENERIC, st, 1 );
@@ -646,6 +711,15 @@ int paladin_gpu_batch_stage_ms( paladin_gpu_batch* b, float* ms, int* launches )
       cudaEventElapsedTime( &ms[s], b->st[s].e0, b->st[s].e1 );
     }
   }
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_batch_phase_cycles( paladin_gpu_batch* b, long long* cycles ) {
+  if ( !b || !cycles ) return fail( PALADIN_GPU_EINVAL, "bad arguments" );
+  DeviceCtx& c = g_ctx[b->device];
+  std::lock_guard<std::mutex> lk( c.mu );
+  PB_CUDA( cudaSetDevice( b->device ) );
+  PB_CUDA( cudaMemcpy( cycles, b->d_stats, sizeof( long long ) * kNumTicks, cudaMemcpyDeviceToHost ) );
   return PALADIN_GPU_OK;
 }
 

@@ -21,6 +21,12 @@
 #define PB_HD inline
 #endif
 
+// Uniformity checks of group-wide control values: compiled only into the threaded host simulator
+// (tests/hostsim defines PB_CHECK_UNIFORM as a call into its barrier), nothing on the device.
+#ifndef PB_CHECK_UNIFORM
+#define PB_CHECK_UNIFORM( g, value, tag )
+#endif
+
 namespace pb {
 
 // ---- machine constants (IEEE double; same values LAPACK's dlamch returns) -------------------------
@@ -55,6 +61,8 @@ struct HostGroup {
   PB_HD int imin_( int x ) const { return x; }
   PB_HD int isum( int x ) const { return x; }
   PB_HD bool any( bool x ) const { return x; }
+  PB_HD void tick( int ) const {}
+  PB_HD void check_uniform( long, const char* ) const {}
 };
 
 #if defined(__CUDACC__)
@@ -90,11 +98,22 @@ struct WarpGroup {
   PB_D int imin_( int x ) const { return -warp_imax( -x ); }
   PB_D int isum( int x ) const { return warp_isum( x ); }
   PB_D bool any( bool x ) const { return __any_sync( 0xffffffffu, x ); }
+  PB_D void tick( int ) const {}
 };
 
 // whole thread block; red points at >= 64 doubles of shared scratch owned by the group
 struct CtaGroup {
   double* red;
+  // optional phase profile: thread 0 adds the cycles since the previous tick to stats[slot]
+  long long* stats = nullptr;
+  mutable long long last = 0;
+  PB_D void tick( int slot ) const {
+    if ( stats != nullptr && threadIdx.x == 0 ) {
+      const long long now = clock64();
+      stats[slot] += now - last;
+      last = now;
+    }
+  }
   PB_D int tid() const { return threadIdx.x; }
   PB_D int size() const { return blockDim.x; }
   PB_D void sync() const { __syncthreads(); }

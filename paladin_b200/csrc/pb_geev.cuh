@@ -12,6 +12,7 @@
 #include "pb_common.cuh"
 #include "pb_small.cuh"
 #include "pb_vec.cuh"
+#include "pb_msqr.cuh"
 
 namespace pb {
 
@@ -57,9 +58,32 @@ PB_D void lascl( const G& g, double cfrom, double cto, int rows, int cols, doubl
 // Scratch carved by the caller: dwork >= 5*n doubles, iwork >= 2*n+2 ints, visible to the group.
 // Returns the LAPACK info value (0, or i > 0 when the QR iteration failed: wr/wi[i..n) are valid).
 // On exit with wantvr, V (n x n, ldv) holds the right eigenvectors. A is destroyed.
-template <class G>
+// QR-stage policies: plain double-shift iteration (n <= 64 and the size-generic path) ...
+struct QrLahqr {
+  template <class G>
+  PB_D int operator()( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, double* H, int ldh, double* wr,
+                       double* wi, double* Z, int ldz ) const {
+    return lahqr( g, wantt, wantz, n, ilo, ihi, H, ldh, wr, wi, 0, n - 1, Z, ldz );
+  }
+};
+
+// ... or windowed multishift sweeps with delayed reflector application (pb_msqr.cuh)
+struct QrMultishift {
+  MsqrCfg cfg;
+  MsqrWork wk;
+  template <class G>
+  PB_D int operator()( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, double* H, int ldh, double* wr,
+                       double* wi, double* Z, int ldz ) const {
+    return hqr_multishift( g, wantt, wantz, n, ilo, ihi, H, ldh, wr, wi, 0, n - 1, Z, ldz, cfg, wk );
+  }
+};
+
+// phase-profile slots (CtaGroup::tick)
+constexpr int kTickBalance = 0, kTickHess = 1, kTickOrghr = 2, kTickQr = 3, kTickTrevc = 4, kTickBak = 5;
+
+template <class G, class QR = QrLahqr>
 PB_D int geev_group( const G& g, int n, double* A, int lda, double* wr, double* wi, bool wantvr, double* V, int ldv,
-                     double* dwork, int* iwork ) {
+                     double* dwork, int* iwork, const QR& qr = QR() ) {
   const int t = g.tid(), nt = g.size();
   if ( n == 0 ) return 0;
   double* tau = dwork;
@@ -97,24 +121,30 @@ PB_D int geev_group( const G& g, int n, double* A, int lda, double* wr, double* 
   int ilo, ihi;
   gebal( g, n, A, lda, &ilo, &ihi, scale, iwork );
   g.sync();
+  g.tick( kTickBalance );
   gehd2( g, n, ilo, ihi, A, lda, tau, cnorm );
+  g.tick( kTickHess );
   if ( wantvr ) orghr( g, n, ilo, ihi, A, lda, tau, V, ldv );
   g.sync();
+  g.tick( kTickOrghr );
   for ( int i = t; i < n; i += nt )
     if ( i < ilo || i > ihi ) {
       wr[i] = PB_A( i, i );
       wi[i] = 0.0;
     }
   g.sync();
-  int info = lahqr( g, wantvr, wantvr, n, ilo, ihi, A, lda, wr, wi, 0, n - 1, V, ldv );
+  int info = qr( g, wantvr, wantvr, n, ilo, ihi, A, lda, wr, wi, V, ldv );
   g.sync();
+  g.tick( kTickQr );
 
   if ( info == 0 && wantvr ) {
     // quasi-triangular T: the reflector storage below the first subdiagonal is never read again
     trevc_right_inplace( g, n, A, lda, V, ldv, cnorm, xr, xi );
+    g.tick( kTickTrevc );
     gebak_right( g, n, ilo, ihi, scale, n, V, ldv );
     g.sync();
     normalize_vectors( g, n, wi, V, ldv );
+    g.tick( kTickBak );
   }
   if ( scalea ) {
     // undo scaling on the converged part (and on the isolated head when the iteration failed)

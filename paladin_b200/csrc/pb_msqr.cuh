@@ -1,0 +1,586 @@
+// pb_msqr.cuh -- QR iteration for mid-size Hessenberg matrices (one CTA per matrix, matrix in global
+// memory / L2): small-bulge multishift sweeps with DELAYED reflector application.
+//
+// Replaces, for 64 < n, the dhseqr stage of the reference's dgeev_ call (reference
+// src/lapack-wrapper.hpp:47-60, src/paladin.hpp:248-254); LAPACK itself switches from the plain
+// double-shift dlahqr to the small-bulge multishift dlaqr0/dlaqr5 for n > 75. This is not dlaqr5:
+//
+//   * a chain of nb tightly packed 3x3 bulges (2 nb shifts = eigenvalues of the trailing 2nb x 2nb
+//     block) is chased through a W x W diagonal WINDOW of H held on chip (shared memory);
+//   * inside the window every macro-step advances all bulges by one row (reflector generation,
+//     row updates, column updates: three barriers), so the latency-bound part touches only on-chip data;
+//   * the 3-element Householder reflectors are RECORDED, not accumulated into a dense orthogonal
+//     factor: the off-window parts of H (right of the window, above it) and the Schur vectors Z are
+//     then updated strip by strip: a tile of lines (columns of the right strip, rows of the upper strip
+//     and of Z) is staged on chip once, each thread streams the recorded reflectors over ITS line with
+//     a three-register sliding window (5 FMAs per reflector and line, no barriers), and the tile is
+//     written back once. Flops are those of the unblocked algorithm (no dense-U overhead) while every
+//     off-window element moves through the memory system once per window instead of once per bulge.
+//   * when the active block is <= ws_small rows, or splits, the block is finished by the plain
+//     double-shift iteration (lahqr) inside the window with its transformations accumulated into a
+//     small orthogonal U that is applied to the strips as x <- U^T x per line.
+//
+// Deflation criterion, exceptional shifts and 2x2 standardisation are those of pb::lahqr (LAPACK dlahqr /
+// dlanv2), so the pair convention consumed by the reference (src/paladin.hpp:262-263) is kept.
+// 0-based inclusive indices. G is a CTA (device) or a host group (tests/hostsim).
+#pragma once
+
+#include "pb_common.cuh"
+#include "pb_small.cuh"
+
+namespace pb {
+
+constexpr int kMsMaxBulges = 16;
+constexpr int kReflStride = 6;  // w2, w3, t1, t2, t3, pad  (three 16-byte loads)
+// phase-profile slots (CtaGroup::tick)
+constexpr int kTickMsScan = 8, kTickMsShifts = 9, kTickMsChase = 10, kTickMsStrips = 11, kTickMsSmall = 12, kTickMsSmallU = 13;
+
+struct MsqrCfg {
+  int nb;        // bulges per chain, <= kMsMaxBulges
+  int W;         // window order, >= 3*nb + 4
+  int ws_small;  // active blocks of order <= ws_small are finished inside the window (<= W)
+  int tl;        // lines per strip tile
+  int nchains;   // chains (of nb bulges) per sweep
+};
+
+// on-chip work space (shared memory on the device)
+struct MsqrWork {
+  double* Hw;     // W x ldw   window of H
+  double* U;      // W x ldw   accumulated transformations of a small solve / scratch for shifts
+  double* tile;   // W x ldt   strip tile, element (pos, line) at pos*ldt + line; the x <- U^T x update
+                  //           uses lines [0, tl/2) as input and [tl/2, tl) as output
+  double* refl;   // nb * W * kReflStride
+  double* sr;     // 2*nb*nchains shifts (real parts)
+  double* si;     //                     (imaginary parts)
+  int* ibuf;      // 3*kMsMaxBulges + 8 ints: kpos, kfirst, kcount
+  int ldw, ldt;
+};
+
+PB_HD size_t msqr_work_doubles( const MsqrCfg& c, int ldw, int ldt ) {
+  return 2 * (size_t)c.W * ldw + (size_t)c.W * ldt + (size_t)c.nb * c.W * kReflStride + 4 * (size_t)c.nb * c.nchains;
+}
+
+// ---- deflation scan: largest k in (lo, hi] with negligible H(k,k-1); lo when none -----------------
+template <class G>
+PB_D int ms_find_split( const G& g, int ilo, int ihi, int lo, int hi, const double* H, int ldh, double smlnum ) {
+  const int t = g.tid(), nt = g.size();
+  int kfound = lo;
+  for ( int k = hi - t; k > lo; k -= nt ) {
+    const double hkk1 = fabs( PB_H( k, k - 1 ) );
+    bool small = false;
+    if ( hkk1 <= smlnum ) {
+      small = true;
+    } else {
+      double tst = fabs( PB_H( k - 1, k - 1 ) ) + fabs( PB_H( k, k ) );
+      if ( tst == 0.0 ) {
+        if ( k - 2 >= ilo ) tst += fabs( PB_H( k - 1, k - 2 ) );
+        if ( k + 1 <= ihi ) tst += fabs( PB_H( k + 1, k ) );
+      }
+      if ( hkk1 <= kUlp * tst ) {
+        const double hk1k = fabs( PB_H( k - 1, k ) );
+        const double ab = dmax( hkk1, hk1k ), ba = dmin( hkk1, hk1k );
+        const double dd = fabs( PB_H( k - 1, k - 1 ) - PB_H( k, k ) );
+        const double aa = dmax( fabs( PB_H( k, k ) ), dd ), bb = dmin( fabs( PB_H( k, k ) ), dd );
+        const double s = aa + ab;
+        if ( ba * ( ab / s ) <= dmax( smlnum, kUlp * ( bb * ( aa / s ) ) ) ) small = true;
+      }
+    }
+    if ( small ) {
+      kfound = k;
+      break;
+    }
+  }
+  return g.imax_( kfound );
+}
+
+// ---- window <-> global ----------------------------------------------------------------------------
+// Only the band r - c <= 3 is meaningful below the diagonal (Hessenberg + parked bulges); whatever else
+// the array holds there (Householder vectors of the reduction) is neither read nor written.
+template <class G>
+PB_D void ms_load_window( const G& g, const double* H, int ldh, int ws, int wlen, double* Hw, int ldw ) {
+  const int t = g.tid(), nt = g.size();
+  for ( int q = t; q < wlen * wlen; q += nt ) {
+    const int c = q / wlen, r = q - c * wlen;
+    Hw[r + c * ldw] = ( r - c <= 3 ) ? PB_H( ws + r, ws + c ) : 0.0;
+  }
+  g.sync();
+}
+template <class G>
+PB_D void ms_store_window( const G& g, double* H, int ldh, int ws, int wlen, const double* Hw, int ldw ) {
+  const int t = g.tid(), nt = g.size();
+  for ( int q = t; q < wlen * wlen; q += nt ) {
+    const int c = q / wlen, r = q - c * wlen;
+    if ( r - c <= 3 ) PB_H( ws + r, ws + c ) = Hw[r + c * ldw];
+  }
+  g.sync();
+}
+
+// ---- strip tiles ----------------------------------------------------------------------------------
+// kind 0: lines are COLUMNS j0.. of M, positions are rows ws..   (strip right of the window)
+// kind 1: lines are ROWS r0.. of M, positions are columns ws..   (strip above the window, Schur vectors)
+template <class G>
+PB_D void ms_tile_load( const G& g, int kind, const double* M, int ldm, int ws, int wlen, int l0, int nl, double* tile,
+                        int ldt ) {
+  const int t = g.tid(), nt = g.size();
+  if ( kind == 0 ) {
+    for ( int q = t; q < wlen * nl; q += nt ) {
+      const int line = q / wlen, pos = q - line * wlen;
+      tile[pos * ldt + line] = M[( ws + pos ) + (size_t)( l0 + line ) * ldm];
+    }
+  } else {
+    for ( int q = t; q < wlen * nl; q += nt ) {
+      const int pos = q / nl, line = q - pos * nl;
+      tile[pos * ldt + line] = M[( l0 + line ) + (size_t)( ws + pos ) * ldm];
+    }
+  }
+  g.sync();
+}
+template <class G>
+PB_D void ms_tile_store( const G& g, int kind, double* M, int ldm, int ws, int wlen, int l0, int nl, const double* tile,
+                         int ldt ) {
+  const int t = g.tid(), nt = g.size();
+  if ( kind == 0 ) {
+    for ( int q = t; q < wlen * nl; q += nt ) {
+      const int line = q / wlen, pos = q - line * wlen;
+      M[( ws + pos ) + (size_t)( l0 + line ) * ldm] = tile[pos * ldt + line];
+    }
+  } else {
+    for ( int q = t; q < wlen * nl; q += nt ) {
+      const int pos = q / nl, line = q - pos * nl;
+      M[( l0 + line ) + (size_t)( ws + pos ) * ldm] = tile[pos * ldt + line];
+    }
+  }
+  g.sync();
+}
+
+// every thread streams the recorded reflectors over its own lines (no barriers inside)
+template <class G>
+PB_D void ms_tile_apply_reflectors( const G& g, int nl, int wlen, int ws, int nbulges, const int* kfirst, const int* kcount,
+                                    const double* refl, int W, double* tile, int ldt ) {
+  const int t = g.tid(), nt = g.size();
+  for ( int line = t; line < nl; line += nt ) {
+    double* x = tile + line;
+    for ( int b = 0; b < nbulges; ++b ) {
+      const int cnt = kcount[b];
+      if ( cnt == 0 ) continue;
+      const int p = kfirst[b] - ws;
+      const double* rf = refl + (size_t)b * W * kReflStride;
+      double x0 = x[p * ldt];
+      double x1 = x[( p + 1 ) * ldt];
+      double x2 = ( p + 2 < wlen ) ? x[( p + 2 ) * ldt] : 0.0;
+      for ( int s = 0; s < cnt; ++s ) {
+        const double w2 = rf[0], w3 = rf[1], t1 = rf[2], t2 = rf[3], t3 = rf[4];
+        rf += kReflStride;
+        const double sum = x0 + w2 * x1 + w3 * x2;
+        x[( p + s ) * ldt] = x0 - sum * t1;
+        x0 = x1 - sum * t2;
+        x1 = x2 - sum * t3;
+        x2 = ( p + s + 3 < wlen ) ? x[( p + s + 3 ) * ldt] : 0.0;
+      }
+      x[( p + cnt ) * ldt] = x0;
+      if ( p + cnt + 1 < wlen ) x[( p + cnt + 1 ) * ldt] = x1;
+    }
+  }
+  g.sync();
+}
+
+// x <- U^T x for every line of the tile (U is m x m, ldu), result in tile2
+template <class G>
+PB_D void ms_tile_apply_u( const G& g, int nl, int m, const double* U, int ldu, const double* tile, double* tile2,
+                           int ldt ) {
+  const int t = g.tid(), nt = g.size();
+  for ( int line = t; line < nl; line += nt ) {
+    const double* x = tile + line;
+    double* y = tile2 + line;
+    for ( int c0 = 0; c0 < m; c0 += 8 ) {
+      double acc[8] = { 0, 0, 0, 0, 0, 0, 0, 0 };
+      const int cw = imin( 8, m - c0 );
+      for ( int p = 0; p < m; ++p ) {
+        const double xv = x[p * ldt];
+        const double* up = U + p;
+#pragma unroll
+        for ( int c = 0; c < 8; ++c )
+          if ( c < cw ) acc[c] += xv * up[(size_t)( c0 + c ) * ldu];
+      }
+#pragma unroll
+      for ( int c = 0; c < 8; ++c )
+        if ( c < cw ) y[( c0 + c ) * ldt] = acc[c];
+    }
+  }
+  g.sync();
+}
+
+// Applies either the recorded reflectors (U == nullptr) or x <- U^T x to every off-window strip.
+template <class G>
+PB_D void ms_update_strips( const G& g, bool wantt, bool wantz, int n, int l, int i, int ws, int wlen, double* H, int ldh,
+                            int iloz, int ihiz, double* Z, int ldz, const MsqrCfg& cfg, const MsqrWork& wk, int nbulges,
+                            const double* U ) {
+  const int we = ws + wlen - 1;
+  const int i1 = wantt ? 0 : l, i2 = wantt ? n - 1 : i;
+  const int* kfirst = wk.ibuf + kMsMaxBulges;
+  const int* kcount = wk.ibuf + 2 * kMsMaxBulges;
+  for ( int pass = 0; pass < 3; ++pass ) {
+    double* M;
+    int ldm, kind, lo, hi;
+    if ( pass == 0 ) {  // right of the window: columns we+1..i2
+      M = H; ldm = ldh; kind = 0; lo = we + 1; hi = i2;
+    } else if ( pass == 1 ) {  // above the window: rows i1..ws-1
+      M = H; ldm = ldh; kind = 1; lo = i1; hi = ws - 1;
+    } else {
+      if ( !wantz ) break;
+      M = Z; ldm = ldz; kind = 1; lo = iloz; hi = ihiz;
+    }
+    const int tl = ( U == nullptr ) ? cfg.tl : cfg.tl / 2;
+    for ( int l0 = lo; l0 <= hi; l0 += tl ) {
+      const int nl = imin( tl, hi - l0 + 1 );
+      ms_tile_load( g, kind, M, ldm, ws, wlen, l0, nl, wk.tile, wk.ldt );
+      if ( U == nullptr ) {
+        ms_tile_apply_reflectors( g, nl, wlen, ws, nbulges, kfirst, kcount, wk.refl, cfg.W, wk.tile, wk.ldt );
+        ms_tile_store( g, kind, M, ldm, ws, wlen, l0, nl, wk.tile, wk.ldt );
+      } else {
+        ms_tile_apply_u( g, nl, wlen, U, wk.ldw, wk.tile, wk.tile + tl, wk.ldt );
+        ms_tile_store( g, kind, M, ldm, ws, wlen, l0, nl, wk.tile + tl, wk.ldt );
+      }
+    }
+  }
+}
+
+// ---- finish a small diagonal block [l..i] (order <= W) inside the window ---------------------------
+// Returns 0 or the lahqr failure index (global, 1-based like LAPACK's info).
+template <class G>
+PB_D int ms_small_solve( const G& g, bool wantt, bool wantz, int n, int l, int i, double* H, int ldh, double* wr, double* wi,
+                         int iloz, int ihiz, double* Z, int ldz, const MsqrCfg& cfg, const MsqrWork& wk ) {
+  const int t = g.tid(), nt = g.size();
+  const int m = i - l + 1;
+  if ( m == 1 ) {
+    if ( t == 0 ) {
+      wr[i] = PB_H( i, i );
+      wi[i] = 0.0;
+    }
+    g.sync();
+    return 0;
+  }
+  const int ldw = wk.ldw;
+  if ( t == 0 ) wk.ibuf[3 * kMsMaxBulges + 3] += 1;
+  ms_load_window( g, H, ldh, l, m, wk.Hw, ldw );
+  const bool acc = wantt || wantz;
+  if ( acc ) {
+    for ( int q = t; q < m * m; q += nt ) {
+      const int c = q / m, r = q - c * m;
+      wk.U[r + c * ldw] = ( r == c ) ? 1.0 : 0.0;
+    }
+    g.sync();
+  }
+  const int info = lahqr( g, acc, acc, m, 0, m - 1, wk.Hw, ldw, wr + l, wi + l, 0, m - 1, wk.U, ldw );
+  g.sync();
+  g.tick( kTickMsSmall );
+  if ( info != 0 ) return l + info;
+  if ( !acc ) return 0;
+  // Schur form of the block back to H (strictly below the first subdiagonal stays untouched)
+  for ( int q = t; q < m * m; q += nt ) {
+    const int c = q / m, r = q - c * m;
+    if ( r - c <= 1 ) PB_H( l + r, l + c ) = wk.Hw[r + c * ldw];
+    else if ( r - c <= 3 ) PB_H( l + r, l + c ) = 0.0;
+  }
+  g.sync();
+  ms_update_strips( g, wantt, wantz, n, l, i, l, m, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, 0, wk.U );
+  g.tick( kTickMsSmallU );
+  return 0;
+}
+
+// ---- shifts: eigenvalues of the trailing ns x ns block of [l..i] -----------------------------------
+// Leaves ns_out (even, >= 2) shifts in wk.sr / wk.si, arranged in pairs (conjugates adjacent, reals two by two).
+template <class G>
+PB_D int ms_compute_shifts( const G& g, int l, int i, const double* H, int ldh, int ns, bool exceptional, const MsqrWork& wk ) {
+  const int t = g.tid(), nt = g.size();
+  double* sr = wk.sr;
+  double* si = wk.si;
+  int ks = 0;  // first valid shift
+  if ( exceptional ) {
+    if ( t == 0 ) {
+      for ( int q = ns - 1; q >= 1; q -= 2 ) {
+        const int r = i - ( ns - 1 - q );  // row of H matched with shift q
+        const double ss = fabs( PB_H( r, r - 1 ) ) + fabs( PB_H( r - 1, r - 2 ) );
+        double aa = 0.75 * ss + PB_H( r, r ), bb = ss, cc = -0.4375 * ss, dd = aa;
+        double cs, sn;
+        dlanv2( aa, bb, cc, dd, sr[q - 1], si[q - 1], sr[q], si[q], cs, sn );
+      }
+    }
+    g.sync();
+  } else {
+    const int ldw = wk.ldw;
+    double* S = wk.U;
+    const int r0 = i - ns + 1;
+    for ( int q = t; q < ns * ns; q += nt ) {
+      const int c = q / ns, r = q - c * ns;
+      S[r + c * ldw] = ( r - c <= 1 ) ? PB_H( r0 + r, r0 + c ) : 0.0;
+    }
+    g.sync();
+    const int inf = lahqr( g, false, false, ns, 0, ns - 1, S, ldw, sr, si, 0, ns - 1, (double*)nullptr, 1 );
+    g.sync();
+    PB_CHECK_UNIFORM( g, inf, "shift lahqr info" );
+    ks = inf;  // shifts ks..ns-1 converged
+    if ( ns - ks < 2 ) {
+      // fall back on the trailing 2x2 block
+      if ( t == 0 ) {
+        double aa = PB_H( i - 1, i - 1 ), bb = PB_H( i - 1, i ), cc = PB_H( i, i - 1 ), dd = PB_H( i, i );
+        double cs, sn;
+        dlanv2( aa, bb, cc, dd, sr[ns - 2], si[ns - 2], sr[ns - 1], si[ns - 1], cs, sn );
+      }
+      g.sync();
+      ks = ns - 2;
+    }
+  }
+  // one thread: sort by decreasing modulus (helps convergence a little), then arrange into pairs
+  if ( t == 0 ) {
+    bool sorted = false;
+    for ( int k = ns - 1; k >= ks + 1 && !sorted; --k ) {
+      sorted = true;
+      for ( int q = ks; q < k; ++q ) {
+        if ( fabs( sr[q] ) + fabs( si[q] ) < fabs( sr[q + 1] ) + fabs( si[q + 1] ) ) {
+          sorted = false;
+          double tmp = sr[q]; sr[q] = sr[q + 1]; sr[q + 1] = tmp;
+          tmp = si[q]; si[q] = si[q + 1]; si[q + 1] = tmp;
+        }
+      }
+    }
+    // conjugate pairs are adjacent after the sort (equal modulus); rotate triples where a real shift
+    // would split a pair
+    for ( int q = ns - 1; q >= ks + 2; q -= 2 ) {
+      if ( si[q] != -si[q - 1] ) {
+        double tmp = sr[q]; sr[q] = sr[q - 1]; sr[q - 1] = sr[q - 2]; sr[q - 2] = tmp;
+        tmp = si[q]; si[q] = si[q - 1]; si[q - 1] = si[q - 2]; si[q - 2] = tmp;
+      }
+    }
+    // an odd count drops the first shift
+    int first = ks;
+    if ( ( ( ns - first ) & 1 ) != 0 ) first += 1;
+    // a pair that is neither conjugate nor real-real (cannot happen with exact conjugates) is made real
+    for ( int q = first; q + 1 < ns; q += 2 ) {
+      if ( si[q] != -si[q + 1] ) {
+        si[q] = 0.0;
+        si[q + 1] = 0.0;
+      }
+    }
+    // compact to the front
+    const int cnt = ns - first;
+    for ( int q = 0; q < cnt; ++q ) {
+      sr[q] = sr[first + q];
+      si[q] = si[first + q];
+    }
+    wk.ibuf[3 * kMsMaxBulges] = cnt;
+  }
+  g.sync();
+  return wk.ibuf[3 * kMsMaxBulges];
+}
+
+// ---- one chain of nbulges bulges swept over the active block [l..i] --------------------------------
+template <class G>
+PB_D void ms_chase_chain( const G& g, bool wantt, bool wantz, int n, int l, int i, double* H, int ldh, int iloz, int ihiz,
+                          double* Z, int ldz, const MsqrCfg& cfg, const MsqrWork& wk, int nbulges, const double* sr,
+                          const double* si ) {
+  const int t = g.tid(), nt = g.size();
+  int* kpos = wk.ibuf;                        // next step of each bulge (l = not yet introduced; > i-1 = finished)
+  int* kfirst = wk.ibuf + kMsMaxBulges;
+  int* kcount = wk.ibuf + 2 * kMsMaxBulges;
+  double* Hw = wk.Hw;
+  const int ldw = wk.ldw;
+  g.sync();  // the previous chain's last look at kpos is over
+  for ( int b = t; b < nbulges; b += nt ) kpos[b] = l;
+  g.sync();
+  int ws = l;
+  for ( ;; ) {
+    // all bulges gone?
+    int first_live = -1, last_live = -1;
+    for ( int b = 0; b < nbulges; ++b )
+      if ( kpos[b] <= i - 1 ) {
+        if ( first_live < 0 ) first_live = b;
+        last_live = b;
+      }
+    PB_CHECK_UNIFORM( g, first_live * 100 + last_live, "live bulges" );
+    if ( first_live < 0 ) break;
+    // the trailing live bulge fixes the window start (its next step k reads column k-1)
+    ws = imax( l, kpos[last_live] - 1 );
+    const int we = imin( i, ws + cfg.W - 1 );
+    const int wlen = we - ws + 1;
+    g.sync();
+    ms_load_window( g, H, ldh, ws, wlen, Hw, ldw );
+    for ( int b = t; b < nbulges; b += nt ) {
+      kfirst[b] = kpos[b];
+      kcount[b] = 0;
+    }
+    g.sync();
+    bool progressed = false;
+#define PB_W( r, c ) Hw[( ( r ) - ws ) + ( ( c ) - ws ) * ldw]
+    for ( ;; ) {
+      // which bulges step now (every thread evaluates the same shared state)
+      unsigned moving = 0;
+      bool ahead_moves = false;
+      int ahead_pos = 0;
+      bool have_ahead = false;
+      for ( int b = 0; b < nbulges; ++b ) {
+        const int k = kpos[b];
+        bool mv = false;
+        if ( k <= i - 1 ) {
+          const bool fits = imin( k + 3, i ) <= we;
+          bool clear = true;
+          if ( have_ahead ) clear = ( ahead_pos >= k + 4 ) || ( ahead_pos == k + 3 && ahead_moves );
+          mv = fits && clear;
+          have_ahead = true;
+          ahead_pos = k;
+          ahead_moves = mv;
+        }
+        if ( mv ) moving |= 1u << b;
+      }
+      PB_CHECK_UNIFORM( g, moving, "moving" );
+      if ( moving == 0 ) break;
+      progressed = true;
+      // phase 1: reflectors (one thread per bulge)
+      for ( int b = t; b < nbulges; b += nt ) {
+        if ( !( moving & ( 1u << b ) ) ) continue;
+        const int k = kpos[b];
+        const int nr = imin( 3, i - k + 1 );
+        double a0, a1, a2 = 0.0, t1;
+        if ( k == l ) {
+          const double rt1r = sr[2 * b], rt1i = si[2 * b], rt2r = sr[2 * b + 1], rt2i = si[2 * b + 1];
+          double h21s = fabs( PB_W( l + 1, l ) );
+          double s = fabs( PB_W( l, l ) - rt2r ) + fabs( rt2i ) + h21s;
+          if ( s == 0.0 ) {
+            a0 = 0.0; a1 = 0.0; a2 = 0.0;
+          } else {
+            h21s = PB_W( l + 1, l ) / s;
+            a0 = h21s * PB_W( l, l + 1 ) + ( PB_W( l, l ) - rt1r ) * ( ( PB_W( l, l ) - rt2r ) / s ) - rt1i * ( rt2i / s );
+            a1 = h21s * ( PB_W( l, l ) + PB_W( l + 1, l + 1 ) - rt1r - rt2r );
+            a2 = ( nr == 3 ) ? h21s * PB_W( l + 2, l + 1 ) : 0.0;
+            s = fabs( a0 ) + fabs( a1 ) + fabs( a2 );
+            if ( s != 0.0 ) {
+              a0 /= s; a1 /= s; a2 /= s;
+            }
+          }
+        } else {
+          a0 = PB_W( k, k - 1 );
+          a1 = PB_W( k + 1, k - 1 );
+          if ( nr == 3 ) a2 = PB_W( k + 2, k - 1 );
+        }
+        dlarfg3( nr, a0, a1, a2, t1 );
+        if ( nr < 3 ) a2 = 0.0;
+        if ( k > l ) {
+          PB_W( k, k - 1 ) = a0;
+          PB_W( k + 1, k - 1 ) = 0.0;
+          if ( nr == 3 ) PB_W( k + 2, k - 1 ) = 0.0;
+        }
+        double* rf = wk.refl + ( (size_t)b * cfg.W + kcount[b] ) * kReflStride;
+        rf[0] = a1;
+        rf[1] = a2;
+        rf[2] = t1;
+        rf[3] = t1 * a1;
+        rf[4] = t1 * a2;
+      }
+      g.sync();
+      // phase 2: row updates inside the window, all moving bulges at once (disjoint rows)
+      for ( int q = t; q < nbulges * wlen; q += nt ) {
+        const int b = q / wlen, jj = q - b * wlen;
+        if ( !( moving & ( 1u << b ) ) ) continue;
+        const int k = kpos[b];
+        const int j = ws + jj;
+        if ( j < k ) continue;
+        const double* rf = wk.refl + ( (size_t)b * cfg.W + kcount[b] ) * kReflStride;
+        const bool three = ( k + 2 <= i );
+        const double x0 = PB_W( k, j ), x1 = PB_W( k + 1, j ), x2 = three ? PB_W( k + 2, j ) : 0.0;
+        const double sum = x0 + rf[0] * x1 + rf[1] * x2;
+        PB_W( k, j ) = x0 - sum * rf[2];
+        PB_W( k + 1, j ) = x1 - sum * rf[3];
+        if ( three ) PB_W( k + 2, j ) = x2 - sum * rf[4];
+      }
+      g.sync();
+      // phase 3: column updates inside the window (disjoint columns)
+      for ( int q = t; q < nbulges * wlen; q += nt ) {
+        const int b = q / wlen, rr = q - b * wlen;
+        if ( !( moving & ( 1u << b ) ) ) continue;
+        const int k = kpos[b];
+        const int r = ws + rr;
+        if ( r > imin( k + 3, i ) ) continue;
+        const double* rf = wk.refl + ( (size_t)b * cfg.W + kcount[b] ) * kReflStride;
+        const bool three = ( k + 2 <= i );
+        const double x0 = PB_W( r, k ), x1 = PB_W( r, k + 1 ), x2 = three ? PB_W( r, k + 2 ) : 0.0;
+        const double sum = x0 + rf[0] * x1 + rf[1] * x2;
+        PB_W( r, k ) = x0 - sum * rf[2];
+        PB_W( r, k + 1 ) = x1 - sum * rf[3];
+        if ( three ) PB_W( r, k + 2 ) = x2 - sum * rf[4];
+      }
+      g.sync();
+      for ( int b = t; b < nbulges; b += nt )
+        if ( moving & ( 1u << b ) ) {
+          kpos[b] += 1;
+          kcount[b] += 1;
+        }
+      g.sync();
+    }
+#undef PB_W
+    if ( !progressed ) break;  // cannot happen for W >= 3*nb + 4; never spin
+    ms_store_window( g, H, ldh, ws, wlen, Hw, ldw );
+    if ( t == 0 ) wk.ibuf[3 * kMsMaxBulges + 2] += 1;
+    g.tick( kTickMsChase );
+    ms_update_strips( g, wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, nbulges, (const double*)nullptr );
+    g.sync();
+    g.tick( kTickMsStrips );
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Driver. H upper Hessenberg in rows/cols ilo..ihi (isolated eigenvalues outside are the caller's
+// business, as in pb::lahqr). Returns 0 or LAPACK's info (i+1: eigenvalues i+1..ihi converged).
+// ------------------------------------------------------------------------------------------------
+template <class G>
+PB_D int hqr_multishift( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, double* H, int ldh, double* wr,
+                         double* wi, int iloz, int ihiz, double* Z, int ldz, const MsqrCfg& cfg, const MsqrWork& wk ) {
+  const int t = g.tid(), nt = g.size();
+  if ( n == 0 || ihi < ilo ) return 0;
+  // clear the band below the subdiagonal that parked bulges use
+  for ( int j = ilo + t; j <= ihi - 2; j += nt ) {
+    PB_H( j + 2, j ) = 0.0;
+    if ( j + 3 <= ihi ) PB_H( j + 3, j ) = 0.0;
+  }
+  g.sync();
+  const int nh = ihi - ilo + 1;
+  const double smlnum = kSafmin * ( (double)nh / kUlp );
+  const int itmax = 30 * imax( 10, nh );
+  int kbot = ihi;
+  int it = 0, nodefl = 0;
+  while ( kbot >= ilo ) {
+    const int ktop = ms_find_split( g, ilo, ihi, ilo, kbot, H, ldh, smlnum );
+    if ( ktop > ilo ) {
+      if ( t == 0 ) PB_H( ktop, ktop - 1 ) = 0.0;
+    }
+    g.sync();
+    const int m = kbot - ktop + 1;
+    PB_CHECK_UNIFORM( g, ktop, "ktop" );
+    g.tick( kTickMsScan );
+    if ( m <= cfg.ws_small ) {
+      const int info = ms_small_solve( g, wantt, wantz, n, ktop, kbot, H, ldh, wr, wi, iloz, ihiz, Z, ldz, cfg, wk );
+      PB_CHECK_UNIFORM( g, info, "small-solve info" );
+      if ( info != 0 ) return info;
+      kbot = ktop - 1;
+      nodefl = 0;
+      continue;
+    }
+    if ( ++it > itmax ) return kbot + 1;
+    if ( t == 0 ) wk.ibuf[3 * kMsMaxBulges + 1] += 1;
+    nodefl += 1;
+    // the shift block is factored inside the U buffer, hence ns <= W
+    const int nshift_want = imin( imin( 2 * cfg.nb * cfg.nchains, cfg.W & ~1 ), ( ( m - 1 ) / 3 ) * 2 );
+    const int ns = ms_compute_shifts( g, ktop, kbot, H, ldh, imax( 2, nshift_want & ~1 ), ( nodefl % 6 ) == 0, wk );
+    PB_CHECK_UNIFORM( g, ns, "ns" );
+    g.tick( kTickMsShifts );
+    for ( int s0 = 0; s0 < ns; s0 += 2 * cfg.nb ) {
+      const int nbul = imin( cfg.nb, ( ns - s0 ) / 2 );
+      ms_chase_chain( g, wantt, wantz, n, ktop, kbot, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, nbul, wk.sr + s0, wk.si + s0 );
+    }
+    // a sweep that exposes a split anywhere in the block resets the exceptional-shift counter
+    const int split = ms_find_split( g, ilo, ihi, ktop, kbot, H, ldh, smlnum );
+    if ( split > ktop ) nodefl = 0;
+  }
+  return 0;
+}
+
+}  // namespace pb

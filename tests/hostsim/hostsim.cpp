@@ -7,25 +7,70 @@
 //   ht_*  : ThreadGroup, nt real threads with a pthread barrier behind sync(); built a second time
 //           with -fsanitize=thread (libhostsim_tsan.so) it reports every missing barrier as a data
 //           race, which is how the kernels' synchronisation is checked without a GPU.
+#include <dlfcn.h>
 #include <pthread.h>
 
+#include <cstdio>
 #include <cstdlib>
+#include <ctime>
 #include <cstring>
 #include <functional>
 #include <thread>
 #include <vector>
 
+#define PB_CHECK_UNIFORM( g, value, tag ) ( g ).check_uniform( (long)( value ), tag )
 #include "../../paladin_b200/csrc/pb_geev.cuh"
 
 namespace {
 
+// Barrier with divergence diagnostics: every thread publishes the call site of its sync(); when some
+// thread fails to arrive within 20 s the sites are printed (resolve them with addr2line -e
+// libhostsim.so) and the process aborts instead of hanging. (Sites are not compared on arrival: the
+// compiler duplicates code paths, so equal source lines can have different return addresses.)
 struct ThreadShared {
-  pthread_barrier_t bar;
-  int nt;
+  pthread_mutex_t mu;
+  pthread_cond_t cv;
+  int nt, arrived = 0;
+  unsigned long gen = 0;
+  std::vector<void*> site;
   std::vector<double> d;
   std::vector<int> i;
-  explicit ThreadShared( int n ) : nt( n ), d( n ), i( n ) { pthread_barrier_init( &bar, nullptr, n ); }
-  ~ThreadShared() { pthread_barrier_destroy( &bar ); }
+  explicit ThreadShared( int n ) : nt( n ), site( n, nullptr ), d( n ), i( n ) {
+    pthread_mutex_init( &mu, nullptr );
+    pthread_cond_init( &cv, nullptr );
+  }
+  ~ThreadShared() {
+    pthread_cond_destroy( &cv );
+    pthread_mutex_destroy( &mu );
+  }
+  void report( const char* why ) {
+    std::fprintf( stderr, "hostsim barrier: %s\n", why );
+    for ( int k = 0; k < nt; ++k ) {
+      Dl_info inf;
+      unsigned long off = 0;
+      if ( dladdr( site[k], &inf ) && inf.dli_fbase ) off = (unsigned long)( (char*)site[k] - (char*)inf.dli_fbase );
+      std::fprintf( stderr, "  thread %d last sync site offset 0x%lx\n", k, off );
+    }
+    std::abort();
+  }
+  void wait( int me, void* where ) {
+    pthread_mutex_lock( &mu );
+    site[me] = where;
+    const unsigned long my_gen = gen;
+    if ( ++arrived == nt ) {
+      arrived = 0;
+      ++gen;
+      pthread_cond_broadcast( &cv );
+    } else {
+      timespec ts;
+      clock_gettime( CLOCK_REALTIME, &ts );
+      ts.tv_sec += 20;
+      while ( gen == my_gen ) {
+        if ( pthread_cond_timedwait( &cv, &mu, &ts ) != 0 && gen == my_gen ) report( "a thread never arrived (divergent control flow)" );
+      }
+    }
+    pthread_mutex_unlock( &mu );
+  }
 };
 
 struct ThreadGroup {
@@ -33,7 +78,8 @@ struct ThreadGroup {
   int me;
   int tid() const { return me; }
   int size() const { return s->nt; }
-  void sync() const { pthread_barrier_wait( &s->bar ); }
+  __attribute__( ( noinline ) ) void sync() const { s->wait( me, __builtin_return_address( 0 ) ); }
+  void tick( int ) const {}
   template <class F>
   double reduce_d( double x, F f ) const {
     s->d[me] = x;
@@ -68,6 +114,15 @@ struct ThreadGroup {
     return reduce_i( x, []( int a, int b ) { return a + b; } );
   }
   bool any( bool x ) const { return imax_( x ? 1 : 0 ) != 0; }
+  void check_uniform( long v, const char* tag ) const {
+    if ( const char* only = std::getenv( "PB_ONLY_CHECK" ) )
+      if ( std::strcmp( only, tag ) != 0 ) return;
+    const int lo = imin_( (int)v ), hi = imax_( (int)v );
+    if ( lo != hi ) {
+      std::fprintf( stderr, "hostsim: value '%s' differs between threads (%d..%d)\n", tag, lo, hi );
+      std::abort();
+    }
+  }
 };
 
 // run f(group) on nt threads; returns thread 0's result
@@ -127,6 +182,69 @@ int hs_geev( int n, double* A, double* wr, double* wi, int wantvr, double* V ) {
   std::vector<double> dw( 5 * n + 5 );
   std::vector<int> iw( 2 * n + 2 );
   return pb::geev_group( g, n, A, n, wr, wi, wantvr != 0, V, n, dw.data(), iw.data() );
+}
+
+struct MsBuffers {
+  std::vector<double> d;
+  std::vector<int> i;
+  pb::MsqrWork wk;
+  MsBuffers( const pb::MsqrCfg& c ) {
+    const int ldw = c.W | 1, ldt = c.tl | 1;
+    d.assign( pb::msqr_work_doubles( c, ldw, ldt ) + 64, 0.0 );
+    i.assign( 3 * pb::kMsMaxBulges + 8, 0 );
+    double* p = d.data();
+    wk.Hw = p; p += (size_t)c.W * ldw;
+    wk.U = p; p += (size_t)c.W * ldw;
+    wk.tile = p; p += (size_t)c.W * ldt;
+    wk.refl = p; p += (size_t)c.nb * c.W * pb::kReflStride;
+    wk.sr = p; p += 2 * c.nb * c.nchains;
+    wk.si = p;
+    wk.ibuf = i.data();
+    wk.ldw = ldw;
+    wk.ldt = ldt;
+  }
+};
+
+int g_ms_counters[4];
+int hs_msqr( int wantt, int wantz, int n, int ilo, int ihi, double* H, double* wr, double* wi, double* Z, int nb, int W,
+             int ws_small, int tl, int nchains ) {
+  pb::HostGroup g;
+  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains };
+  MsBuffers buf( c );
+  const int r = pb::hqr_multishift( g, wantt != 0, wantz != 0, n, ilo, ihi, H, n, wr, wi, 0, n - 1, Z, n, c, buf.wk );
+  for ( int k = 0; k < 4; ++k ) g_ms_counters[k] = buf.i[3 * pb::kMsMaxBulges + k];
+  return r;
+}
+const int* hs_ms_counters() { return g_ms_counters; }
+
+int ht_msqr( int nt, int wantt, int wantz, int n, int ilo, int ihi, double* H, double* wr, double* wi, double* Z, int nb,
+             int W, int ws_small, int tl, int nchains ) {
+  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains };
+  MsBuffers buf( c );
+  return run_threads( nt, [&]( const ThreadGroup& g ) {
+    return pb::hqr_multishift( g, wantt != 0, wantz != 0, n, ilo, ihi, H, n, wr, wi, 0, n - 1, Z, n, c, buf.wk );
+  } );
+}
+
+int hs_geev_ms( int n, double* A, double* wr, double* wi, int wantvr, double* V, int nb, int W, int ws_small, int tl,
+                int nchains ) {
+  pb::HostGroup g;
+  std::vector<double> dw( 5 * n + 5 );
+  std::vector<int> iw( 2 * n + 2 );
+  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains };
+  MsBuffers buf( c );
+  return pb::geev_group( g, n, A, n, wr, wi, wantvr != 0, V, n, dw.data(), iw.data(), pb::QrMultishift{ c, buf.wk } );
+}
+
+int ht_geev_ms( int nt, int n, double* A, double* wr, double* wi, int wantvr, double* V, int nb, int W, int ws_small, int tl,
+                int nchains ) {
+  std::vector<double> dw( 5 * n + 5 );
+  std::vector<int> iw( 2 * n + 2 );
+  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains };
+  MsBuffers buf( c );
+  return run_threads( nt, [&]( const ThreadGroup& g ) {
+    return pb::geev_group( g, n, A, n, wr, wi, wantvr != 0, V, n, dw.data(), iw.data(), pb::QrMultishift{ c, buf.wk } );
+  } );
 }
 
 // ---- threaded versions (race checking under -fsanitize=thread) ----

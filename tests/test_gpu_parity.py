@@ -214,6 +214,9 @@ def test_badly_scaled_and_structured(pg):
     for k, (A, (wr, wi, VR), inf) in enumerate(zip(cases, res, info)):
         assert inf == 0, k
         wr0, wi0, _, VR0, _ = po.dgeev(A, right=True)
+        if k in (1, 2):  # compare in the unscaled frame (the checker's own norms would overflow otherwise)
+            s = 1e-200 if k == 1 else 1e200
+            A, wr, wi, wr0, wi0 = A / s, wr / s, wi / s, wr0 / s, wi0 / s
         nrm = max(1.0, np.linalg.norm(A, 2))
         err = po.match_eigenvalues(po.eigenvalues(wr, wi), po.eigenvalues(wr0, wi0))
         # defective / ill-conditioned cases: compare with what LAPACK itself achieves
@@ -277,7 +280,7 @@ def test_staged_api_and_stage_timers(pg):
     ms = b.stage_ms()
     b.destroy()
     assert not info.any()
-    assert ms["scatter"][0] > 0 and ms["small"][0] > 0 and ms["generic"][0] > 0
+    assert ms["scatter"][0] > 0 and ms["small"][0] > 0 and ms["mid"][0] > 0
     from paladin_b200.api import split_results
     for m, (w1, w2, V) in zip(mats, split_results(n, wr, wi, vr)):
         _check_eigs(po.dense_matrix(*m), w1, w2, V, 0, True)

@@ -63,6 +63,62 @@ def test_geev_pipeline_matches_lapack(hs, n):
         assert infoe == 0 and po.match_eigenvalues((wre + 1j * wie) / s, w0) <= 1e-9 * nrm
 
 
+def _hessenberg_case(n, seed, sparse=False):
+    rng = np.random.default_rng([seed, n])
+    A = rng.standard_normal((n, n))
+    if sparse:
+        A[rng.random((n, n)) < 0.7] = 0
+    B, ilo, ihi, sc = ls.dgebal(np.asfortranarray(A))
+    H, tau = ls.dgehrd(B, ilo, ihi)
+    Q = ls.dorghr(H, tau, ilo, ihi)
+    # what dgehrd leaves below the subdiagonal (reflector storage) must be ignored by the QR stage
+    Hj = np.asfortranarray(np.triu(H, -1) + np.tril(rng.standard_normal((n, n)), -2))
+    return B, ilo, ihi, np.asfortranarray(np.triu(H, -1)), Hj, Q
+
+
+MS_CONFIGS = [(8, 49, 48, 128, 1), (8, 49, 48, 256, 2), (4, 17, 16, 7, 1), (2, 10, 6, 5, 3), (16, 97, 64, 64, 1)]
+
+
+@pytest.mark.parametrize("n", [10, 49, 50, 80, 130, 200])
+@pytest.mark.parametrize("cfg", MS_CONFIGS)
+def test_multishift_qr_matches_lapack_dhseqr(hs, n, cfg):
+    nb, W, wss, tl, nch = cfg
+    for sparse in (False, True):
+        B, ilo, ihi, H, Hj, Q = _hessenberg_case(n, 5, sparse)
+        T0, wr0, wi0, Z0, info0 = ls.dhseqr(H, ilo, ihi, Z=Q)
+        sl = slice(ilo - 1, ihi)
+        for wantt in (1, 0):
+            H2, Z2 = Hj.copy(order="F"), Q.copy(order="F")
+            wr, wi = np.zeros(n), np.zeros(n)
+            info = hs.hs_msqr(wantt, wantt, n, ilo - 1, ihi - 1, dp(H2), dp(wr), dp(wi), dp(Z2), nb, W, wss, tl, nch)
+            assert info == 0 and info0 == 0
+            nrm = max(1.0, np.linalg.norm(B, 2))
+            assert po.match_eigenvalues(wr[sl] + 1j * wi[sl], wr0[sl] + 1j * wi0[sl]) <= 1e-9 * nrm
+            if wantt:
+                T = np.triu(H2, -1)
+                assert np.abs(Z2 @ T @ Z2.T - B).max() <= 1e-12 * nrm * n
+                assert np.abs(Z2.T @ Z2 - np.eye(n)).max() <= 1e-12 * n
+                sub = np.diag(T, -1)
+                for k in np.nonzero(sub)[0]:  # standardised 2x2 blocks (dlanv2), never two in a row
+                    assert T[k, k] == T[k + 1, k + 1] and T[k, k + 1] * T[k + 1, k] < 0
+                    assert k + 1 >= n - 1 or sub[k + 1] == 0
+
+
+def test_multishift_geev_pipeline(hs):
+    rng = np.random.default_rng(77)
+    for n in (65, 100, 257):
+        A = rng.standard_normal((n, n))
+        for wantvr in (1, 0):
+            A2 = np.array(A, order="F")
+            wr, wi, V = np.zeros(n), np.zeros(n), np.zeros((n, n), order="F")
+            info = hs.hs_geev_ms(n, dp(A2), dp(wr), dp(wi), wantvr, dp(V), 8, 49, 48, 256, 2)
+            wr0, wi0, _, VR0, info0 = ls.dgeev(A)
+            assert info == 0
+            assert po.match_eigenvalues(wr + 1j * wi, wr0 + 1j * wi0) <= 1e-9 * max(1.0, np.linalg.norm(A, 2))
+            if wantvr:
+                assert po.backward_error(A, wr, wi, V) <= 100
+
+
 def test_stage_functions_match_lapack(hs):
     rng = np.random.default_rng(3)
     for n in (6, 20, 50):
@@ -123,6 +179,15 @@ from oracle import lapack_stages as ls, paladin_oracle as po
 hs = ctypes.CDLL(%r)
 dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 rng = np.random.default_rng(1)
+for n, nt, (nb, W, wss, tl, nch) in [(30, 4, (2, 10, 6, 5, 2)), (40, 3, (3, 14, 8, 6, 1)), (26, 5, (2, 11, 7, 4, 3))]:
+    A = rng.standard_normal((n, n))
+    for wantvr in (0, 1):
+        A2 = np.array(A, order='F'); wr = np.zeros(n); wi = np.zeros(n); V = np.zeros((n, n), order='F')
+        info = hs.ht_geev_ms(nt, n, dp(A2), dp(wr), dp(wi), wantvr, dp(V), nb, W, wss, tl, nch)
+        wr0, wi0, _, VR0, info0 = ls.dgeev(A)
+        assert info == 0
+        assert po.match_eigenvalues(wr + 1j * wi, wr0 + 1j * wi0) <= 1e-9 * max(1, np.linalg.norm(A, 2))
+        if wantvr: assert po.backward_error(A, wr, wi, V) <= 100
 for n, nt in [(1, 3), (2, 3), (3, 4), (7, 4), (12, 3), (20, 5)]:
     for trial in range(2):
         A = rng.standard_normal((n, n))
