@@ -53,7 +53,7 @@ extern "C" {
 #define PALADIN_GPU_STAGE_VECTORS 4    /* eigenvectors of T, back-transform, un-balance, normalise */
 #define PALADIN_GPU_STAGE_SMALL 5      /* fused warp-per-matrix path for n <= 64 (all stages in one kernel) */
 #define PALADIN_GPU_STAGE_GENERIC 6    /* fused CTA-per-matrix path in global memory (all stages; debug fallback) */
-#define PALADIN_GPU_STAGE_MID 7        /* CTA-per-matrix path for n > 64: windowed multishift QR (all stages in one kernel) */
+#define PALADIN_GPU_STAGE_MID 7        /* unused (the CTA-per-matrix path for n > 64 reports stages 2, 3 and 4) */
 #define PALADIN_GPU_NUM_STAGES 8
 
 /* ---- lifecycle ------------------------------------------------------------------------------- */
@@ -134,7 +134,7 @@ int paladin_gpu_batch_download( paladin_gpu_batch* b, double* wr, double* wi, do
 int paladin_gpu_batch_stage_ms( paladin_gpu_batch* b, float* ms, int* launches );
 
 /* Phase profile of the most recent CTA-per-matrix solve: SM cycles summed over all CTAs, 16 slots
- * (0 balance, 1 Hessenberg, 2 form Q, 3 QR total, 4 eigenvectors of T, 5 un-balance + normalise,
+ * (0 balance, 1 Hessenberg, 2 form Q, 3 QR remainder, 4 eigenvectors of T, 5 un-balance + normalise, 6 back-transform GEMM,
  *  8 deflation scans, 9 shift computation, 10 in-window bulge chasing, 11 strip updates by recorded
  *  reflectors, 12 small-block solves, 13 strip updates by small U). Diagnostic only. */
 int paladin_gpu_batch_phase_cycles( paladin_gpu_batch* b, long long* cycles );

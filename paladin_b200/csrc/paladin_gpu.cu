@@ -15,6 +15,8 @@
 
 #include "../../include/paladin_gpu.h"
 #include "pb_geev.cuh"
+#include "pb_hess.cuh"
+#include "pb_vecs.cuh"
 #include "pb_scatter.cuh"
 
 namespace {
@@ -160,15 +162,114 @@ constexpr int kNumTicks = 16;
 
 __host__ __device__ inline pb::MsqrCfg mid_cfg() { return pb::MsqrCfg{ 8, 49, 48, 256, 2 }; }
 
-inline size_t mid_smem_bytes() {
-  const pb::MsqrCfg c = mid_cfg();
-  return sizeof( double ) * pb::msqr_work_doubles( c, c.W | 1, c.tl | 1 ) + sizeof( int ) * ( 3 * pb::kMsMaxBulges + 8 ) +
-         sizeof( long long ) * kNumTicks;
+constexpr int kMidMaxFusedN = 1024;  // warp-level kernels keep a matrix column in 32 * MAXCH registers per warp
+
+// per-matrix state handed from stage to stage (global memory)
+struct MidMeta {
+  int ilo, ihi, info, scalea;
+  double anrm, cscale;
+};
+
+struct MidArgs {
+  BatchView bv;
+  const int* ids;
+  int count;
+  MidMeta* meta;
+  long long* stats;
+  int* counter;    // work queue head of the persistent vectors kernel
+  double* xwork;   // slots of n_max^2 doubles for the triangular eigenvector factor
+  size_t xslot;    // doubles per slot
+};
+
+__device__ __forceinline__ void mid_pointers( const BatchView& bv, int id, int n, double*& A, double*& V, double*& wr, double*& wi,
+                                              double*& dw, int*& iw ) {
+  A = bv.A + bv.a_off[id];
+  V = bv.wantvr ? bv.V + bv.a_off[id] : nullptr;
+  wr = bv.wr + bv.w_off[id];
+  wi = bv.wi + bv.w_off[id];
+  dw = bv.dwork + 5 * bv.w_off[id];
+  iw = bv.iwork + 2 * bv.w_off[id] + 2 * id;
 }
 
-__global__ void __launch_bounds__( kMidThreads ) geev_mid_kernel( BatchView bv, const int* ids, long long* stats ) {
+__device__ __forceinline__ void stats_begin( pb::CtaGroup& g, long long* stats, long long* lstats ) {
+  if ( threadIdx.x < kNumTicks ) lstats[threadIdx.x] = 0;
+  __syncthreads();
+  if ( stats != nullptr ) {
+    g.stats = lstats;
+    g.last = clock64();
+  }
+}
+__device__ __forceinline__ void stats_end( long long* stats, const long long* lstats ) {
+  __syncthreads();
+  if ( stats != nullptr && threadIdx.x < kNumTicks && lstats[threadIdx.x] != 0 )
+    atomicAdd( reinterpret_cast<unsigned long long*>( stats ) + threadIdx.x, (unsigned long long)lstats[threadIdx.x] );
+}
+
+// ---- stage 1: scale check, balancing, Hessenberg reduction, explicit Q ----------------------------------
+inline size_t prep_smem_bytes( int nmax ) {
+  return sizeof( double ) * ( nmax <= kMidMaxFusedN ? pb::hess_smem_doubles( nmax ) : 64 );
+}
+
+__global__ void __launch_bounds__( pb::kHessThreads ) mid_prep_kernel( MidArgs a ) {
   extern __shared__ double smem[];
   __shared__ double red[64];
+  __shared__ long long lstats[kNumTicks];
+  const int id = a.ids[blockIdx.x];
+  const int n = a.bv.n[id];
+  pb::CtaGroup g{ red };
+  stats_begin( g, a.stats, lstats );
+  double *A, *V, *wr, *wi, *dw;
+  int* iw;
+  mid_pointers( a.bv, id, n, A, V, wr, wi, dw, iw );
+  double* tau = dw;
+  double* scale = dw + n;
+  pb::GeevScaling sc;
+  int ilo = 0, ihi = n - 1, info = 0;
+  if ( !pb::geev_prologue( g, n, A, n, sc, &ilo, &ihi, scale, iw ) ) {
+    info = PALADIN_GPU_INFO_NONFINITE;
+    sc.scalea = false;
+    sc.anrm = 0.0;
+    sc.cscale = 1.0;
+  } else {
+    g.tick( pb::kTickBalance );
+    if ( n <= 512 ) pb::hess_fused<16>( n, ilo, ihi, A, n, tau, smem );
+    else if ( n <= kMidMaxFusedN ) pb::hess_fused<32>( n, ilo, ihi, A, n, tau, smem );
+    else pb::gehd2( g, n, ilo, ihi, A, n, tau, dw + 2 * n );
+    __syncthreads();
+    g.tick( pb::kTickHess );
+    if ( a.bv.wantvr ) {
+      if ( n <= 512 ) pb::form_q<16>( n, ilo, ihi, A, n, tau, V, n );
+      else if ( n <= kMidMaxFusedN ) pb::form_q<32>( n, ilo, ihi, A, n, tau, V, n );
+      else pb::orghr( g, n, ilo, ihi, A, n, tau, V, n );
+    }
+    __syncthreads();
+    g.tick( pb::kTickOrghr );
+    pb::geev_isolated_eigenvalues( g, n, ilo, ihi, A, n, wr, wi );
+  }
+  if ( threadIdx.x == 0 ) {
+    MidMeta m;
+    m.ilo = ilo;
+    m.ihi = ihi;
+    m.info = info;
+    m.scalea = sc.scalea ? 1 : 0;
+    m.anrm = sc.anrm;
+    m.cscale = sc.cscale;
+    a.meta[id] = m;
+    a.bv.info[id] = info;
+  }
+  stats_end( a.stats, lstats );
+}
+
+// ---- stage 2: QR iteration (windowed multishift sweeps) --------------------------------------------------
+inline size_t qr_smem_bytes() {
+  const pb::MsqrCfg c = mid_cfg();
+  return sizeof( double ) * pb::msqr_work_doubles( c, c.W | 1, c.tl | 1 ) + sizeof( int ) * ( 3 * pb::kMsMaxBulges + 8 );
+}
+
+__global__ void __launch_bounds__( kMidThreads ) mid_qr_kernel( MidArgs a ) {
+  extern __shared__ double smem[];
+  __shared__ double red[64];
+  __shared__ long long lstats[kNumTicks];
   const pb::MsqrCfg c = mid_cfg();
   const int ldw = c.W | 1, ldt = c.tl | 1;
   pb::MsqrWork wk;
@@ -179,31 +280,79 @@ __global__ void __launch_bounds__( kMidThreads ) geev_mid_kernel( BatchView bv, 
   wk.refl = p; p += (size_t)c.nb * c.W * pb::kReflStride;
   wk.sr = p; p += 2 * c.nb * c.nchains;
   wk.si = p; p += 2 * c.nb * c.nchains;
-  long long* lstats = reinterpret_cast<long long*>( p );
-  wk.ibuf = reinterpret_cast<int*>( lstats + kNumTicks );
+  wk.ibuf = reinterpret_cast<int*>( p );
   wk.ldw = ldw;
   wk.ldt = ldt;
-  if ( threadIdx.x < kNumTicks ) lstats[threadIdx.x] = 0;
   if ( threadIdx.x < 3 * pb::kMsMaxBulges + 8 ) wk.ibuf[threadIdx.x] = 0;
-  __syncthreads();
-
-  const int id = ids[blockIdx.x];
-  const int n = bv.n[id];
+  const int id = a.ids[blockIdx.x];
+  const int n = a.bv.n[id];
   pb::CtaGroup g{ red };
-  if ( stats != nullptr ) {
-    g.stats = lstats;
-    g.last = clock64();
-  }
-  double* A = bv.A + bv.a_off[id];
-  double* V = bv.wantvr ? bv.V + bv.a_off[id] : nullptr;
-  double* wr = bv.wr + bv.w_off[id];
-  double* wi = bv.wi + bv.w_off[id];
-  double* dw = bv.dwork + 5 * bv.w_off[id];
-  int* iw = bv.iwork + 2 * bv.w_off[id] + 2 * id;
-  const int info = pb::geev_group( g, n, A, n, wr, wi, bv.wantvr != 0, V, n, dw, iw, pb::QrMultishift{ c, wk } );
-  if ( threadIdx.x == 0 ) bv.info[id] = info;
+  stats_begin( g, a.stats, lstats );
+  const MidMeta m = a.meta[id];
+  if ( m.info != 0 ) return;
+  double *A, *V, *wr, *wi, *dw;
+  int* iw;
+  mid_pointers( a.bv, id, n, A, V, wr, wi, dw, iw );
+  const bool wantvr = a.bv.wantvr != 0;
+  const int info = pb::hqr_multishift( g, wantvr, wantvr, n, m.ilo, m.ihi, A, n, wr, wi, 0, n - 1, V, n, c, wk );
   __syncthreads();
-  if ( stats != nullptr && threadIdx.x < kNumTicks ) atomicAdd( reinterpret_cast<unsigned long long*>( stats ) + threadIdx.x, (unsigned long long)lstats[threadIdx.x] );
+  g.tick( pb::kTickQr );
+  pb::GeevScaling sc{ m.scalea != 0, m.anrm, m.cscale };
+  pb::geev_unscale( g, n, sc, info, m.ilo, wr, wi );
+  if ( threadIdx.x == 0 ) {
+    a.meta[id].info = info;
+    a.bv.info[id] = info;
+  }
+  stats_end( a.stats, lstats );
+}
+
+// ---- stage 3: eigenvectors (persistent CTAs, one work slot each) -----------------------------------------
+inline size_t vec_smem_bytes( int nmax ) { return sizeof( double ) * pb::vecs_gemm_smem_doubles() + sizeof( int ) * nmax; }
+
+__global__ void __launch_bounds__( pb::kVecThreads ) mid_vec_kernel( MidArgs a ) {
+  extern __shared__ double smem[];
+  __shared__ double red[64];
+  __shared__ long long lstats[kNumTicks];
+  __shared__ int s_next;
+  int* perm = reinterpret_cast<int*>( smem + pb::vecs_gemm_smem_doubles() );
+  pb::CtaGroup g{ red };
+  stats_begin( g, a.stats, lstats );
+  double* X = a.xwork + (size_t)blockIdx.x * a.xslot;
+  for ( ;; ) {
+    __syncthreads();
+    if ( threadIdx.x == 0 ) s_next = atomicAdd( a.counter, 1 );
+    __syncthreads();
+    const int k = s_next;
+    if ( k >= a.count ) break;
+    const int id = a.ids[k];
+    const int n = a.bv.n[id];
+    const MidMeta m = a.meta[id];
+    if ( m.info != 0 ) continue;
+    double *A, *V, *wr, *wi, *dw;
+    int* iw;
+    mid_pointers( a.bv, id, n, A, V, wr, wi, dw, iw );
+    double* scale = dw + n;
+    double* cnorm = dw + 2 * n;
+    if ( n <= kMidMaxFusedN ) {
+      pb::vecs_solve( n, A, n, X, n, cnorm );
+      g.tick( pb::kTickTrevc );
+      pb::vecs_gemm( n, V, n, X, n, A, n, smem );   // T is dead once every solve of this matrix finished
+      __syncthreads();
+      g.tick( pb::kTickVecGemm );
+      if ( n <= 512 ) pb::vecs_finish<16>( n, m.ilo, m.ihi, scale, wi, A, n, V, n, perm );
+      else pb::vecs_finish<32>( n, m.ilo, m.ihi, scale, wi, A, n, V, n, perm );
+      __syncthreads();
+      g.tick( pb::kTickBak );
+    } else {
+      pb::trevc_right_inplace( g, n, A, n, V, n, cnorm, dw + 3 * n, dw + 4 * n );
+      g.tick( pb::kTickTrevc );
+      pb::gebak_right( g, n, m.ilo, m.ihi, scale, n, V, n );
+      __syncthreads();
+      pb::normalize_vectors( g, n, wi, V, n );
+      g.tick( pb::kTickBak );
+    }
+  }
+  stats_end( a.stats, lstats );
 }
 
 struct StageTimer {
@@ -235,7 +384,12 @@ struct paladin_gpu_batch {
   std::vector<int> flags;                    // scatter flags per matrix
   std::vector<int> ids;                      // all ids grouped by class
   struct Group { int first, count, nmax, kind; };  // kind 0 = warp bucket, 1 = CTA per matrix
-  long long* d_stats = nullptr;              // phase profile of the CTA-per-matrix kernel (cycles)
+  long long* d_stats = nullptr;              // phase profile of the CTA-per-matrix kernels (cycles)
+  MidMeta* d_meta = nullptr;
+  int* d_counter = nullptr;
+  double* d_xwork = nullptr;
+  size_t xslot = 0;
+  int xslots = 0;
   std::vector<Group> groups;
   StageTimer st[PALADIN_GPU_NUM_STAGES];
   bool scattered = false;
@@ -249,7 +403,7 @@ void free_batch( paladin_gpu_batch* b ) {
   cudaFree( b->d_n ); cudaFree( b->d_nnz_off ); cudaFree( b->d_a_off ); cudaFree( b->d_w_off );
   cudaFree( b->d_coo_i ); cudaFree( b->d_coo_j ); cudaFree( b->d_coo_v );
   cudaFree( b->d_A ); cudaFree( b->d_V ); cudaFree( b->d_wr ); cudaFree( b->d_wi ); cudaFree( b->d_dwork );
-  cudaFree( b->d_stats );
+  cudaFree( b->d_stats ); cudaFree( b->d_meta ); cudaFree( b->d_counter ); cudaFree( b->d_xwork );
   cudaFree( b->d_info ); cudaFree( b->d_iwork ); cudaFree( b->d_flags ); cudaFree( b->d_ids ); cudaFree( b->d_chunks );
   for ( auto& s : b->st ) {
     if ( s.e0 ) cudaEventDestroy( s.e0 );
@@ -484,6 +638,31 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
   A( dev_alloc( &b->d_ids, b->ids.size() ) );
   A( dev_alloc( &b->d_chunks, chunks.size() ) );
   A( dev_alloc( &b->d_stats, kNumTicks ) );
+  A( dev_alloc( &b->d_meta, count ) );
+  A( dev_alloc( &b->d_counter, 1 ) );
+  {
+    // work slots of the eigenvector stage: two resident CTAs per SM at most
+    int nmid = 0, nmax = 0;
+    for ( const auto& g : b->groups )
+      if ( g.kind == 1 ) {
+        nmid += g.count;
+        nmax = std::max( nmax, g.nmax );
+      }
+    if ( jobvr == 'V' && nmid > 0 && nmax <= kMidMaxFusedN ) {
+      b->xslots = std::min( nmid, 2 * c.sm_count );
+      b->xslot = (size_t)nmax * nmax;
+      A( dev_alloc( &b->d_xwork, b->xslot * b->xslots ) );
+    } else if ( jobvr == 'V' && nmid > 0 ) {
+      // matrices beyond the warp-level kernels' reach use the in-place path: no slots needed, but sizes <= 1024
+      // in the same batch still need them
+      int nmax_fused = 0;
+      for ( int k = 0; k < count; ++k )
+        if ( n[k] > kSmallMax && n[k] <= kMidMaxFusedN ) nmax_fused = std::max( nmax_fused, n[k] );
+      b->xslots = std::min( nmid, 2 * c.sm_count );
+      b->xslot = (size_t)std::max( nmax_fused, 1 ) * std::max( nmax_fused, 1 );
+      A( dev_alloc( &b->d_xwork, b->xslot * b->xslots ) );
+    }
+  }
   if ( rc != PALADIN_GPU_OK ) {
     free_batch( b );
     return rc;
@@ -649,12 +828,33 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
       }
     }
     static const bool force_generic = std::getenv( "PALADIN_GPU_FORCE_GENERIC" ) != nullptr;
-    if ( g.kind == 1 && !force_generic && mid_smem_bytes() <= (size_t)c.max_smem_optin ) {
-      PB_CUDA( cudaFuncSetAttribute( geev_mid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)mid_smem_bytes() ) );
+    if ( g.kind == 1 && !force_generic ) {
+      MidArgs ma;
+      ma.bv = bv;
+      ma.ids = ids;
+      ma.count = cnt;
+      ma.meta = b->d_meta;
+      ma.stats = b->d_stats;
+      ma.counter = b->d_counter;
+      ma.xwork = b->d_xwork;
+      ma.xslot = b->xslot;
       PB_CUDA( cudaMemsetAsync( b->d_stats, 0, sizeof( long long ) * kNumTicks, st ) );
-      stage_begin( b, PALADIN_GPU_STAGE_MID, st );
-      geev_mid_kernel<<<cnt, kMidThreads, mid_smem_bytes(), st>>>( bv, ids, b->d_stats );
-      stage_end( b, PALADIN_GPU_STAGE_MID, st, 1 );
+      PB_CUDA( cudaMemsetAsync( b->d_counter, 0, sizeof( int ), st ) );
+      const size_t s1 = prep_smem_bytes( g.nmax ), s2 = qr_smem_bytes(), s3 = vec_smem_bytes( g.nmax );
+      PB_CUDA( cudaFuncSetAttribute( mid_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1 ) );
+      PB_CUDA( cudaFuncSetAttribute( mid_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2 ) );
+      PB_CUDA( cudaFuncSetAttribute( mid_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3 ) );
+      stage_begin( b, PALADIN_GPU_STAGE_HESSENBERG, st );
+      mid_prep_kernel<<<cnt, pb::kHessThreads, s1, st>>>( ma );
+      stage_end( b, PALADIN_GPU_STAGE_HESSENBERG, st, 1 );
+      stage_begin( b, PALADIN_GPU_STAGE_QR, st );
+      mid_qr_kernel<<<cnt, kMidThreads, s2, st>>>( ma );
+      stage_end( b, PALADIN_GPU_STAGE_QR, st, 1 );
+      if ( wantvr ) {
+        stage_begin( b, PALADIN_GPU_STAGE_VECTORS, st );
+        mid_vec_kernel<<<std::max( 1, std::min( cnt, b->xslots ) ), pb::kVecThreads, s3, st>>>( ma );
+        stage_end( b, PALADIN_GPU_STAGE_VECTORS, st, 1 );
+      }
       PB_CUDA( cudaGetLastError() );
       continue;
     }

@@ -79,20 +79,18 @@ struct QrMultishift {
 };
 
 // phase-profile slots (CtaGroup::tick)
-constexpr int kTickBalance = 0, kTickHess = 1, kTickOrghr = 2, kTickQr = 3, kTickTrevc = 4, kTickBak = 5;
+constexpr int kTickBalance = 0, kTickHess = 1, kTickOrghr = 2, kTickQr = 3, kTickTrevc = 4, kTickBak = 5, kTickVecGemm = 6;
 
-template <class G, class QR = QrLahqr>
-PB_D int geev_group( const G& g, int n, double* A, int lda, double* wr, double* wi, bool wantvr, double* V, int ldv,
-                     double* dwork, int* iwork, const QR& qr = QR() ) {
+// scale check (dlange 'M' + dlascl) and balancing. Returns false when the matrix holds a non-finite entry.
+struct GeevScaling {
+  bool scalea;
+  double anrm, cscale;
+};
+
+template <class G>
+PB_D bool geev_prologue( const G& g, int n, double* A, int lda, GeevScaling& sc, int* ilo, int* ihi, double* scale,
+                         int* iwork ) {
   const int t = g.tid(), nt = g.size();
-  if ( n == 0 ) return 0;
-  double* tau = dwork;
-  double* scale = dwork + n;
-  double* cnorm = dwork + 2 * n;
-  double* xr = dwork + 3 * n;
-  double* xi = dwork + 4 * n;
-
-  // ---- scale check ----
   double anrm = 0.0;
   bool bad = false;
   for ( int c = 0; c < n; ++c )
@@ -103,40 +101,72 @@ PB_D int geev_group( const G& g, int n, double* A, int lda, double* wr, double* 
     }
   anrm = g.max( anrm );
   bad = g.any( bad );
-  if ( bad ) return -4;  // non-finite input (argument 4 of dgeev), nothing is computed
+  if ( bad ) return false;
   const double smlnum0 = sqrt( kSafmin ) / kUlp;
   const double bignum0 = 1.0 / smlnum0;
-  bool scalea = false;
-  double cscale = 1.0;
+  sc.scalea = false;
+  sc.anrm = anrm;
+  sc.cscale = 1.0;
   if ( anrm > 0.0 && anrm < smlnum0 ) {
-    scalea = true;
-    cscale = smlnum0;
+    sc.scalea = true;
+    sc.cscale = smlnum0;
   } else if ( anrm > bignum0 ) {
-    scalea = true;
-    cscale = bignum0;
+    sc.scalea = true;
+    sc.cscale = bignum0;
   }
-  if ( scalea ) lascl( g, anrm, cscale, n, n, A, lda );
+  if ( sc.scalea ) lascl( g, anrm, sc.cscale, n, n, A, lda );
+  gebal( g, n, A, lda, ilo, ihi, scale, iwork );
+  g.sync();
+  return true;
+}
 
-  // ---- balance, reduce, iterate ----
-  int ilo, ihi;
-  gebal( g, n, A, lda, &ilo, &ihi, scale, iwork );
+// undo the scaling on the converged eigenvalues (and on the isolated head when the iteration failed)
+template <class G>
+PB_D void geev_unscale( const G& g, int n, const GeevScaling& sc, int info, int ilo, double* wr, double* wi ) {
+  if ( sc.scalea ) {
+    lascl( g, sc.cscale, sc.anrm, n - info, 1, wr + info, n );
+    lascl( g, sc.cscale, sc.anrm, n - info, 1, wi + info, n );
+    if ( info > 0 ) {
+      lascl( g, sc.cscale, sc.anrm, ilo, 1, wr, n );
+      lascl( g, sc.cscale, sc.anrm, ilo, 1, wi, n );
+    }
+  }
   g.sync();
-  g.tick( kTickBalance );
-  gehd2( g, n, ilo, ihi, A, lda, tau, cnorm );
-  g.tick( kTickHess );
-  if ( wantvr ) orghr( g, n, ilo, ihi, A, lda, tau, V, ldv );
-  g.sync();
-  g.tick( kTickOrghr );
+}
+
+template <class G>
+PB_D void geev_isolated_eigenvalues( const G& g, int n, int ilo, int ihi, const double* A, int lda, double* wr, double* wi ) {
+  const int t = g.tid(), nt = g.size();
   for ( int i = t; i < n; i += nt )
     if ( i < ilo || i > ihi ) {
       wr[i] = PB_A( i, i );
       wi[i] = 0.0;
     }
   g.sync();
+}
+
+template <class G, class QR = QrLahqr>
+PB_D int geev_group( const G& g, int n, double* A, int lda, double* wr, double* wi, bool wantvr, double* V, int ldv,
+                     double* dwork, int* iwork, const QR& qr = QR() ) {
+  if ( n == 0 ) return 0;
+  double* tau = dwork;
+  double* scale = dwork + n;
+  double* cnorm = dwork + 2 * n;
+  double* xr = dwork + 3 * n;
+  double* xi = dwork + 4 * n;
+  GeevScaling sc;
+  int ilo, ihi;
+  if ( !geev_prologue( g, n, A, lda, sc, &ilo, &ihi, scale, iwork ) ) return -4;  // non-finite input (argument 4 of dgeev)
+  g.tick( kTickBalance );
+  gehd2( g, n, ilo, ihi, A, lda, tau, cnorm );
+  g.tick( kTickHess );
+  if ( wantvr ) orghr( g, n, ilo, ihi, A, lda, tau, V, ldv );
+  g.sync();
+  g.tick( kTickOrghr );
+  geev_isolated_eigenvalues( g, n, ilo, ihi, A, lda, wr, wi );
   int info = qr( g, wantvr, wantvr, n, ilo, ihi, A, lda, wr, wi, V, ldv );
   g.sync();
   g.tick( kTickQr );
-
   if ( info == 0 && wantvr ) {
     // quasi-triangular T: the reflector storage below the first subdiagonal is never read again
     trevc_right_inplace( g, n, A, lda, V, ldv, cnorm, xr, xi );
@@ -146,16 +176,7 @@ PB_D int geev_group( const G& g, int n, double* A, int lda, double* wr, double* 
     normalize_vectors( g, n, wi, V, ldv );
     g.tick( kTickBak );
   }
-  if ( scalea ) {
-    // undo scaling on the converged part (and on the isolated head when the iteration failed)
-    lascl( g, cscale, anrm, n - info, 1, wr + info, n );
-    lascl( g, cscale, anrm, n - info, 1, wi + info, n );
-    if ( info > 0 ) {
-      lascl( g, cscale, anrm, ilo, 1, wr, n );
-      lascl( g, cscale, anrm, ilo, 1, wi, n );
-    }
-  }
-  g.sync();
+  geev_unscale( g, n, sc, info, ilo, wr, wi );
   return info;
 }
 

@@ -1,0 +1,251 @@
+// pb_hess.cuh -- Hessenberg reduction and explicit Q for one matrix per CTA (device only).
+//
+// Replaces the dgehrd / dorghr stages of the reference's dgeev_ call (reference
+// src/lapack-wrapper.hpp:47-60, src/paladin.hpp:248-254). Same Householder reflectors as LAPACK's
+// unblocked dgehd2 (v(j+1) = 1, stored below the subdiagonal, tau[j]); the schedule is different:
+//
+// hess_fused: the matrix (n^2 doubles, 2 MiB at n = 512) lives in global memory / L2 and does not fit
+//   on one SM, so the reduction is bound by how often it streams past the SM. Step j needs
+//   y = A v and z = A^T v over the whole trailing matrix before it can update it (3 sweeps per column
+//   in the textbook form). Here the rank-2 form  A <- A - v z'^T - y' v^T  (y' = tau y - (tau^2 a/2) v,
+//   z' = tau z - (tau^2 a/2) v, a = v^T A v) of step j-1 is applied IN THE SAME sweep that accumulates
+//   y and z of step j: column j is brought up to date first (look-ahead), its reflector is generated,
+//   then every trailing element is read once, updated, written once and immediately used for both
+//   products. One read + one write of the trailing matrix per column: 16 n^3 / 2 bytes in total.
+//   A warp owns a column at a time (lanes along rows: coalesced 256-byte accesses), z(c) is a warp
+//   shuffle reduction, y(r) accumulates in registers across the warp's columns and is combined across
+//   warps once per step through shared memory.
+//
+// form_q: column c of Q = H(ilo) ... H(ihi-2) only depends on reflectors j < c. A warp builds one column
+//   entirely in registers (start from e_c, apply j = c-1 ... ilo), and stores it once: no barriers, no
+//   intermediate traffic; the reflector vectors are re-read from L1/L2.
+#pragma once
+
+#include "pb_common.cuh"
+
+#if defined( __CUDACC__ )
+
+namespace pb {
+
+constexpr int kHessThreads = 256;
+constexpr int kHessWarps = kHessThreads / 32;
+
+// shared memory (doubles): vprev, ypp, vcur, zpp, ycur, zcur : 6 n ; ypart: kHessWarps * n ; red: 64
+__host__ __device__ inline size_t hess_smem_doubles( int n ) { return (size_t)( 6 + kHessWarps ) * n + 64; }
+
+__device__ __forceinline__ double cta_sum( double x, double* red ) {
+  x = warp_sum( x );
+  const int w = threadIdx.x >> 5;
+  __syncthreads();
+  if ( ( threadIdx.x & 31 ) == 0 ) red[w] = x;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for ( int i = 0; i < kHessWarps; ++i ) t += red[i];
+  return t;
+}
+__device__ __forceinline__ double cta_max( double x, double* red ) {
+  x = warp_max( x );
+  const int w = threadIdx.x >> 5;
+  __syncthreads();
+  if ( ( threadIdx.x & 31 ) == 0 ) red[w] = x;
+  __syncthreads();
+  double t = red[0];
+#pragma unroll
+  for ( int i = 1; i < kHessWarps; ++i ) t = fmax( t, red[i] );
+  return t;
+}
+
+// MAXCH: row chunks of 32 a lane may own (n <= 32 * MAXCH)
+template <int MAXCH>
+__device__ void hess_fused( int n, int ilo, int ihi, double* A, int lda, double* tau, double* sm ) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* vprev = sm;
+  double* ypp = sm + n;
+  double* vcur = sm + 2 * n;
+  double* zpp = sm + 3 * n;
+  double* ycur = sm + 4 * n;
+  double* zcur = sm + 5 * n;
+  double* ypart = sm + 6 * n;
+  double* red = sm + ( 6 + kHessWarps ) * n;
+  const int nrow = ihi + 1;                    // rows 0..ihi take part
+  const int nch = ( nrow + 31 ) >> 5;
+
+  for ( int r = tid; r < n; r += kHessThreads ) {
+    vprev[r] = 0.0;
+    ypp[r] = 0.0;
+    zpp[r] = 0.0;
+    vcur[r] = 0.0;
+  }
+  for ( int j = tid; j < n; j += kHessThreads )
+    if ( j < ilo || j >= ihi ) tau[j] = 0.0;  // only ilo..ihi-1 are generated below (ihi-1 is trivially 0)
+  __syncthreads();
+  bool have_prev = false;
+
+  for ( int j = ilo; j <= ihi - 1; ++j ) {
+    // (a) column j up to date with respect to step j-1 (v_{j-1}(j) = 1)
+    if ( have_prev ) {
+      const double zj = zpp[j];
+      for ( int r = tid; r < nrow; r += kHessThreads ) A[r + (size_t)j * lda] -= vprev[r] * zj + ypp[r];
+    }
+    __syncthreads();
+    // (b) reflector from A(j+1:ihi, j)
+    double tj = 0.0, beta;
+    {
+      const double alpha = A[( j + 1 ) + (size_t)j * lda];
+      double mx = 0.0;
+      for ( int r = j + 2 + tid; r <= ihi; r += kHessThreads ) mx = fmax( mx, fabs( A[r + (size_t)j * lda] ) );
+      mx = cta_max( mx, red );
+      beta = alpha;
+      double sc = 0.0;
+      if ( mx != 0.0 ) {
+        double ss = 0.0;
+        for ( int r = j + 2 + tid; r <= ihi; r += kHessThreads ) {
+          const double x = A[r + (size_t)j * lda] / mx;
+          ss += x * x;
+        }
+        double xnorm = mx * sqrt( cta_sum( ss, red ) );
+        double al = alpha;
+        beta = -dsign( dlapy2( al, xnorm ), al );
+        const double safmin = kSafmin / kEps;
+        int knt = 0;
+        double pre = 1.0;
+        if ( fabs( beta ) < safmin ) {
+          const double rsafmn = 1.0 / safmin;
+          do {
+            ++knt;
+            pre *= rsafmn;
+            xnorm *= rsafmn;
+            beta *= rsafmn;
+            al *= rsafmn;
+          } while ( fabs( beta ) < safmin && knt < 20 );
+          beta = -dsign( dlapy2( al, xnorm ), al );
+        }
+        tj = ( beta - al ) / beta;
+        sc = pre / ( al - beta );
+        for ( int q = 0; q < knt; ++q ) beta *= safmin;
+      }
+      __syncthreads();
+      // v_j into shared memory (0 outside j+1..ihi) and below the subdiagonal of A
+      for ( int r = tid; r < n; r += kHessThreads ) {
+        double v = 0.0;
+        if ( r == j + 1 ) v = 1.0;
+        else if ( r >= j + 2 && r <= ihi ) {
+          v = A[r + (size_t)j * lda] * sc;
+          A[r + (size_t)j * lda] = v;
+        }
+        vcur[r] = v;
+      }
+      if ( tid == 0 ) {
+        A[( j + 1 ) + (size_t)j * lda] = beta;
+        tau[j] = tj;
+      }
+    }
+    __syncthreads();
+
+    // (c) one sweep over columns j+1..n-1: apply step j-1, accumulate y_j (rows) and z_j (columns)
+    double yacc[MAXCH];
+#pragma unroll
+    for ( int k = 0; k < MAXCH; ++k ) yacc[k] = 0.0;
+    for ( int c = j + 1 + warp; c < n; c += kHessWarps ) {
+      double* col = A + (size_t)c * lda;
+      const double zc = zpp[c], vpc = vprev[c];
+      const double vcc = ( c <= ihi ) ? vcur[c] : 0.0;
+      // all loads of the column first (clamped addresses, no branches), so that they are in flight together
+      double a[MAXCH];
+#pragma unroll
+      for ( int k = 0; k < MAXCH; ++k ) a[k] = __ldcg( col + imin( lane + 32 * k, nrow - 1 ) );
+      double zsum = 0.0;
+#pragma unroll
+      for ( int k = 0; k < MAXCH; ++k ) {
+        const int r = lane + 32 * k;
+        const int rc = imin( r, nrow - 1 );
+        const bool ok = r < nrow;
+        const double x = a[k] - ( vprev[rc] * zc + ypp[rc] * vpc );
+        a[k] = x;
+        yacc[k] += ok ? x * vcc : 0.0;
+        zsum += ok ? vcur[rc] * x : 0.0;
+      }
+      if ( have_prev ) {
+#pragma unroll
+        for ( int k = 0; k < MAXCH; ++k ) {
+          const int r = lane + 32 * k;
+          if ( r < nrow ) col[r] = a[k];
+        }
+      }
+      zsum = warp_sum( zsum );
+      if ( lane == 0 ) zcur[c] = zsum;
+    }
+    // (d) combine: y = sum over warps, alpha = v^T y, then y', z'
+#pragma unroll
+    for ( int k = 0; k < MAXCH; ++k ) {
+      const int r = lane + 32 * k;
+      if ( k < nch && r < nrow ) ypart[warp * n + r] = yacc[k];
+    }
+    __syncthreads();
+    double av = 0.0;
+    for ( int r = tid; r < nrow; r += kHessThreads ) {
+      double y = 0.0;
+#pragma unroll
+      for ( int w = 0; w < kHessWarps; ++w ) y += ypart[w * n + r];
+      ycur[r] = y;
+      av += vcur[r] * y;
+    }
+    const double alpha2 = cta_sum( av, red );
+    const double half = 0.5 * tj * tj * alpha2;
+    __syncthreads();
+    for ( int r = tid; r < n; r += kHessThreads ) {
+      const double v = vcur[r];
+      vprev[r] = v;
+      ypp[r] = ( r < nrow ) ? tj * ycur[r] - half * v : 0.0;
+      zpp[r] = ( r > j ) ? tj * zcur[r] - half * v : 0.0;
+    }
+    have_prev = true;
+    __syncthreads();
+  }
+  // the last generated step is j = ihi-1 with tau = 0: nothing is left to apply
+}
+
+// Q (n x n, ldq) = H(ilo) ... H(ihi-2) from the reflectors stored in A / tau. One warp per column.
+template <int MAXCH>
+__device__ void form_q( int n, int ilo, int ihi, const double* A, int lda, const double* tau, double* Q, int ldq ) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nch = ( n + 31 ) >> 5;
+  for ( int c = warp; c < n; c += kHessWarps ) {
+    double q[MAXCH];
+#pragma unroll
+    for ( int k = 0; k < MAXCH; ++k ) q[k] = ( lane + 32 * k == c ) ? 1.0 : 0.0;
+    if ( c > ilo && c <= ihi ) {
+      for ( int j = imin( c - 1, ihi - 2 ); j >= ilo; --j ) {
+        const double tj = tau[j];
+        if ( tj == 0.0 ) continue;
+        const double* v = A + (size_t)j * lda;  // v(j+1) = 1, v(r) = A(r,j) for j+2 <= r <= ihi
+        double vr[MAXCH];
+        double w = 0.0;
+        // unconditional (clamped) loads first, selection afterwards: the loads overlap
+#pragma unroll
+        for ( int k = 0; k < MAXCH; ++k ) vr[k] = v[imin( imax( lane + 32 * k, j + 2 ), imax( ihi, j + 2 ) )];
+#pragma unroll
+        for ( int k = 0; k < MAXCH; ++k ) {
+          const int r = lane + 32 * k;
+          double x = ( r >= j + 2 && r <= ihi ) ? vr[k] : 0.0;
+          if ( r == j + 1 ) x = 1.0;
+          vr[k] = x;
+          w += x * q[k];
+        }
+        w = warp_sum( w ) * tj;
+#pragma unroll
+        for ( int k = 0; k < MAXCH; ++k ) q[k] -= w * vr[k];
+      }
+    }
+#pragma unroll
+    for ( int k = 0; k < MAXCH; ++k ) {
+      const int r = lane + 32 * k;
+      if ( k < nch && r < n ) Q[r + (size_t)c * ldq] = q[k];
+    }
+  }
+}
+
+}  // namespace pb
+
+#endif  // __CUDACC__

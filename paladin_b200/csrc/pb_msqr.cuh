@@ -93,15 +93,31 @@ PB_D int ms_find_split( const G& g, int ilo, int ihi, int lo, int hi, const doub
   return g.imax_( kfound );
 }
 
+constexpr int kWinBatch = 8;
+
 // ---- window <-> global ----------------------------------------------------------------------------
 // Only the band r - c <= 3 is meaningful below the diagonal (Hessenberg + parked bulges); whatever else
 // the array holds there (Householder vectors of the reduction) is neither read nor written.
 template <class G>
-PB_D void ms_load_window( const G& g, const double* H, int ldh, int ws, int wlen, double* Hw, int ldw ) {
+PB_D void ms_load_window( const G& g, const double* __restrict__ H, int ldh, int ws, int wlen, double* __restrict__ Hw, int ldw ) {
   const int t = g.tid(), nt = g.size();
-  for ( int q = t; q < wlen * wlen; q += nt ) {
-    const int c = q / wlen, r = q - c * wlen;
-    Hw[r + c * ldw] = ( r - c <= 3 ) ? PB_H( ws + r, ws + c ) : 0.0;
+  const int total = wlen * wlen;
+  for ( int q0 = t; q0 < total; q0 += nt * kWinBatch ) {
+    double v[kWinBatch];
+#pragma unroll
+    for ( int u = 0; u < kWinBatch; ++u ) {
+      const int q = imin( q0 + u * nt, total - 1 );
+      const int c = q / wlen, r = q - c * wlen;
+      v[u] = PB_H( ws + r, ws + c );
+    }
+#pragma unroll
+    for ( int u = 0; u < kWinBatch; ++u ) {
+      const int q = q0 + u * nt;
+      if ( q < total ) {
+        const int c = q / wlen, r = q - c * wlen;
+        Hw[r + c * ldw] = ( r - c <= 3 ) ? v[u] : 0.0;
+      }
+    }
   }
   g.sync();
 }
@@ -118,26 +134,43 @@ PB_D void ms_store_window( const G& g, double* H, int ldh, int ws, int wlen, con
 // ---- strip tiles ----------------------------------------------------------------------------------
 // kind 0: lines are COLUMNS j0.. of M, positions are rows ws..   (strip right of the window)
 // kind 1: lines are ROWS r0.. of M, positions are columns ws..   (strip above the window, Schur vectors)
+// Loads are issued in batches of kTileBatch before the dependent shared-memory stores: the compiler may not
+// reorder a global load above a store through a generic pointer, so a load/store-per-iteration loop would
+// expose the full memory latency for every element.
+constexpr int kTileBatch = 8;
+
 template <class G>
-PB_D void ms_tile_load( const G& g, int kind, const double* M, int ldm, int ws, int wlen, int l0, int nl, double* tile,
-                        int ldt ) {
+PB_D void ms_tile_load( const G& g, int kind, const double* __restrict__ M, int ldm, int ws, int wlen, int l0, int nl,
+                        double* __restrict__ tile, int ldt ) {
   const int t = g.tid(), nt = g.size();
-  if ( kind == 0 ) {
-    for ( int q = t; q < wlen * nl; q += nt ) {
-      const int line = q / wlen, pos = q - line * wlen;
-      tile[pos * ldt + line] = M[( ws + pos ) + (size_t)( l0 + line ) * ldm];
+  const int total = wlen * nl;
+  for ( int q0 = t; q0 < total; q0 += nt * kTileBatch ) {
+    double v[kTileBatch];
+    int dst[kTileBatch];
+#pragma unroll
+    for ( int u = 0; u < kTileBatch; ++u ) {
+      const int q = imin( q0 + u * nt, total - 1 );
+      int line, pos;
+      if ( kind == 0 ) {
+        line = q / wlen;
+        pos = q - line * wlen;
+        v[u] = M[( ws + pos ) + (size_t)( l0 + line ) * ldm];
+      } else {
+        pos = q / nl;
+        line = q - pos * nl;
+        v[u] = M[( l0 + line ) + (size_t)( ws + pos ) * ldm];
+      }
+      dst[u] = pos * ldt + line;
     }
-  } else {
-    for ( int q = t; q < wlen * nl; q += nt ) {
-      const int pos = q / nl, line = q - pos * nl;
-      tile[pos * ldt + line] = M[( l0 + line ) + (size_t)( ws + pos ) * ldm];
-    }
+#pragma unroll
+    for ( int u = 0; u < kTileBatch; ++u )
+      if ( q0 + u * nt < total ) tile[dst[u]] = v[u];
   }
   g.sync();
 }
 template <class G>
-PB_D void ms_tile_store( const G& g, int kind, double* M, int ldm, int ws, int wlen, int l0, int nl, const double* tile,
-                         int ldt ) {
+PB_D void ms_tile_store( const G& g, int kind, double* __restrict__ M, int ldm, int ws, int wlen, int l0, int nl,
+                         const double* __restrict__ tile, int ldt ) {
   const int t = g.tid(), nt = g.size();
   if ( kind == 0 ) {
     for ( int q = t; q < wlen * nl; q += nt ) {

@@ -174,6 +174,14 @@ def test_generic_path_matches_oracle(pg, jobvr):
         _check_eigs(po.dense_matrix(*m), wr, wi, VR, inf, jobvr == "V")
 
 
+def test_sizes_across_kernel_variants(pg):
+    # 513..1024: 32-row-chunk variant of the fused Hessenberg; > 1024: unblocked fallback inside the CTA path
+    mats = _random_mats([600, 1000, 1100], 23)
+    res, info = pg.geev_batch(*_concat(mats), jobvr="V")
+    for m, (wr, wi, VR), inf in zip(mats, res, info):
+        _check_eigs(po.dense_matrix(*m), wr, wi, VR, inf, True)
+
+
 def test_n512_full_decomposition(pg):
     mats = _random_mats([512, 512], 3)
     res, info = pg.geev_batch(*_concat(mats), jobvr="V")
