@@ -207,7 +207,8 @@ __device__ __forceinline__ void stats_end( long long* stats, const long long* ls
 
 // ---- stage 1: scale check, balancing, Hessenberg reduction, explicit Q ----------------------------------
 inline size_t prep_smem_bytes( int nmax ) {
-  return sizeof( double ) * ( nmax <= kMidMaxFusedN ? pb::hess_smem_doubles( nmax ) : 64 );
+  // a group may mix sizes on both sides of kMidMaxFusedN: size for the largest matrix the fused kernel can meet
+  return sizeof( double ) * pb::hess_smem_doubles( std::min( nmax, kMidMaxFusedN ) );
 }
 
 __global__ void __launch_bounds__( pb::kHessThreads ) mid_prep_kernel( MidArgs a ) {
@@ -274,10 +275,10 @@ __global__ void __launch_bounds__( kMidThreads ) mid_qr_kernel( MidArgs a ) {
   const int ldw = c.W | 1, ldt = c.tl | 1;
   pb::MsqrWork wk;
   double* p = smem;
-  wk.Hw = p; p += (size_t)c.W * ldw;
-  wk.U = p; p += (size_t)c.W * ldw;
-  wk.tile = p; p += (size_t)c.W * ldt;
-  wk.refl = p; p += (size_t)c.nb * c.W * pb::kReflStride;
+  wk.Hw = p; p += pb::ms_even( (size_t)c.W * ldw );
+  wk.U = p; p += pb::ms_even( (size_t)c.W * ldw );
+  wk.tile = p; p += pb::ms_even( (size_t)c.W * ldt );
+  wk.refl = p; p += (size_t)c.nb * c.W * pb::kReflStride;  // 16-byte aligned: read as double2
   wk.sr = p; p += 2 * c.nb * c.nchains;
   wk.si = p; p += 2 * c.nb * c.nchains;
   wk.ibuf = reinterpret_cast<int*>( p );
@@ -568,8 +569,10 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
     }
     b->nnz_off[k] = nnz_offsets[k] - nnz_offsets[0];
     // every dense matrix starts on a 16-byte boundary so that paired stores stay aligned
+    // ... and consecutive matrices are staggered by 33 cache lines: with power-of-two sizes (2 MiB at n = 512)
+    // every CTA would otherwise walk the same memory-channel pattern in lockstep
     int64_t nn = (int64_t)n[k] * n[k];
-    b->a_off[k + 1] = b->a_off[k] + ( ( nn + 1 ) & ~1LL );
+    b->a_off[k + 1] = b->a_off[k] + ( ( nn + 1 ) & ~1LL ) + ( nn >= 4096 ? 528 : 0 );
     b->w_off[k + 1] = b->w_off[k] + n[k];
   }
   if ( count > 0 ) b->nnz_off[count] = nnz_offsets[count] - nnz_offsets[0];
@@ -650,7 +653,7 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
       }
     if ( jobvr == 'V' && nmid > 0 && nmax <= kMidMaxFusedN ) {
       b->xslots = std::min( nmid, 2 * c.sm_count );
-      b->xslot = (size_t)nmax * nmax;
+      b->xslot = (size_t)nmax * nmax + 528;
       A( dev_alloc( &b->d_xwork, b->xslot * b->xslots ) );
     } else if ( jobvr == 'V' && nmid > 0 ) {
       // matrices beyond the warp-level kernels' reach use the in-place path: no slots needed, but sizes <= 1024
@@ -659,7 +662,7 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
       for ( int k = 0; k < count; ++k )
         if ( n[k] > kSmallMax && n[k] <= kMidMaxFusedN ) nmax_fused = std::max( nmax_fused, n[k] );
       b->xslots = std::min( nmid, 2 * c.sm_count );
-      b->xslot = (size_t)std::max( nmax_fused, 1 ) * std::max( nmax_fused, 1 );
+      b->xslot = (size_t)std::max( nmax_fused, 1 ) * std::max( nmax_fused, 1 ) + 528;
       A( dev_alloc( &b->d_xwork, b->xslot * b->xslots ) );
     }
   }
@@ -882,9 +885,16 @@ int paladin_gpu_batch_download( paladin_gpu_batch* b, double* wr, double* wi, do
   if ( vr && b->jobvr == 'V' ) {
     // device matrices are padded to even length; the host layout is the plain concatenation
     bool padded = false;
-    for ( int k = 0; k < b->count; ++k ) padded = padded || ( b->n[k] & 1 );
+    for ( int k = 0; k < b->count; ++k ) padded = padded || ( b->n[k] & 1 ) || ( (int64_t)b->n[k] * b->n[k] >= 4096 );
+    bool uniform = b->count > 0;
+    for ( int k = 1; k < b->count; ++k ) uniform = uniform && ( b->n[k] == b->n[0] );
     if ( !padded ) {
       if ( b->total_nn ) PB_CUDA( cudaMemcpyAsync( vr, b->d_V, sizeof( double ) * b->total_nn, cudaMemcpyDeviceToHost, st ) );
+    } else if ( uniform && b->n[0] > 0 ) {
+      // equal sizes: one strided copy (device pitch = padded matrix, host pitch = packed matrix)
+      const size_t nn = (size_t)b->n[0] * b->n[0];
+      PB_CUDA( cudaMemcpy2DAsync( vr, nn * sizeof( double ), b->d_V, (size_t)( b->a_off[1] - b->a_off[0] ) * sizeof( double ),
+                                  nn * sizeof( double ), b->count, cudaMemcpyDeviceToHost, st ) );
     } else {
       int64_t dst = 0;
       for ( int k = 0; k < b->count; ++k ) {

@@ -52,6 +52,7 @@ PB_HD double dlapy2( double x, double y ) {
 
 // ---- groups ------------------------------------------------------------------------------------
 struct HostGroup {
+  static constexpr bool kIsCta = false;
   PB_HD int tid() const { return 0; }
   PB_HD int size() const { return 1; }
   PB_HD void sync() const {}
@@ -89,6 +90,7 @@ PB_D int warp_isum( int x ) {
 
 // one warp; every lane receives bit-identical reduction results (xor butterflies)
 struct WarpGroup {
+  static constexpr bool kIsCta = false;
   PB_D int tid() const { return threadIdx.x & 31; }
   PB_D int size() const { return 32; }
   PB_D void sync() const { __syncwarp(); }
@@ -103,6 +105,7 @@ struct WarpGroup {
 
 // whole thread block; red points at >= 64 doubles of shared scratch owned by the group
 struct CtaGroup {
+  static constexpr bool kIsCta = true;
   double* red;
   // optional phase profile: thread 0 adds the cycles since the previous tick to stats[slot]
   long long* stats = nullptr;

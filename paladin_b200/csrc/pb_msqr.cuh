@@ -27,6 +27,7 @@
 
 #include "pb_common.cuh"
 #include "pb_small.cuh"
+#include "pb_strips.cuh"
 
 namespace pb {
 
@@ -56,8 +57,9 @@ struct MsqrWork {
   int ldw, ldt;
 };
 
+PB_HD size_t ms_even( size_t x ) { return ( x + 1 ) & ~(size_t)1; }  // keeps every sub-buffer 16-byte aligned
 PB_HD size_t msqr_work_doubles( const MsqrCfg& c, int ldw, int ldt ) {
-  return 2 * (size_t)c.W * ldw + (size_t)c.W * ldt + (size_t)c.nb * c.W * kReflStride + 4 * (size_t)c.nb * c.nchains;
+  return 2 * ms_even( (size_t)c.W * ldw ) + ms_even( (size_t)c.W * ldt ) + (size_t)c.nb * c.W * kReflStride + 4 * (size_t)c.nb * c.nchains;
 }
 
 // ---- deflation scan: largest k in (lo, hi] with negligible H(k,k-1); lo when none -----------------
@@ -554,7 +556,20 @@ PB_D void ms_chase_chain( const G& g, bool wantt, bool wantz, int n, int l, int 
     ms_store_window( g, H, ldh, ws, wlen, Hw, ldw );
     if ( t == 0 ) wk.ibuf[3 * kMsMaxBulges + 2] += 1;
     g.tick( kTickMsChase );
-    ms_update_strips( g, wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, nbulges, (const double*)nullptr );
+#if defined( __CUDACC__ )
+    if constexpr ( G::kIsCta ) {
+      // device fast path: lines in registers, warps independent (pb_strips.cuh); needs the compile-time window order
+      if ( cfg.W == kStripW && cfg.tl >= 32 * ( g.size() >> 5 ) ) {
+        ms_strips_regs( wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, nbulges, kfirst, kcount, wk.refl, wk.tile,
+                        wk.ldt );
+      } else {
+        ms_update_strips( g, wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, nbulges, (const double*)nullptr );
+      }
+    } else
+#endif
+    {
+      ms_update_strips( g, wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, nbulges, (const double*)nullptr );
+    }
     g.sync();
     g.tick( kTickMsStrips );
   }

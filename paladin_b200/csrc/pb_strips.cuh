@@ -1,0 +1,150 @@
+// pb_strips.cuh -- off-window strip updates of the multishift QR with every line held in registers
+// (device only). Fast path of pb::ms_update_strips (pb_msqr.cuh) for the recorded-reflector mode.
+//
+// A "line" is a column of H right of the window, a row of H above it, or a row of the Schur vectors Z;
+// inside the window's index range it has W entries. One thread owns one line: it loads the W entries into
+// registers, streams every recorded 3-element reflector of the window over them (5 FMAs each, operands at
+// compile-time register indices, reflector parameters broadcast from shared memory with 16-byte loads) and
+// stores the line once. Warps work on batches of 32 lines independently: there is no CTA barrier inside the
+// strip phase.
+//   rows (upper strip, Z): lane = row, so every global access of a warp is one contiguous 256-byte segment;
+//   columns (right strip): a column's W entries are contiguous in memory; the warp reads them with lanes
+//     along the rows (coalesced) and transposes through its private 32-line slice of the shared tile.
+// Each bulge's reflectors act on consecutive positions p, p+1, ..., so the unrolled step list is entered at
+// position p through a jump table and left after the bulge's last step (uniform branches only).
+#pragma once
+
+#include "pb_common.cuh"
+
+#if defined( __CUDACC__ )
+
+namespace pb {
+
+// x[P], x[P+1], x[P+2] <- reflector at rf (w2,w3 | t1,t2 | t3,pad as three 16-byte words)
+#define PB_STRIP_STEP( P )                                              \
+  case P: {                                                             \
+    const double2 w = rf[0], tt = rf[1];                                \
+    const double t3 = reinterpret_cast<const double*>( rf )[4];         \
+    rf += 3;                                                            \
+    const double sum = x[P] + w.x * x[P + 1] + w.y * x[P + 2];          \
+    x[P] -= sum * tt.x;                                                 \
+    x[P + 1] -= sum * tt.y;                                             \
+    x[P + 2] -= sum * t3;                                               \
+    if ( --cnt == 0 ) break;                                            \
+  }
+
+#define PB_STRIP_STEPS_8( B ) \
+  PB_STRIP_STEP( B + 0 ) PB_STRIP_STEP( B + 1 ) PB_STRIP_STEP( B + 2 ) PB_STRIP_STEP( B + 3 ) \
+  PB_STRIP_STEP( B + 4 ) PB_STRIP_STEP( B + 5 ) PB_STRIP_STEP( B + 6 ) PB_STRIP_STEP( B + 7 )
+
+// W = 49: positions 0..48, steps may start at 0..47 (x[49], x[50] are padding that only a final 2-row
+// reflector with w3 = t3 = 0 touches)
+constexpr int kStripW = 49;
+
+__device__ __forceinline__ void strip_apply_line( double ( &x )[kStripW + 2], int nbulges, const int* kfirst, const int* kcount,
+                                                  int ws, const double* refl ) {
+  for ( int b = 0; b < nbulges; ++b ) {
+    int cnt = kcount[b];
+    if ( cnt == 0 ) continue;
+    const int p = kfirst[b] - ws;
+    const double2* rf = reinterpret_cast<const double2*>( refl + (size_t)b * kStripW * 6 );
+    switch ( p ) {
+      PB_STRIP_STEPS_8( 0 )
+      PB_STRIP_STEPS_8( 8 )
+      PB_STRIP_STEPS_8( 16 )
+      PB_STRIP_STEPS_8( 24 )
+      PB_STRIP_STEPS_8( 32 )
+      PB_STRIP_STEPS_8( 40 )
+      default:
+        break;
+    }
+  }
+}
+
+// Every off-window strip of one window move. refl / kfirst / kcount live in shared memory; tile is the
+// W x ldt shared tile (ldt >= 32 * warps + 1, odd); the caller synchronises the CTA before and after.
+__device__ inline void ms_strips_regs( bool wantt, bool wantz, int n, int l, int i, int ws, int wlen, double* __restrict__ H,
+                                       int ldh, int iloz, int ihiz, double* __restrict__ Z, int ldz, int nbulges,
+                                       const int* kfirst, const int* kcount, const double* refl, double* tile, int ldt ) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int we = ws + wlen - 1;
+  const int i1 = wantt ? 0 : l, i2 = wantt ? n - 1 : i;
+  const int nright = imax( 0, i2 - we ), nup = imax( 0, ws - i1 ), nz = wantz ? ( ihiz - iloz + 1 ) : 0;
+  const int bright = ( nright + 31 ) >> 5, bup = ( nup + 31 ) >> 5, bz = ( nz + 31 ) >> 5;
+  double* wt = tile + 32 * warp;  // this warp's 32-line slice: element (pos, line) at pos*ldt + line
+  for ( int bt = warp; bt < bright + bup + bz; bt += nwarps ) {
+    double x[kStripW + 2];
+    x[kStripW] = 0.0;
+    x[kStripW + 1] = 0.0;
+    if ( bt < bright ) {
+      // ---- 32 columns of the right strip ----
+      const int j0 = we + 1 + 32 * bt;
+      const int nl = imin( 32, i2 - j0 + 1 );
+      // coalesced reads (lanes along rows), 8 columns in flight, transposed into the slice
+      for ( int c0 = 0; c0 < nl; c0 += 8 ) {
+        double v0[8], v1[8];
+#pragma unroll
+        for ( int u = 0; u < 8; ++u ) {
+          const int cc = imin( c0 + u, nl - 1 );
+          const double* col = H + (size_t)( j0 + cc ) * ldh + ws;
+          v0[u] = col[imin( lane, wlen - 1 )];
+          v1[u] = col[imin( 32 + lane, wlen - 1 )];
+        }
+#pragma unroll
+        for ( int u = 0; u < 8; ++u ) {
+          if ( c0 + u < nl ) {
+            if ( lane < wlen ) wt[lane * ldt + c0 + u] = v0[u];
+            if ( 32 + lane < wlen ) wt[( 32 + lane ) * ldt + c0 + u] = v1[u];
+          }
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for ( int p = 0; p < kStripW; ++p ) x[p] = ( p < wlen ) ? wt[p * ldt + lane] : 0.0;
+      __syncwarp();
+      strip_apply_line( x, nbulges, kfirst, kcount, ws, refl );
+#pragma unroll
+      for ( int p = 0; p < kStripW; ++p )
+        if ( p < wlen ) wt[p * ldt + lane] = x[p];
+      __syncwarp();
+      for ( int cc = 0; cc < nl; ++cc ) {
+        double* col = H + (size_t)( j0 + cc ) * ldh + ws;
+        if ( lane < wlen ) col[lane] = wt[lane * ldt + cc];
+        if ( 32 + lane < wlen ) col[32 + lane] = wt[( 32 + lane ) * ldt + cc];
+      }
+      __syncwarp();
+    } else {
+      // ---- 32 rows of the strip above the window or of Z ----
+      double* M;
+      int ldm, r0, nl;
+      if ( bt < bright + bup ) {
+        M = H;
+        ldm = ldh;
+        r0 = i1 + 32 * ( bt - bright );
+        nl = imin( 32, ws - r0 );
+      } else {
+        M = Z;
+        ldm = ldz;
+        r0 = iloz + 32 * ( bt - bright - bup );
+        nl = imin( 32, ihiz - r0 + 1 );
+      }
+      const int r = r0 + imin( lane, nl - 1 );
+      double* row = M + r + (size_t)ws * ldm;
+#pragma unroll
+      for ( int p = 0; p < kStripW; ++p ) {
+        const double v = row[(size_t)imin( p, wlen - 1 ) * ldm];
+        x[p] = ( p < wlen ) ? v : 0.0;
+      }
+      strip_apply_line( x, nbulges, kfirst, kcount, ws, refl );
+      if ( lane < nl ) {
+#pragma unroll
+        for ( int p = 0; p < kStripW; ++p )
+          if ( p < wlen ) row[(size_t)p * ldm] = x[p];
+      }
+    }
+  }
+}
+
+}  // namespace pb
+
+#endif  // __CUDACC__

@@ -1,0 +1,322 @@
+// paladin_host.cpp -- host side of the GPU path with the reference's command line, listing format, load
+// measures, static balancer, unpack logic, output formats and timing report
+// (reference src/paladin.hpp:57-421, src/compute-write-with-timings.cpp:29-36), calling libpaladin_gpu.so
+// through include/paladin_gpu.h instead of dgeev_.
+//
+// A "pod" is an MPI rank in the reference and a GPU here: the balancer runs with numRanks = number of GPUs, every
+// pod is driven by one host thread, pods never exchange data (the reference's compute() has no communication
+// either). Extra keys: --gpus=N (default: all usable devices), --batch=B (matrices per library call),
+// --dump-partition=FILE (write the sorted listing with pod colours and exit; needs no GPU).
+//
+// Built twice: as the executable paladin-gpu and (with -DPALADIN_HOST_LIBRARY) as libpaladin_host.so, whose
+// extern "C" hooks let tests/ drive the parser, balancer and writers without a GPU.
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/paladin_gpu.h"
+#include "balance.hpp"
+#include "cli.hpp"
+#include "mm_coo.hpp"
+#include "spectrum_io.hpp"
+
+namespace paladin {
+
+struct Options {
+  std::string listing = "no matrices given!", rootdir = ".", dump_partition;
+  int repeats = 1, gpus = -1, batch = 256;
+  bool showdist = false, right = false, left = false;
+  LoadPredictor measure = LoadPredictor::NUMNONZEROS;
+  double threshold = 1.0e-3;
+};
+
+struct Plan {
+  std::vector<std::string> paths;  // sorted by measure, descending
+  std::vector<double> measures;
+  std::vector<int> colour;         // pod of each sorted entry
+};
+
+inline void print_header() {
+  std::cout << "\n\npaladin-gpu: many independent FP64 eigendecompositions on B200 (sm_100a)\n"
+            << "drop-in for the paladin executable (listing, --measure, --left/--right, output files unchanged)\n"
+            << "library: " << paladin_gpu_version() << "\n\n";
+}
+
+inline Options parse_options( int argc, char* argv[], bool quiet ) {
+  CommandLineParser clp( argc, argv );
+  Options o;
+  o.listing = clp.getValue( "listing", o.listing );
+  o.rootdir = clp.getValue( "rootdir", "." );
+  o.repeats = std::stoi( clp.getValue( "repeats", "1" ) );
+  o.showdist = clp.checkExists( "showdist" );
+  o.right = clp.checkExists( "right" );
+  o.left = clp.checkExists( "left" );
+  o.measure = string_to_measure_type( clp.getValue( "measure", "nnz" ) );
+  o.threshold = std::stod( clp.getValue( "write-threshold", "1e-3" ) );
+  o.gpus = std::stoi( clp.getValue( "gpus", "-1" ) );
+  o.batch = std::max( 1, std::stoi( clp.getValue( "batch", "256" ) ) );
+  o.dump_partition = clp.getValue( "dump-partition", "" );
+  if ( !quiet ) {
+    bool bad = false;
+    for ( const auto& k : clp.get_keys() ) {
+      static const char* known[] = { "listing", "repeats", "showdist", "measure", "rootdir", "left", "right",
+                                     "write-threshold", "gpus", "batch", "dump-partition" };
+      if ( std::none_of( std::begin( known ), std::end( known ), [&]( const char* s ) { return k == s; } ) ) {
+        std::cout << "\n-- POTENTIAL ERROR: key " << k << " is not a recognized option!";
+        bad = true;
+      }
+    }
+    if ( bad )
+      std::cout << "\n-- Allowable keys: listing, repeats, showdist, measure, rootdir, left, right, write-threshold, "
+                   "gpus, batch, dump-partition\n\n";
+  }
+  return o;
+}
+
+// listing -> measures -> std::sort -> greedy colouring (reference src/paladin.hpp:123-155)
+inline Plan make_plan( const Options& o, int pods ) {
+  std::ifstream listing( o.listing );
+  if ( !listing ) {
+    std::cerr << "Couldn't open the matrix listing file, " << o.listing << ", exiting!" << '\n';
+    std::exit( 1 );
+  }
+  std::vector<NameMeasurePairT> entries;
+  std::string line;
+  while ( std::getline( listing, line ) && !line.empty() ) {  // stops at the first empty line, like the reference
+    const std::string path = o.rootdir + "/" + line;
+    int n = 0, nnz = 0;
+    try {
+      read_matrix_sizes_from_mm_file( path, n, nnz );
+    } catch ( const std::exception& e ) {
+      std::cerr << e.what() << ", exiting!" << '\n';
+      std::exit( 1 );
+    }
+    entries.emplace_back( path, matrix_measure( n, nnz, o.measure ) );
+  }
+  sort_name_measure_pairs( entries );
+  Plan p;
+  p.colour = color_pods( entries, pods );
+  for ( const auto& e : entries ) {
+    p.paths.push_back( e.first );
+    p.measures.push_back( e.second );
+  }
+  return p;
+}
+
+inline void write_file( const std::string& path, const std::string& text ) {
+  std::FILE* f = std::fopen( path.c_str(), "wb" );
+  if ( !f ) {
+    std::cerr << "Couldn't open the output file, " << path << '\n';
+    return;
+  }
+  std::fwrite( text.data(), 1, text.size(), f );
+  std::fclose( f );
+}
+
+struct PodTimes {
+  double read = 0.0, eig = 0.0, total = 0.0;
+};
+
+// One pod = one GPU: parse -> batched library call -> unpack -> write, batch by batch.
+inline int run_pod( int device, const std::vector<std::string>& pod, const Options& o, PodTimes& times ) {
+  using clock = std::chrono::steady_clock;
+  const auto t_start = clock::now();
+  const char jobvr = o.right ? 'V' : 'N';
+  int failures = 0;
+  for ( int rep = 0; rep < o.repeats; ++rep ) {
+    for ( std::size_t first = 0; first < pod.size(); first += o.batch ) {
+      const std::size_t count = std::min<std::size_t>( o.batch, pod.size() - first );
+      const auto t_read = clock::now();
+      std::vector<CooMatrix> mats( count );
+      for ( std::size_t k = 0; k < count; ++k ) {
+        try {
+          mats[k] = read_coo_from_mm_file( pod[first + k] );
+        } catch ( const std::exception& e ) {
+          std::cerr << e.what() << ", exiting!" << '\n';
+          std::exit( 1 );
+        }
+      }
+      std::vector<int> n( count );
+      std::vector<int64_t> off( count + 1, 0 );
+      for ( std::size_t k = 0; k < count; ++k ) {
+        n[k] = mats[k].nrows_;
+        off[k + 1] = off[k] + mats[k].nnz_;
+      }
+      std::vector<int> ci( off[count] ), cj( off[count] );
+      std::vector<double> cv( off[count] );
+      for ( std::size_t k = 0; k < count; ++k ) {
+        std::copy( mats[k].row.begin(), mats[k].row.end(), ci.begin() + off[k] );
+        std::copy( mats[k].col.begin(), mats[k].col.end(), cj.begin() + off[k] );
+        std::copy( mats[k].val.begin(), mats[k].val.end(), cv.begin() + off[k] );
+      }
+      times.read += std::chrono::duration<double>( clock::now() - t_read ).count();
+
+      std::vector<std::vector<double>> wr( count ), wi( count ), vr( count );
+      std::vector<double*> pwr( count ), pwi( count ), pvr( count, nullptr );
+      for ( std::size_t k = 0; k < count; ++k ) {
+        wr[k].assign( n[k], 0.0 );
+        wi[k].assign( n[k], 0.0 );
+        if ( o.right ) vr[k].assign( static_cast<std::size_t>( n[k] ) * n[k], 0.0 );
+        pwr[k] = wr[k].data();
+        pwi[k] = wi[k].data();
+        pvr[k] = o.right ? vr[k].data() : nullptr;
+      }
+      std::vector<int> info( count, 0 );
+      const int rc = paladin_gpu_geev_batch( device, static_cast<int>( count ), n.data(), off.data(), ci.data(), cj.data(),
+                                             cv.data(), 'N', jobvr, pwr.data(), pwi.data(), nullptr, pvr.data(), info.data() );
+      if ( rc != PALADIN_GPU_OK ) {
+        std::cerr << "paladin_gpu_geev_batch failed on device " << device << ": " << paladin_gpu_last_error() << '\n';
+        return -1;
+      }
+      if ( rep != 0 ) continue;  // like the reference, only the first repeat produces output
+      for ( std::size_t k = 0; k < count; ++k ) {
+        if ( info[k] != 0 ) {
+          ++failures;
+          std::cerr << "warning: " << pod[first + k] << ": info = " << info[k] << '\n';
+        }
+        SpectralDecomposition s( n[k], o.threshold );
+        s.unpack( n[k], wr[k].data(), wi[k].data(), o.right && info[k] == 0 ? vr[k].data() : nullptr );
+        std::string text;
+        s.write_eigenvalues( text );
+        write_file( pod[first + k] + ".spectrum", text );
+        if ( o.right ) {
+          text.clear();
+          s.write_right_eigenvectors( text );
+          write_file( pod[first + k] + ".rightvecs", text );
+        }
+      }
+    }
+  }
+  times.total = std::chrono::duration<double>( clock::now() - t_start ).count() / o.repeats;
+  times.read /= o.repeats;
+  times.eig = times.total - times.read;
+  return failures;
+}
+
+inline void display_timings( const std::vector<PodTimes>& t, int repeats ) {
+  std::cout << '\n' << "Timings averaged over " << repeats << " runs:" << '\n';
+  std::cout << "                      runtimes (s)\t\t\t  fractions\n";
+  std::cout << "        -----------------------------------------\t-------------\n";
+  std::cout << "pod\tread\t\teig.\t\ttotal\t\tread\teig.\n";
+  PodTimes mn = t[0], mx = t[0], sum;
+  for ( std::size_t r = 0; r < t.size(); ++r ) {
+    std::printf( "%zu\t%0.3e\t%0.3e\t%0.3e\t%0.2f\t%0.2f\n", r, t[r].read, t[r].eig, t[r].total, t[r].read / t[r].total,
+                 t[r].eig / t[r].total );
+    mn.read = std::min( mn.read, t[r].read ); mn.eig = std::min( mn.eig, t[r].eig ); mn.total = std::min( mn.total, t[r].total );
+    mx.read = std::max( mx.read, t[r].read ); mx.eig = std::max( mx.eig, t[r].eig ); mx.total = std::max( mx.total, t[r].total );
+    sum.read += t[r].read; sum.eig += t[r].eig; sum.total += t[r].total;
+  }
+  const double p = static_cast<double>( t.size() );
+  std::cout << "---------------------------------------------------------------------\n";
+  std::printf( "min\t%0.3e\t%0.3e\t%0.3e\n", mn.read, mn.eig, mn.total );
+  std::printf( "avg\t%0.3e\t%0.3e\t%0.3e\t%0.2f\t%0.2f\n", sum.read / p, sum.eig / p, sum.total / p, sum.read / sum.total,
+               sum.eig / sum.total );
+  std::printf( "max\t%0.3e\t%0.3e\t%0.3e\n", mx.read, mx.eig, mx.total );
+  std::cout << '\n' << "load imbalance = " << 100 * ( mx.total / ( sum.total / p ) - 1.0 ) << "%" << '\n';
+}
+
+inline int host_main( int argc, char* argv[] ) {
+  const Options o = parse_options( argc, argv, false );
+  print_header();
+  if ( o.left ) {
+    std::cerr << "paladin-gpu: --left (left eigenvectors) is not implemented by the GPU library yet; run the reference for "
+                 "left vectors\n";
+    return 2;
+  }
+  int pods = o.gpus;
+  if ( pods <= 0 ) pods = o.dump_partition.empty() ? paladin_gpu_device_count() : 1;
+  if ( pods <= 0 ) {
+    std::cerr << "paladin-gpu: no usable sm_100 device (there is no CPU fallback)\n";
+    return 3;
+  }
+  const int total = count_nonempty_lines( o.listing );
+  std::cout << "\nCommand line parsed!" << '\n';
+  std::cout << "GPUs (pods)        : " << pods << '\n';
+  std::cout << "Matrix listing     : " << o.listing << '\n';
+  std::cout << "Number of matrices : " << total << '\n';
+  std::cout << "Load measure type  : " << measure_type_description( o.measure ) << '\n';
+  std::cout << "Timing repeats     : " << o.repeats << '\n' << '\n';
+  const Plan plan = make_plan( o, pods );
+  if ( !o.dump_partition.empty() ) {
+    std::ofstream out( o.dump_partition );
+    for ( std::size_t s = 0; s < plan.paths.size(); ++s ) out << s << " " << plan.colour[s] << " " << plan.paths[s] << '\n';
+    return 0;
+  }
+  std::vector<std::vector<std::string>> pod( pods );
+  for ( std::size_t s = 0; s < plan.paths.size(); ++s ) pod[plan.colour[s]].push_back( plan.paths[s] );
+  for ( int r = 0; r < pods; ++r ) {
+    std::cout << "pod " << r << ": " << pod[r].size() << " matrices" << '\n';
+    if ( o.showdist )
+      for ( std::size_t s = 0; s < plan.paths.size(); ++s )
+        if ( plan.colour[s] == r ) std::printf( "%s%0.1e%s%s\n", "    ", plan.measures[s], "   ", plan.paths[s].c_str() );
+  }
+  std::vector<PodTimes> times( pods );
+  std::vector<int> status( pods, 0 );
+  std::vector<std::thread> workers;
+  for ( int r = 0; r < pods; ++r ) workers.emplace_back( [&, r] { status[r] = run_pod( r, pod[r], o, times[r] ); } );
+  for ( auto& w : workers ) w.join();
+  for ( int r = 0; r < pods; ++r )
+    if ( status[r] < 0 ) return 4;
+  display_timings( times, o.repeats );
+  return 0;
+}
+
+}  // namespace paladin
+
+#ifndef PALADIN_HOST_LIBRARY
+int main( int argc, char* argv[] ) { return paladin::host_main( argc, argv ); }
+#else
+// ---- test hooks (CPU only) ----------------------------------------------------------------------------------------
+extern "C" {
+
+// returns nnz (>= 0) or -1; call with null arrays first to size them
+int ph_parse_mm( const char* path, int* n, int cap, int* row, int* col, double* val ) {
+  try {
+    const paladin::CooMatrix m = paladin::read_coo_from_mm_file( path );
+    *n = m.nrows_;
+    if ( row && cap >= m.nnz_ ) {
+      std::copy( m.row.begin(), m.row.end(), row );
+      std::copy( m.col.begin(), m.col.end(), col );
+      std::copy( m.val.begin(), m.val.end(), val );
+    }
+    return m.nnz_;
+  } catch ( const std::exception& ) {
+    return -1;
+  }
+}
+
+double ph_measure( int n, int nnz, const char* kind ) { return paladin::matrix_measure( n, nnz, paladin::string_to_measure_type( kind ) ); }
+
+// order[s] = listing index at sorted position s, colour[s] = its pod
+void ph_partition( int count, const double* measures, int pods, int* order, int* colour ) {
+  std::vector<paladin::NameMeasurePairT> entries;
+  for ( int k = 0; k < count; ++k ) entries.emplace_back( std::to_string( k ), measures[k] );
+  paladin::sort_name_measure_pairs( entries );
+  const std::vector<int> c = paladin::color_pods( entries, pods );
+  for ( int s = 0; s < count; ++s ) {
+    order[s] = std::stoi( entries[s].first );
+    colour[s] = c[s];
+  }
+}
+
+// formats into caller buffers; returns the byte count needed
+long ph_format( int n, const double* wr, const double* wi, const double* vr, double threshold, int which, char* out, long cap ) {
+  paladin::SpectralDecomposition s( n, threshold );
+  s.unpack( n, wr, wi, vr );
+  std::string str;
+  if ( which == 0 ) s.write_eigenvalues( str );
+  else s.write_right_eigenvectors( str );
+  if ( out && cap >= static_cast<long>( str.size() ) ) std::memcpy( out, str.data(), str.size() );
+  return static_cast<long>( str.size() );
+}
+
+int ph_main( int argc, char** argv ) { return paladin::host_main( argc, argv ); }
+}
+#endif

@@ -74,6 +74,7 @@ struct ThreadShared {
 };
 
 struct ThreadGroup {
+  static constexpr bool kIsCta = false;
   ThreadShared* s;
   int me;
   int tid() const { return me; }
@@ -193,9 +194,9 @@ struct MsBuffers {
     d.assign( pb::msqr_work_doubles( c, ldw, ldt ) + 64, 0.0 );
     i.assign( 3 * pb::kMsMaxBulges + 8, 0 );
     double* p = d.data();
-    wk.Hw = p; p += (size_t)c.W * ldw;
-    wk.U = p; p += (size_t)c.W * ldw;
-    wk.tile = p; p += (size_t)c.W * ldt;
+    wk.Hw = p; p += pb::ms_even( (size_t)c.W * ldw );
+    wk.U = p; p += pb::ms_even( (size_t)c.W * ldw );
+    wk.tile = p; p += pb::ms_even( (size_t)c.W * ldt );
     wk.refl = p; p += (size_t)c.nb * c.W * pb::kReflStride;
     wk.sr = p; p += 2 * c.nb * c.nchains;
     wk.si = p;

@@ -288,7 +288,32 @@ def test_staged_api_and_stage_timers(pg):
     ms = b.stage_ms()
     b.destroy()
     assert not info.any()
-    assert ms["scatter"][0] > 0 and ms["small"][0] > 0 and ms["mid"][0] > 0
+    assert ms["scatter"][0] > 0 and ms["small"][0] > 0 and ms["hessenberg"][0] > 0 and ms["qr"][0] > 0 and ms["vectors"][0] > 0
     from paladin_b200.api import split_results
     for m, (w1, w2, V) in zip(mats, split_results(n, wr, wi, vr)):
         _check_eigs(po.dense_matrix(*m), w1, w2, V, 0, True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# (d) the drop-in executable: reference CLI, listing and output files, GPUs as pods
+# ---------------------------------------------------------------------------------------------------
+def test_paladin_gpu_executable_reproduces_ctest_goldens(pg, tmp_path):
+    import shutil
+    import subprocess
+    from paladin_b200 import host
+    for suite, listing in [("canonical-2x2", "listing1"), ("canonical-2x2", "listing2"), ("multiple-matrices", "listing")]:
+        src = os.path.join(GOLD, "ref_ctest", suite)
+        dst = tmp_path / (suite + "-" + listing)
+        shutil.copytree(src, dst)
+        lst = os.path.join(dst, listing)
+        if not os.path.exists(lst):  # fixtures keep one listing per suite
+            lst = sorted(glob.glob(os.path.join(dst, "listing*")))[-1]
+        r = subprocess.run([host.exe_path(), "--listing=" + lst, "--rootdir=" + str(dst), "--right", "--gpus=1", "--showdist"],
+                           capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert "load imbalance" in r.stdout
+        for m in sorted(glob.glob(os.path.join(dst, "*.matrix"))):
+            if not os.path.exists(m + ".spectrum"):
+                continue  # not named by this listing
+            assert open(m + ".spectrum", "rb").read() == open(m + ".spectrum.exact", "rb").read(), m
+            assert open(m + ".rightvecs", "rb").read() == open(m + ".rightvecs.exact", "rb").read(), m
