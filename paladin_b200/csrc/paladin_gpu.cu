@@ -211,7 +211,10 @@ inline size_t prep_smem_bytes( int nmax ) {
   return sizeof( double ) * pb::hess_smem_doubles( std::min( nmax, kMidMaxFusedN ) );
 }
 
-__global__ void __launch_bounds__( pb::kHessThreads ) mid_prep_kernel( MidArgs a ) {
+// MAXCH = 16: n <= 512, two CTAs per SM (<= 128 registers); MAXCH = 32: n <= 1024; MAXCH = 0: any n, unblocked
+// group code in global memory (slow, correctness path for the largest matrices)
+template <int MAXCH>
+__global__ void __launch_bounds__( pb::kHessThreads, ( MAXCH == 16 ? 2 : 1 ) ) mid_prep_kernel( MidArgs a ) {
   extern __shared__ double smem[];
   __shared__ double red[64];
   __shared__ long long lstats[kNumTicks];
@@ -233,14 +236,12 @@ __global__ void __launch_bounds__( pb::kHessThreads ) mid_prep_kernel( MidArgs a
     sc.cscale = 1.0;
   } else {
     g.tick( pb::kTickBalance );
-    if ( n <= 512 ) pb::hess_fused<16>( n, ilo, ihi, A, n, tau, smem );
-    else if ( n <= kMidMaxFusedN ) pb::hess_fused<32>( n, ilo, ihi, A, n, tau, smem );
+    if constexpr ( MAXCH > 0 ) pb::hess_fused<MAXCH>( n, ilo, ihi, A, n, tau, smem );
     else pb::gehd2( g, n, ilo, ihi, A, n, tau, dw + 2 * n );
     __syncthreads();
     g.tick( pb::kTickHess );
     if ( a.bv.wantvr ) {
-      if ( n <= 512 ) pb::form_q<16>( n, ilo, ihi, A, n, tau, V, n );
-      else if ( n <= kMidMaxFusedN ) pb::form_q<32>( n, ilo, ihi, A, n, tau, V, n );
+      if constexpr ( MAXCH > 0 ) pb::form_q<MAXCH>( n, ilo, ihi, A, n, tau, V, n );
       else pb::orghr( g, n, ilo, ihi, A, n, tau, V, n );
     }
     __syncthreads();
@@ -843,13 +844,43 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
       ma.xslot = b->xslot;
       PB_CUDA( cudaMemsetAsync( b->d_stats, 0, sizeof( long long ) * kNumTicks, st ) );
       PB_CUDA( cudaMemsetAsync( b->d_counter, 0, sizeof( int ), st ) );
-      const size_t s1 = prep_smem_bytes( g.nmax ), s2 = qr_smem_bytes(), s3 = vec_smem_bytes( g.nmax );
-      PB_CUDA( cudaFuncSetAttribute( mid_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1 ) );
+      const size_t s2 = qr_smem_bytes(), s3 = vec_smem_bytes( g.nmax );
+      PB_CUDA( cudaFuncSetAttribute( mid_prep_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem_bytes( 512 ) ) );
+      PB_CUDA( cudaFuncSetAttribute( mid_prep_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem_bytes( 1024 ) ) );
       PB_CUDA( cudaFuncSetAttribute( mid_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2 ) );
       PB_CUDA( cudaFuncSetAttribute( mid_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3 ) );
       stage_begin( b, PALADIN_GPU_STAGE_HESSENBERG, st );
-      mid_prep_kernel<<<cnt, pb::kHessThreads, s1, st>>>( ma );
-      stage_end( b, PALADIN_GPU_STAGE_HESSENBERG, st, 1 );
+      {
+        // the group's ids are sorted by decreasing n: [0, nbig) need the unblocked path, [nbig, nmid) the 32-chunk
+        // kernel, the rest the 16-chunk kernel
+        int nbig = 0, nmid = 0;
+        for ( int q = 0; q < g.count; ++q ) {
+          const int nq = b->n[b->ids[g.first + q]];
+          if ( nq > kMidMaxFusedN ) nbig = q + 1;
+          if ( nq > 512 ) nmid = q + 1;
+        }
+        nbig = std::min( nbig, cnt );
+        nmid = std::min( nmid, cnt );
+        int launches = 0;
+        if ( nbig > 0 ) {
+          MidArgs m0 = ma;
+          mid_prep_kernel<0><<<nbig, pb::kHessThreads, 64 * sizeof( double ), st>>>( m0 );
+          ++launches;
+        }
+        if ( nmid > nbig ) {
+          MidArgs m1 = ma;
+          m1.ids = ids + nbig;
+          mid_prep_kernel<32><<<nmid - nbig, pb::kHessThreads, prep_smem_bytes( 1024 ), st>>>( m1 );
+          ++launches;
+        }
+        if ( cnt > nmid ) {
+          MidArgs m2 = ma;
+          m2.ids = ids + nmid;
+          mid_prep_kernel<16><<<cnt - nmid, pb::kHessThreads, prep_smem_bytes( 512 ), st>>>( m2 );
+          ++launches;
+        }
+        stage_end( b, PALADIN_GPU_STAGE_HESSENBERG, st, launches );
+      }
       stage_begin( b, PALADIN_GPU_STAGE_QR, st );
       mid_qr_kernel<<<cnt, kMidThreads, s2, st>>>( ma );
       stage_end( b, PALADIN_GPU_STAGE_QR, st, 1 );

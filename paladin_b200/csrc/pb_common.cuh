@@ -318,6 +318,34 @@ PB_HD void dlarfg3( int n, double& alpha, double& x1, double& x2, double& tau ) 
   alpha = beta;
 }
 
+// 3-element Householder reflector, fast path: one square root and two independent divisions; falls back on the
+// rescaling dlarfg3 when the entries are so large or small that the plain sum of squares could over/underflow.
+// Same contract as dlarfg3 (alpha <- beta, x <- v, tau); for n < 3 the unused entry is returned as 0.
+PB_HD void larfg3_fast( int n, double& a0, double& a1, double& a2, double& t1 ) {
+  if ( n < 3 ) a2 = 0.0;
+  if ( n <= 1 ) {
+    t1 = 0.0;
+    return;
+  }
+  const double m = dmax( fabs( a0 ), dmax( fabs( a1 ), fabs( a2 ) ) );
+  if ( !( m > 1.0e-140 && m < 1.0e140 ) ) {
+    dlarfg3( n, a0, a1, a2, t1 );
+    if ( n < 3 ) a2 = 0.0;
+    return;
+  }
+  const double xn2 = a1 * a1 + a2 * a2;
+  if ( xn2 == 0.0 ) {
+    t1 = 0.0;
+    return;
+  }
+  const double beta = -dsign( sqrt( a0 * a0 + xn2 ), a0 );
+  const double rb = 1.0 / beta, rs = 1.0 / ( a0 - beta );
+  t1 = ( beta - a0 ) * rb;
+  a1 *= rs;
+  a2 *= rs;
+  a0 = beta;
+}
+
 // dlartg (LAPACK 3.10+ la_lartg semantics for the unscaled range): r has the sign of f
 PB_HD void dlartg( double f, double g, double& c, double& s, double& r ) {
   if ( g == 0.0 ) {

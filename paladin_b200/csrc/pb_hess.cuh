@@ -206,43 +206,61 @@ __device__ void hess_fused( int n, int ilo, int ihi, double* A, int lda, double*
   // the last generated step is j = ihi-1 with tau = 0: nothing is left to apply
 }
 
-// Q (n x n, ldq) = H(ilo) ... H(ihi-2) from the reflectors stored in A / tau. One warp per column.
+// Q (n x n, ldq) = H(ilo) ... H(ihi-2) from the reflectors stored in A / tau, by backward accumulation:
+// for j = ihi-2 ... ilo the block Q(j+1:ihi, j+1:ihi) <- (I - tau v v^T) Q(...). Same streaming pattern as the
+// reduction itself: a warp owns a column at a time (loads it once, reduces v^T q with shuffles, updates, stores it
+// once), v_j sits in registers for the whole step. Two reflectors (j, j-1) are applied per sweep, which halves the
+// traffic: the second one only needs the already-updated column, which is still in registers.
 template <int MAXCH>
-__device__ void form_q( int n, int ilo, int ihi, const double* A, int lda, const double* tau, double* Q, int ldq ) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nch = ( n + 31 ) >> 5;
-  for ( int c = warp; c < n; c += kHessWarps ) {
-    double q[MAXCH];
-#pragma unroll
-    for ( int k = 0; k < MAXCH; ++k ) q[k] = ( lane + 32 * k == c ) ? 1.0 : 0.0;
-    if ( c > ilo && c <= ihi ) {
-      for ( int j = imin( c - 1, ihi - 2 ); j >= ilo; --j ) {
-        const double tj = tau[j];
-        if ( tj == 0.0 ) continue;
-        const double* v = A + (size_t)j * lda;  // v(j+1) = 1, v(r) = A(r,j) for j+2 <= r <= ihi
-        double vr[MAXCH];
-        double w = 0.0;
-        // unconditional (clamped) loads first, selection afterwards: the loads overlap
-#pragma unroll
-        for ( int k = 0; k < MAXCH; ++k ) vr[k] = v[imin( imax( lane + 32 * k, j + 2 ), imax( ihi, j + 2 ) )];
-#pragma unroll
-        for ( int k = 0; k < MAXCH; ++k ) {
-          const int r = lane + 32 * k;
-          double x = ( r >= j + 2 && r <= ihi ) ? vr[k] : 0.0;
-          if ( r == j + 1 ) x = 1.0;
-          vr[k] = x;
-          w += x * q[k];
-        }
-        w = warp_sum( w ) * tj;
-#pragma unroll
-        for ( int k = 0; k < MAXCH; ++k ) q[k] -= w * vr[k];
-      }
-    }
+__device__ void form_q( int n, int ilo, int ihi, const double* __restrict__ A, int lda, const double* __restrict__ tau,
+                        double* __restrict__ Q, int ldq ) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // identity
+  for ( int c = warp; c < n; c += kHessWarps )
+    for ( int r = lane; r < n; r += 32 ) Q[r + (size_t)c * ldq] = ( r == c ) ? 1.0 : 0.0;
+  __syncthreads();
+  int j = ihi - 2;
+  while ( j >= ilo ) {
+    const bool two = ( j - 1 >= ilo );
+    const int ja = j, jb = two ? j - 1 : j;           // apply H(ja) first, then H(jb)
+    const double ta = tau[ja], tb = two ? tau[jb] : 0.0;
+    // rows involved: jb+1 .. ihi ; first chunk that matters
+    const int k0 = ( jb + 1 ) >> 5;
+    double va[MAXCH], vb[MAXCH];
 #pragma unroll
     for ( int k = 0; k < MAXCH; ++k ) {
       const int r = lane + 32 * k;
-      if ( k < nch && r < n ) Q[r + (size_t)c * ldq] = q[k];
+      const int rc = imin( r, n - 1 );
+      const double xa = A[rc + (size_t)ja * lda], xb = A[rc + (size_t)jb * lda];
+      va[k] = ( r == ja + 1 ) ? 1.0 : ( ( r >= ja + 2 && r <= ihi ) ? xa : 0.0 );
+      vb[k] = !two ? 0.0 : ( ( r == jb + 1 ) ? 1.0 : ( ( r >= jb + 2 && r <= ihi ) ? xb : 0.0 ) );
     }
+    // columns jb+1 .. ihi (column jb+1 = e_{jb+1} is only touched by H(jb))
+    for ( int c = jb + 1 + warp; c <= ihi; c += kHessWarps ) {
+      double* col = Q + (size_t)c * ldq;
+      double q[MAXCH];
+#pragma unroll
+      for ( int k = 0; k < MAXCH; ++k ) q[k] = ( k >= k0 ) ? col[imin( lane + 32 * k, n - 1 )] : 0.0;
+      double wa = 0.0;
+#pragma unroll
+      for ( int k = 0; k < MAXCH; ++k ) wa += va[k] * q[k];
+      wa = warp_sum( wa ) * ta;
+      double wb = 0.0;
+#pragma unroll
+      for ( int k = 0; k < MAXCH; ++k ) {
+        q[k] -= wa * va[k];
+        wb += vb[k] * q[k];
+      }
+      wb = warp_sum( wb ) * tb;
+#pragma unroll
+      for ( int k = 0; k < MAXCH; ++k ) {
+        q[k] -= wb * vb[k];
+        const int r = lane + 32 * k;
+        if ( k >= k0 && r <= ihi ) col[r] = q[k];
+      }
+    }
+    __syncthreads();
+    j -= two ? 2 : 1;
   }
 }
 

@@ -351,7 +351,21 @@ PB_D int ms_compute_shifts( const G& g, int l, int i, const double* H, int ldh, 
       S[r + c * ldw] = ( r - c <= 1 ) ? PB_H( r0 + r, r0 + c ) : 0.0;
     }
     g.sync();
-    const int inf = lahqr( g, false, false, ns, 0, ns - 1, S, ldw, sr, si, 0, ns - 1, (double*)nullptr, 1 );
+    int inf = 0;
+    bool warp_done = false;
+#if defined( __CUDACC__ )
+    if constexpr ( G::kIsCta ) {
+      // a 2nb x 2nb problem keeps one warp busy at best: run it on warp 0 with warp-level barriers only
+      if ( ( threadIdx.x >> 5 ) == 0 ) {
+        const int r = lahqr<WarpGroup, true>( WarpGroup(), false, false, ns, 0, ns - 1, S, ldw, sr, si, 0, ns - 1, (double*)nullptr, 1 );
+        if ( threadIdx.x == 0 ) wk.ibuf[3 * kMsMaxBulges + 4] = r;
+      }
+      __syncthreads();
+      inf = wk.ibuf[3 * kMsMaxBulges + 4];
+      warp_done = true;
+    }
+#endif
+    if ( !warp_done ) inf = lahqr( g, false, false, ns, 0, ns - 1, S, ldw, sr, si, 0, ns - 1, (double*)nullptr, 1 );
     g.sync();
     PB_CHECK_UNIFORM( g, inf, "shift lahqr info" );
     ks = inf;  // shifts ks..ns-1 converged
@@ -409,6 +423,125 @@ PB_D int ms_compute_shifts( const G& g, int l, int i, const double* H, int ldh, 
   return wk.ibuf[3 * kMsMaxBulges];
 }
 
+#if defined( __CUDACC__ )
+// Device version of the macro-step loop of one window: warp b owns bulge b (reflector generation and both
+// updates are warp-local), two CTA barriers per macro-step separate the row phase from the column phase.
+// Every thread tracks all bulge positions in registers. Requires nbulges <= number of warps, nbulges <= 8.
+__device__ inline bool ms_window_steps_fast( int l, int i, int ws, int we, int nbulges, int* kpos_s, int* kcount_s, double* Hw, int ldw,
+                                             double* refl, int W, const double* sr, const double* si ) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int kp[8], kc = 0;
+#pragma unroll
+  for ( int b = 0; b < 8; ++b ) kp[b] = ( b < nbulges ) ? kpos_s[b] : ( i + 1 );
+  bool progressed = false;
+#define PB_W( r, c ) Hw[( ( r ) - ws ) + ( ( c ) - ws ) * ldw]
+  for ( ;; ) {
+    unsigned moving = 0;
+    bool ahead_moves = false, have_ahead = false;
+    int ahead_pos = 0;
+#pragma unroll
+    for ( int b = 0; b < 8; ++b ) {
+      const int k = kp[b];
+      bool mv = false;
+      if ( b < nbulges && k <= i - 1 ) {
+        const bool fits = imin( k + 3, i ) <= we;
+        bool clear = true;
+        if ( have_ahead ) clear = ( ahead_pos >= k + 4 ) || ( ahead_pos == k + 3 && ahead_moves );
+        mv = fits && clear;
+        have_ahead = true;
+        ahead_pos = k;
+        ahead_moves = mv;
+      }
+      if ( mv ) moving |= 1u << b;
+    }
+    if ( moving == 0 ) break;
+    progressed = true;
+    int k = 0;
+#pragma unroll
+    for ( int b = 0; b < 8; ++b )
+      if ( b == warp ) k = kp[b];
+    const bool mine = ( warp < nbulges ) && ( ( moving >> warp ) & 1u );
+    const bool three = ( k + 2 <= i );
+    double w2 = 0.0, w3 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    if ( mine ) {
+      const int nr = three ? 3 : 2;
+      double a0, a1, a2 = 0.0;
+      if ( k == l ) {
+        const double rt1r = sr[2 * warp], rt1i = si[2 * warp], rt2r = sr[2 * warp + 1], rt2i = si[2 * warp + 1];
+        const double h00 = PB_W( l, l ), h10 = PB_W( l + 1, l ), h01 = PB_W( l, l + 1 ), h11 = PB_W( l + 1, l + 1 );
+        double s = fabs( h00 - rt2r ) + fabs( rt2i ) + fabs( h10 );
+        if ( s == 0.0 ) {
+          a0 = a1 = a2 = 0.0;
+        } else {
+          const double h21s = h10 / s;
+          a0 = h21s * h01 + ( h00 - rt1r ) * ( ( h00 - rt2r ) / s ) - rt1i * ( rt2i / s );
+          a1 = h21s * ( h00 + h11 - rt1r - rt2r );
+          a2 = three ? h21s * PB_W( l + 2, l + 1 ) : 0.0;
+          s = fabs( a0 ) + fabs( a1 ) + fabs( a2 );
+          if ( s != 0.0 ) {
+            const double rs = 1.0 / s;
+            a0 *= rs; a1 *= rs; a2 *= rs;
+          }
+        }
+      } else {
+        a0 = PB_W( k, k - 1 );
+        a1 = PB_W( k + 1, k - 1 );
+        if ( three ) a2 = PB_W( k + 2, k - 1 );
+      }
+      larfg3_fast( nr, a0, a1, a2, t1 );
+      w2 = a1;
+      w3 = a2;
+      t2 = t1 * w2;
+      t3 = t1 * w3;
+      __syncwarp();  // every lane has read the bulge column before lane 0 rewrites it
+      if ( lane == 0 ) {
+        if ( k > l ) {
+          PB_W( k, k - 1 ) = a0;
+          PB_W( k + 1, k - 1 ) = 0.0;
+          if ( three ) PB_W( k + 2, k - 1 ) = 0.0;
+        }
+        double* rf = refl + ( (size_t)warp * W + kc ) * kReflStride;
+        rf[0] = w2; rf[1] = w3; rf[2] = t1; rf[3] = t2; rf[4] = t3;
+      }
+      // row update: rows k..k+2, columns k..we
+      for ( int j = k + lane; j <= we; j += 32 ) {
+        const double x0 = PB_W( k, j ), x1 = PB_W( k + 1, j ), x2 = three ? PB_W( k + 2, j ) : 0.0;
+        const double sum = x0 + w2 * x1 + w3 * x2;
+        PB_W( k, j ) = x0 - sum * t1;
+        PB_W( k + 1, j ) = x1 - sum * t2;
+        if ( three ) PB_W( k + 2, j ) = x2 - sum * t3;
+      }
+    }
+    __syncthreads();
+    if ( mine ) {
+      // column update: columns k..k+2, rows ws..min(k+3, i)
+      const int rend = imin( k + 3, i );
+      for ( int r = ws + lane; r <= rend; r += 32 ) {
+        const double x0 = PB_W( r, k ), x1 = PB_W( r, k + 1 ), x2 = three ? PB_W( r, k + 2 ) : 0.0;
+        const double sum = x0 + w2 * x1 + w3 * x2;
+        PB_W( r, k ) = x0 - sum * t1;
+        PB_W( r, k + 1 ) = x1 - sum * t2;
+        if ( three ) PB_W( r, k + 2 ) = x2 - sum * t3;
+      }
+      kc += 1;
+    }
+    __syncthreads();
+#pragma unroll
+    for ( int b = 0; b < 8; ++b )
+      if ( ( moving >> b ) & 1u ) kp[b] += 1;
+  }
+#undef PB_W
+  if ( lane == 0 && warp < nbulges ) {
+#pragma unroll
+    for ( int b = 0; b < 8; ++b )
+      if ( b == warp ) kpos_s[b] = kp[b];
+    kcount_s[warp] = kc;
+  }
+  __syncthreads();
+  return progressed;
+}
+#endif  // __CUDACC__
+
 // ---- one chain of nbulges bulges swept over the active block [l..i] --------------------------------
 template <class G>
 PB_D void ms_chase_chain( const G& g, bool wantt, bool wantz, int n, int l, int i, double* H, int ldh, int iloz, int ihiz,
@@ -446,8 +579,17 @@ PB_D void ms_chase_chain( const G& g, bool wantt, bool wantz, int n, int l, int 
     }
     g.sync();
     bool progressed = false;
+    bool done_fast = false;
+#if defined( __CUDACC__ )
+    if constexpr ( G::kIsCta ) {
+      if ( nbulges <= 8 && nbulges <= ( g.size() >> 5 ) ) {
+        progressed = ms_window_steps_fast( l, i, ws, we, nbulges, kpos, kcount, Hw, ldw, wk.refl, cfg.W, sr, si );
+        done_fast = true;
+      }
+    }
+#endif
 #define PB_W( r, c ) Hw[( ( r ) - ws ) + ( ( c ) - ws ) * ldw]
-    for ( ;; ) {
+    for ( ; !done_fast; ) {
       // which bulges step now (every thread evaluates the same shared state)
       unsigned moving = 0;
       bool ahead_moves = false;
@@ -497,8 +639,7 @@ PB_D void ms_chase_chain( const G& g, bool wantt, bool wantz, int n, int l, int 
           a1 = PB_W( k + 1, k - 1 );
           if ( nr == 3 ) a2 = PB_W( k + 2, k - 1 );
         }
-        dlarfg3( nr, a0, a1, a2, t1 );
-        if ( nr < 3 ) a2 = 0.0;
+        larfg3_fast( nr, a0, a1, a2, t1 );
         if ( k > l ) {
           PB_W( k, k - 1 ) = a0;
           PB_W( k + 1, k - 1 ) = 0.0;
@@ -554,7 +695,13 @@ PB_D void ms_chase_chain( const G& g, bool wantt, bool wantz, int n, int l, int 
 #undef PB_W
     if ( !progressed ) break;  // cannot happen for W >= 3*nb + 4; never spin
     ms_store_window( g, H, ldh, ws, wlen, Hw, ldw );
-    if ( t == 0 ) wk.ibuf[3 * kMsMaxBulges + 2] += 1;
+    if ( t == 0 ) {
+      wk.ibuf[3 * kMsMaxBulges + 2] += 1;
+      bool reg = ( nbulges == cfg.nb ) && ( wlen == cfg.W );
+      for ( int b = 0; b < nbulges; ++b )
+        reg = reg && ( kfirst[b] - ws == 1 + 3 * ( cfg.nb - 1 - b ) ) && ( kcount[b] == cfg.W - 1 - 3 * cfg.nb );
+      if ( reg ) wk.ibuf[3 * kMsMaxBulges + 5] += 1;  // steady-state windows (diagnostic)
+    }
     g.tick( kTickMsChase );
 #if defined( __CUDACC__ )
     if constexpr ( G::kIsCta ) {

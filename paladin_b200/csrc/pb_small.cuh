@@ -341,7 +341,9 @@ PB_D void orghr( const G& g, int n, int ilo, int ihi, const double* A, int lda, 
 // transformations are accumulated into rows iloz..ihiz of Z.
 // Returns 0, or (i+1) when the QR iteration failed to converge for eigenvalue index i.
 // ------------------------------------------------------------------------------------------------
-template <class G>
+// FASTREFL: generate the 3-element reflectors with larfg3_fast (one sqrt, two reciprocals) instead of the
+// rescaling dlarfg3; used where the result only steers the iteration (shift computation).
+template <class G, bool FASTREFL = false>
 PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, double* H, int ldh,
                 double* wr, double* wi, int iloz, int ihiz, double* Z, int ldz ) {
   const int t = g.tid(), nt = g.size();
@@ -517,7 +519,8 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
           a1 = v1;
           a2 = v2;
         }
-        dlarfg3( nr, a0, a1, a2, t1 );
+        if ( FASTREFL ) larfg3_fast( nr, a0, a1, a2, t1 );
+        else dlarfg3( nr, a0, a1, a2, t1 );
         const double w2 = a1, t2 = t1 * w2;
         // column k-1 is rewritten by thread 0 only after the barrier that follows the left
         // application, i.e. once every thread has read it

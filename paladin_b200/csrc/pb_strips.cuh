@@ -61,6 +61,38 @@ __device__ __forceinline__ void strip_apply_line( double ( &x )[kStripW + 2], in
   }
 }
 
+// Steady-state window: all kStripNB bulges enter tightly packed (bulge b at position 1 + 3 (NB-1-b)) and advance
+// kStripD rows in lockstep. Every position is then known at compile time, and the steps are issued macro-step by
+// macro-step: the NB reflectors of one macro-step touch disjoint positions, so a thread has NB independent
+// 5-FMA groups in flight instead of one serial chain (the bulge-major order of the generic path is equivalent:
+// a step of bulge b only depends on EARLIER macro-steps of the bulges ahead of it).
+constexpr int kStripNB = 8, kStripD = 24;
+
+__device__ __forceinline__ bool strip_window_is_regular( int nbulges, int wlen, int ws, const int* kfirst, const int* kcount ) {
+  if ( nbulges != kStripNB || wlen != kStripW ) return false;
+  bool ok = true;
+#pragma unroll
+  for ( int b = 0; b < kStripNB; ++b ) ok = ok && ( kfirst[b] - ws == 1 + 3 * ( kStripNB - 1 - b ) ) && ( kcount[b] == kStripD );
+  return ok;
+}
+
+__device__ __forceinline__ void strip_apply_line_regular( double ( &x )[kStripW + 2], const double* refl ) {
+#pragma unroll
+  for ( int t = 0; t < kStripD; ++t ) {
+#pragma unroll
+    for ( int b = 0; b < kStripNB; ++b ) {
+      const int P = 1 + 3 * ( kStripNB - 1 - b ) + t;
+      const double2* rf = reinterpret_cast<const double2*>( refl + ( (size_t)b * kStripW + t ) * 6 );
+      const double2 w = rf[0], tt = rf[1];
+      const double t3 = reinterpret_cast<const double*>( rf )[4];
+      const double sum = x[P] + w.x * x[P + 1] + w.y * x[P + 2];
+      x[P] -= sum * tt.x;
+      x[P + 1] -= sum * tt.y;
+      x[P + 2] -= sum * t3;
+    }
+  }
+}
+
 // Every off-window strip of one window move. refl / kfirst / kcount live in shared memory; tile is the
 // W x ldt shared tile (ldt >= 32 * warps + 1, odd); the caller synchronises the CTA before and after.
 __device__ inline void ms_strips_regs( bool wantt, bool wantz, int n, int l, int i, int ws, int wlen, double* __restrict__ H,
@@ -72,6 +104,7 @@ __device__ inline void ms_strips_regs( bool wantt, bool wantz, int n, int l, int
   const int nright = imax( 0, i2 - we ), nup = imax( 0, ws - i1 ), nz = wantz ? ( ihiz - iloz + 1 ) : 0;
   const int bright = ( nright + 31 ) >> 5, bup = ( nup + 31 ) >> 5, bz = ( nz + 31 ) >> 5;
   double* wt = tile + 32 * warp;  // this warp's 32-line slice: element (pos, line) at pos*ldt + line
+  const bool regular = strip_window_is_regular( nbulges, wlen, ws, kfirst, kcount );
   for ( int bt = warp; bt < bright + bup + bz; bt += nwarps ) {
     double x[kStripW + 2];
     x[kStripW] = 0.0;
@@ -102,7 +135,8 @@ __device__ inline void ms_strips_regs( bool wantt, bool wantz, int n, int l, int
 #pragma unroll
       for ( int p = 0; p < kStripW; ++p ) x[p] = ( p < wlen ) ? wt[p * ldt + lane] : 0.0;
       __syncwarp();
-      strip_apply_line( x, nbulges, kfirst, kcount, ws, refl );
+      if ( regular ) strip_apply_line_regular( x, refl );
+      else strip_apply_line( x, nbulges, kfirst, kcount, ws, refl );
 #pragma unroll
       for ( int p = 0; p < kStripW; ++p )
         if ( p < wlen ) wt[p * ldt + lane] = x[p];
@@ -135,7 +169,8 @@ __device__ inline void ms_strips_regs( bool wantt, bool wantz, int n, int l, int
         const double v = row[(size_t)imin( p, wlen - 1 ) * ldm];
         x[p] = ( p < wlen ) ? v : 0.0;
       }
-      strip_apply_line( x, nbulges, kfirst, kcount, ws, refl );
+      if ( regular ) strip_apply_line_regular( x, refl );
+      else strip_apply_line( x, nbulges, kfirst, kcount, ws, refl );
       if ( lane < nl ) {
 #pragma unroll
         for ( int p = 0; p < kStripW; ++p )

@@ -206,14 +206,14 @@ struct MsBuffers {
   }
 };
 
-int g_ms_counters[4];
+int g_ms_counters[8];
 int hs_msqr( int wantt, int wantz, int n, int ilo, int ihi, double* H, double* wr, double* wi, double* Z, int nb, int W,
              int ws_small, int tl, int nchains ) {
   pb::HostGroup g;
   pb::MsqrCfg c{ nb, W, ws_small, tl, nchains };
   MsBuffers buf( c );
   const int r = pb::hqr_multishift( g, wantt != 0, wantz != 0, n, ilo, ihi, H, n, wr, wi, 0, n - 1, Z, n, c, buf.wk );
-  for ( int k = 0; k < 4; ++k ) g_ms_counters[k] = buf.i[3 * pb::kMsMaxBulges + k];
+  for ( int k = 0; k < 8; ++k ) g_ms_counters[k] = buf.i[3 * pb::kMsMaxBulges + k];
   return r;
 }
 const int* hs_ms_counters() { return g_ms_counters; }
