@@ -231,11 +231,34 @@ def ours(args):
         batch.scatter()
         batch.solve()
 
+    # e2e: the step's matrices go through the C-ABI as two half batches driven by two host threads; every batch owns
+    # a stream, so the copies of one half run under the kernels of the other
+    halves = []
+    if B >= 2:
+        h0 = B // 2
+        for lo, hi in ((0, h0), (h0, B)):
+            hb = pg.Batch(nvec[lo:hi], off[lo:hi + 1] - off[lo], jobvr=job, device=dev)
+            halves.append((hb, lo, hi))
+
+    def run_half(hb, lo, hi):
+        hb.upload(pi.array[lo * nn:hi * nn], pj.array[lo * nn:hi * nn], pv.array[lo * nn:hi * nn])
+        hb.scatter()
+        hb.solve()
+        hb.download(out_wr.array[lo * n:hi * n], out_wi.array[lo * n:hi * n],
+                    out_vr.array[lo * nn:hi * nn] if job == "V" else None, out_info.array[lo:hi])
+
     def step_e2e():
-        batch.upload(pi.array, pj.array, pv.array)
-        batch.scatter()
-        batch.solve()
-        batch.download(out_wr.array, out_wi.array, out_vr.array if job == "V" else None, out_info.array)
+        if not halves:
+            batch.upload(pi.array, pj.array, pv.array)
+            batch.scatter()
+            batch.solve()
+            batch.download(out_wr.array, out_wi.array, out_vr.array if job == "V" else None, out_info.array)
+            return
+        th = [threading.Thread(target=run_half, args=h) for h in halves]
+        for t_ in th:
+            t_.start()
+        for t_ in th:
+            t_.join()
 
     # ---- value: inputs resident in HBM ----
     for _ in range(args.warmup):
@@ -245,14 +268,14 @@ def ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     barrier()
-    api.timer_start(dev)
+    batch.timer_start()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_resident()
         for k, (ms, ln) in batch.stage_ms().items():
             stage_acc[k] = stage_acc.get(k, 0.0) + ms
             launches += ln
-    dev_ms = api.timer_stop(dev)
+    dev_ms = batch.timer_stop()
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.result()
@@ -341,6 +364,8 @@ def ours(args):
         }
         print(json.dumps(line), flush=True)
     batch.destroy()
+    for hb, _, _ in halves:
+        hb.destroy()
     for p in (pi, pj, pv, out_wr, out_wi, out_vr, out_info):
         p.free()
     if world > 1:

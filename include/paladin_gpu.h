@@ -17,8 +17,9 @@
  * There is NO CPU fallback: every compute entry fails with PALADIN_GPU_ENODEVICE when no sm_100
  * device is usable.
  *
- * Thread model: one host thread per device may call concurrently; calls that name the same device
- * are serialised inside the library.
+ * Thread model: the library is thread-safe. Every batch owns a CUDA stream, so batches driven from different
+ * host threads overlap on one device (copies of one batch run under the kernels of another); calls on ONE batch
+ * must come from one thread at a time.
  */
 #ifndef PALADIN_GPU_H_
 #define PALADIN_GPU_H_
@@ -132,6 +133,11 @@ int paladin_gpu_batch_download( paladin_gpu_batch* b, double* wr, double* wi, do
  * events on the library's own stream. ms must hold PALADIN_GPU_NUM_STAGES floats. launches (may be
  * NULL) receives the number of kernel launches of each stage. */
 int paladin_gpu_batch_stage_ms( paladin_gpu_batch* b, float* ms, int* launches );
+
+/* Stopwatch on the batch's own stream (CUDA events): the device time between start and stop of everything
+ * enqueued for this batch in between. */
+int paladin_gpu_batch_timer_start( paladin_gpu_batch* b );
+int paladin_gpu_batch_timer_stop( paladin_gpu_batch* b, float* ms );
 
 /* Phase profile of the most recent CTA-per-matrix solve: SM cycles summed over all CTAs, 16 slots
  * (0 balance, 1 Hessenberg, 2 form Q, 3 QR remainder, 4 eigenvectors of T, 5 un-balance + normalise, 6 back-transform GEMM,

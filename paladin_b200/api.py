@@ -64,6 +64,8 @@ def lib():
     L.paladin_gpu_batch_stage_ms.argtypes = [ctypes.c_void_p, _c_flt_p, _c_int_p]
     L.paladin_gpu_batch_destroy.argtypes = [ctypes.c_void_p]
     L.paladin_gpu_batch_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]
+    L.paladin_gpu_batch_timer_start.argtypes = [ctypes.c_void_p]
+    L.paladin_gpu_batch_timer_stop.argtypes = [ctypes.c_void_p, _c_flt_p]
     L.paladin_gpu_timer_start.argtypes = [ctypes.c_int]
     L.paladin_gpu_timer_stop.argtypes = [ctypes.c_int, _c_flt_p]
     L.paladin_gpu_dgeev_.restype = None
@@ -171,6 +173,14 @@ class Batch:
         ln = (ctypes.c_int * NUM_STAGES)()
         _check(lib().paladin_gpu_batch_stage_ms(self._h, ms, ln))
         return {STAGE_NAMES[i]: (float(ms[i]), int(ln[i])) for i in range(NUM_STAGES)}
+
+    def timer_start(self):
+        _check(lib().paladin_gpu_batch_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = ctypes.c_float()
+        _check(lib().paladin_gpu_batch_timer_stop(self._h, ctypes.byref(ms)))
+        return float(ms.value)
 
     def phase_cycles(self):
         cyc = (ctypes.c_longlong * 16)()

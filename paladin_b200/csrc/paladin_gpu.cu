@@ -395,6 +395,8 @@ struct paladin_gpu_batch {
   std::vector<Group> groups;
   StageTimer st[PALADIN_GPU_NUM_STAGES];
   bool scattered = false;
+  cudaStream_t stream = nullptr;             // every batch owns its stream: batches of one device overlap
+  cudaEvent_t t0 = nullptr, t1 = nullptr;    // stopwatch (paladin_gpu_batch_timer_*)
 };
 
 namespace {
@@ -411,6 +413,9 @@ void free_batch( paladin_gpu_batch* b ) {
     if ( s.e0 ) cudaEventDestroy( s.e0 );
     if ( s.e1 ) cudaEventDestroy( s.e1 );
   }
+  if ( b->t0 ) cudaEventDestroy( b->t0 );
+  if ( b->t1 ) cudaEventDestroy( b->t1 );
+  if ( b->stream ) cudaStreamDestroy( b->stream );
   delete b;
 }
 
@@ -675,7 +680,13 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
     cudaEventCreate( &s.e0 );
     cudaEventCreate( &s.e1 );
   }
-  cudaStream_t st = c.stream;
+  cudaEventCreate( &b->t0 );
+  cudaEventCreate( &b->t1 );
+  if ( cudaStreamCreateWithFlags( &b->stream, cudaStreamNonBlocking ) != cudaSuccess ) {
+    free_batch( b );
+    return fail( PALADIN_GPU_ECUDA, "cudaStreamCreate failed" );
+  }
+  cudaStream_t st = b->stream;
   auto H2D = [&]( void* d, const void* h, size_t bytes ) {
     if ( rc == PALADIN_GPU_OK && bytes ) {
       cudaError_t e = cudaMemcpyAsync( d, h, bytes, cudaMemcpyHostToDevice, st );
@@ -706,23 +717,23 @@ int paladin_gpu_batch_upload( paladin_gpu_batch* b, const int* coo_i, const int*
   if ( !b ) return fail( PALADIN_GPU_EINVAL, "null batch" );
   if ( b->total_nnz > 0 && ( !coo_i || !coo_j || !coo_v ) ) return fail( PALADIN_GPU_EINVAL, "null COO arrays" );
   DeviceCtx& c = g_ctx[b->device];
-  std::lock_guard<std::mutex> lk( c.mu );
+  (void)c;
   PB_CUDA( cudaSetDevice( b->device ) );
   if ( b->total_nnz > 0 ) {
-    PB_CUDA( cudaMemcpyAsync( b->d_coo_i, coo_i, sizeof( int ) * b->total_nnz, cudaMemcpyHostToDevice, c.stream ) );
-    PB_CUDA( cudaMemcpyAsync( b->d_coo_j, coo_j, sizeof( int ) * b->total_nnz, cudaMemcpyHostToDevice, c.stream ) );
-    PB_CUDA( cudaMemcpyAsync( b->d_coo_v, coo_v, sizeof( double ) * b->total_nnz, cudaMemcpyHostToDevice, c.stream ) );
+    PB_CUDA( cudaMemcpyAsync( b->d_coo_i, coo_i, sizeof( int ) * b->total_nnz, cudaMemcpyHostToDevice, b->stream ) );
+    PB_CUDA( cudaMemcpyAsync( b->d_coo_j, coo_j, sizeof( int ) * b->total_nnz, cudaMemcpyHostToDevice, b->stream ) );
+    PB_CUDA( cudaMemcpyAsync( b->d_coo_v, coo_v, sizeof( double ) * b->total_nnz, cudaMemcpyHostToDevice, b->stream ) );
   }
-  PB_CUDA( cudaStreamSynchronize( c.stream ) );
+  PB_CUDA( cudaStreamSynchronize( b->stream ) );
   return PALADIN_GPU_OK;
 }
 
 int paladin_gpu_batch_scatter( paladin_gpu_batch* b ) {
   if ( !b ) return fail( PALADIN_GPU_EINVAL, "null batch" );
   DeviceCtx& c = g_ctx[b->device];
-  std::lock_guard<std::mutex> lk( c.mu );
+  (void)c;
   PB_CUDA( cudaSetDevice( b->device ) );
-  cudaStream_t st = c.stream;
+  cudaStream_t st = b->stream;
   stage_reset( b, PALADIN_GPU_STAGE_SCATTER );
   if ( b->count == 0 ) {
     b->scattered = true;
@@ -767,17 +778,17 @@ int paladin_gpu_batch_upload_dense( paladin_gpu_batch* b, const double* dense ) 
   if ( !b ) return fail( PALADIN_GPU_EINVAL, "null batch" );
   if ( b->total_nn > 0 && !dense ) return fail( PALADIN_GPU_EINVAL, "null dense array" );
   DeviceCtx& c = g_ctx[b->device];
-  std::lock_guard<std::mutex> lk( c.mu );
+  (void)c;
   PB_CUDA( cudaSetDevice( b->device ) );
   int64_t src = 0;
   for ( int k = 0; k < b->count; ++k ) {
     const int64_t nn = (int64_t)b->n[k] * b->n[k];
     if ( nn )
-      PB_CUDA( cudaMemcpyAsync( b->d_A + b->a_off[k], dense + src, sizeof( double ) * nn, cudaMemcpyHostToDevice, c.stream ) );
+      PB_CUDA( cudaMemcpyAsync( b->d_A + b->a_off[k], dense + src, sizeof( double ) * nn, cudaMemcpyHostToDevice, b->stream ) );
     src += nn;
   }
-  PB_CUDA( cudaMemsetAsync( b->d_info, 0, sizeof( int ) * std::max( b->count, 1 ), c.stream ) );
-  PB_CUDA( cudaStreamSynchronize( c.stream ) );
+  PB_CUDA( cudaMemsetAsync( b->d_info, 0, sizeof( int ) * std::max( b->count, 1 ), b->stream ) );
+  PB_CUDA( cudaStreamSynchronize( b->stream ) );
   std::fill( b->flags.begin(), b->flags.end(), 0 );
   b->scattered = true;
   return PALADIN_GPU_OK;
@@ -786,11 +797,11 @@ int paladin_gpu_batch_upload_dense( paladin_gpu_batch* b, const double* dense ) 
 int paladin_gpu_batch_get_dense( paladin_gpu_batch* b, int k, double* out ) {
   if ( !b || k < 0 || k >= b->count || !out ) return fail( PALADIN_GPU_EINVAL, "bad arguments" );
   DeviceCtx& c = g_ctx[b->device];
-  std::lock_guard<std::mutex> lk( c.mu );
+  (void)c;
   PB_CUDA( cudaSetDevice( b->device ) );
   const int64_t nn = (int64_t)b->n[k] * b->n[k];
-  if ( nn ) PB_CUDA( cudaMemcpyAsync( out, b->d_A + b->a_off[k], sizeof( double ) * nn, cudaMemcpyDeviceToHost, c.stream ) );
-  PB_CUDA( cudaStreamSynchronize( c.stream ) );
+  if ( nn ) PB_CUDA( cudaMemcpyAsync( out, b->d_A + b->a_off[k], sizeof( double ) * nn, cudaMemcpyDeviceToHost, b->stream ) );
+  PB_CUDA( cudaStreamSynchronize( b->stream ) );
   return PALADIN_GPU_OK;
 }
 
@@ -798,9 +809,9 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
   if ( !b ) return fail( PALADIN_GPU_EINVAL, "null batch" );
   if ( !b->scattered ) return fail( PALADIN_GPU_EINVAL, "solve called before scatter / upload_dense" );
   DeviceCtx& c = g_ctx[b->device];
-  std::lock_guard<std::mutex> lk( c.mu );
+  (void)c;
   PB_CUDA( cudaSetDevice( b->device ) );
-  cudaStream_t st = c.stream;
+  cudaStream_t st = b->stream;
   for ( int s = 1; s < PALADIN_GPU_NUM_STAGES; ++s ) stage_reset( b, s );
   BatchView bv = batch_view( b );
   const bool wantvr = b->jobvr == 'V';
@@ -907,9 +918,9 @@ int paladin_gpu_batch_download( paladin_gpu_batch* b, double* wr, double* wi, do
   if ( !b ) return fail( PALADIN_GPU_EINVAL, "null batch" );
   (void)vl;
   DeviceCtx& c = g_ctx[b->device];
-  std::lock_guard<std::mutex> lk( c.mu );
+  (void)c;
   PB_CUDA( cudaSetDevice( b->device ) );
-  cudaStream_t st = c.stream;
+  cudaStream_t st = b->stream;
   if ( wr && b->total_n ) PB_CUDA( cudaMemcpyAsync( wr, b->d_wr, sizeof( double ) * b->total_n, cudaMemcpyDeviceToHost, st ) );
   if ( wi && b->total_n ) PB_CUDA( cudaMemcpyAsync( wi, b->d_wi, sizeof( double ) * b->total_n, cudaMemcpyDeviceToHost, st ) );
   if ( info && b->count ) PB_CUDA( cudaMemcpyAsync( info, b->d_info, sizeof( int ) * b->count, cudaMemcpyDeviceToHost, st ) );
@@ -942,7 +953,7 @@ int paladin_gpu_batch_download( paladin_gpu_batch* b, double* wr, double* wi, do
 int paladin_gpu_batch_stage_ms( paladin_gpu_batch* b, float* ms, int* launches ) {
   if ( !b || !ms ) return fail( PALADIN_GPU_EINVAL, "bad arguments" );
   DeviceCtx& c = g_ctx[b->device];
-  std::lock_guard<std::mutex> lk( c.mu );
+  (void)c;
   PB_CUDA( cudaSetDevice( b->device ) );
   for ( int s = 0; s < PALADIN_GPU_NUM_STAGES; ++s ) {
     ms[s] = 0.0f;
@@ -958,16 +969,30 @@ int paladin_gpu_batch_stage_ms( paladin_gpu_batch* b, float* ms, int* launches )
 int paladin_gpu_batch_phase_cycles( paladin_gpu_batch* b, long long* cycles ) {
   if ( !b || !cycles ) return fail( PALADIN_GPU_EINVAL, "bad arguments" );
   DeviceCtx& c = g_ctx[b->device];
-  std::lock_guard<std::mutex> lk( c.mu );
+  (void)c;
   PB_CUDA( cudaSetDevice( b->device ) );
   PB_CUDA( cudaMemcpy( cycles, b->d_stats, sizeof( long long ) * kNumTicks, cudaMemcpyDeviceToHost ) );
   return PALADIN_GPU_OK;
 }
 
+int paladin_gpu_batch_timer_start( paladin_gpu_batch* b ) {
+  if ( !b ) return fail( PALADIN_GPU_EINVAL, "null batch" );
+  PB_CUDA( cudaSetDevice( b->device ) );
+  PB_CUDA( cudaEventRecord( b->t0, b->stream ) );
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_batch_timer_stop( paladin_gpu_batch* b, float* ms ) {
+  if ( !b || !ms ) return fail( PALADIN_GPU_EINVAL, "bad arguments" );
+  PB_CUDA( cudaSetDevice( b->device ) );
+  PB_CUDA( cudaEventRecord( b->t1, b->stream ) );
+  PB_CUDA( cudaEventSynchronize( b->t1 ) );
+  PB_CUDA( cudaEventElapsedTime( ms, b->t0, b->t1 ) );
+  return PALADIN_GPU_OK;
+}
+
 int paladin_gpu_batch_destroy( paladin_gpu_batch* b ) {
   if ( !b ) return PALADIN_GPU_OK;
-  DeviceCtx& c = g_ctx[b->device];
-  std::lock_guard<std::mutex> lk( c.mu );
   free_batch( b );
   return PALADIN_GPU_OK;
 }
@@ -986,10 +1011,8 @@ int paladin_gpu_geev_batch( int device, int count, const int* n, const int64_t* 
   if ( rc == PALADIN_GPU_OK ) rc = paladin_gpu_batch_solve( b );
   if ( rc == PALADIN_GPU_OK ) {
     // results straight into the caller's per-matrix buffers
-    DeviceCtx& c = g_ctx[device];
-    std::lock_guard<std::mutex> lk( c.mu );
     cudaSetDevice( device );
-    cudaStream_t st = c.stream;
+    cudaStream_t st = b->stream;
     cudaError_t e = cudaMemcpyAsync( info, b->d_info, sizeof( int ) * count, cudaMemcpyDeviceToHost, st );
     for ( int k = 0; k < count && e == cudaSuccess; ++k ) {
       const int nk = b->n[k];
