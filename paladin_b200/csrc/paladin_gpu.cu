@@ -160,9 +160,10 @@ __global__ void __launch_bounds__( kGenericThreads ) geev_cta_kernel( BatchView 
 constexpr int kMidThreads = 256;
 constexpr int kNumTicks = 16;
 
-__host__ __device__ inline pb::MsqrCfg mid_cfg() { return pb::MsqrCfg{ 8, 49, 48, 256, 2 }; }
+__host__ __device__ inline pb::MsqrCfg mid_cfg() { return pb::MsqrCfg{ 8, pb::kStripW, pb::kStripW - 1, 128, 2, 32 }; }
 
 constexpr int kMidMaxFusedN = 1024;  // warp-level kernels keep a matrix column in 32 * MAXCH registers per warp
+constexpr int kMidMaxBigN = 4608;    // streaming variants: 6 n + 64 doubles of shared memory
 
 // per-matrix state handed from stage to stage (global memory)
 struct MidMeta {
@@ -177,8 +178,9 @@ struct MidArgs {
   MidMeta* meta;
   long long* stats;
   int* counter;    // work queue head of the persistent vectors kernel
-  double* xwork;   // slots of n_max^2 doubles for the triangular eigenvector factor
+  double* xwork;   // slots of xn_max^2 doubles for the triangular eigenvector factor
   size_t xslot;    // doubles per slot
+  int xn_max;      // largest order a slot can hold (larger matrices use the in-place path)
 };
 
 __device__ __forceinline__ void mid_pointers( const BatchView& bv, int id, int n, double*& A, double*& V, double*& wr, double*& wi,
@@ -236,13 +238,21 @@ __global__ void __launch_bounds__( pb::kHessThreads, ( MAXCH == 16 ? 2 : 1 ) ) m
     sc.cscale = 1.0;
   } else {
     g.tick( pb::kTickBalance );
-    if constexpr ( MAXCH > 0 ) pb::hess_fused<MAXCH>( n, ilo, ihi, A, n, tau, smem );
-    else pb::gehd2( g, n, ilo, ihi, A, n, tau, dw + 2 * n );
+    if constexpr ( MAXCH > 0 ) {
+      pb::hess_fused<MAXCH>( n, ilo, ihi, A, n, tau, smem );
+    } else {
+      if ( n <= kMidMaxBigN ) pb::hess_fused_big( n, ilo, ihi, A, n, tau, smem );
+      else pb::gehd2( g, n, ilo, ihi, A, n, tau, dw + 2 * n );
+    }
     __syncthreads();
     g.tick( pb::kTickHess );
     if ( a.bv.wantvr ) {
-      if constexpr ( MAXCH > 0 ) pb::form_q<MAXCH>( n, ilo, ihi, A, n, tau, V, n );
-      else pb::orghr( g, n, ilo, ihi, A, n, tau, V, n );
+      if constexpr ( MAXCH > 0 ) {
+        pb::form_q<MAXCH>( n, ilo, ihi, A, n, tau, V, n );
+      } else {
+        if ( n <= kMidMaxBigN ) pb::form_q_big( n, ilo, ihi, A, n, tau, V, n, smem );
+        else pb::orghr( g, n, ilo, ihi, A, n, tau, V, n );
+      }
     }
     __syncthreads();
     g.tick( pb::kTickOrghr );
@@ -268,7 +278,7 @@ inline size_t qr_smem_bytes() {
   return sizeof( double ) * pb::msqr_work_doubles( c, c.W | 1, c.tl | 1 ) + sizeof( int ) * ( 3 * pb::kMsMaxBulges + 8 );
 }
 
-__global__ void __launch_bounds__( kMidThreads ) mid_qr_kernel( MidArgs a ) {
+__global__ void __launch_bounds__( kMidThreads, ( pb::kStripW <= 41 ? 2 : 1 ) ) mid_qr_kernel( MidArgs a ) {
   extern __shared__ double smem[];
   __shared__ double red[64];
   __shared__ long long lstats[kNumTicks];
@@ -335,14 +345,15 @@ __global__ void __launch_bounds__( pb::kVecThreads ) mid_vec_kernel( MidArgs a )
     mid_pointers( a.bv, id, n, A, V, wr, wi, dw, iw );
     double* scale = dw + n;
     double* cnorm = dw + 2 * n;
-    if ( n <= kMidMaxFusedN ) {
+    if ( n <= a.xn_max ) {
       pb::vecs_solve( n, A, n, X, n, cnorm );
       g.tick( pb::kTickTrevc );
       pb::vecs_gemm( n, V, n, X, n, A, n, smem );   // T is dead once every solve of this matrix finished
       __syncthreads();
       g.tick( pb::kTickVecGemm );
       if ( n <= 512 ) pb::vecs_finish<16>( n, m.ilo, m.ihi, scale, wi, A, n, V, n, perm );
-      else pb::vecs_finish<32>( n, m.ilo, m.ihi, scale, wi, A, n, V, n, perm );
+      else if ( n <= kMidMaxFusedN ) pb::vecs_finish<32>( n, m.ilo, m.ihi, scale, wi, A, n, V, n, perm );
+      else pb::vecs_finish_big( n, m.ilo, m.ihi, scale, wi, A, n, V, n, perm );
       __syncthreads();
       g.tick( pb::kTickBak );
     } else {
@@ -391,7 +402,7 @@ struct paladin_gpu_batch {
   int* d_counter = nullptr;
   double* d_xwork = nullptr;
   size_t xslot = 0;
-  int xslots = 0;
+  int xslots = 0, xn_max = 0;
   std::vector<Group> groups;
   StageTimer st[PALADIN_GPU_NUM_STAGES];
   bool scattered = false;
@@ -657,18 +668,14 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
         nmid += g.count;
         nmax = std::max( nmax, g.nmax );
       }
-    if ( jobvr == 'V' && nmid > 0 && nmax <= kMidMaxFusedN ) {
-      b->xslots = std::min( nmid, 2 * c.sm_count );
+    if ( jobvr == 'V' && nmid > 0 ) {
+      // one slot holds the triangular factor of the largest matrix; at most two resident CTAs per SM, at most
+      // 24 GB in total (fewer slots for very large matrices)
+      b->xn_max = nmax;
       b->xslot = (size_t)nmax * nmax + 528;
-      A( dev_alloc( &b->d_xwork, b->xslot * b->xslots ) );
-    } else if ( jobvr == 'V' && nmid > 0 ) {
-      // matrices beyond the warp-level kernels' reach use the in-place path: no slots needed, but sizes <= 1024
-      // in the same batch still need them
-      int nmax_fused = 0;
-      for ( int k = 0; k < count; ++k )
-        if ( n[k] > kSmallMax && n[k] <= kMidMaxFusedN ) nmax_fused = std::max( nmax_fused, n[k] );
-      b->xslots = std::min( nmid, 2 * c.sm_count );
-      b->xslot = (size_t)std::max( nmax_fused, 1 ) * std::max( nmax_fused, 1 ) + 528;
+      const size_t budget = (size_t)24 << 30;
+      const int by_mem = (int)std::max<size_t>( 1, budget / ( b->xslot * sizeof( double ) ) );
+      b->xslots = std::max( 1, std::min( std::min( nmid, 2 * c.sm_count ), by_mem ) );
       A( dev_alloc( &b->d_xwork, b->xslot * b->xslots ) );
     }
   }
@@ -853,6 +860,7 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
       ma.counter = b->d_counter;
       ma.xwork = b->d_xwork;
       ma.xslot = b->xslot;
+      ma.xn_max = b->xn_max;
       PB_CUDA( cudaMemsetAsync( b->d_stats, 0, sizeof( long long ) * kNumTicks, st ) );
       PB_CUDA( cudaMemsetAsync( b->d_counter, 0, sizeof( int ), st ) );
       const size_t s2 = qr_smem_bytes(), s3 = vec_smem_bytes( g.nmax );
@@ -875,7 +883,9 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
         int launches = 0;
         if ( nbig > 0 ) {
           MidArgs m0 = ma;
-          mid_prep_kernel<0><<<nbig, pb::kHessThreads, 64 * sizeof( double ), st>>>( m0 );
+          const size_t sbig = sizeof( double ) * pb::hess_big_smem_doubles( std::min( g.nmax, kMidMaxBigN ) );
+          PB_CUDA( cudaFuncSetAttribute( mid_prep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbig ) );
+          mid_prep_kernel<0><<<nbig, pb::kHessThreads, sbig, st>>>( m0 );
           ++launches;
         }
         if ( nmid > nbig ) {

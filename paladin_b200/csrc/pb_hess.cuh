@@ -264,6 +264,182 @@ __device__ void form_q( int n, int ilo, int ihi, const double* __restrict__ A, i
   }
 }
 
+// ---- any n (n <= ~4700: 6n + 64 doubles of shared memory): the same single-sweep reduction with the row
+// accumulators of A v in shared memory (atomicAdd) instead of registers, row chunks walked eight at a time ------
+__host__ __device__ inline size_t hess_big_smem_doubles( int n ) { return (size_t)6 * n + 64; }
+
+__device__ inline void hess_fused_big( int n, int ilo, int ihi, double* A, int lda, double* tau, double* sm ) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* vprev = sm;
+  double* ypp = sm + n;
+  double* vcur = sm + 2 * n;
+  double* zpp = sm + 3 * n;
+  double* ycur = sm + 4 * n;
+  double* zcur = sm + 5 * n;
+  double* red = sm + 6 * n;
+  const int nrow = ihi + 1;
+  const int nch = ( nrow + 31 ) >> 5;
+  for ( int r = tid; r < n; r += kHessThreads ) {
+    vprev[r] = 0.0;
+    ypp[r] = 0.0;
+    zpp[r] = 0.0;
+    vcur[r] = 0.0;
+    ycur[r] = 0.0;
+  }
+  for ( int j = tid; j < n; j += kHessThreads )
+    if ( j < ilo || j >= ihi ) tau[j] = 0.0;
+  __syncthreads();
+  bool have_prev = false;
+  for ( int j = ilo; j <= ihi - 1; ++j ) {
+    if ( have_prev ) {
+      const double zj = zpp[j];
+      for ( int r = tid; r < nrow; r += kHessThreads ) A[r + (size_t)j * lda] -= vprev[r] * zj + ypp[r];
+    }
+    __syncthreads();
+    double tj = 0.0, beta;
+    {
+      const double alpha = A[( j + 1 ) + (size_t)j * lda];
+      double mx = 0.0;
+      for ( int r = j + 2 + tid; r <= ihi; r += kHessThreads ) mx = fmax( mx, fabs( A[r + (size_t)j * lda] ) );
+      mx = cta_max( mx, red );
+      beta = alpha;
+      double sc = 0.0;
+      if ( mx != 0.0 ) {
+        double ss = 0.0;
+        for ( int r = j + 2 + tid; r <= ihi; r += kHessThreads ) {
+          const double x = A[r + (size_t)j * lda] / mx;
+          ss += x * x;
+        }
+        double xnorm = mx * sqrt( cta_sum( ss, red ) );
+        double al = alpha;
+        beta = -dsign( dlapy2( al, xnorm ), al );
+        const double safmin = kSafmin / kEps;
+        int knt = 0;
+        double pre = 1.0;
+        if ( fabs( beta ) < safmin ) {
+          const double rsafmn = 1.0 / safmin;
+          do {
+            ++knt;
+            pre *= rsafmn;
+            xnorm *= rsafmn;
+            beta *= rsafmn;
+            al *= rsafmn;
+          } while ( fabs( beta ) < safmin && knt < 20 );
+          beta = -dsign( dlapy2( al, xnorm ), al );
+        }
+        tj = ( beta - al ) / beta;
+        sc = pre / ( al - beta );
+        for ( int q = 0; q < knt; ++q ) beta *= safmin;
+      }
+      __syncthreads();
+      for ( int r = tid; r < n; r += kHessThreads ) {
+        double v = 0.0;
+        if ( r == j + 1 ) v = 1.0;
+        else if ( r >= j + 2 && r <= ihi ) {
+          v = A[r + (size_t)j * lda] * sc;
+          A[r + (size_t)j * lda] = v;
+        }
+        vcur[r] = v;
+      }
+      if ( tid == 0 ) {
+        A[( j + 1 ) + (size_t)j * lda] = beta;
+        tau[j] = tj;
+      }
+    }
+    __syncthreads();
+    for ( int c = j + 1 + warp; c < n; c += kHessWarps ) {
+      double* col = A + (size_t)c * lda;
+      const double zc = zpp[c], vpc = vprev[c];
+      const double vcc = ( c <= ihi ) ? vcur[c] : 0.0;
+      double zsum = 0.0;
+      for ( int kb = 0; kb < nch; kb += 8 ) {
+        double a[8];
+#pragma unroll
+        for ( int u = 0; u < 8; ++u ) a[u] = __ldcg( col + imin( lane + 32 * ( kb + u ), nrow - 1 ) );
+#pragma unroll
+        for ( int u = 0; u < 8; ++u ) {
+          const int r = lane + 32 * ( kb + u );
+          const int rc = imin( r, nrow - 1 );
+          const bool ok = r < nrow;
+          const double x = a[u] - ( vprev[rc] * zc + ypp[rc] * vpc );
+          a[u] = x;
+          if ( ok && vcc != 0.0 ) atomicAdd( ycur + r, x * vcc );
+          zsum += ok ? vcur[rc] * x : 0.0;
+        }
+        if ( have_prev ) {
+#pragma unroll
+          for ( int u = 0; u < 8; ++u ) {
+            const int r = lane + 32 * ( kb + u );
+            if ( r < nrow ) col[r] = a[u];
+          }
+        }
+      }
+      zsum = warp_sum( zsum );
+      if ( lane == 0 ) zcur[c] = zsum;
+    }
+    __syncthreads();
+    double av = 0.0;
+    for ( int r = tid; r < nrow; r += kHessThreads ) av += vcur[r] * ycur[r];
+    const double alpha2 = cta_sum( av, red );
+    const double half = 0.5 * tj * tj * alpha2;
+    __syncthreads();
+    for ( int r = tid; r < n; r += kHessThreads ) {
+      const double v = vcur[r];
+      vprev[r] = v;
+      ypp[r] = ( r < nrow ) ? tj * ycur[r] - half * v : 0.0;
+      zpp[r] = ( r > j ) ? tj * zcur[r] - half * v : 0.0;
+      ycur[r] = 0.0;
+    }
+    have_prev = true;
+    __syncthreads();
+  }
+}
+
+// explicit Q for any n: one reflector per sweep, v in shared memory (sm: n doubles), two passes over each column
+// (dot product, update; the second pass hits L1/L2)
+__device__ inline void form_q_big( int n, int ilo, int ihi, const double* __restrict__ A, int lda, const double* __restrict__ tau,
+                                   double* __restrict__ Q, int ldq, double* sm ) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* vs = sm;
+  for ( int c = warp; c < n; c += kHessWarps )
+    for ( int r = lane; r < n; r += 32 ) Q[r + (size_t)c * ldq] = ( r == c ) ? 1.0 : 0.0;
+  __syncthreads();
+  for ( int j = ihi - 2; j >= ilo; --j ) {
+    const double tj = tau[j];
+    if ( tj == 0.0 ) continue;
+    for ( int r = j + 1 + tid; r <= ihi; r += kHessThreads ) vs[r] = ( r == j + 1 ) ? 1.0 : A[r + (size_t)j * lda];
+    __syncthreads();
+    const int nr = ihi - j;  // rows j+1..ihi
+    for ( int c = j + 1 + warp; c <= ihi; c += kHessWarps ) {
+      double* col = Q + (size_t)c * ldq + ( j + 1 );
+      const double* v = vs + ( j + 1 );
+      double w = 0.0;
+      for ( int r0 = 0; r0 < nr; r0 += 256 ) {
+        double q[8];
+#pragma unroll
+        for ( int u = 0; u < 8; ++u ) q[u] = col[imin( r0 + lane + 32 * u, nr - 1 )];
+#pragma unroll
+        for ( int u = 0; u < 8; ++u ) {
+          const int r = r0 + lane + 32 * u;
+          w += ( r < nr ) ? v[imin( r, nr - 1 )] * q[u] : 0.0;
+        }
+      }
+      w = warp_sum( w ) * tj;
+      for ( int r0 = 0; r0 < nr; r0 += 256 ) {
+        double q[8];
+#pragma unroll
+        for ( int u = 0; u < 8; ++u ) q[u] = col[imin( r0 + lane + 32 * u, nr - 1 )];
+#pragma unroll
+        for ( int u = 0; u < 8; ++u ) {
+          const int r = r0 + lane + 32 * u;
+          if ( r < nr ) col[r] = q[u] - w * v[r];
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 }  // namespace pb
 
 #endif  // __CUDACC__

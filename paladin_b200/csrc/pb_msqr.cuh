@@ -42,6 +42,7 @@ struct MsqrCfg {
   int ws_small;  // active blocks of order <= ws_small are finished inside the window (<= W)
   int tl;        // lines per strip tile
   int nchains;   // chains (of nb bulges) per sweep
+  int nshift;    // shifts computed per sweep (<= 2*nb*nchains); chains beyond nshift/(2 nb) reuse them cyclically
 };
 
 // on-chip work space (shared memory on the device)
@@ -306,7 +307,21 @@ PB_D int ms_small_solve( const G& g, bool wantt, bool wantz, int n, int l, int i
     }
     g.sync();
   }
-  const int info = lahqr( g, acc, acc, m, 0, m - 1, wk.Hw, ldw, wr + l, wi + l, 0, m - 1, wk.U, ldw );
+  int info = 0;
+  bool warp_done = false;
+#if defined( __CUDACC__ )
+  if constexpr ( G::kIsCta ) {
+    // a block of <= 48 rows keeps one warp busy at best: warp 0 runs it with warp-level barriers only
+    if ( ( threadIdx.x >> 5 ) == 0 ) {
+      const int r = lahqr( WarpGroup(), acc, acc, m, 0, m - 1, wk.Hw, ldw, wr + l, wi + l, 0, m - 1, wk.U, ldw );
+      if ( threadIdx.x == 0 ) wk.ibuf[3 * kMsMaxBulges + 4] = r;
+    }
+    __syncthreads();
+    info = wk.ibuf[3 * kMsMaxBulges + 4];
+    warp_done = true;
+  }
+#endif
+  if ( !warp_done ) info = lahqr( g, acc, acc, m, 0, m - 1, wk.Hw, ldw, wr + l, wi + l, 0, m - 1, wk.U, ldw );
   g.sync();
   g.tick( kTickMsSmall );
   if ( info != 0 ) return l + info;
@@ -434,9 +449,19 @@ __device__ inline bool ms_window_steps_fast( int l, int i, int ws, int we, int n
 #pragma unroll
   for ( int b = 0; b < 8; ++b ) kp[b] = ( b < nbulges ) ? kpos_s[b] : ( i + 1 );
   bool progressed = false;
+  // steady-state window (all 8 bulges tightly packed at the window start, window strictly inside the block): every
+  // bulge moves in every macro-step for exactly W - 1 - 3*8 steps, no scheduling logic is needed
+  bool lockstep = ( nbulges == 8 ) && ( we - ws + 1 == W ) && ( i > we );
+#pragma unroll
+  for ( int b = 0; b < 8; ++b ) lockstep = lockstep && ( kp[b] == ws + 1 + 3 * ( 7 - b ) );
+  int lock_left = W - 1 - 3 * 8;
 #define PB_W( r, c ) Hw[( ( r ) - ws ) + ( ( c ) - ws ) * ldw]
   for ( ;; ) {
     unsigned moving = 0;
+    if ( lockstep ) {
+      moving = ( lock_left > 0 ) ? 0xffu : 0u;
+      lock_left -= 1;
+    } else {
     bool ahead_moves = false, have_ahead = false;
     int ahead_pos = 0;
 #pragma unroll
@@ -453,6 +478,7 @@ __device__ inline bool ms_window_steps_fast( int l, int i, int ws, int we, int n
         ahead_moves = mv;
       }
       if ( mv ) moving |= 1u << b;
+    }
     }
     if ( moving == 0 ) break;
     progressed = true;
@@ -706,7 +732,7 @@ PB_D void ms_chase_chain( const G& g, bool wantt, bool wantz, int n, int l, int 
 #if defined( __CUDACC__ )
     if constexpr ( G::kIsCta ) {
       // device fast path: lines in registers, warps independent (pb_strips.cuh); needs the compile-time window order
-      if ( cfg.W == kStripW && cfg.tl >= 32 * ( g.size() >> 5 ) ) {
+      if ( cfg.W == kStripW && cfg.tl >= 16 * ( g.size() >> 5 ) ) {
         ms_strips_regs( wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, nbulges, kfirst, kcount, wk.refl, wk.tile,
                         wk.ldt );
       } else {
@@ -763,12 +789,17 @@ PB_D int hqr_multishift( const G& g, bool wantt, bool wantz, int n, int ilo, int
     if ( t == 0 ) wk.ibuf[3 * kMsMaxBulges + 1] += 1;
     nodefl += 1;
     // the shift block is factored inside the U buffer, hence ns <= W
-    const int nshift_want = imin( imin( 2 * cfg.nb * cfg.nchains, cfg.W & ~1 ), ( ( m - 1 ) / 3 ) * 2 );
+    const int nshift_cfg = imin( cfg.nshift > 0 ? cfg.nshift : 2 * cfg.nb * cfg.nchains, 2 * cfg.nb * cfg.nchains );
+    const int nshift_want = imin( imin( nshift_cfg, cfg.W & ~1 ), ( ( m - 1 ) / 3 ) * 2 );
     const int ns = ms_compute_shifts( g, ktop, kbot, H, ldh, imax( 2, nshift_want & ~1 ), ( nodefl % 6 ) == 0, wk );
     PB_CHECK_UNIFORM( g, ns, "ns" );
     g.tick( kTickMsShifts );
-    for ( int s0 = 0; s0 < ns; s0 += 2 * cfg.nb ) {
+    // chains of nb bulges; with fewer computed shifts than chains * 2 nb the set is reused cyclically
+    const int nchain_run = ( nshift_cfg < 2 * cfg.nb * cfg.nchains && ns >= 2 * cfg.nb ) ? cfg.nchains : ( ns + 2 * cfg.nb - 1 ) / ( 2 * cfg.nb );
+    for ( int ch = 0; ch < nchain_run; ++ch ) {
+      const int s0 = ( ch * 2 * cfg.nb ) % ns;
       const int nbul = imin( cfg.nb, ( ns - s0 ) / 2 );
+      if ( nbul <= 0 ) continue;
       ms_chase_chain( g, wantt, wantz, n, ktop, kbot, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, nbul, wk.sr + s0, wk.si + s0 );
     }
     // a sweep that exposes a split anywhere in the block resets the exceptional-shift counter

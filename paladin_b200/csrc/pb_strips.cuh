@@ -37,9 +37,15 @@ namespace pb {
   PB_STRIP_STEP( B + 0 ) PB_STRIP_STEP( B + 1 ) PB_STRIP_STEP( B + 2 ) PB_STRIP_STEP( B + 3 ) \
   PB_STRIP_STEP( B + 4 ) PB_STRIP_STEP( B + 5 ) PB_STRIP_STEP( B + 6 ) PB_STRIP_STEP( B + 7 )
 
-// W = 49: positions 0..48, steps may start at 0..47 (x[49], x[50] are padding that only a final 2-row
-// reflector with w3 = t3 = 0 touches)
-constexpr int kStripW = 49;
+// Window order of the device path (compile time: the line registers are indexed statically). PB_WINDOW = 49 keeps
+// one CTA per SM (49 + 2 doubles of line state per thread); 41 leaves room for two CTAs per SM.
+// positions 0..W-1, steps may start at 0..W-2 (x[W], x[W+1] are padding that only a final 2-row reflector with
+// w3 = t3 = 0 touches)
+#ifndef PB_WINDOW
+#define PB_WINDOW 49
+#endif
+constexpr int kStripW = PB_WINDOW;
+static_assert( kStripW == 41 || kStripW == 49, "the step table below is written for W = 41 or 49" );
 
 __device__ __forceinline__ void strip_apply_line( double ( &x )[kStripW + 2], int nbulges, const int* kfirst, const int* kcount,
                                                   int ws, const double* refl ) {
@@ -54,7 +60,9 @@ __device__ __forceinline__ void strip_apply_line( double ( &x )[kStripW + 2], in
       PB_STRIP_STEPS_8( 16 )
       PB_STRIP_STEPS_8( 24 )
       PB_STRIP_STEPS_8( 32 )
+#if PB_WINDOW == 49
       PB_STRIP_STEPS_8( 40 )
+#endif
       default:
         break;
     }
@@ -66,7 +74,7 @@ __device__ __forceinline__ void strip_apply_line( double ( &x )[kStripW + 2], in
 // macro-step: the NB reflectors of one macro-step touch disjoint positions, so a thread has NB independent
 // 5-FMA groups in flight instead of one serial chain (the bulge-major order of the generic path is equivalent:
 // a step of bulge b only depends on EARLIER macro-steps of the bulges ahead of it).
-constexpr int kStripNB = 8, kStripD = 24;
+constexpr int kStripNB = 8, kStripD = kStripW - 1 - 3 * kStripNB;
 
 __device__ __forceinline__ bool strip_window_is_regular( int nbulges, int wlen, int ws, const int* kfirst, const int* kcount ) {
   if ( nbulges != kStripNB || wlen != kStripW ) return false;
@@ -94,7 +102,7 @@ __device__ __forceinline__ void strip_apply_line_regular( double ( &x )[kStripW 
 }
 
 // Every off-window strip of one window move. refl / kfirst / kcount live in shared memory; tile is the
-// W x ldt shared tile (ldt >= 32 * warps + 1, odd); the caller synchronises the CTA before and after.
+// W x ldt shared tile (ldt >= 16 * warps + 1, odd); the caller synchronises the CTA before and after.
 __device__ inline void ms_strips_regs( bool wantt, bool wantz, int n, int l, int i, int ws, int wlen, double* __restrict__ H,
                                        int ldh, int iloz, int ihiz, double* __restrict__ Z, int ldz, int nbulges,
                                        const int* kfirst, const int* kcount, const double* refl, double* tile, int ldt ) {
@@ -103,7 +111,7 @@ __device__ inline void ms_strips_regs( bool wantt, bool wantz, int n, int l, int
   const int i1 = wantt ? 0 : l, i2 = wantt ? n - 1 : i;
   const int nright = imax( 0, i2 - we ), nup = imax( 0, ws - i1 ), nz = wantz ? ( ihiz - iloz + 1 ) : 0;
   const int bright = ( nright + 31 ) >> 5, bup = ( nup + 31 ) >> 5, bz = ( nz + 31 ) >> 5;
-  double* wt = tile + 32 * warp;  // this warp's 32-line slice: element (pos, line) at pos*ldt + line
+  double* wt = tile + 16 * warp;  // this warp's 16-line slice: element (pos, line) at pos*ldt + line
   const bool regular = strip_window_is_regular( nbulges, wlen, ws, kfirst, kcount );
   for ( int bt = warp; bt < bright + bup + bz; bt += nwarps ) {
     double x[kStripW + 2];
@@ -113,40 +121,51 @@ __device__ inline void ms_strips_regs( bool wantt, bool wantz, int n, int l, int
       // ---- 32 columns of the right strip ----
       const int j0 = we + 1 + 32 * bt;
       const int nl = imin( 32, i2 - j0 + 1 );
-      // coalesced reads (lanes along rows), 8 columns in flight, transposed into the slice
-      for ( int c0 = 0; c0 < nl; c0 += 8 ) {
-        double v0[8], v1[8];
+      // coalesced reads (lanes along rows), 8 columns in flight, transposed through the slice in two halves of 16
+      // columns: lanes 16h..16h+15 pick up their column after half h
 #pragma unroll
-        for ( int u = 0; u < 8; ++u ) {
-          const int cc = imin( c0 + u, nl - 1 );
-          const double* col = H + (size_t)( j0 + cc ) * ldh + ws;
-          v0[u] = col[imin( lane, wlen - 1 )];
-          v1[u] = col[imin( 32 + lane, wlen - 1 )];
-        }
+      for ( int h = 0; h < 2; ++h ) {
+        for ( int c0 = 16 * h; c0 < imin( nl, 16 * h + 16 ); c0 += 8 ) {
+          double v0[8], v1[8];
 #pragma unroll
-        for ( int u = 0; u < 8; ++u ) {
-          if ( c0 + u < nl ) {
-            if ( lane < wlen ) wt[lane * ldt + c0 + u] = v0[u];
-            if ( 32 + lane < wlen ) wt[( 32 + lane ) * ldt + c0 + u] = v1[u];
+          for ( int u = 0; u < 8; ++u ) {
+            const int cc = imin( c0 + u, nl - 1 );
+            const double* col = H + (size_t)( j0 + cc ) * ldh + ws;
+            v0[u] = col[imin( lane, wlen - 1 )];
+            v1[u] = col[imin( 32 + lane, wlen - 1 )];
+          }
+#pragma unroll
+          for ( int u = 0; u < 8; ++u ) {
+            if ( c0 + u < nl ) {
+              if ( lane < wlen ) wt[lane * ldt + c0 + u - 16 * h] = v0[u];
+              if ( 32 + lane < wlen ) wt[( 32 + lane ) * ldt + c0 + u - 16 * h] = v1[u];
+            }
           }
         }
-      }
-      __syncwarp();
+        __syncwarp();
+        if ( ( lane >> 4 ) == h ) {
 #pragma unroll
-      for ( int p = 0; p < kStripW; ++p ) x[p] = ( p < wlen ) ? wt[p * ldt + lane] : 0.0;
-      __syncwarp();
+          for ( int p = 0; p < kStripW; ++p ) x[p] = ( p < wlen ) ? wt[p * ldt + ( lane & 15 )] : 0.0;
+        }
+        __syncwarp();
+      }
       if ( regular ) strip_apply_line_regular( x, refl );
       else strip_apply_line( x, nbulges, kfirst, kcount, ws, refl );
 #pragma unroll
-      for ( int p = 0; p < kStripW; ++p )
-        if ( p < wlen ) wt[p * ldt + lane] = x[p];
-      __syncwarp();
-      for ( int cc = 0; cc < nl; ++cc ) {
-        double* col = H + (size_t)( j0 + cc ) * ldh + ws;
-        if ( lane < wlen ) col[lane] = wt[lane * ldt + cc];
-        if ( 32 + lane < wlen ) col[32 + lane] = wt[( 32 + lane ) * ldt + cc];
+      for ( int h = 0; h < 2; ++h ) {
+        if ( ( lane >> 4 ) == h ) {
+#pragma unroll
+          for ( int p = 0; p < kStripW; ++p )
+            if ( p < wlen ) wt[p * ldt + ( lane & 15 )] = x[p];
+        }
+        __syncwarp();
+        for ( int cc = 16 * h; cc < imin( nl, 16 * h + 16 ); ++cc ) {
+          double* col = H + (size_t)( j0 + cc ) * ldh + ws;
+          if ( lane < wlen ) col[lane] = wt[lane * ldt + cc - 16 * h];
+          if ( 32 + lane < wlen ) col[32 + lane] = wt[( 32 + lane ) * ldt + cc - 16 * h];
+        }
+        __syncwarp();
       }
-      __syncwarp();
     } else {
       // ---- 32 rows of the strip above the window or of Z ----
       double* M;

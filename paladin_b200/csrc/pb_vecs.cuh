@@ -266,6 +266,97 @@ __device__ void vecs_finish( int n, int ilo, int ihi, const double* scale, const
   }
 }
 
+// any n: the same un-balance + normalise with the column(s) streamed from memory in several passes (L2 hits)
+__device__ inline void vecs_finish_big( int n, int ilo, int ihi, const double* scale, const double* wi, const double* __restrict__ C,
+                                        int ldc, double* __restrict__ V, int ldv, int* perm ) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if ( tid == 0 ) {
+    for ( int r = 0; r < n; ++r ) perm[r] = r;
+    for ( int ii = 0; ii < n; ++ii ) {
+      int i = ii;
+      if ( i >= ilo && i <= ihi ) continue;
+      if ( i < ilo ) i = ilo - 1 - ii;
+      const int k = (int)scale[i];
+      if ( k == i ) continue;
+      const int tmp = perm[i];
+      perm[i] = perm[k];
+      perm[k] = tmp;
+    }
+  }
+  __syncthreads();
+  int blk = 0;
+  int c = 0;
+  while ( c < n ) {
+    const bool pair = ( wi[c] > 0.0 && c + 1 < n );
+    if ( ( blk % kVecWarps ) == warp ) {
+      const double* ca = C + (size_t)c * ldc;
+      const double* cb = C + (size_t)( pair ? c + 1 : c ) * ldc;
+      auto rowscale = [&]( int src ) { return ( src >= ilo && src <= ihi && ilo != ihi ) ? scale[src] : 1.0; };
+      double mx = 0.0;
+      for ( int r = lane; r < n; r += 32 ) {
+        const int src = perm[r];
+        const double s = rowscale( src );
+        mx = fmax( mx, fabs( ca[src] * s ) );
+        if ( pair ) mx = fmax( mx, fabs( cb[src] * s ) );
+      }
+      mx = warp_max( mx );
+      double scl = 0.0;
+      if ( mx > 0.0 && mx <= DBL_MAX ) {
+        const double inv = 1.0 / mx;
+        double ss = 0.0;
+        for ( int r = lane; r < n; r += 32 ) {
+          const int src = perm[r];
+          const double s = rowscale( src ) * inv;
+          const double p = ca[src] * s, q = pair ? cb[src] * s : 0.0;
+          ss += p * p + q * q;
+        }
+        ss = warp_sum( ss );
+        scl = 1.0 / ( mx * sqrt( ss ) );
+      }
+      double cs = 1.0, sn = 0.0;
+      int cand = n;
+      if ( pair ) {
+        double best = -1.0;
+        int bestr = n;
+        for ( int r = lane; r < n; r += 32 ) {
+          const int src = perm[r];
+          const double s = rowscale( src );
+          const double a = ca[src] * s * scl, b = cb[src] * s * scl;
+          const double w = a * a + b * b;
+          if ( w > best ) {
+            best = w;
+            bestr = r;
+          }
+        }
+        const double gbest = warp_max( best );
+        cand = ( best == gbest ) ? bestr : n;
+#pragma unroll
+        for ( int o = 16; o > 0; o >>= 1 ) cand = ::min( cand, __shfl_xor_sync( 0xffffffffu, cand, o ) );
+        if ( cand < n ) {
+          const int src = perm[cand];
+          const double s = rowscale( src );
+          double rr;
+          dlartg( ca[src] * s * scl, cb[src] * s * scl, cs, sn, rr );
+        }
+      }
+      for ( int r = lane; r < n; r += 32 ) {
+        const int src = perm[r];
+        const double s = rowscale( src );
+        const double a = ca[src] * s * scl;
+        if ( pair ) {
+          const double b = cb[src] * s * scl;
+          V[r + (size_t)c * ldv] = cs * a + sn * b;
+          V[r + (size_t)( c + 1 ) * ldv] = ( r == cand ) ? 0.0 : cs * b - sn * a;
+        } else {
+          V[r + (size_t)c * ldv] = a;
+        }
+      }
+    }
+    c += pair ? 2 : 1;
+    blk += 1;
+  }
+}
+
 }  // namespace pb
 
 #endif  // __CUDACC__
