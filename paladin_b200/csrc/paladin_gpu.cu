@@ -278,7 +278,7 @@ inline size_t qr_smem_bytes() {
   return sizeof( double ) * pb::msqr_work_doubles( c, c.W | 1, c.tl | 1 ) + sizeof( int ) * ( 3 * pb::kMsMaxBulges + 8 );
 }
 
-__global__ void __launch_bounds__( kMidThreads, ( pb::kStripW <= 41 ? 2 : 1 ) ) mid_qr_kernel( MidArgs a ) {
+__global__ void __launch_bounds__( kMidThreads, 2 ) mid_qr_kernel( MidArgs a ) {
   extern __shared__ double smem[];
   __shared__ double red[64];
   __shared__ long long lstats[kNumTicks];

@@ -732,9 +732,10 @@ PB_D void ms_chase_chain( const G& g, bool wantt, bool wantz, int n, int l, int 
 #if defined( __CUDACC__ )
     if constexpr ( G::kIsCta ) {
       // device fast path: lines in registers, warps independent (pb_strips.cuh); needs the compile-time window order
-      if ( cfg.W == kStripW && cfg.tl >= 16 * ( g.size() >> 5 ) ) {
-        ms_strips_regs( wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, nbulges, kfirst, kcount, wk.refl, wk.tile,
-                        wk.ldt );
+      // steady-state windows only (about five in six); the others take the tile path below
+      if ( cfg.W == kStripW && cfg.nb == kStripNB && cfg.tl >= 16 * ( g.size() >> 5 ) &&
+           strip_window_is_regular( nbulges, wlen, ws, kfirst, kcount ) ) {
+        ms_strips_regs( wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, wk.refl, wk.tile, wk.ldt );
       } else {
         ms_update_strips( g, wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, nbulges, (const double*)nullptr );
       }

@@ -101,73 +101,124 @@ __device__ __forceinline__ void strip_apply_line_regular( double ( &x )[kStripW 
   }
 }
 
+// Streaming form of the steady-state update: at macro-step t only positions 1+t .. 24+t are live (the trailing bulge
+// has left everything below, the leading one has not reached anything above), so a line never needs more than
+// 3*NB + kStripPF positions in registers: position 24+PF+1+t is fetched while macro-step t runs and position 1+t is
+// stored right after it. Positions 0 and W-1 are never touched by a steady-state window and are neither loaded
+// nor stored. LD(p) / ST(p, v) access position p of the thread's line.
+constexpr int kStripPF = 10;
+
+template <class LD, class ST>
+__device__ __forceinline__ void strip_regular_stream( LD ld, ST st, const double* refl ) {
+  constexpr int kTop = 3 * kStripNB;  // highest position touched by macro-step 0
+  double x[kStripW + 2];
+#pragma unroll
+  for ( int p = 1; p <= kTop + kStripPF; ++p )
+    if ( p <= kStripW - 2 ) x[p] = ld( p );
+#pragma unroll
+  for ( int t = 0; t < kStripD; ++t ) {
+    const int pn = kTop + kStripPF + 1 + t;
+    if ( pn <= kStripW - 2 ) x[pn] = ld( pn );
+#pragma unroll
+    for ( int b = 0; b < kStripNB; ++b ) {
+      const int P = 1 + 3 * ( kStripNB - 1 - b ) + t;
+      const double2* rf = reinterpret_cast<const double2*>( refl + ( (size_t)b * kStripW + t ) * 6 );
+      const double2 w = rf[0], tt = rf[1];
+      const double t3 = reinterpret_cast<const double*>( rf )[4];
+      const double sum = x[P] + w.x * x[P + 1] + w.y * x[P + 2];
+      x[P] -= sum * tt.x;
+      x[P + 1] -= sum * tt.y;
+      x[P + 2] -= sum * t3;
+    }
+    st( 1 + t, x[1 + t] );
+  }
+#pragma unroll
+  for ( int p = 1 + kStripD; p <= kStripW - 2; ++p ) st( p, x[p] );
+}
+
 // Every off-window strip of one window move. refl / kfirst / kcount live in shared memory; tile is the
 // W x ldt shared tile (ldt >= 16 * warps + 1, odd); the caller synchronises the CTA before and after.
+__device__ __forceinline__ void prefetch_l2( const void* p ) { asm volatile( "prefetch.global.L2 [%0];" ::"l"( p ) ); }
+
 __device__ inline void ms_strips_regs( bool wantt, bool wantz, int n, int l, int i, int ws, int wlen, double* __restrict__ H,
-                                       int ldh, int iloz, int ihiz, double* __restrict__ Z, int ldz, int nbulges,
-                                       const int* kfirst, const int* kcount, const double* refl, double* tile, int ldt ) {
+                                       int ldh, int iloz, int ihiz, double* __restrict__ Z, int ldz, const double* refl,
+                                       double* tile, int ldt ) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int we = ws + wlen - 1;
   const int i1 = wantt ? 0 : l, i2 = wantt ? n - 1 : i;
   const int nright = imax( 0, i2 - we ), nup = imax( 0, ws - i1 ), nz = wantz ? ( ihiz - iloz + 1 ) : 0;
   const int bright = ( nright + 31 ) >> 5, bup = ( nup + 31 ) >> 5, bz = ( nz + 31 ) >> 5;
   double* wt = tile + 16 * warp;  // this warp's 16-line slice: element (pos, line) at pos*ldt + line
-  const bool regular = strip_window_is_regular( nbulges, wlen, ws, kfirst, kcount );
-  for ( int bt = warp; bt < bright + bup + bz; bt += nwarps ) {
-    double x[kStripW + 2];
-    x[kStripW] = 0.0;
-    x[kStripW + 1] = 0.0;
+  // L2 prefetch of a whole batch (issued one batch ahead: the register allocator sinks the line loads next to
+  // their first use, so the latency that is left to hide should be an L2 hit, not a DRAM access)
+  auto prefetch_batch = [&]( int bt ) {
+    if ( bt >= bright + bup + bz ) return;
     if ( bt < bright ) {
-      // ---- 32 columns of the right strip ----
       const int j0 = we + 1 + 32 * bt;
       const int nl = imin( 32, i2 - j0 + 1 );
-      // coalesced reads (lanes along rows), 8 columns in flight, transposed through the slice in two halves of 16
-      // columns: lanes 16h..16h+15 pick up their column after half h
+      if ( lane < nl ) {
+        const double* col = H + (size_t)( j0 + lane ) * ldh + ws;
 #pragma unroll
+        for ( int q = 0; q < kStripW; q += 4 ) prefetch_l2( col + q );  // 32-byte sectors
+      }
+    } else {
+      const double* M = ( bt < bright + bup ) ? H : Z;
+      const int ldm = ( bt < bright + bup ) ? ldh : ldz;
+      const int r0 = ( bt < bright + bup ) ? i1 + 32 * ( bt - bright ) : iloz + 32 * ( bt - bright - bup );
+      // one 256-byte row segment per position: four lanes cover it
+      const double* base = M + r0 + (size_t)ws * ldm;
+      for ( int p = 1 + ( lane >> 2 ); p <= kStripW - 2; p += 8 ) prefetch_l2( base + (size_t)p * ldm + 4 * ( lane & 3 ) * 2 );
+    }
+  };
+  prefetch_batch( warp );
+  for ( int bt = warp; bt < bright + bup + bz; bt += nwarps ) {
+    prefetch_batch( bt + nwarps );
+    if ( bt < bright ) {
+      // ---- 32 columns of the right strip: coalesced reads (lanes along rows), transposed through the slice in two
+      // halves of 16 columns; lanes 16h..16h+15 work on half h (the other lanes repeat the work of lane & 15 on the
+      // same shared data and simply do not write back)
+      const int j0 = we + 1 + 32 * bt;
+      const int nl = imin( 32, i2 - j0 + 1 );
       for ( int h = 0; h < 2; ++h ) {
-        for ( int c0 = 16 * h; c0 < imin( nl, 16 * h + 16 ); c0 += 8 ) {
+        const int cbeg = 16 * h, cend = imin( nl, 16 * h + 16 );
+        if ( cbeg >= cend ) break;
+        for ( int c0 = cbeg; c0 < cend; c0 += 8 ) {
           double v0[8], v1[8];
 #pragma unroll
           for ( int u = 0; u < 8; ++u ) {
             const int cc = imin( c0 + u, nl - 1 );
             const double* col = H + (size_t)( j0 + cc ) * ldh + ws;
-            v0[u] = col[imin( lane, wlen - 1 )];
-            v1[u] = col[imin( 32 + lane, wlen - 1 )];
+            v0[u] = col[lane];
+            v1[u] = col[imin( 32 + lane, kStripW - 1 )];
           }
 #pragma unroll
           for ( int u = 0; u < 8; ++u ) {
-            if ( c0 + u < nl ) {
-              if ( lane < wlen ) wt[lane * ldt + c0 + u - 16 * h] = v0[u];
-              if ( 32 + lane < wlen ) wt[( 32 + lane ) * ldt + c0 + u - 16 * h] = v1[u];
+            if ( c0 + u < cend ) {
+              wt[lane * ldt + c0 + u - cbeg] = v0[u];
+              if ( 32 + lane < kStripW ) wt[( 32 + lane ) * ldt + c0 + u - cbeg] = v1[u];
             }
           }
         }
         __syncwarp();
-        if ( ( lane >> 4 ) == h ) {
-#pragma unroll
-          for ( int p = 0; p < kStripW; ++p ) x[p] = ( p < wlen ) ? wt[p * ldt + ( lane & 15 )] : 0.0;
+        {
+          double* mine = wt + ( lane & 15 );
+          const bool owner = ( lane < 16 ) && ( cbeg + lane < cend );
+          strip_regular_stream( [&]( int p ) { return mine[p * ldt]; },
+                                [&]( int p, double v ) {
+                                  if ( owner ) mine[p * ldt] = v;
+                                },
+                                refl );
         }
         __syncwarp();
-      }
-      if ( regular ) strip_apply_line_regular( x, refl );
-      else strip_apply_line( x, nbulges, kfirst, kcount, ws, refl );
-#pragma unroll
-      for ( int h = 0; h < 2; ++h ) {
-        if ( ( lane >> 4 ) == h ) {
-#pragma unroll
-          for ( int p = 0; p < kStripW; ++p )
-            if ( p < wlen ) wt[p * ldt + ( lane & 15 )] = x[p];
-        }
-        __syncwarp();
-        for ( int cc = 16 * h; cc < imin( nl, 16 * h + 16 ); ++cc ) {
+        for ( int cc = cbeg; cc < cend; ++cc ) {
           double* col = H + (size_t)( j0 + cc ) * ldh + ws;
-          if ( lane < wlen ) col[lane] = wt[lane * ldt + cc - 16 * h];
-          if ( 32 + lane < wlen ) col[32 + lane] = wt[( 32 + lane ) * ldt + cc - 16 * h];
+          col[lane] = wt[lane * ldt + cc - cbeg];
+          if ( 32 + lane < kStripW ) col[32 + lane] = wt[( 32 + lane ) * ldt + cc - cbeg];
         }
         __syncwarp();
       }
     } else {
-      // ---- 32 rows of the strip above the window or of Z ----
+      // ---- 32 rows of the strip above the window or of Z: lane = row, every access is a contiguous 256-byte segment
       double* M;
       int ldm, r0, nl;
       if ( bt < bright + bup ) {
@@ -183,18 +234,12 @@ __device__ inline void ms_strips_regs( bool wantt, bool wantz, int n, int l, int
       }
       const int r = r0 + imin( lane, nl - 1 );
       double* row = M + r + (size_t)ws * ldm;
-#pragma unroll
-      for ( int p = 0; p < kStripW; ++p ) {
-        const double v = row[(size_t)imin( p, wlen - 1 ) * ldm];
-        x[p] = ( p < wlen ) ? v : 0.0;
-      }
-      if ( regular ) strip_apply_line_regular( x, refl );
-      else strip_apply_line( x, nbulges, kfirst, kcount, ws, refl );
-      if ( lane < nl ) {
-#pragma unroll
-        for ( int p = 0; p < kStripW; ++p )
-          if ( p < wlen ) row[(size_t)p * ldm] = x[p];
-      }
+      const bool owner = lane < nl;
+      strip_regular_stream( [&]( int p ) { return __ldcg( row + (size_t)p * ldm ); },
+                            [&]( int p, double v ) {
+                              if ( owner ) __stcg( row + (size_t)p * ldm, v );
+                            },
+                            refl );
     }
   }
 }
