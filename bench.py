@@ -321,16 +321,32 @@ def ours(args):
         phase_share = {k: round(v / tot, 4) for k, v in cyc.items() if v}
         peaks, peak_kind = measured_peaks()
         flops = (FLOPS_PER_N3_VEC if job == "V" else FLOPS_PER_N3_VAL) * n ** 3
-        # dominant kernel: the eigen-solve (everything but the scatter)
+        # dominant kernel: mid_qr_kernel (the QR iteration, one launch per step). Algorithmic work of that stage:
+        # 20 n^3 flops with Schur vectors / 6.67 n^3 values-only (SURVEY.md 2.1 stage table)
+        qr_ms = stage_acc.get("qr", 0.0) / args.steps
         solve_ms = sum(v for k, v in stage_acc.items() if k != "scatter") / args.steps
+        qr_flops = (20.0 if job == "V" else 6.67) * n ** 3
         fp64_peak = fp64_peak_tflops(dev)
-        achieved = B * flops / (solve_ms * 1e-3) / 1e12
-        roofline = {"bound": "tensor", "kernel": "eigen-solve kernels (all stages after the scatter)",
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "qr_traffic.json")
+        if os.path.exists(tpath) and n == 512 and job == "V":
+            tj = json.load(open(tpath))  # ncu --set full capture of the same kernel, scaled to this launch's matrix count
+            traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["matrices_per_launch"] * B
+        if qr_ms > 0:
+            achieved = B * qr_flops / (qr_ms * 1e-3) / 1e12
+            kernel_name = "mid_qr_kernel (windowed multishift QR, CTA per matrix)"
+        else:  # n <= 64: everything runs in the fused warp-per-matrix kernel
+            achieved = B * flops / (solve_ms * 1e-3) / 1e12
+            kernel_name = "geev_warp_kernel (all stages)"
+        roofline = {"bound": "tensor", "kernel": kernel_name,
                     "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                    "traffic": None,
-                    "peak_source": "FP64 cuBLAS DGEMM 6144^3 measured in this run (MEASURED_PEAKS.json has no FP64 "
+                    "traffic": traffic,
+                    "peak_source": "FP64 cuBLAS DGEMM 6144^3 measured in this run (DMMA path; MEASURED_PEAKS.json has no FP64 "
                                    "entry; its hbm_gbs=%.1f (%s) is the scatter denominator)" % (peaks["hbm_gbs"], peak_kind),
-                    "flops_per_unit": flops}
+                    "flops_per_unit": qr_flops if qr_ms > 0 else flops,
+                    "kernel_ms_per_launch": qr_ms if qr_ms > 0 else solve_ms,
+                    "whole_solve": {"flops_per_unit": flops, "achieved": B * flops / (solve_ms * 1e-3) / 1e12,
+                                    "frac": B * flops / (solve_ms * 1e-3) / 1e12 / fp64_peak}}
         scat_ms = stage_acc.get("scatter", 0.0) / args.steps
         scat_bytes = B * (16 * nn + 8 * nn)
         scatter = {"bound": "hbm", "achieved": scat_bytes / (scat_ms * 1e-3) / 1e9 if scat_ms > 0 else None,

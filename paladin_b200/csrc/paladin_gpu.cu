@@ -321,7 +321,7 @@ __global__ void __launch_bounds__( kMidThreads, 2 ) mid_qr_kernel( MidArgs a ) {
 // ---- stage 3: eigenvectors (persistent CTAs, one work slot each) -----------------------------------------
 inline size_t vec_smem_bytes( int nmax ) { return sizeof( double ) * pb::vecs_gemm_smem_doubles() + sizeof( int ) * nmax; }
 
-__global__ void __launch_bounds__( pb::kVecThreads ) mid_vec_kernel( MidArgs a ) {
+__global__ void __launch_bounds__( pb::kVecThreads, 2 ) mid_vec_kernel( MidArgs a ) {
   extern __shared__ double smem[];
   __shared__ double red[64];
   __shared__ long long lstats[kNumTicks];
