@@ -311,8 +311,8 @@ def ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t[0]) / args.steps
     e2e_value = world * B / (e2e_ms * 1e-3)
-    h2d = B * nn * 16
-    d2h = B * (2 * n * 8 + 4) + (B * nn * 8 if job == "V" else 0)
+    h2d = world * B * nn * 16                                                   # whole job, like `value`
+    d2h = world * (B * (2 * n * 8 + 4) + (B * nn * 8 if job == "V" else 0))
 
     if rank == 0:
         cyc = batch.phase_cycles()

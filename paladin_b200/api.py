@@ -158,14 +158,17 @@ class Batch:
     def solve(self):
         _check(lib().paladin_gpu_batch_solve(self._h))
 
-    def download(self, wr=None, wi=None, vr=None, info=None):
+    def download(self, wr=None, wi=None, vr=None, info=None, vl=None):
         wr = np.empty(self.total_n) if wr is None else wr
         wi = np.empty(self.total_n) if wi is None else wi
         info = np.empty(self.count, dtype=np.int32) if info is None else info
         if self.jobvr == "V" and vr is None:
             vr = np.empty(self.total_nn)
-        _check(lib().paladin_gpu_batch_download(self._h, _ptr(wr), _ptr(wi), None, _ptr(vr) if self.jobvr == "V" else None,
-                                                _ptr(info)))
+        if self.jobvl == "V" and vl is None:
+            vl = np.empty(self.total_nn)
+        _check(lib().paladin_gpu_batch_download(self._h, _ptr(wr), _ptr(wi), _ptr(vl) if self.jobvl == "V" else None,
+                                                _ptr(vr) if self.jobvr == "V" else None, _ptr(info)))
+        self.vl = vl  # left vectors of the last download (None unless jobvl == 'V')
         return wr, wi, vr, info
 
     def stage_ms(self):
@@ -215,8 +218,9 @@ def split_results(n, wr, wi, vr):
     return out
 
 
-def geev_batch(n, nnz_offsets, coo_i, coo_j, coo_v, jobvr="N", device=0):
-    """One-shot entry paladin_gpu_geev_batch with host buffers. Returns (list of (wr, wi, VR), info)."""
+def geev_batch(n, nnz_offsets, coo_i, coo_j, coo_v, jobvr="N", device=0, jobvl="N"):
+    """One-shot entry paladin_gpu_geev_batch with host buffers. Returns (list of (wr, wi, VR), info); with
+    jobvl='V' the list holds (wr, wi, VR, VL)."""
     n = np.ascontiguousarray(n, dtype=np.int32)
     off = np.ascontiguousarray(nnz_offsets, dtype=np.int64)
     coo_i = np.ascontiguousarray(coo_i, dtype=np.int32)
@@ -226,21 +230,27 @@ def geev_batch(n, nnz_offsets, coo_i, coo_j, coo_v, jobvr="N", device=0):
     wr = [np.zeros(int(k)) for k in n]
     wi = [np.zeros(int(k)) for k in n]
     vr = [np.zeros((int(k), int(k)), order="F") if jobvr == "V" else None for k in n]
+    vl = [np.zeros((int(k), int(k)), order="F") if jobvl == "V" else None for k in n]
     info = np.zeros(max(count, 1), dtype=np.int32)
     PP = _c_dbl_p * max(count, 1)
     pwr = PP(*[a.ctypes.data_as(_c_dbl_p) for a in wr])
     pwi = PP(*[a.ctypes.data_as(_c_dbl_p) for a in wi])
     pvr = PP(*[(a.ctypes.data_as(_c_dbl_p) if a is not None else None) for a in vr])
+    pvl = PP(*[(a.ctypes.data_as(_c_dbl_p) if a is not None else None) for a in vl])
     _check(lib().paladin_gpu_geev_batch(device, count, n.ctypes.data_as(_c_int_p), off.ctypes.data_as(_c_i64_p),
                                         coo_i.ctypes.data_as(_c_int_p), coo_j.ctypes.data_as(_c_int_p),
-                                        coo_v.ctypes.data_as(_c_dbl_p), b"N", jobvr.encode(), pwr, pwi, None,
-                                        pvr if jobvr == "V" else None, info.ctypes.data_as(_c_int_p)))
+                                        coo_v.ctypes.data_as(_c_dbl_p), jobvl.encode(), jobvr.encode(), pwr, pwi,
+                                        pvl if jobvl == "V" else None, pvr if jobvr == "V" else None,
+                                        info.ctypes.data_as(_c_int_p)))
+    if jobvl == "V":
+        return list(zip(wr, wi, vr, vl)), info[:count]
     return list(zip(wr, wi, vr)), info[:count]
 
 
-def dgeev(A, jobvr="V"):
+def dgeev(A, jobvr="V", jobvl="N"):
     """Single dense matrix through the Fortran-signature shim paladin_gpu_dgeev_ (query + solve, exactly the
-    two calls of reference src/paladin.hpp:247-254). Returns wr, wi, VR, info."""
+    two calls of reference src/paladin.hpp:247-254). Returns wr, wi, VR, info (and VL as a fifth value when
+    jobvl='V')."""
     A = np.array(A, dtype=np.float64, order="F")
     n = A.shape[0]
     ld = max(n, 1)
@@ -252,10 +262,12 @@ def dgeev(A, jobvr="V"):
     ci = lambda v: ctypes.byref(ctypes.c_int(v))
     dp = lambda a: a.ctypes.data_as(_c_dbl_p)
     f = lib().paladin_gpu_dgeev_
-    f(b"N", jobvr.encode(), ci(n), dp(A), ci(ld), dp(wr), dp(wi), dp(VL), ci(ld), dp(VR), ci(ld), dp(wk), ci(-1),
+    f(jobvl.encode(), jobvr.encode(), ci(n), dp(A), ci(ld), dp(wr), dp(wi), dp(VL), ci(ld), dp(VR), ci(ld), dp(wk), ci(-1),
       ctypes.byref(info))
     lwork = max(1, int(wk[0]))
     work = np.zeros(lwork)
-    f(b"N", jobvr.encode(), ci(n), dp(A), ci(ld), dp(wr), dp(wi), dp(VL), ci(ld), dp(VR), ci(ld), dp(work), ci(lwork),
+    f(jobvl.encode(), jobvr.encode(), ci(n), dp(A), ci(ld), dp(wr), dp(wi), dp(VL), ci(ld), dp(VR), ci(ld), dp(work), ci(lwork),
       ctypes.byref(info))
+    if jobvl == "V":
+        return wr[:n], wi[:n], VR[:n, :n], info.value, VL[:n, :n]
     return wr[:n], wi[:n], VR[:n, :n], info.value

@@ -99,12 +99,14 @@ struct BatchView {
   const int64_t* w_off;  // eigenvalue offsets (doubles)
   double* A;
   double* V;   // right vectors / Schur vectors (nullptr when not wanted)
+  double* VL;  // left vectors (nullptr when not wanted)
   double* wr;
   double* wi;
   int* info;
   double* dwork;  // 5 doubles per eigenvalue slot (generic path)
   int* iwork;     // 2 ints per eigenvalue slot + 2 per matrix
   int wantvr;
+  int wantvl;
 };
 
 // ---- warp-per-matrix path, n <= 64: the matrix (and Z) live in shared memory ---------------------
@@ -114,9 +116,14 @@ __global__ void __launch_bounds__( 32 ) geev_warp_kernel( BatchView bv, const in
   const int id = ids[blockIdx.x];
   const int n = bv.n[id];
   const int lane = threadIdx.x;
+  const size_t msz = (size_t)lds * nmax;
   double* As = smem;
-  double* Vs = As + (size_t)lds * nmax;
-  double* dw = bv.wantvr ? Vs + (size_t)lds * nmax : Vs;
+  double* p = As + msz;
+  double* Vs = p;
+  if ( bv.wantvr ) p += msz;
+  double* Ls = p;
+  if ( bv.wantvl ) p += msz;
+  double* dw = p;
   int* iw = reinterpret_cast<int*>( dw + 5 * nmax );
   const double* Ag = bv.A + bv.a_off[id];
   const int nn = n * n;
@@ -128,13 +135,22 @@ __global__ void __launch_bounds__( 32 ) geev_warp_kernel( BatchView bv, const in
   pb::WarpGroup g;
   double* wr = bv.wr + bv.w_off[id];
   double* wi = bv.wi + bv.w_off[id];
-  const int info = pb::geev_group( g, n, As, lds, wr, wi, bv.wantvr != 0, Vs, lds, dw, iw );
+  const int info = pb::geev_group( g, n, As, lds, wr, wi, bv.wantvl != 0, Ls, lds, bv.wantvr != 0, Vs, lds, dw, iw );
   __syncwarp();
-  if ( bv.wantvr && info == 0 ) {
-    double* Vg = bv.V + bv.a_off[id];
-    for ( int q = lane; q < nn; q += 32 ) {
-      const int c = q / n, r = q - c * n;
-      Vg[q] = Vs[r + c * lds];
+  if ( info == 0 ) {
+    if ( bv.wantvr ) {
+      double* Vg = bv.V + bv.a_off[id];
+      for ( int q = lane; q < nn; q += 32 ) {
+        const int c = q / n, r = q - c * n;
+        Vg[q] = Vs[r + c * lds];
+      }
+    }
+    if ( bv.wantvl ) {
+      double* Lg = bv.VL + bv.a_off[id];
+      for ( int q = lane; q < nn; q += 32 ) {
+        const int c = q / n, r = q - c * n;
+        Lg[q] = Ls[r + c * lds];
+      }
     }
   }
   if ( lane == 0 ) bv.info[id] = info;
@@ -148,11 +164,12 @@ __global__ void __launch_bounds__( kGenericThreads ) geev_cta_kernel( BatchView 
   pb::CtaGroup g{ red };
   double* A = bv.A + bv.a_off[id];
   double* V = bv.wantvr ? bv.V + bv.a_off[id] : nullptr;
+  double* VL = bv.wantvl ? bv.VL + bv.a_off[id] : nullptr;
   double* wr = bv.wr + bv.w_off[id];
   double* wi = bv.wi + bv.w_off[id];
   double* dw = bv.dwork + 5 * bv.w_off[id];
   int* iw = bv.iwork + 2 * bv.w_off[id] + 2 * id;
-  const int info = pb::geev_group( g, n, A, n, wr, wi, bv.wantvr != 0, V, n, dw, iw );
+  const int info = pb::geev_group( g, n, A, n, wr, wi, bv.wantvl != 0, VL, n, bv.wantvr != 0, V, n, dw, iw );
   if ( threadIdx.x == 0 ) bv.info[id] = info;
 }
 
@@ -186,7 +203,8 @@ struct MidArgs {
 __device__ __forceinline__ void mid_pointers( const BatchView& bv, int id, int n, double*& A, double*& V, double*& wr, double*& wi,
                                               double*& dw, int*& iw ) {
   A = bv.A + bv.a_off[id];
-  V = bv.wantvr ? bv.V + bv.a_off[id] : nullptr;
+  // Schur vectors are accumulated in the right-vector array when it exists, else in the left-vector array
+  V = bv.wantvr ? bv.V + bv.a_off[id] : ( bv.wantvl ? bv.VL + bv.a_off[id] : nullptr );
   wr = bv.wr + bv.w_off[id];
   wi = bv.wi + bv.w_off[id];
   dw = bv.dwork + 5 * bv.w_off[id];
@@ -246,7 +264,7 @@ __global__ void __launch_bounds__( pb::kHessThreads, ( MAXCH == 16 ? 2 : 1 ) ) m
     }
     __syncthreads();
     g.tick( pb::kTickHess );
-    if ( a.bv.wantvr ) {
+    if ( a.bv.wantvr || a.bv.wantvl ) {
       if constexpr ( MAXCH > 0 ) {
         pb::form_q<MAXCH>( n, ilo, ihi, A, n, tau, V, n );
       } else {
@@ -305,8 +323,8 @@ __global__ void __launch_bounds__( kMidThreads, 2 ) mid_qr_kernel( MidArgs a ) {
   double *A, *V, *wr, *wi, *dw;
   int* iw;
   mid_pointers( a.bv, id, n, A, V, wr, wi, dw, iw );
-  const bool wantvr = a.bv.wantvr != 0;
-  const int info = pb::hqr_multishift( g, wantvr, wantvr, n, m.ilo, m.ihi, A, n, wr, wi, 0, n - 1, V, n, c, wk );
+  const bool wantz = a.bv.wantvr != 0 || a.bv.wantvl != 0;
+  const int info = pb::hqr_multishift( g, wantz, wantz, n, m.ilo, m.ihi, A, n, wr, wi, 0, n - 1, V, n, c, wk );
   __syncthreads();
   g.tick( pb::kTickQr );
   pb::GeevScaling sc{ m.scalea != 0, m.anrm, m.cscale };
@@ -345,23 +363,59 @@ __global__ void __launch_bounds__( pb::kVecThreads, 2 ) mid_vec_kernel( MidArgs 
     mid_pointers( a.bv, id, n, A, V, wr, wi, dw, iw );
     double* scale = dw + n;
     double* cnorm = dw + 2 * n;
+    const bool wantvr = a.bv.wantvr != 0, wantvl = a.bv.wantvl != 0;
+    double* VLout = wantvl ? a.bv.VL + a.bv.a_off[id] : nullptr;
     if ( n <= a.xn_max ) {
-      pb::vecs_solve( n, A, n, X, n, cnorm );
+      // V = Schur vectors Z (right-vector array if it exists, else the left-vector array); T = A
+      double* Y = X + (size_t)n * n + 16;  // second half of the slot (both sides wanted)
+      if ( wantvr ) pb::vecs_solve( n, A, n, X, n, cnorm, false );
+      if ( wantvl ) pb::vecs_solve( n, A, n, wantvr ? Y : X, n, cnorm, true );
       g.tick( pb::kTickTrevc );
-      pb::vecs_gemm( n, V, n, X, n, A, n, smem );   // T is dead once every solve of this matrix finished
-      __syncthreads();
+      // T is dead once every solve of this matrix finished
+      if ( wantvr ) {
+        pb::vecs_gemm( n, V, n, X, n, A, n, smem, false );         // A <- Z X
+        __syncthreads();
+        if ( wantvl ) {
+          pb::vecs_gemm( n, V, n, Y, n, X, n, smem, true );        // X <- Z Y   (X is free again)
+          __syncthreads();
+        }
+      } else {
+        pb::vecs_gemm( n, V, n, X, n, A, n, smem, true );          // A <- Z Y
+        __syncthreads();
+      }
       g.tick( pb::kTickVecGemm );
-      if ( n <= 512 ) pb::vecs_finish<16>( n, m.ilo, m.ihi, scale, wi, A, n, V, n, perm );
-      else if ( n <= kMidMaxFusedN ) pb::vecs_finish<32>( n, m.ilo, m.ihi, scale, wi, A, n, V, n, perm );
-      else pb::vecs_finish_big( n, m.ilo, m.ihi, scale, wi, A, n, V, n, perm );
-      __syncthreads();
+      // Z is dead: the right vectors go where it was
+      for ( int side = 0; side < 2; ++side ) {
+        const bool left = side == 1;
+        if ( left ? !wantvl : !wantvr ) continue;
+        const double* src = ( left && wantvr ) ? X : A;
+        double* dst = left ? VLout : V;
+        if ( n <= 512 ) pb::vecs_finish<16>( n, m.ilo, m.ihi, scale, wi, src, n, dst, n, perm, left );
+        else if ( n <= kMidMaxFusedN ) pb::vecs_finish<32>( n, m.ilo, m.ihi, scale, wi, src, n, dst, n, perm, left );
+        else pb::vecs_finish_big( n, m.ilo, m.ihi, scale, wi, src, n, dst, n, perm, left );
+        __syncthreads();
+      }
       g.tick( pb::kTickBak );
     } else {
-      pb::trevc_right_inplace( g, n, A, n, V, n, cnorm, dw + 3 * n, dw + 4 * n );
+      // in-place path for matrices no work slot can hold
+      if ( wantvl && wantvr ) {
+        for ( size_t q = threadIdx.x; q < (size_t)n * n; q += blockDim.x ) VLout[q] = V[q];
+        __syncthreads();
+      }
+      double* Lz = wantvl ? VLout : nullptr;
+      if ( wantvl ) pb::trevc_left_inplace( g, n, A, n, Lz, n, cnorm, dw + 3 * n, dw + 4 * n );
+      if ( wantvr ) pb::trevc_right_inplace( g, n, A, n, V, n, cnorm, dw + 3 * n, dw + 4 * n );
       g.tick( pb::kTickTrevc );
-      pb::gebak_right( g, n, m.ilo, m.ihi, scale, n, V, n );
-      __syncthreads();
-      pb::normalize_vectors( g, n, wi, V, n );
+      if ( wantvl ) {
+        pb::gebak_vectors( g, true, n, m.ilo, m.ihi, scale, n, Lz, n );
+        __syncthreads();
+        pb::normalize_vectors( g, n, wi, Lz, n );
+      }
+      if ( wantvr ) {
+        pb::gebak_vectors( g, false, n, m.ilo, m.ihi, scale, n, V, n );
+        __syncthreads();
+        pb::normalize_vectors( g, n, wi, V, n );
+      }
       g.tick( pb::kTickBak );
     }
   }
@@ -389,7 +443,7 @@ struct paladin_gpu_batch {
   int64_t *d_nnz_off = nullptr, *d_a_off = nullptr, *d_w_off = nullptr;
   int *d_coo_i = nullptr, *d_coo_j = nullptr;
   double* d_coo_v = nullptr;
-  double *d_A = nullptr, *d_V = nullptr, *d_wr = nullptr, *d_wi = nullptr, *d_dwork = nullptr;
+  double *d_A = nullptr, *d_V = nullptr, *d_VL = nullptr, *d_wr = nullptr, *d_wi = nullptr, *d_dwork = nullptr;
   int *d_info = nullptr, *d_iwork = nullptr, *d_flags = nullptr, *d_ids = nullptr;
   pb::ScatterChunk* d_chunks = nullptr;
   int nchunks = 0;
@@ -417,7 +471,7 @@ void free_batch( paladin_gpu_batch* b ) {
   cudaSetDevice( b->device );
   cudaFree( b->d_n ); cudaFree( b->d_nnz_off ); cudaFree( b->d_a_off ); cudaFree( b->d_w_off );
   cudaFree( b->d_coo_i ); cudaFree( b->d_coo_j ); cudaFree( b->d_coo_v );
-  cudaFree( b->d_A ); cudaFree( b->d_V ); cudaFree( b->d_wr ); cudaFree( b->d_wi ); cudaFree( b->d_dwork );
+  cudaFree( b->d_A ); cudaFree( b->d_V ); cudaFree( b->d_VL ); cudaFree( b->d_wr ); cudaFree( b->d_wi ); cudaFree( b->d_dwork );
   cudaFree( b->d_stats ); cudaFree( b->d_meta ); cudaFree( b->d_counter ); cudaFree( b->d_xwork );
   cudaFree( b->d_info ); cudaFree( b->d_iwork ); cudaFree( b->d_flags ); cudaFree( b->d_ids ); cudaFree( b->d_chunks );
   for ( auto& s : b->st ) {
@@ -486,12 +540,14 @@ BatchView batch_view( paladin_gpu_batch* b ) {
   v.dwork = b->d_dwork;
   v.iwork = b->d_iwork;
   v.wantvr = ( b->jobvr == 'V' ) ? 1 : 0;
+  v.wantvl = ( b->jobvl == 'V' ) ? 1 : 0;
+  v.VL = b->d_VL;
   return v;
 }
 
-size_t warp_smem_bytes( int nmax, bool wantvr ) {
+size_t warp_smem_bytes( int nmax, int nvec ) {
   const int lds = nmax | 1;
-  return sizeof( double ) * ( (size_t)lds * nmax * ( wantvr ? 2 : 1 ) + 5 * (size_t)nmax ) + sizeof( int ) * ( 2 * (size_t)nmax + 2 );
+  return sizeof( double ) * ( (size_t)lds * nmax * ( 1 + nvec ) + 5 * (size_t)nmax ) + sizeof( int ) * ( 2 * (size_t)nmax + 2 );
 }
 
 }  // namespace
@@ -564,7 +620,6 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
   if ( count < 0 || ( count > 0 && ( !n || !nnz_offsets ) ) ) return fail( PALADIN_GPU_EINVAL, "bad count / null sizes" );
   if ( ( jobvl != 'N' && jobvl != 'V' ) || ( jobvr != 'N' && jobvr != 'V' ) )
     return fail( PALADIN_GPU_EINVAL, "jobvl/jobvr must be 'N' or 'V'" );
-  if ( jobvl == 'V' ) return fail( PALADIN_GPU_ENOTSUP, "left eigenvectors are not implemented yet" );
   PB_TRY( ensure_ctx( device ) );
   DeviceCtx& c = g_ctx[device];
   std::lock_guard<std::mutex> lk( c.mu );
@@ -649,6 +704,7 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
   A( dev_alloc( &b->d_coo_v, b->total_nnz + 2 ) );
   A( dev_alloc( &b->d_A, b->total_nn ) );
   if ( jobvr == 'V' ) A( dev_alloc( &b->d_V, b->total_nn ) );
+  if ( jobvl == 'V' ) A( dev_alloc( &b->d_VL, b->total_nn ) );
   A( dev_alloc( &b->d_wr, b->total_n ) );
   A( dev_alloc( &b->d_wi, b->total_n ) );
   A( dev_alloc( &b->d_dwork, 5 * b->total_n ) );
@@ -668,11 +724,11 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
         nmid += g.count;
         nmax = std::max( nmax, g.nmax );
       }
-    if ( jobvr == 'V' && nmid > 0 ) {
-      // one slot holds the triangular factor of the largest matrix; at most two resident CTAs per SM, at most
-      // 24 GB in total (fewer slots for very large matrices)
+    if ( ( jobvr == 'V' || jobvl == 'V' ) && nmid > 0 ) {
+      // one slot holds the triangular factor(s) of the largest matrix (two when both sides are wanted); at most two
+      // resident CTAs per SM, at most 24 GB in total (fewer slots for very large matrices)
       b->xn_max = nmax;
-      b->xslot = (size_t)nmax * nmax + 528;
+      b->xslot = ( (size_t)nmax * nmax + 16 ) * ( jobvr == 'V' && jobvl == 'V' ? 2 : 1 ) + 528;
       const size_t budget = (size_t)24 << 30;
       const int by_mem = (int)std::max<size_t>( 1, budget / ( b->xslot * sizeof( double ) ) );
       b->xslots = std::max( 1, std::min( std::min( nmid, 2 * c.sm_count ), by_mem ) );
@@ -822,6 +878,7 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
   for ( int s = 1; s < PALADIN_GPU_NUM_STAGES; ++s ) stage_reset( b, s );
   BatchView bv = batch_view( b );
   const bool wantvr = b->jobvr == 'V';
+  const bool wantvl = b->jobvl == 'V';
   bool any_bad = false;
   for ( int k = 0; k < b->count; ++k ) any_bad = any_bad || ( b->flags[k] & pb::kFlagBadIndex );
   std::vector<int> ids_filtered;
@@ -839,7 +896,7 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
     }
     if ( cnt == 0 ) continue;
     if ( g.kind == 0 ) {
-      const size_t smem = warp_smem_bytes( g.nmax, wantvr );
+      const size_t smem = warp_smem_bytes( g.nmax, ( wantvr ? 1 : 0 ) + ( wantvl ? 1 : 0 ) );
       if ( smem <= (size_t)c.max_smem_optin ) {
         PB_CUDA( cudaFuncSetAttribute( geev_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
         stage_begin( b, PALADIN_GPU_STAGE_SMALL, st );
@@ -905,7 +962,7 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
       stage_begin( b, PALADIN_GPU_STAGE_QR, st );
       mid_qr_kernel<<<cnt, kMidThreads, s2, st>>>( ma );
       stage_end( b, PALADIN_GPU_STAGE_QR, st, 1 );
-      if ( wantvr ) {
+      if ( wantvr || wantvl ) {
         stage_begin( b, PALADIN_GPU_STAGE_VECTORS, st );
         mid_vec_kernel<<<std::max( 1, std::min( cnt, b->xslots ) ), pb::kVecThreads, s3, st>>>( ma );
         stage_end( b, PALADIN_GPU_STAGE_VECTORS, st, 1 );
@@ -926,7 +983,6 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
 
 int paladin_gpu_batch_download( paladin_gpu_batch* b, double* wr, double* wi, double* vl, double* vr, int* info ) {
   if ( !b ) return fail( PALADIN_GPU_EINVAL, "null batch" );
-  (void)vl;
   DeviceCtx& c = g_ctx[b->device];
   (void)c;
   PB_CUDA( cudaSetDevice( b->device ) );
@@ -934,24 +990,27 @@ int paladin_gpu_batch_download( paladin_gpu_batch* b, double* wr, double* wi, do
   if ( wr && b->total_n ) PB_CUDA( cudaMemcpyAsync( wr, b->d_wr, sizeof( double ) * b->total_n, cudaMemcpyDeviceToHost, st ) );
   if ( wi && b->total_n ) PB_CUDA( cudaMemcpyAsync( wi, b->d_wi, sizeof( double ) * b->total_n, cudaMemcpyDeviceToHost, st ) );
   if ( info && b->count ) PB_CUDA( cudaMemcpyAsync( info, b->d_info, sizeof( int ) * b->count, cudaMemcpyDeviceToHost, st ) );
-  if ( vr && b->jobvr == 'V' ) {
-    // device matrices are padded to even length; the host layout is the plain concatenation
+  for ( int side = 0; side < 2; ++side ) {
+    double* host = side == 0 ? vr : vl;
+    const double* dev = side == 0 ? b->d_V : b->d_VL;
+    if ( !host || ( side == 0 ? b->jobvr : b->jobvl ) != 'V' ) continue;
+    // device matrices are padded and staggered; the host layout is the plain concatenation
     bool padded = false;
     for ( int k = 0; k < b->count; ++k ) padded = padded || ( b->n[k] & 1 ) || ( (int64_t)b->n[k] * b->n[k] >= 4096 );
     bool uniform = b->count > 0;
     for ( int k = 1; k < b->count; ++k ) uniform = uniform && ( b->n[k] == b->n[0] );
     if ( !padded ) {
-      if ( b->total_nn ) PB_CUDA( cudaMemcpyAsync( vr, b->d_V, sizeof( double ) * b->total_nn, cudaMemcpyDeviceToHost, st ) );
+      if ( b->total_nn ) PB_CUDA( cudaMemcpyAsync( host, dev, sizeof( double ) * b->total_nn, cudaMemcpyDeviceToHost, st ) );
     } else if ( uniform && b->n[0] > 0 ) {
       // equal sizes: one strided copy (device pitch = padded matrix, host pitch = packed matrix)
       const size_t nn = (size_t)b->n[0] * b->n[0];
-      PB_CUDA( cudaMemcpy2DAsync( vr, nn * sizeof( double ), b->d_V, (size_t)( b->a_off[1] - b->a_off[0] ) * sizeof( double ),
+      PB_CUDA( cudaMemcpy2DAsync( host, nn * sizeof( double ), dev, (size_t)( b->a_off[1] - b->a_off[0] ) * sizeof( double ),
                                   nn * sizeof( double ), b->count, cudaMemcpyDeviceToHost, st ) );
     } else {
       int64_t dst = 0;
       for ( int k = 0; k < b->count; ++k ) {
         const int64_t nn = (int64_t)b->n[k] * b->n[k];
-        if ( nn ) PB_CUDA( cudaMemcpyAsync( vr + dst, b->d_V + b->a_off[k], sizeof( double ) * nn, cudaMemcpyDeviceToHost, st ) );
+        if ( nn ) PB_CUDA( cudaMemcpyAsync( host + dst, dev + b->a_off[k], sizeof( double ) * nn, cudaMemcpyDeviceToHost, st ) );
         dst += nn;
       }
     }
@@ -1010,9 +1069,9 @@ int paladin_gpu_batch_destroy( paladin_gpu_batch* b ) {
 int paladin_gpu_geev_batch( int device, int count, const int* n, const int64_t* nnz_offsets, const int* coo_i,
                             const int* coo_j, const double* coo_v, char jobvl, char jobvr, double* const* wr,
                             double* const* wi, double* const* vl, double* const* vr, int* info ) {
-  (void)vl;
   if ( count < 0 || ( count > 0 && ( !wr || !wi || !info ) ) ) return fail( PALADIN_GPU_EINVAL, "null output arrays" );
   if ( jobvr == 'V' && count > 0 && !vr ) return fail( PALADIN_GPU_EINVAL, "vr is null but jobvr == 'V'" );
+  if ( jobvl == 'V' && count > 0 && !vl ) return fail( PALADIN_GPU_EINVAL, "vl is null but jobvl == 'V'" );
   paladin_gpu_batch* b = nullptr;
   PB_TRY( paladin_gpu_batch_create( device, count, n, nnz_offsets, jobvl, jobvr, &b ) );
   int rc = paladin_gpu_batch_upload( b, coo_i ? coo_i + nnz_offsets[0] : nullptr, coo_j ? coo_j + nnz_offsets[0] : nullptr,
@@ -1031,6 +1090,8 @@ int paladin_gpu_geev_batch( int device, int count, const int* n, const int64_t* 
       if ( e == cudaSuccess ) e = cudaMemcpyAsync( wi[k], b->d_wi + b->w_off[k], sizeof( double ) * nk, cudaMemcpyDeviceToHost, st );
       if ( e == cudaSuccess && jobvr == 'V' && vr[k] )
         e = cudaMemcpyAsync( vr[k], b->d_V + b->a_off[k], sizeof( double ) * nk * nk, cudaMemcpyDeviceToHost, st );
+      if ( e == cudaSuccess && jobvl == 'V' && vl[k] )
+        e = cudaMemcpyAsync( vl[k], b->d_VL + b->a_off[k], sizeof( double ) * nk * nk, cudaMemcpyDeviceToHost, st );
     }
     if ( e == cudaSuccess ) e = cudaStreamSynchronize( st );
     if ( e != cudaSuccess ) rc = fail( PALADIN_GPU_ECUDA, cudaGetErrorString( e ) );
@@ -1041,8 +1102,6 @@ int paladin_gpu_geev_batch( int device, int count, const int* n, const int64_t* 
 
 void paladin_gpu_dgeev_( const char* jobvl, const char* jobvr, int* n, double* a, int* lda, double* wr, double* wi,
                          double* vl, int* ldvl, double* vr, int* ldvr, double* work, int* lwork, int* info ) {
-  (void)vl;
-  (void)ldvl;
   if ( !info ) return;
   *info = 0;
   const char jl = jobvl ? ( *jobvl == 'v' ? 'V' : ( *jobvl == 'n' ? 'N' : *jobvl ) ) : '?';
@@ -1051,6 +1110,7 @@ void paladin_gpu_dgeev_( const char* jobvl, const char* jobvr, int* n, double* a
   if ( jr != 'N' && jr != 'V' ) { *info = -2; return; }
   if ( !n || *n < 0 ) { *info = -3; return; }
   if ( !lda || *lda < std::max( 1, *n ) ) { *info = -5; return; }
+  if ( !ldvl || *ldvl < 1 || ( jl == 'V' && *ldvl < *n ) ) { *info = -9; return; }
   if ( !ldvr || *ldvr < 1 || ( jr == 'V' && *ldvr < *n ) ) { *info = -11; return; }
   if ( lwork && *lwork == -1 ) {  // workspace query (reference src/paladin.hpp:247-249): the device path owns its workspace
     if ( work ) work[0] = 1.0;
@@ -1068,11 +1128,12 @@ void paladin_gpu_dgeev_( const char* jobvl, const char* jobvr, int* n, double* a
     *info = -1000 - rc;  // no CPU fallback: fail loudly
     return;
   }
-  std::vector<double> dense( (size_t)N * N ), w( 2 * (size_t)N ), V( jr == 'V' ? (size_t)N * N : 0 );
+  std::vector<double> dense( (size_t)N * N ), w( 2 * (size_t)N ), VR( jr == 'V' ? (size_t)N * N : 0 ), VL( jl == 'V' ? (size_t)N * N : 0 );
   for ( int c2 = 0; c2 < N; ++c2 ) std::memcpy( &dense[(size_t)c2 * N], a + (size_t)c2 * *lda, sizeof( double ) * N );
   rc = paladin_gpu_batch_upload_dense( b, dense.data() );
   if ( rc == PALADIN_GPU_OK ) rc = paladin_gpu_batch_solve( b );
-  if ( rc == PALADIN_GPU_OK ) rc = paladin_gpu_batch_download( b, w.data(), w.data() + N, nullptr, jr == 'V' ? V.data() : nullptr, info );
+  if ( rc == PALADIN_GPU_OK )
+    rc = paladin_gpu_batch_download( b, w.data(), w.data() + N, jl == 'V' ? VL.data() : nullptr, jr == 'V' ? VR.data() : nullptr, info );
   paladin_gpu_batch_destroy( b );
   if ( rc != PALADIN_GPU_OK ) {
     std::fprintf( stderr, "paladin_gpu_dgeev_: %s\n", paladin_gpu_last_error() );
@@ -1082,7 +1143,9 @@ void paladin_gpu_dgeev_( const char* jobvl, const char* jobvr, int* n, double* a
   std::memcpy( wr, w.data(), sizeof( double ) * N );
   std::memcpy( wi, w.data() + N, sizeof( double ) * N );
   if ( jr == 'V' && vr )
-    for ( int c2 = 0; c2 < N; ++c2 ) std::memcpy( vr + (size_t)c2 * *ldvr, &V[(size_t)c2 * N], sizeof( double ) * N );
+    for ( int c2 = 0; c2 < N; ++c2 ) std::memcpy( vr + (size_t)c2 * *ldvr, &VR[(size_t)c2 * N], sizeof( double ) * N );
+  if ( jl == 'V' && vl )
+    for ( int c2 = 0; c2 < N; ++c2 ) std::memcpy( vl + (size_t)c2 * *ldvl, &VL[(size_t)c2 * N], sizeof( double ) * N );
 }
 
 }  // extern "C"

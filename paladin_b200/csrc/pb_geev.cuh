@@ -145,9 +145,12 @@ PB_D void geev_isolated_eigenvalues( const G& g, int n, int ilo, int ihi, const 
   g.sync();
 }
 
+// wantvl / wantvr: left / right eigenvectors into VL / VR (n x n). With both, the Schur vectors are accumulated in VL
+// and copied to VR before the triangular solves, as dgeev does.
 template <class G, class QR = QrLahqr>
-PB_D int geev_group( const G& g, int n, double* A, int lda, double* wr, double* wi, bool wantvr, double* V, int ldv,
-                     double* dwork, int* iwork, const QR& qr = QR() ) {
+PB_D int geev_group( const G& g, int n, double* A, int lda, double* wr, double* wi, bool wantvl, double* VL, int ldvl, bool wantvr,
+                     double* VR, int ldvr, double* dwork, int* iwork, const QR& qr = QR() ) {
+  const int t = g.tid(), nt = g.size();
   if ( n == 0 ) return 0;
   double* tau = dwork;
   double* scale = dwork + n;
@@ -160,20 +163,36 @@ PB_D int geev_group( const G& g, int n, double* A, int lda, double* wr, double* 
   g.tick( kTickBalance );
   gehd2( g, n, ilo, ihi, A, lda, tau, cnorm );
   g.tick( kTickHess );
-  if ( wantvr ) orghr( g, n, ilo, ihi, A, lda, tau, V, ldv );
+  const bool wantz = wantvl || wantvr;
+  double* Z = wantvl ? VL : VR;
+  const int ldz = wantvl ? ldvl : ldvr;
+  if ( wantz ) orghr( g, n, ilo, ihi, A, lda, tau, Z, ldz );
   g.sync();
   g.tick( kTickOrghr );
   geev_isolated_eigenvalues( g, n, ilo, ihi, A, lda, wr, wi );
-  int info = qr( g, wantvr, wantvr, n, ilo, ihi, A, lda, wr, wi, V, ldv );
+  int info = qr( g, wantz, wantz, n, ilo, ihi, A, lda, wr, wi, Z, ldz );
   g.sync();
   g.tick( kTickQr );
-  if ( info == 0 && wantvr ) {
+  if ( info == 0 && wantz ) {
+    if ( wantvl && wantvr ) {
+      for ( int c = 0; c < n; ++c )
+        for ( int r = t; r < n; r += nt ) VR[r + (size_t)c * ldvr] = VL[r + (size_t)c * ldvl];
+      g.sync();
+    }
     // quasi-triangular T: the reflector storage below the first subdiagonal is never read again
-    trevc_right_inplace( g, n, A, lda, V, ldv, cnorm, xr, xi );
+    if ( wantvl ) trevc_left_inplace( g, n, A, lda, VL, ldvl, cnorm, xr, xi );
+    if ( wantvr ) trevc_right_inplace( g, n, A, lda, VR, ldvr, cnorm, xr, xi );
     g.tick( kTickTrevc );
-    gebak_right( g, n, ilo, ihi, scale, n, V, ldv );
-    g.sync();
-    normalize_vectors( g, n, wi, V, ldv );
+    if ( wantvl ) {
+      gebak_vectors( g, true, n, ilo, ihi, scale, n, VL, ldvl );
+      g.sync();
+      normalize_vectors( g, n, wi, VL, ldvl );
+    }
+    if ( wantvr ) {
+      gebak_vectors( g, false, n, ilo, ihi, scale, n, VR, ldvr );
+      g.sync();
+      normalize_vectors( g, n, wi, VR, ldvr );
+    }
     g.tick( kTickBak );
   }
   geev_unscale( g, n, sc, info, ilo, wr, wi );

@@ -519,16 +519,222 @@ PB_D void trevc_right_inplace( const G& g, int n, const double* T, int ldt, doub
 }
 
 // ------------------------------------------------------------------------------------------------
+// One LEFT eigenvector of T (the solve phase of dtrevc3, left side): forward substitution with the
+// transposed blocks, dot-product form (column segments of T, contiguous).
+// ki must be a real eigenvalue or the FIRST index of a pair (pair = ki, ki+1).
+// Real:    xr[ki..n-1] receives y (xr[ki] = 1 before scaling).
+// Complex: xr[ki..n-1], xi[ki..n-1] = real and imaginary parts (packed columns ki and ki+1).
+// ------------------------------------------------------------------------------------------------
+template <class G>
+PB_D void trevc_left_solve( const G& g, int n, const double* T, int ldt, int ki, bool cplx, const double* cnorm, double* xr,
+                            double* xi ) {
+  const int t = g.tid(), nt = g.size();
+  const double smlnum = kSafmin * ( (double)n / kUlp );
+  const double bignum = ( 1.0 - kUlp ) / smlnum;
+  const double wr = PB_T( ki, ki );
+  double wi = 0.0;
+  if ( cplx ) wi = sqrt( fabs( PB_T( ki, ki + 1 ) ) ) * sqrt( fabs( PB_T( ki + 1, ki ) ) );
+  const double smin = dmax( kUlp * ( fabs( wr ) + fabs( wi ) ), smlnum );
+  double vmax = 1.0, vcrit = bignum;
+
+  if ( !cplx ) {
+    for ( int k = ki + 1 + t; k < n; k += nt ) xr[k] = -PB_T( ki, k );
+    if ( t == 0 ) xr[ki] = 1.0;
+    g.sync();
+    int j = ki + 1;
+    while ( j < n ) {
+      const bool two = ( j < n - 1 && PB_T( j + 1, j ) != 0.0 );
+      const double beta = two ? dmax( cnorm[j], cnorm[j + 1] ) : cnorm[j];
+      if ( beta > vcrit ) {
+        const double rec = 1.0 / vmax;
+        for ( int k = ki + t; k < n; k += nt ) xr[k] *= rec;
+        vmax = 1.0;
+        vcrit = bignum;
+        g.sync();
+      }
+      double d0 = 0.0, d1 = 0.0;
+      for ( int k = ki + 1 + t; k < j; k += nt ) {
+        const double xk = xr[k];
+        d0 += PB_T( k, j ) * xk;
+        if ( two ) d1 += PB_T( k, j + 1 ) * xk;
+      }
+      d0 = g.sum( d0 );
+      if ( two ) d1 = g.sum( d1 );
+      double x[4], scale, xnorm;
+      if ( !two ) {
+        const double a[4] = { PB_T( j, j ), 0.0, 0.0, 0.0 };
+        const double b[4] = { xr[j] - d0, 0.0, 0.0, 0.0 };
+        dlaln2( false, 1, 1, smin, a, b, wr, 0.0, x, scale, xnorm );
+      } else {
+        const double a[4] = { PB_T( j, j ), PB_T( j + 1, j ), PB_T( j, j + 1 ), PB_T( j + 1, j + 1 ) };
+        const double b[4] = { xr[j] - d0, xr[j + 1] - d1, 0.0, 0.0 };
+        dlaln2( true, 2, 1, smin, a, b, wr, 0.0, x, scale, xnorm );
+      }
+      g.sync();
+      if ( scale != 1.0 )
+        for ( int k = ki + t; k < n; k += nt ) xr[k] *= scale;
+      g.sync();
+      if ( t == 0 ) {
+        xr[j] = x[0];
+        if ( two ) xr[j + 1] = x[1];
+      }
+      vmax = dmax( fabs( x[0] ), vmax );
+      if ( two ) vmax = dmax( fabs( x[1] ), vmax );
+      vcrit = bignum / vmax;
+      g.sync();
+      j += two ? 2 : 1;
+    }
+    return;
+  }
+
+  // complex pair (ki, ki+1), eigenvalue wr - i wi of T^T
+  {
+    double a1, b2;  // xr[ki], xi[ki+1]
+    if ( fabs( PB_T( ki, ki + 1 ) ) >= fabs( PB_T( ki + 1, ki ) ) ) {
+      a1 = wi / PB_T( ki, ki + 1 );
+      b2 = 1.0;
+    } else {
+      a1 = 1.0;
+      b2 = -wi / PB_T( ki + 1, ki );
+    }
+    for ( int k = ki + 2 + t; k < n; k += nt ) {
+      xr[k] = -a1 * PB_T( ki, k );
+      xi[k] = -b2 * PB_T( ki + 1, k );
+    }
+    if ( t == 0 ) {
+      xr[ki] = a1;
+      xi[ki + 1] = b2;
+      xr[ki + 1] = 0.0;
+      xi[ki] = 0.0;
+    }
+    g.sync();
+  }
+  int j = ki + 2;
+  while ( j < n ) {
+    const bool two = ( j < n - 1 && PB_T( j + 1, j ) != 0.0 );
+    const double beta = two ? dmax( cnorm[j], cnorm[j + 1] ) : cnorm[j];
+    if ( beta > vcrit ) {
+      const double rec = 1.0 / vmax;
+      for ( int k = ki + t; k < n; k += nt ) {
+        xr[k] *= rec;
+        xi[k] *= rec;
+      }
+      vmax = 1.0;
+      vcrit = bignum;
+      g.sync();
+    }
+    double dr0 = 0.0, di0 = 0.0, dr1 = 0.0, di1 = 0.0;
+    for ( int k = ki + 2 + t; k < j; k += nt ) {
+      const double t0 = PB_T( k, j ), xrk = xr[k], xik = xi[k];
+      dr0 += t0 * xrk;
+      di0 += t0 * xik;
+      if ( two ) {
+        const double t1 = PB_T( k, j + 1 );
+        dr1 += t1 * xrk;
+        di1 += t1 * xik;
+      }
+    }
+    dr0 = g.sum( dr0 );
+    di0 = g.sum( di0 );
+    if ( two ) {
+      dr1 = g.sum( dr1 );
+      di1 = g.sum( di1 );
+    }
+    double x[4], scale, xnorm;
+    if ( !two ) {
+      const double a[4] = { PB_T( j, j ), 0.0, 0.0, 0.0 };
+      const double b[4] = { xr[j] - dr0, 0.0, xi[j] - di0, 0.0 };
+      dlaln2( false, 1, 2, smin, a, b, wr, -wi, x, scale, xnorm );
+    } else {
+      const double a[4] = { PB_T( j, j ), PB_T( j + 1, j ), PB_T( j, j + 1 ), PB_T( j + 1, j + 1 ) };
+      const double b[4] = { xr[j] - dr0, xr[j + 1] - dr1, xi[j] - di0, xi[j + 1] - di1 };
+      dlaln2( true, 2, 2, smin, a, b, wr, -wi, x, scale, xnorm );
+    }
+    g.sync();
+    if ( scale != 1.0 )
+      for ( int k = ki + t; k < n; k += nt ) {
+        xr[k] *= scale;
+        xi[k] *= scale;
+      }
+    g.sync();
+    if ( t == 0 ) {
+      xr[j] = x[0];
+      xi[j] = x[2];
+      if ( two ) {
+        xr[j + 1] = x[1];
+        xi[j + 1] = x[3];
+      }
+    }
+    vmax = dmax( dmax( fabs( x[0] ), fabs( x[2] ) ), vmax );
+    if ( two ) vmax = dmax( dmax( fabs( x[1] ), fabs( x[3] ) ), vmax );
+    vcrit = bignum / vmax;
+    g.sync();
+    j += two ? 2 : 1;
+  }
+}
+
+// All left eigenvectors, back-transformed in place: on entry V = Z, on exit V(:,k) = real-packed left eigenvectors
+// of Z T Z^T (dtrevc3 'L','B', one vector at a time; ascending order keeps columns > ki untouched until used).
+template <class G>
+PB_D void trevc_left_inplace( const G& g, int n, const double* T, int ldt, double* V, int ldv, double* cnorm, double* xr,
+                              double* xi ) {
+  const int t = g.tid(), nt = g.size();
+  colnorms( g, n, T, ldt, cnorm );
+  int ki = 0;
+  while ( ki < n ) {
+    const bool cplx = ( ki < n - 1 && PB_T( ki + 1, ki ) != 0.0 );
+    trevc_left_solve( g, n, T, ldt, ki, cplx, cnorm, xr, xi );
+    if ( !cplx ) {
+      double emax = 0.0;
+      for ( int r = t; r < n; r += nt ) {
+        double s = xr[ki] * PB_V( r, ki );
+        for ( int c = ki + 1; c < n; ++c ) s += PB_V( r, c ) * xr[c];
+        PB_V( r, ki ) = s;
+        emax = dmax( emax, fabs( s ) );
+      }
+      emax = g.max( emax );
+      const double remax = 1.0 / emax;
+      for ( int r = t; r < n; r += nt ) PB_V( r, ki ) *= remax;
+      g.sync();
+      ki += 1;
+    } else {
+      double emax = 0.0;
+      for ( int r = t; r < n; r += nt ) {
+        double sr = xr[ki] * PB_V( r, ki );
+        double si = xi[ki + 1] * PB_V( r, ki + 1 );
+        for ( int c = ki + 2; c < n; ++c ) {
+          const double v = PB_V( r, c );
+          sr += v * xr[c];
+          si += v * xi[c];
+        }
+        PB_V( r, ki ) = sr;
+        PB_V( r, ki + 1 ) = si;
+        emax = dmax( emax, fabs( sr ) + fabs( si ) );
+      }
+      emax = g.max( emax );
+      const double remax = 1.0 / emax;
+      for ( int r = t; r < n; r += nt ) {
+        PB_V( r, ki ) *= remax;
+        PB_V( r, ki + 1 ) *= remax;
+      }
+      g.sync();
+      ki += 2;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // gebak 'B','R' on the rows of V (n x m). scale[] as produced by gebal (0-based permutation indices
 // outside ilo..ihi, scaling factors inside).
 // ------------------------------------------------------------------------------------------------
+// left = true: dgebak 'B','L' (rows are divided by the scaling factors instead of multiplied)
 template <class G>
-PB_D void gebak_right( const G& g, int n, int ilo, int ihi, const double* scale, int m, double* V, int ldv ) {
+PB_D void gebak_vectors( const G& g, bool left, int n, int ilo, int ihi, const double* scale, int m, double* V, int ldv ) {
   const int t = g.tid(), nt = g.size();
   if ( n == 0 || m == 0 ) return;
   if ( ilo != ihi ) {
     for ( int c = 0; c < m; ++c )
-      for ( int r = ilo + t; r <= ihi; r += nt ) PB_V( r, c ) *= scale[r];
+      for ( int r = ilo + t; r <= ihi; r += nt ) PB_V( r, c ) *= left ? 1.0 / scale[r] : scale[r];
   }
   g.sync();
   for ( int ii = 0; ii < n; ++ii ) {
@@ -544,6 +750,11 @@ PB_D void gebak_right( const G& g, int n, int ilo, int ihi, const double* scale,
     }
     g.sync();
   }
+}
+
+template <class G>
+PB_D void gebak_right( const G& g, int n, int ilo, int ihi, const double* scale, int m, double* V, int ldv ) {
+  gebak_vectors( g, false, n, ilo, ihi, scale, m, V, ldv );
 }
 
 // overflow-safe 2-norm of a column by the group

@@ -1,4 +1,4 @@
-// pb_vecs.cuh -- right eigenvectors for one matrix per CTA (device only), the dtrevc3 'R','B' + dgebak 'B','R' +
+// pb_vecs.cuh -- right and left eigenvectors for one matrix per CTA (device only), the dtrevc3 'R'/'L','B' + dgebak 'B' +
 // normalisation tail of the reference's dgeev_ call (reference src/lapack-wrapper.hpp:47-60,
 // src/paladin.hpp:248-254; the packed layout is consumed at src/paladin.hpp:256-333).
 //
@@ -24,7 +24,7 @@ constexpr int kVecWarps = kVecThreads / 32;
 // ---- 1. triangular solves ---------------------------------------------------------------------------
 // X(:, ki) (real) or X(:, ki-1), X(:, ki) (pair, real and imaginary parts) <- eigenvector of T; entries
 // below the block are zeroed so that the GEMM may treat X as dense.
-__device__ inline void vecs_solve( int n, const double* T, int ldt, double* X, int ldx, double* cnorm ) {
+__device__ inline void vecs_solve( int n, const double* T, int ldt, double* X, int ldx, double* cnorm, bool left ) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // column 1-norms of the strictly upper part (warp per column, lanes along rows)
   for ( int j = warp; j < n; j += kVecWarps ) {
@@ -35,28 +35,46 @@ __device__ inline void vecs_solve( int n, const double* T, int ldt, double* X, i
   }
   __syncthreads();
   WarpGroup g;
-  // blocks are numbered from the bottom; every warp walks the same block list and takes every kVecWarps-th
+  // every warp walks the same block list and takes every kVecWarps-th block (the expensive blocks first)
   int blk = 0;
-  int ki = n - 1;
-  while ( ki >= 0 ) {
-    const bool cplx = ( ki > 0 && T[ki + (size_t)( ki - 1 ) * ldt] != 0.0 );
-    if ( ( blk % kVecWarps ) == warp ) {
-      if ( !cplx ) {
-        double* xr = X + (size_t)ki * ldx;
-        trevc_right_solve( g, n, T, ldt, ki, false, cnorm, xr, xr );
-        for ( int r = ki + 1 + lane; r < n; r += 32 ) xr[r] = 0.0;
-      } else {
-        double* xr = X + (size_t)( ki - 1 ) * ldx;
-        double* xi = X + (size_t)ki * ldx;
-        trevc_right_solve( g, n, T, ldt, ki, true, cnorm, xr, xi );
-        for ( int r = ki + 1 + lane; r < n; r += 32 ) {
-          xr[r] = 0.0;
-          xi[r] = 0.0;
+  if ( !left ) {
+    int ki = n - 1;
+    while ( ki >= 0 ) {
+      const bool cplx = ( ki > 0 && T[ki + (size_t)( ki - 1 ) * ldt] != 0.0 );
+      if ( ( blk % kVecWarps ) == warp ) {
+        if ( !cplx ) {
+          double* xr = X + (size_t)ki * ldx;
+          trevc_right_solve( g, n, T, ldt, ki, false, cnorm, xr, xr );
+          for ( int r = ki + 1 + lane; r < n; r += 32 ) xr[r] = 0.0;
+        } else {
+          double* xr = X + (size_t)( ki - 1 ) * ldx;
+          double* xi = X + (size_t)ki * ldx;
+          trevc_right_solve( g, n, T, ldt, ki, true, cnorm, xr, xi );
+          for ( int r = ki + 1 + lane; r < n; r += 32 ) {
+            xr[r] = 0.0;
+            xi[r] = 0.0;
+          }
         }
       }
+      ki -= cplx ? 2 : 1;
+      blk += 1;
     }
-    ki -= cplx ? 2 : 1;
-    blk += 1;
+  } else {
+    int ki = 0;
+    while ( ki < n ) {
+      const bool cplx = ( ki < n - 1 && T[( ki + 1 ) + (size_t)ki * ldt] != 0.0 );
+      if ( ( blk % kVecWarps ) == warp ) {
+        double* xr = X + (size_t)ki * ldx;
+        double* xi = cplx ? X + (size_t)( ki + 1 ) * ldx : xr;
+        trevc_left_solve( g, n, T, ldt, ki, cplx, cnorm, xr, xi );
+        for ( int r = lane; r < ki; r += 32 ) {
+          xr[r] = 0.0;
+          if ( cplx ) xi[r] = 0.0;
+        }
+      }
+      ki += cplx ? 2 : 1;
+      blk += 1;
+    }
   }
   __syncthreads();
 }
@@ -74,22 +92,24 @@ __device__ __forceinline__ void dmma_m8n8k4( double& c0, double& c1, double a, d
 }
 
 // C (n x n, ldc) = Z (n x n, ldz) * X (n x n, ldx); column block [c0, c0+BN) of X is zero below row c0+BN
+// lower = true: X is lower (quasi-)triangular (left eigenvectors): column block [n0, n0+BN) is zero above row n0-1
 __device__ inline void vecs_gemm( int n, const double* __restrict__ Z, int ldz, const double* __restrict__ X, int ldx,
-                                  double* __restrict__ C, int ldc, double* sm ) {
+                                  double* __restrict__ C, int ldc, double* sm, bool lower ) {
   double* As = sm;                                 // [BK][LdA]
   double* Bs = sm + (size_t)kGemmBK * kGemmLdA;    // [BN][LdB]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int wm = warp & 3, wn = warp >> 2;         // 4 x 2 warps, each 32 x 32
   const int gid = lane >> 2, tig = lane & 3;
   for ( int n0 = 0; n0 < n; n0 += kGemmBN ) {
-    const int kend = imin( n, n0 + kGemmBN + 1 );
+    const int kend = lower ? n : imin( n, n0 + kGemmBN + 1 );
+    const int kbeg = lower ? ( imax( 0, n0 - 1 ) / kGemmBK ) * kGemmBK : 0;
     for ( int m0 = 0; m0 < n; m0 += kGemmBM ) {
       double acc[4][4][2];
 #pragma unroll
       for ( int i = 0; i < 4; ++i )
 #pragma unroll
         for ( int j = 0; j < 4; ++j ) acc[i][j][0] = acc[i][j][1] = 0.0;
-      for ( int k0 = 0; k0 < kend; k0 += kGemmBK ) {
+      for ( int k0 = kbeg; k0 < kend; k0 += kGemmBK ) {
         // stage Z(m0:m0+BM, k0:k0+BK) and X(k0:k0+BK, n0:n0+BN), zero padded
         double za[8], xb[4];
 #pragma unroll
@@ -152,7 +172,7 @@ __device__ inline void vecs_gemm( int n, const double* __restrict__ Z, int ldz, 
 // perm: n ints of shared/global scratch (final row of each source row after dgebak's swaps)
 template <int MAXCH>
 __device__ void vecs_finish( int n, int ilo, int ihi, const double* scale, const double* wi, const double* __restrict__ C,
-                             int ldc, double* __restrict__ V, int ldv, int* perm ) {
+                             int ldc, double* __restrict__ V, int ldv, int* perm, bool left ) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // dgebak 'B','R': rows ilo..ihi are scaled, then row swaps are applied for i = ilo-1..0 and ihi+1..n-1.
   // dest[p] = row where source row p ends up.
@@ -186,7 +206,8 @@ __device__ void vecs_finish( int n, int ilo, int ihi, const double* scale, const
         b[k] = 0.0;
         if ( k < nch && r < n ) {
           const int src = perm[r];
-          const double s = ( src >= ilo && src <= ihi && ilo != ihi ) ? scale[src] : 1.0;
+          double s = ( src >= ilo && src <= ihi && ilo != ihi ) ? scale[src] : 1.0;
+          if ( left ) s = 1.0 / s;  // dgebak 'L' divides
           a[k] = C[src + (size_t)c * ldc] * s;
           if ( pair ) b[k] = C[src + (size_t)( c + 1 ) * ldc] * s;
         }
@@ -268,7 +289,7 @@ __device__ void vecs_finish( int n, int ilo, int ihi, const double* scale, const
 
 // any n: the same un-balance + normalise with the column(s) streamed from memory in several passes (L2 hits)
 __device__ inline void vecs_finish_big( int n, int ilo, int ihi, const double* scale, const double* wi, const double* __restrict__ C,
-                                        int ldc, double* __restrict__ V, int ldv, int* perm ) {
+                                        int ldc, double* __restrict__ V, int ldv, int* perm, bool left ) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if ( tid == 0 ) {
     for ( int r = 0; r < n; ++r ) perm[r] = r;
@@ -291,7 +312,10 @@ __device__ inline void vecs_finish_big( int n, int ilo, int ihi, const double* s
     if ( ( blk % kVecWarps ) == warp ) {
       const double* ca = C + (size_t)c * ldc;
       const double* cb = C + (size_t)( pair ? c + 1 : c ) * ldc;
-      auto rowscale = [&]( int src ) { return ( src >= ilo && src <= ihi && ilo != ihi ) ? scale[src] : 1.0; };
+      auto rowscale = [&]( int src ) {
+        const double f = ( src >= ilo && src <= ihi && ilo != ihi ) ? scale[src] : 1.0;
+        return left ? 1.0 / f : f;
+      };
       double mx = 0.0;
       for ( int r = lane; r < n; r += 32 ) {
         const int src = perm[r];

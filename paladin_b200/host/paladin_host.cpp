@@ -129,6 +129,7 @@ inline int run_pod( int device, const std::vector<std::string>& pod, const Optio
   using clock = std::chrono::steady_clock;
   const auto t_start = clock::now();
   const char jobvr = o.right ? 'V' : 'N';
+  const char jobvl = o.left ? 'V' : 'N';
   int failures = 0;
   for ( int rep = 0; rep < o.repeats; ++rep ) {
     for ( std::size_t first = 0; first < pod.size(); first += o.batch ) {
@@ -158,19 +159,21 @@ inline int run_pod( int device, const std::vector<std::string>& pod, const Optio
       }
       times.read += std::chrono::duration<double>( clock::now() - t_read ).count();
 
-      std::vector<std::vector<double>> wr( count ), wi( count ), vr( count );
-      std::vector<double*> pwr( count ), pwi( count ), pvr( count, nullptr );
+      std::vector<std::vector<double>> wr( count ), wi( count ), vr( count ), vl( count );
+      std::vector<double*> pwr( count ), pwi( count ), pvr( count, nullptr ), pvl( count, nullptr );
       for ( std::size_t k = 0; k < count; ++k ) {
         wr[k].assign( n[k], 0.0 );
         wi[k].assign( n[k], 0.0 );
         if ( o.right ) vr[k].assign( static_cast<std::size_t>( n[k] ) * n[k], 0.0 );
+        if ( o.left ) vl[k].assign( static_cast<std::size_t>( n[k] ) * n[k], 0.0 );
         pwr[k] = wr[k].data();
         pwi[k] = wi[k].data();
         pvr[k] = o.right ? vr[k].data() : nullptr;
+        pvl[k] = o.left ? vl[k].data() : nullptr;
       }
       std::vector<int> info( count, 0 );
       const int rc = paladin_gpu_geev_batch( device, static_cast<int>( count ), n.data(), off.data(), ci.data(), cj.data(),
-                                             cv.data(), 'N', jobvr, pwr.data(), pwi.data(), nullptr, pvr.data(), info.data() );
+                                             cv.data(), jobvl, jobvr, pwr.data(), pwi.data(), pvl.data(), pvr.data(), info.data() );
       if ( rc != PALADIN_GPU_OK ) {
         std::cerr << "paladin_gpu_geev_batch failed on device " << device << ": " << paladin_gpu_last_error() << '\n';
         return -1;
@@ -182,10 +185,16 @@ inline int run_pod( int device, const std::vector<std::string>& pod, const Optio
           std::cerr << "warning: " << pod[first + k] << ": info = " << info[k] << '\n';
         }
         SpectralDecomposition s( n[k], o.threshold );
-        s.unpack( n[k], wr[k].data(), wi[k].data(), o.right && info[k] == 0 ? vr[k].data() : nullptr );
+        s.unpack( n[k], wr[k].data(), wi[k].data(), o.right && info[k] == 0 ? vr[k].data() : nullptr,
+                  o.left && info[k] == 0 ? vl[k].data() : nullptr );
         std::string text;
         s.write_eigenvalues( text );
         write_file( pod[first + k] + ".spectrum", text );
+        if ( o.left ) {
+          text.clear();
+          s.write_left_eigenvectors( text );
+          write_file( pod[first + k] + ".leftvecs", text );
+        }
         if ( o.right ) {
           text.clear();
           s.write_right_eigenvectors( text );
@@ -225,11 +234,6 @@ inline void display_timings( const std::vector<PodTimes>& t, int repeats ) {
 inline int host_main( int argc, char* argv[] ) {
   const Options o = parse_options( argc, argv, false );
   print_header();
-  if ( o.left ) {
-    std::cerr << "paladin-gpu: --left (left eigenvectors) is not implemented by the GPU library yet; run the reference for "
-                 "left vectors\n";
-    return 2;
-  }
   int pods = o.gpus;
   if ( pods <= 0 ) pods = o.dump_partition.empty() ? paladin_gpu_device_count() : 1;
   if ( pods <= 0 ) {
@@ -307,12 +311,14 @@ void ph_partition( int count, const double* measures, int pods, int* order, int*
 }
 
 // formats into caller buffers; returns the byte count needed
+// which: 0 spectrum, 1 right-vector file (vr = right vectors), 2 left-vector file (vr = left vectors)
 long ph_format( int n, const double* wr, const double* wi, const double* vr, double threshold, int which, char* out, long cap ) {
   paladin::SpectralDecomposition s( n, threshold );
-  s.unpack( n, wr, wi, vr );
+  s.unpack( n, wr, wi, which == 2 ? nullptr : vr, which == 2 ? vr : nullptr );
   std::string str;
   if ( which == 0 ) s.write_eigenvalues( str );
-  else s.write_right_eigenvectors( str );
+  else if ( which == 1 ) s.write_right_eigenvectors( str );
+  else s.write_left_eigenvectors( str );
   if ( out && cap >= static_cast<long>( str.size() ) ) std::memcpy( out, str.data(), str.size() );
   return static_cast<long>( str.size() );
 }

@@ -20,7 +20,7 @@ namespace paladin {
 
 class SpectralDecomposition {
   std::vector<std::complex<double>> eigenvalues_;
-  std::vector<std::vector<std::complex<double>>> rightEigenvectors_;
+  std::vector<std::vector<std::complex<double>>> rightEigenvectors_, leftEigenvectors_;
   double vectorWriteThreshold_;
 
  public:
@@ -32,18 +32,25 @@ class SpectralDecomposition {
   const std::vector<std::complex<double>>& eigenvalues() const { return eigenvalues_; }
   const std::vector<std::vector<std::complex<double>>>& right_eigenvectors() const { return rightEigenvectors_; }
 
-  // wr, wi: n values; vr: n x n column-major real-packed vectors or nullptr
-  void unpack( int n, const double* wr, const double* wi, const double* vr ) {
+  // wr, wi: n values; vr / vl: n x n column-major real-packed vectors or nullptr. The reference pairs the left
+  // vectors exactly like the right ones: (re, +im) for the first eigenvalue of a pair, (re, -im) for its conjugate
+  // (src/paladin.hpp:265-274).
+  void unpack( int n, const double* wr, const double* wi, const double* vr, const double* vl = nullptr ) {
     eigenvalues_.clear();
     rightEigenvectors_.clear();
+    leftEigenvectors_.clear();
     auto column = [&]( int c, int imag_col, double imag_sign ) {
-      std::vector<std::complex<double>> v( n );
-      for ( int r = 0; r < n; ++r ) {
-        const double re = vr[r + static_cast<std::size_t>( n ) * c];
-        const double im = imag_col < 0 ? 0.0 : imag_sign * vr[r + static_cast<std::size_t>( n ) * imag_col];
-        v[r] = std::complex<double>( re, im );
+      for ( int side = 0; side < 2; ++side ) {
+        const double* src = side == 0 ? vr : vl;
+        if ( src == nullptr ) continue;
+        std::vector<std::complex<double>> v( n );
+        for ( int r = 0; r < n; ++r ) {
+          const double re = src[r + static_cast<std::size_t>( n ) * c];
+          const double im = imag_col < 0 ? 0.0 : imag_sign * src[r + static_cast<std::size_t>( n ) * imag_col];
+          v[r] = std::complex<double>( re, im );
+        }
+        ( side == 0 ? rightEigenvectors_ : leftEigenvectors_ ).push_back( std::move( v ) );
       }
-      rightEigenvectors_.push_back( std::move( v ) );
     };
     bool second_of_pair = false;
     for ( int c = 0; c < n; ++c ) {
@@ -53,7 +60,7 @@ class SpectralDecomposition {
         continue;  // vector already emitted together with its conjugate
       }
       const bool pair = ( c + 1 < n ) && wi[c] == -wi[c + 1] && wi[c] != 0.0;
-      if ( vr != nullptr ) {
+      if ( vr != nullptr || vl != nullptr ) {
         if ( pair ) {
           column( c, c + 1, 1.0 );
           column( c, c + 1, -1.0 );
@@ -83,6 +90,7 @@ class SpectralDecomposition {
   }
 
   void write_right_eigenvectors( std::string& out ) const { write_vectors( out, rightEigenvectors_ ); }
+  void write_left_eigenvectors( std::string& out ) const { write_vectors( out, leftEigenvectors_ ); }
 
  private:
   void write_vectors( std::string& out, const std::vector<std::vector<std::complex<double>>>& vecs ) const {

@@ -168,6 +168,17 @@ void hs_trevc_right( int n, const double* T, double* V ) {
   pb::trevc_right_inplace( g, n, T, n, V, n, w.data(), w.data() + n, w.data() + 2 * n );
 }
 
+void hs_trevc_left( int n, const double* T, double* V ) {
+  pb::HostGroup g;
+  std::vector<double> w( 3 * n + 3 );
+  pb::trevc_left_inplace( g, n, T, n, V, n, w.data(), w.data() + n, w.data() + 2 * n );
+}
+
+void hs_gebak_left( int n, int ilo, int ihi, const double* scale, double* V ) {
+  pb::HostGroup g;
+  pb::gebak_vectors( g, true, n, ilo, ihi, scale, n, V, n );
+}
+
 void hs_gebak_right( int n, int ilo, int ihi, const double* scale, double* V ) {
   pb::HostGroup g;
   pb::gebak_right( g, n, ilo, ihi, scale, n, V, n );
@@ -178,11 +189,26 @@ int hs_dlaln2( int ltrans, int na, int nw, double smin, const double* a, const d
   return pb::dlaln2( ltrans != 0, na, nw, smin, a, b, wr, wi, x, *scale, *xnorm );
 }
 
+int hs_geev_lr( int n, double* A, double* wr, double* wi, int wantvl, double* VL, int wantvr, double* VR ) {
+  pb::HostGroup g;
+  std::vector<double> dw( 5 * n + 5 );
+  std::vector<int> iw( 2 * n + 2 );
+  return pb::geev_group( g, n, A, n, wr, wi, wantvl != 0, VL, n, wantvr != 0, VR, n, dw.data(), iw.data() );
+}
+
+int ht_geev_lr( int nt, int n, double* A, double* wr, double* wi, int wantvl, double* VL, int wantvr, double* VR ) {
+  std::vector<double> dw( 5 * n + 5 );
+  std::vector<int> iw( 2 * n + 2 );
+  return run_threads( nt, [&]( const ThreadGroup& g ) {
+    return pb::geev_group( g, n, A, n, wr, wi, wantvl != 0, VL, n, wantvr != 0, VR, n, dw.data(), iw.data() );
+  } );
+}
+
 int hs_geev( int n, double* A, double* wr, double* wi, int wantvr, double* V ) {
   pb::HostGroup g;
   std::vector<double> dw( 5 * n + 5 );
   std::vector<int> iw( 2 * n + 2 );
-  return pb::geev_group( g, n, A, n, wr, wi, wantvr != 0, V, n, dw.data(), iw.data() );
+  return pb::geev_group( g, n, A, n, wr, wi, false, (double*)nullptr, n, wantvr != 0, V, n, dw.data(), iw.data() );
 }
 
 struct MsBuffers {
@@ -234,7 +260,7 @@ int hs_geev_ms( int n, double* A, double* wr, double* wi, int wantvr, double* V,
   std::vector<int> iw( 2 * n + 2 );
   pb::MsqrCfg c{ nb, W, ws_small, tl, nchains % 100, nchains / 100 };
   MsBuffers buf( c );
-  return pb::geev_group( g, n, A, n, wr, wi, wantvr != 0, V, n, dw.data(), iw.data(), pb::QrMultishift{ c, buf.wk } );
+  return pb::geev_group( g, n, A, n, wr, wi, false, (double*)nullptr, n, wantvr != 0, V, n, dw.data(), iw.data(), pb::QrMultishift{ c, buf.wk } );
 }
 
 int ht_geev_ms( int nt, int n, double* A, double* wr, double* wi, int wantvr, double* V, int nb, int W, int ws_small, int tl,
@@ -244,7 +270,7 @@ int ht_geev_ms( int nt, int n, double* A, double* wr, double* wi, int wantvr, do
   pb::MsqrCfg c{ nb, W, ws_small, tl, nchains % 100, nchains / 100 };
   MsBuffers buf( c );
   return run_threads( nt, [&]( const ThreadGroup& g ) {
-    return pb::geev_group( g, n, A, n, wr, wi, wantvr != 0, V, n, dw.data(), iw.data(), pb::QrMultishift{ c, buf.wk } );
+    return pb::geev_group( g, n, A, n, wr, wi, false, (double*)nullptr, n, wantvr != 0, V, n, dw.data(), iw.data(), pb::QrMultishift{ c, buf.wk } );
   } );
 }
 
@@ -253,7 +279,7 @@ int ht_geev( int nt, int n, double* A, double* wr, double* wi, int wantvr, doubl
   std::vector<double> dw( 5 * n + 5 );
   std::vector<int> iw( 2 * n + 2 );
   return run_threads( nt, [&]( const ThreadGroup& g ) {
-    return pb::geev_group( g, n, A, n, wr, wi, wantvr != 0, V, n, dw.data(), iw.data() );
+    return pb::geev_group( g, n, A, n, wr, wi, false, (double*)nullptr, n, wantvr != 0, V, n, dw.data(), iw.data() );
   } );
 }
 

@@ -234,6 +234,28 @@ def test_badly_scaled_and_structured(pg):
         assert be <= BACKWARD_TOL, (k, be)
 
 
+@pytest.mark.parametrize("sides", ["L", "LR"])
+def test_left_eigenvectors(pg, sides):
+    # every kernel variant: warp path, CTA path (16- and 32-chunk), streaming path
+    sizes = [1, 2, 3, 7, 20, 33, 64, 65, 100, 200, 512, 600, 1100]
+    mats = _random_mats(sizes, 41)
+    res, info = pg.geev_batch(*_concat(mats), jobvr="V" if "R" in sides else "N", jobvl="V")
+    assert not info.any()
+    for m, (wr, wi, VR, VL) in zip(mats, res):
+        A = po.dense_matrix(*m)
+        n = A.shape[0]
+        wr0, wi0, _, _, _ = po.dgeev(A)
+        assert po.match_eigenvalues(po.eigenvalues(wr, wi), po.eigenvalues(wr0, wi0)) <= EIG_TOL * max(1.0, np.linalg.norm(A, 2))
+        assert po.left_backward_error(A, wr, wi, VL) <= BACKWARD_TOL, n
+        assert np.allclose(np.linalg.norm(np.array(po.unpack(wr, wi, VL)), axis=1), 1.0, atol=1e-12)
+        if "R" in sides:
+            assert po.backward_error(A, wr, wi, VR) <= BACKWARD_TOL, n
+    # the Fortran-signature shim
+    A = po.dense_matrix(*mats[5])
+    wr, wi, VR, inf, VL = pg.dgeev(A, jobvr="V", jobvl="V")
+    assert inf == 0 and po.left_backward_error(A, wr, wi, VL) <= BACKWARD_TOL and po.backward_error(A, wr, wi, VR) <= BACKWARD_TOL
+
+
 def test_nonfinite_input_flagged(pg):
     A = np.ones((5, 5))
     A[2, 2] = np.nan
@@ -308,7 +330,8 @@ def test_paladin_gpu_executable_reproduces_ctest_goldens(pg, tmp_path):
         lst = os.path.join(dst, listing)
         if not os.path.exists(lst):  # fixtures keep one listing per suite
             lst = sorted(glob.glob(os.path.join(dst, "listing*")))[-1]
-        r = subprocess.run([host.exe_path(), "--listing=" + lst, "--rootdir=" + str(dst), "--right", "--gpus=1", "--showdist"],
+        # exactly the reference's ctest invocation (test/compare_spectra.cmake:8-13): --left --right
+        r = subprocess.run([host.exe_path(), "--listing=" + lst, "--rootdir=" + str(dst), "--left", "--right", "--gpus=1", "--showdist"],
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         assert "load imbalance" in r.stdout
@@ -317,3 +340,4 @@ def test_paladin_gpu_executable_reproduces_ctest_goldens(pg, tmp_path):
                 continue  # not named by this listing
             assert open(m + ".spectrum", "rb").read() == open(m + ".spectrum.exact", "rb").read(), m
             assert open(m + ".rightvecs", "rb").read() == open(m + ".rightvecs.exact", "rb").read(), m
+            assert open(m + ".leftvecs", "rb").read() == open(m + ".leftvecs.exact", "rb").read(), m

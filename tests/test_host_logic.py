@@ -78,9 +78,10 @@ def test_writers_byte_exact(ph, path):
     # eigen data from the oracle's dgeev, formatted by the product's writers, against the reference's own files
     n, nnz, ii, jj, vv = po.read_mm(path)
     A = po.dense_matrix(n, ii, jj, vv)
-    wr, wi, VL, VR, info = po.dgeev(A, left=False, right=True)
+    wr, wi, VL, VR, info = po.dgeev(A, left=True, right=True)
     assert ph.format_output(wr, wi, None, 0) == open(path + ".spectrum.exact", "rb").read()
     assert ph.format_output(wr, wi, VR, 1) == open(path + ".rightvecs.exact", "rb").read()
+    assert ph.format_output(wr, wi, VL, 2) == open(path + ".leftvecs.exact", "rb").read()
 
 
 def test_executable_partition_dump(ph, tmp_path):
@@ -102,8 +103,11 @@ def test_executable_partition_dump(ph, tmp_path):
     r = subprocess.run([ph.exe_path(), "--listing=" + os.path.join(d, "listing"), "--rootdir=" + d, "--gpus=2", "--load-measure=dim",
                         "--dump-partition=" + str(out)], capture_output=True, text=True)
     assert r.returncode == 0 and "not a recognized option" in r.stdout
-    r = subprocess.run([ph.exe_path(), "--listing=" + os.path.join(d, "listing"), "--rootdir=" + d, "--left"], capture_output=True, text=True)
-    assert r.returncode == 2
+    # without a GPU the executable refuses to compute (no CPU fallback)
+    import paladin_b200 as pg
+    if pg.device_count() == 0:
+        r = subprocess.run([ph.exe_path(), "--listing=" + os.path.join(d, "listing"), "--rootdir=" + d, "--left"], capture_output=True, text=True)
+        assert r.returncode == 3 and "no CPU fallback" in r.stderr
 
 
 GLOO_WORKER = r"""

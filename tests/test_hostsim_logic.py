@@ -119,6 +119,38 @@ def test_multishift_geev_pipeline(hs):
                 assert po.backward_error(A, wr, wi, V) <= 100
 
 
+def test_left_eigenvectors_match_lapack(hs):
+    rng = np.random.default_rng(31)
+    for n in (1, 2, 3, 6, 20, 50, 90):
+        A = rng.standard_normal((n, n))
+        if n >= 6:
+            A[rng.random((n, n)) < 0.4] = 0
+            A[:, 2] *= 1e6
+        A = np.asfortranarray(A)
+        B, ilo, ihi, sc = ls.dgebal(A)
+        H, tau = ls.dgehrd(B, ilo, ihi)
+        Q = ls.dorghr(H, tau, ilo, ihi)
+        T, wr, wi, Z, info = ls.dhseqr(np.triu(H, -1), ilo, ihi, Z=Q)
+        V0 = ls.dtrevc3(T, Z, side=b"L")
+        V = Z.copy(order="F")
+        hs.hs_trevc_left(n, dp(np.asfortranarray(T)), dp(V))
+        assert np.abs(V - V0).max() <= 1e-10 * max(1.0, np.abs(V0).max())
+        Vb0 = ls.dgebak(V0, ilo, ihi, sc, side=b"L")
+        sc2 = sc.copy()
+        for k in list(range(0, ilo - 1)) + list(range(ihi, n)):
+            sc2[k] -= 1
+        hs.hs_gebak_left(n, ilo - 1, ihi - 1, dp(sc2), dp(V))
+        assert np.abs(V - Vb0).max() <= 1e-10 * max(1.0, np.abs(Vb0).max())
+        # full pipeline, both sides, against dgeev
+        A2 = np.array(A, order="F")
+        w1, w2 = np.zeros(n), np.zeros(n)
+        VL, VR = np.zeros((n, n), order="F"), np.zeros((n, n), order="F")
+        assert hs.hs_geev_lr(n, dp(A2), dp(w1), dp(w2), 1, dp(VL), 1, dp(VR)) == 0
+        wr0, wi0, VL0, VR0, info0 = ls.dgeev(A, jobvl=b"V", jobvr=b"V")
+        assert po.match_eigenvalues(w1 + 1j * w2, wr0 + 1j * wi0) <= 1e-9 * max(1.0, np.linalg.norm(A, 2))
+        assert po.backward_error(A, w1, w2, VR) <= 100 and po.left_backward_error(A, w1, w2, VL) <= 100
+
+
 def test_stage_functions_match_lapack(hs):
     rng = np.random.default_rng(3)
     for n in (6, 20, 50):
@@ -188,6 +220,12 @@ for n, nt, (nb, W, wss, tl, nch) in [(30, 4, (2, 10, 6, 5, 2)), (40, 3, (3, 14, 
         assert info == 0
         assert po.match_eigenvalues(wr + 1j * wi, wr0 + 1j * wi0) <= 1e-9 * max(1, np.linalg.norm(A, 2))
         if wantvr: assert po.backward_error(A, wr, wi, V) <= 100
+for n, nt in [(5, 3), (14, 4)]:
+    A = rng.standard_normal((n, n))
+    A2 = np.array(A, order='F'); wr = np.zeros(n); wi = np.zeros(n)
+    VL = np.zeros((n, n), order='F'); VR = np.zeros((n, n), order='F')
+    assert hs.ht_geev_lr(nt, n, dp(A2), dp(wr), dp(wi), 1, dp(VL), 1, dp(VR)) == 0
+    assert po.backward_error(A, wr, wi, VR) <= 100 and po.left_backward_error(A, wr, wi, VL) <= 100
 for n, nt in [(1, 3), (2, 3), (3, 4), (7, 4), (12, 3), (20, 5)]:
     for trial in range(2):
         A = rng.standard_normal((n, n))
