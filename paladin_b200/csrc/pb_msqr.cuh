@@ -720,6 +720,7 @@ PB_D void ms_chase_chain( const G& g, bool wantt, bool wantz, int n, int l, int 
     }
 #undef PB_W
     if ( !progressed ) break;  // cannot happen for W >= 3*nb + 4; never spin
+    if ( t == 0 ) wk.ibuf[3 * kMsMaxBulges + 6] = 0;  // work queue of the strip phase (visible after the barrier below)
     ms_store_window( g, H, ldh, ws, wlen, Hw, ldw );
     if ( t == 0 ) {
       wk.ibuf[3 * kMsMaxBulges + 2] += 1;
@@ -735,7 +736,8 @@ PB_D void ms_chase_chain( const G& g, bool wantt, bool wantz, int n, int l, int 
       // steady-state windows only (about five in six); the others take the tile path below
       if ( cfg.W == kStripW && cfg.nb == kStripNB && cfg.tl >= 16 * ( g.size() >> 5 ) &&
            strip_window_is_regular( nbulges, wlen, ws, kfirst, kcount ) ) {
-        ms_strips_regs( wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, wk.refl, wk.tile, wk.ldt );
+        ms_strips_regs( wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, wk.refl, wk.tile, wk.ldt,
+                        wk.ibuf + 3 * kMsMaxBulges + 6 );
       } else {
         ms_update_strips( g, wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, nbulges, (const double*)nullptr );
       }

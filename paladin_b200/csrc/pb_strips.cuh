@@ -140,107 +140,111 @@ __device__ __forceinline__ void strip_regular_stream( LD ld, ST st, const double
 // W x ldt shared tile (ldt >= 16 * warps + 1, odd); the caller synchronises the CTA before and after.
 __device__ __forceinline__ void prefetch_l2( const void* p ) { asm volatile( "prefetch.global.L2 [%0];" ::"l"( p ) ); }
 
+// Steady-state windows only. counter: one int of shared memory, zeroed by the caller before the CTA barrier that
+// precedes this call (work queue of the row batches).
 __device__ inline void ms_strips_regs( bool wantt, bool wantz, int n, int l, int i, int ws, int wlen, double* __restrict__ H,
                                        int ldh, int iloz, int ihiz, double* __restrict__ Z, int ldz, const double* refl,
-                                       double* tile, int ldt ) {
+                                       double* tile, int ldt, int* counter ) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int we = ws + wlen - 1;
   const int i1 = wantt ? 0 : l, i2 = wantt ? n - 1 : i;
   const int nright = imax( 0, i2 - we ), nup = imax( 0, ws - i1 ), nz = wantz ? ( ihiz - iloz + 1 ) : 0;
   const int bright = ( nright + 31 ) >> 5, bup = ( nup + 31 ) >> 5, bz = ( nz + 31 ) >> 5;
-  double* wt = tile + 16 * warp;  // this warp's 16-line slice: element (pos, line) at pos*ldt + line
-  // L2 prefetch of a whole batch (issued one batch ahead: the register allocator sinks the line loads next to
-  // their first use, so the latency that is left to hide should be an L2 hit, not a DRAM access)
-  auto prefetch_batch = [&]( int bt ) {
-    if ( bt >= bright + bup + bz ) return;
-    if ( bt < bright ) {
+  // ---- right strip: 32 columns per batch, even warps only. A column's W entries are contiguous in memory: the warp
+  // reads them with lanes along the rows (coalesced) and transposes through a 32-line slice of the shared tile
+  // (slice w/2 spans the 16-line slices of warps w and w+1; odd warps never use theirs here), then lane = column.
+  if ( ( warp & 1 ) == 0 ) {
+    double* wt = tile + 32 * ( warp >> 1 );
+    for ( int bt = warp >> 1; bt < bright; bt += ( nwarps + 1 ) >> 1 ) {
       const int j0 = we + 1 + 32 * bt;
       const int nl = imin( 32, i2 - j0 + 1 );
-      if ( lane < nl ) {
-        const double* col = H + (size_t)( j0 + lane ) * ldh + ws;
+      if ( lane < nl ) {  // L2 prefetch of the next batch of this warp
+        const int jn = j0 + 32 * ( ( nwarps + 1 ) >> 1 ) + lane;
+        if ( jn <= i2 ) {
+          const double* col = H + (size_t)jn * ldh + ws;
 #pragma unroll
-        for ( int q = 0; q < kStripW; q += 4 ) prefetch_l2( col + q );  // 32-byte sectors
+          for ( int q = 0; q < kStripW; q += 4 ) prefetch_l2( col + q );
+        }
       }
+      for ( int c0 = 0; c0 < nl; c0 += 8 ) {
+        double v0[8], v1[8];
+#pragma unroll
+        for ( int u = 0; u < 8; ++u ) {
+          const int cc = imin( c0 + u, nl - 1 );
+          const double* col = H + (size_t)( j0 + cc ) * ldh + ws;
+          v0[u] = col[lane];
+          v1[u] = col[imin( 32 + lane, kStripW - 1 )];
+        }
+#pragma unroll
+        for ( int u = 0; u < 8; ++u ) {
+          if ( c0 + u < nl ) {
+            wt[lane * ldt + c0 + u] = v0[u];
+            if ( 32 + lane < kStripW ) wt[( 32 + lane ) * ldt + c0 + u] = v1[u];
+          }
+        }
+      }
+      __syncwarp();
+      {
+        double* mine = wt + lane;
+        const bool owner = lane < nl;
+        strip_regular_stream( [&]( int p ) { return mine[p * ldt]; },
+                              [&]( int p, double v ) {
+                                if ( owner ) mine[p * ldt] = v;
+                              },
+                              refl );
+      }
+      __syncwarp();
+      for ( int cc = 0; cc < nl; ++cc ) {
+        double* col = H + (size_t)( j0 + cc ) * ldh + ws;
+        col[lane] = wt[lane * ldt + cc];
+        if ( 32 + lane < kStripW ) col[32 + lane] = wt[( 32 + lane ) * ldt + cc];
+      }
+      __syncwarp();
+    }
+  }
+  // ---- rows of the strip above the window and of Z: lane = row, every access is a contiguous 256-byte segment;
+  // batches are handed out through a shared counter (odd warps start here at once, even warps join after their
+  // share of the right strip)
+  const int nrow_batches = bup + bz;
+  auto row_batch = [&]( int bt, double*& M, int& ldm, int& r0, int& nl ) {
+    if ( bt < bup ) {
+      M = H;
+      ldm = ldh;
+      r0 = i1 + 32 * bt;
+      nl = imin( 32, ws - r0 );
     } else {
-      const double* M = ( bt < bright + bup ) ? H : Z;
-      const int ldm = ( bt < bright + bup ) ? ldh : ldz;
-      const int r0 = ( bt < bright + bup ) ? i1 + 32 * ( bt - bright ) : iloz + 32 * ( bt - bright - bup );
-      // one 256-byte row segment per position: four lanes cover it
-      const double* base = M + r0 + (size_t)ws * ldm;
-      for ( int p = 1 + ( lane >> 2 ); p <= kStripW - 2; p += 8 ) prefetch_l2( base + (size_t)p * ldm + 4 * ( lane & 3 ) * 2 );
+      M = Z;
+      ldm = ldz;
+      r0 = iloz + 32 * ( bt - bup );
+      nl = imin( 32, ihiz - r0 + 1 );
     }
   };
-  prefetch_batch( warp );
-  for ( int bt = warp; bt < bright + bup + bz; bt += nwarps ) {
-    prefetch_batch( bt + nwarps );
-    if ( bt < bright ) {
-      // ---- 32 columns of the right strip: coalesced reads (lanes along rows), transposed through the slice in two
-      // halves of 16 columns; lanes 16h..16h+15 work on half h (the other lanes repeat the work of lane & 15 on the
-      // same shared data and simply do not write back)
-      const int j0 = we + 1 + 32 * bt;
-      const int nl = imin( 32, i2 - j0 + 1 );
-      for ( int h = 0; h < 2; ++h ) {
-        const int cbeg = 16 * h, cend = imin( nl, 16 * h + 16 );
-        if ( cbeg >= cend ) break;
-        for ( int c0 = cbeg; c0 < cend; c0 += 8 ) {
-          double v0[8], v1[8];
-#pragma unroll
-          for ( int u = 0; u < 8; ++u ) {
-            const int cc = imin( c0 + u, nl - 1 );
-            const double* col = H + (size_t)( j0 + cc ) * ldh + ws;
-            v0[u] = col[lane];
-            v1[u] = col[imin( 32 + lane, kStripW - 1 )];
-          }
-#pragma unroll
-          for ( int u = 0; u < 8; ++u ) {
-            if ( c0 + u < cend ) {
-              wt[lane * ldt + c0 + u - cbeg] = v0[u];
-              if ( 32 + lane < kStripW ) wt[( 32 + lane ) * ldt + c0 + u - cbeg] = v1[u];
-            }
-          }
-        }
-        __syncwarp();
-        {
-          double* mine = wt + ( lane & 15 );
-          const bool owner = ( lane < 16 ) && ( cbeg + lane < cend );
-          strip_regular_stream( [&]( int p ) { return mine[p * ldt]; },
-                                [&]( int p, double v ) {
-                                  if ( owner ) mine[p * ldt] = v;
-                                },
-                                refl );
-        }
-        __syncwarp();
-        for ( int cc = cbeg; cc < cend; ++cc ) {
-          double* col = H + (size_t)( j0 + cc ) * ldh + ws;
-          col[lane] = wt[lane * ldt + cc - cbeg];
-          if ( 32 + lane < kStripW ) col[32 + lane] = wt[( 32 + lane ) * ldt + cc - cbeg];
-        }
-        __syncwarp();
+  for ( ;; ) {
+    int bt = 0;
+    if ( lane == 0 ) bt = atomicAdd( counter, 1 );
+    bt = __shfl_sync( 0xffffffffu, bt, 0 );
+    if ( bt >= nrow_batches ) break;
+    double* M;
+    int ldm, r0, nl;
+    row_batch( bt, M, ldm, r0, nl );
+    {  // L2 prefetch of a batch a few positions ahead in the queue
+      const int bn = bt + nwarps;
+      if ( bn < nrow_batches ) {
+        double* Mn;
+        int ldn, rn, nn;
+        row_batch( bn, Mn, ldn, rn, nn );
+        const double* base = Mn + rn + (size_t)ws * ldn;
+        for ( int p = 1 + ( lane >> 2 ); p <= kStripW - 2; p += 8 ) prefetch_l2( base + (size_t)p * ldn + 8 * ( lane & 3 ) );
       }
-    } else {
-      // ---- 32 rows of the strip above the window or of Z: lane = row, every access is a contiguous 256-byte segment
-      double* M;
-      int ldm, r0, nl;
-      if ( bt < bright + bup ) {
-        M = H;
-        ldm = ldh;
-        r0 = i1 + 32 * ( bt - bright );
-        nl = imin( 32, ws - r0 );
-      } else {
-        M = Z;
-        ldm = ldz;
-        r0 = iloz + 32 * ( bt - bright - bup );
-        nl = imin( 32, ihiz - r0 + 1 );
-      }
-      const int r = r0 + imin( lane, nl - 1 );
-      double* row = M + r + (size_t)ws * ldm;
-      const bool owner = lane < nl;
-      strip_regular_stream( [&]( int p ) { return __ldcg( row + (size_t)p * ldm ); },
-                            [&]( int p, double v ) {
-                              if ( owner ) __stcg( row + (size_t)p * ldm, v );
-                            },
-                            refl );
     }
+    const int r = r0 + imin( lane, nl - 1 );
+    double* row = M + r + (size_t)ws * ldm;
+    const bool owner = lane < nl;
+    strip_regular_stream( [&]( int p ) { return __ldcg( row + (size_t)p * ldm ); },
+                          [&]( int p, double v ) {
+                            if ( owner ) __stcg( row + (size_t)p * ldm, v );
+                          },
+                          refl );
   }
 }
 
