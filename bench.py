@@ -396,7 +396,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=512)
     ap.add_argument("--job", default="V", choices=["N", "V"])
-    ap.add_argument("--batch", type=int, default=296, help="matrices per GPU per step")
+    ap.add_argument("--batch", type=int, default=592, help="matrices per GPU per step (two waves of 2 CTAs x 148 SMs)")
     ap.add_argument("--distinct", type=int, default=37, help="distinct matrices per GPU (repeated listing-style)")
     ap.add_argument("--ref-per-rank", type=int, default=2, help="matrices per host core in the reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
