@@ -11,7 +11,9 @@
 #ifndef PALADIN_GPU_HOST_MM_COO_HPP_
 #define PALADIN_GPU_HOST_MM_COO_HPP_
 
+#include <charconv>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 #include <sstream>
 #include <stdexcept>
@@ -77,6 +79,44 @@ inline void parse_size_line( const char* text, const char* end, bool with_banner
 
 }  // namespace detail
 
+namespace detail {
+
+// atoi on a field known to be short: optional blanks, optional sign, digits (same value as atoi for every input atoi
+// defines)
+inline int field_to_int( const char* p, const char* end ) {
+  while ( p < end && ( *p == ' ' || ( *p >= '\t' && *p <= '\r' ) ) ) ++p;
+  bool neg = false;
+  if ( p < end && ( *p == '+' || *p == '-' ) ) neg = ( *p++ == '-' );
+  int v = 0;
+  while ( p < end && *p >= '0' && *p <= '9' ) v = v * 10 + ( *p++ - '0' );
+  return neg ? -v : v;
+}
+
+// atof on a field: std::from_chars (correctly rounded, like strtod, several times faster) for plain decimal numbers,
+// the C library for everything else it accepts (hex floats, inf/nan spellings, out-of-range values, odd signs), so
+// the result is bit-identical to the reference's atof call (src/square-matrix.hpp:114).
+inline double field_to_double( const char* p, const char* end ) {
+  const char* q = p;
+  while ( q < end && ( *q == ' ' || ( *q >= '\t' && *q <= '\r' ) ) ) ++q;
+  const char* num = q;
+  if ( num < end && *num == '+' ) ++num;  // from_chars takes no '+'
+  const char* dig = ( num < end && *num == '-' && num == q ) ? num + 1 : num;
+  const bool plain = dig < end && ( ( *dig >= '0' && *dig <= '9' ) || *dig == '.' ) &&
+                     !( dig + 1 < end && *dig == '0' && ( dig[1] == 'x' || dig[1] == 'X' ) );
+  if ( plain ) {
+    double v = 0.0;
+    const std::from_chars_result r = std::from_chars( num, end, v, std::chars_format::general );
+    if ( r.ec == std::errc() ) return v;
+  }
+  char buf[40];
+  const std::size_t len = std::min<std::size_t>( static_cast<std::size_t>( end - p ), sizeof( buf ) - 1 );
+  std::memcpy( buf, p, len );
+  buf[len] = '\0';
+  return std::atof( buf );
+}
+
+}  // namespace detail
+
 inline std::string slurp( const std::string& path ) {
   std::ifstream in( path, std::ios::binary );
   if ( !in ) throw std::runtime_error( "Couldn't open the matrix file, " + path );
@@ -103,7 +143,6 @@ inline CooMatrix parse_mm_text( const std::string& text, const std::string& what
   m.row.resize( m.nnz_ );
   m.col.resize( m.nnz_ );
   m.val.resize( m.nnz_ );
-  char field[40];
   for ( int k = 0; k < m.nnz_; ++k ) {
     const char* f[3];
     std::size_t len[3];
@@ -117,13 +156,9 @@ inline CooMatrix parse_mm_text( const std::string& text, const std::string& what
     if ( len[0] > 5 || len[1] > 5 || len[2] > 31 )
       throw std::runtime_error( what + ": entry " + std::to_string( k + 1 ) +
                                 " has a field longer than the reference reader's buffers (5/5/31 characters)" );
-    for ( int part = 0; part < 3; ++part ) {
-      std::memcpy( field, f[part], len[part] );
-      field[len[part]] = '\0';
-      if ( part == 0 ) m.row[k] = std::atoi( field );
-      else if ( part == 1 ) m.col[k] = std::atoi( field );
-      else m.val[k] = std::atof( field );
-    }
+    m.row[k] = detail::field_to_int( f[0], f[0] + len[0] );
+    m.col[k] = detail::field_to_int( f[1], f[1] + len[1] );
+    m.val[k] = detail::field_to_double( f[2], f[2] + len[2] );
   }
   return m;
 }

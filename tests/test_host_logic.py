@@ -142,3 +142,28 @@ def test_two_rank_sharding_over_gloo(ph, tmp_path):
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr=127.0.0.1",
                         "--master-port=29517", str(script)], capture_output=True, text=True, timeout=300)
     assert "SHARDING-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_fast_number_parse_is_bit_identical_to_atof(ph, tmp_path):
+    # every spelling the C library accepts must convert to the same bits as the reference's atof/atoi calls
+    rng = np.random.default_rng(9)
+    vals = []
+    for k in range(3000):
+        x = float(rng.standard_normal()) * 10.0 ** int(rng.integers(-320, 309))
+        fmt = ["%.17g", "%.16e", "%.8g", "%g", "%.3f", "%.25e", "%+.17g"][k % 7]
+        s = fmt % x
+        if len(s) <= 31:
+            vals.append(s)
+    vals += ["0", "-0", "-0.0", "1e400", "-1e400", "4.9e-324", "2.4e-324", "1e-400", "nan", "-nan", "inf", "-inf", "Infinity", "NaN",
+             "0x1p3", "0x1.8p1", "1.5D0", "1.5d3", ".5", "5.", "-.5e1", "+3", "+-1", "1e", "1e+", "abc", "", "  7.25", "\t2.5", "1,5",
+             "9007199254740993", "0.1e-1x", "123456789012345678901234567890"]
+    n = 80
+    assert len(vals) <= n * n
+    lines = ["%d %d %s" % (k % n + 1, k // n + 1, v) for k, v in enumerate(vals)]
+    path = tmp_path / "numbers.matrix"
+    path.write_text("%%MatrixMarket matrix coordinate real general\n%d %d %d\n" % (n, n, len(vals)) + "\n".join(lines))
+    n1, nnz1, i1, j1, v1 = ph.parse_mm(str(path))
+    n0, nnz0, i0, j0, v0 = po.read_mm(str(path))
+    assert (n1, nnz1) == (n0, nnz0) and i1.tobytes() == i0.tobytes() and j1.tobytes() == j0.tobytes()
+    bad = [vals[k] for k in range(nnz0) if v1[k:k + 1].tobytes() != v0[k:k + 1].tobytes()]
+    assert not bad, bad[:10]
