@@ -266,7 +266,7 @@ __global__ void __launch_bounds__( pb::kHessThreads, ( MAXCH == 16 ? 2 : 1 ) ) m
     g.tick( pb::kTickHess );
     if ( a.bv.wantvr || a.bv.wantvl ) {
       if constexpr ( MAXCH > 0 ) {
-        pb::form_q<MAXCH>( n, ilo, ihi, A, n, tau, V, n );
+        pb::form_q<MAXCH>( n, ilo, ihi, A, n, tau, V, n, smem );
       } else {
         if ( n <= kMidMaxBigN ) pb::form_q_big( n, ilo, ihi, A, n, tau, V, n, smem );
         else pb::orghr( g, n, ilo, ihi, A, n, tau, V, n );

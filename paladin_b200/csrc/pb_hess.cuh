@@ -31,7 +31,7 @@ constexpr int kHessThreads = 256;
 constexpr int kHessWarps = kHessThreads / 32;
 
 // shared memory (doubles): vprev, ypp, vcur, zpp, ycur, zcur : 6 n ; ypart: kHessWarps * n ; red: 64
-__host__ __device__ inline size_t hess_smem_doubles( int n ) { return (size_t)( 6 + kHessWarps ) * n + 64; }
+__host__ __device__ inline size_t hess_smem_doubles( int n ) { return (size_t)( 6 + kHessWarps ) * n + 64; }  // >= form_q's kFormQGroup*32*MAXCH + kFormQGroup
 
 __device__ __forceinline__ double cta_sum( double x, double* red ) {
   x = warp_sum( x );
@@ -208,59 +208,60 @@ __device__ void hess_fused( int n, int ilo, int ihi, double* A, int lda, double*
 
 // Q (n x n, ldq) = H(ilo) ... H(ihi-2) from the reflectors stored in A / tau, by backward accumulation:
 // for j = ihi-2 ... ilo the block Q(j+1:ihi, j+1:ihi) <- (I - tau v v^T) Q(...). Same streaming pattern as the
-// reduction itself: a warp owns a column at a time (loads it once, reduces v^T q with shuffles, updates, stores it
-// once), v_j sits in registers for the whole step. Two reflectors (j, j-1) are applied per sweep, which halves the
-// traffic: the second one only needs the already-updated column, which is still in registers.
+// reduction itself: a warp owns a column at a time (loads it once into registers, stores it once); kFormQGroup
+// consecutive reflectors are applied per sweep from shared memory (their vectors are staged there, zero outside their
+// support), which divides the traffic by kFormQGroup: every later reflector of the group only needs the
+// already-updated column, which is still in registers.
+constexpr int kFormQGroup = 8;
+
 template <int MAXCH>
 __device__ void form_q( int n, int ilo, int ihi, const double* __restrict__ A, int lda, const double* __restrict__ tau,
-                        double* __restrict__ Q, int ldq ) {
+                        double* __restrict__ Q, int ldq, double* sm ) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* vs = sm;                               // kFormQGroup vectors of length 32 * MAXCH
+  double* ts = sm + kFormQGroup * 32 * MAXCH;    // their tau
   // identity
   for ( int c = warp; c < n; c += kHessWarps )
     for ( int r = lane; r < n; r += 32 ) Q[r + (size_t)c * ldq] = ( r == c ) ? 1.0 : 0.0;
   __syncthreads();
   int j = ihi - 2;
   while ( j >= ilo ) {
-    const bool two = ( j - 1 >= ilo );
-    const int ja = j, jb = two ? j - 1 : j;           // apply H(ja) first, then H(jb)
-    const double ta = tau[ja], tb = two ? tau[jb] : 0.0;
-    // rows involved: jb+1 .. ihi ; first chunk that matters
-    const int k0 = ( jb + 1 ) >> 5;
-    double va[MAXCH], vb[MAXCH];
-#pragma unroll
-    for ( int k = 0; k < MAXCH; ++k ) {
-      const int r = lane + 32 * k;
-      const int rc = imin( r, n - 1 );
-      const double xa = A[rc + (size_t)ja * lda], xb = A[rc + (size_t)jb * lda];
-      va[k] = ( r == ja + 1 ) ? 1.0 : ( ( r >= ja + 2 && r <= ihi ) ? xa : 0.0 );
-      vb[k] = !two ? 0.0 : ( ( r == jb + 1 ) ? 1.0 : ( ( r >= jb + 2 && r <= ihi ) ? xb : 0.0 ) );
+    const int ng = imin( kFormQGroup, j - ilo + 1 );   // reflectors j, j-1, ..., j-ng+1, applied in this order
+    const int jlast = j - ng + 1;
+    for ( int q = tid; q < ng * 32 * MAXCH; q += kHessThreads ) {
+      const int g = q / ( 32 * MAXCH ), r = q - g * ( 32 * MAXCH );
+      const int jj = j - g;
+      double v = 0.0;
+      if ( r == jj + 1 ) v = 1.0;
+      else if ( r >= jj + 2 && r <= ihi ) v = A[r + (size_t)jj * lda];
+      vs[q] = v;
     }
-    // columns jb+1 .. ihi (column jb+1 = e_{jb+1} is only touched by H(jb))
-    for ( int c = jb + 1 + warp; c <= ihi; c += kHessWarps ) {
+    if ( tid < ng ) ts[tid] = tau[j - tid];
+    __syncthreads();
+    const int k0 = ( jlast + 1 ) >> 5;  // first 32-row chunk that any reflector of the group touches
+    // columns jlast+1 .. ihi (a column left of a reflector's support is simply not changed by it: v^T q = 0)
+    for ( int c = jlast + 1 + warp; c <= ihi; c += kHessWarps ) {
       double* col = Q + (size_t)c * ldq;
       double q[MAXCH];
 #pragma unroll
       for ( int k = 0; k < MAXCH; ++k ) q[k] = ( k >= k0 ) ? col[imin( lane + 32 * k, n - 1 )] : 0.0;
-      double wa = 0.0;
+      for ( int g = 0; g < ng; ++g ) {
+        const double* v = vs + g * 32 * MAXCH + lane;
+        double w = 0.0;
 #pragma unroll
-      for ( int k = 0; k < MAXCH; ++k ) wa += va[k] * q[k];
-      wa = warp_sum( wa ) * ta;
-      double wb = 0.0;
+        for ( int k = 0; k < MAXCH; ++k ) w += v[32 * k] * q[k];
+        w = warp_sum( w ) * ts[g];
 #pragma unroll
-      for ( int k = 0; k < MAXCH; ++k ) {
-        q[k] -= wa * va[k];
-        wb += vb[k] * q[k];
+        for ( int k = 0; k < MAXCH; ++k ) q[k] -= w * v[32 * k];
       }
-      wb = warp_sum( wb ) * tb;
 #pragma unroll
       for ( int k = 0; k < MAXCH; ++k ) {
-        q[k] -= wb * vb[k];
         const int r = lane + 32 * k;
         if ( k >= k0 && r <= ihi ) col[r] = q[k];
       }
     }
     __syncthreads();
-    j -= two ? 2 : 1;
+    j -= ng;
   }
 }
 
