@@ -177,7 +177,7 @@ __global__ void __launch_bounds__( kGenericThreads ) geev_cta_kernel( BatchView 
 constexpr int kMidThreads = 256;
 constexpr int kNumTicks = 16;
 
-__host__ __device__ inline pb::MsqrCfg mid_cfg() { return pb::MsqrCfg{ 8, pb::kStripW, pb::kStripW - 1, 128, 2, 32 }; }
+__host__ __device__ inline pb::MsqrCfg mid_cfg() { return pb::MsqrCfg{ 8, pb::kStripW, pb::kStripW - 1, 128, 2, 32, pb::kStripW - 1 }; }
 
 constexpr int kMidMaxFusedN = 1024;  // warp-level kernels keep a matrix column in 32 * MAXCH registers per warp
 constexpr int kMidMaxBigN = 4608;    // streaming variants: 6 n + 64 doubles of shared memory
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__( pb::kHessThreads, ( MAXCH == 16 ? 2 : 1 ) ) m
 // ---- stage 2: QR iteration (windowed multishift sweeps) --------------------------------------------------
 inline size_t qr_smem_bytes() {
   const pb::MsqrCfg c = mid_cfg();
-  return sizeof( double ) * pb::msqr_work_doubles( c, c.W | 1, c.tl | 1 ) + sizeof( int ) * ( 3 * pb::kMsMaxBulges + 8 );
+  return sizeof( double ) * pb::msqr_work_doubles( c, c.W | 1, c.tl | 1 ) + sizeof( int ) * pb::kMsIbufInts;
 }
 
 __global__ void __launch_bounds__( kMidThreads, 2 ) mid_qr_kernel( MidArgs a ) {
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__( kMidThreads, 2 ) mid_qr_kernel( MidArgs a ) {
   wk.ibuf = reinterpret_cast<int*>( p );
   wk.ldw = ldw;
   wk.ldt = ldt;
-  if ( threadIdx.x < 3 * pb::kMsMaxBulges + 8 ) wk.ibuf[threadIdx.x] = 0;
+  if ( threadIdx.x < pb::kMsIbufInts ) wk.ibuf[threadIdx.x] = 0;
   const int id = a.ids[blockIdx.x];
   const int n = a.bv.n[id];
   pb::CtaGroup g{ red };

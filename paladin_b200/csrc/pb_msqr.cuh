@@ -28,13 +28,18 @@
 #include "pb_common.cuh"
 #include "pb_small.cuh"
 #include "pb_strips.cuh"
+#include "pb_aed.cuh"
 
 namespace pb {
 
 constexpr int kMsMaxBulges = 16;
+// ints of MsqrWork::ibuf: kpos, kfirst, kcount (kMsMaxBulges each), then
+//   +0 shift count  +1 sweeps  +2 windows  +3 small solves  +4 scratch  +5 steady-state windows  +6 strip work queue
+//   +8..+10 AED results (ns, lahqr code, changed)  +11 AED calls  +12 eigenvalues deflated by AED  +13 sweeps skipped
+constexpr int kMsIbufInts = 3 * kMsMaxBulges + 16;
 constexpr int kReflStride = 6;  // w2, w3, t1, t2, t3, pad  (three 16-byte loads)
 // phase-profile slots (CtaGroup::tick)
-constexpr int kTickMsScan = 8, kTickMsShifts = 9, kTickMsChase = 10, kTickMsStrips = 11, kTickMsSmall = 12, kTickMsSmallU = 13;
+constexpr int kTickMsScan = 8, kTickMsShifts = 9, kTickMsChase = 10, kTickMsStrips = 11, kTickMsSmall = 12, kTickMsSmallU = 13, kTickMsAed = 14;
 
 struct MsqrCfg {
   int nb;        // bulges per chain, <= kMsMaxBulges
@@ -43,6 +48,7 @@ struct MsqrCfg {
   int tl;        // lines per strip tile
   int nchains;   // chains (of nb bulges) per sweep
   int nshift;    // shifts computed per sweep (<= 2*nb*nchains); chains beyond nshift/(2 nb) reuse them cyclically
+  int aed = 0;   // order of the aggressive-early-deflation window (<= W - 1); 0 = no AED
 };
 
 // on-chip work space (shared memory on the device)
@@ -54,7 +60,7 @@ struct MsqrWork {
   double* refl;   // nb * W * kReflStride
   double* sr;     // 2*nb*nchains shifts (real parts)
   double* si;     //                     (imaginary parts)
-  int* ibuf;      // 3*kMsMaxBulges + 8 ints: kpos, kfirst, kcount
+  int* ibuf;      // kMsIbufInts ints: kpos, kfirst, kcount, counters
   int ldw, ldt;
 };
 
@@ -338,6 +344,55 @@ PB_D int ms_small_solve( const G& g, bool wantt, bool wantz, int n, int l, int i
   return 0;
 }
 
+// ---- shift list -> pairs ----------------------------------------------------------------------------
+// in: candidates ks..ns-1 of sr/si (any arrays visible to the group); out: at most `keep` of them (the smallest
+// moduli) at the front of wk.sr / wk.si, arranged in pairs (conjugates adjacent, reals two by two). Returns the count.
+template <class G>
+PB_D int ms_arrange_shifts( const G& g, double* sr, double* si, int ks, int ns, int keep, const MsqrWork& wk ) {
+  const int t = g.tid();
+  // one thread: sort by decreasing modulus (helps convergence a little), then arrange into pairs
+  if ( t == 0 ) {
+    bool sorted = false;
+    for ( int k = ns - 1; k >= ks + 1 && !sorted; --k ) {
+      sorted = true;
+      for ( int q = ks; q < k; ++q ) {
+        if ( fabs( sr[q] ) + fabs( si[q] ) < fabs( sr[q + 1] ) + fabs( si[q + 1] ) ) {
+          sorted = false;
+          double tmp = sr[q]; sr[q] = sr[q + 1]; sr[q + 1] = tmp;
+          tmp = si[q]; si[q] = si[q + 1]; si[q + 1] = tmp;
+        }
+      }
+    }
+    // conjugate pairs are adjacent after the sort (equal modulus); rotate triples where a real shift
+    // would split a pair
+    for ( int q = ns - 1; q >= ks + 2; q -= 2 ) {
+      if ( si[q] != -si[q - 1] ) {
+        double tmp = sr[q]; sr[q] = sr[q - 1]; sr[q - 1] = sr[q - 2]; sr[q - 2] = tmp;
+        tmp = si[q]; si[q] = si[q - 1]; si[q - 1] = si[q - 2]; si[q - 2] = tmp;
+      }
+    }
+    // keep the trailing (smallest) ones; an odd count drops the first shift
+    int first = imax( ks, ns - keep );
+    if ( ( ( ns - first ) & 1 ) != 0 ) first += 1;
+    // a pair that is neither conjugate nor real-real (cannot happen with exact conjugates) is made real
+    for ( int q = first; q + 1 < ns; q += 2 ) {
+      if ( si[q] != -si[q + 1] ) {
+        si[q] = 0.0;
+        si[q + 1] = 0.0;
+      }
+    }
+    // compact to the front of the work arrays
+    const int cnt = ns - first;
+    for ( int q = 0; q < cnt; ++q ) {
+      wk.sr[q] = sr[first + q];
+      wk.si[q] = si[first + q];
+    }
+    wk.ibuf[3 * kMsMaxBulges] = cnt;
+  }
+  g.sync();
+  return wk.ibuf[3 * kMsMaxBulges];
+}
+
 // ---- shifts: eigenvalues of the trailing ns x ns block of [l..i] -----------------------------------
 // Leaves ns_out (even, >= 2) shifts in wk.sr / wk.si, arranged in pairs (conjugates adjacent, reals two by two).
 template <class G>
@@ -395,47 +450,7 @@ PB_D int ms_compute_shifts( const G& g, int l, int i, const double* H, int ldh, 
       ks = ns - 2;
     }
   }
-  // one thread: sort by decreasing modulus (helps convergence a little), then arrange into pairs
-  if ( t == 0 ) {
-    bool sorted = false;
-    for ( int k = ns - 1; k >= ks + 1 && !sorted; --k ) {
-      sorted = true;
-      for ( int q = ks; q < k; ++q ) {
-        if ( fabs( sr[q] ) + fabs( si[q] ) < fabs( sr[q + 1] ) + fabs( si[q + 1] ) ) {
-          sorted = false;
-          double tmp = sr[q]; sr[q] = sr[q + 1]; sr[q + 1] = tmp;
-          tmp = si[q]; si[q] = si[q + 1]; si[q + 1] = tmp;
-        }
-      }
-    }
-    // conjugate pairs are adjacent after the sort (equal modulus); rotate triples where a real shift
-    // would split a pair
-    for ( int q = ns - 1; q >= ks + 2; q -= 2 ) {
-      if ( si[q] != -si[q - 1] ) {
-        double tmp = sr[q]; sr[q] = sr[q - 1]; sr[q - 1] = sr[q - 2]; sr[q - 2] = tmp;
-        tmp = si[q]; si[q] = si[q - 1]; si[q - 1] = si[q - 2]; si[q - 2] = tmp;
-      }
-    }
-    // an odd count drops the first shift
-    int first = ks;
-    if ( ( ( ns - first ) & 1 ) != 0 ) first += 1;
-    // a pair that is neither conjugate nor real-real (cannot happen with exact conjugates) is made real
-    for ( int q = first; q + 1 < ns; q += 2 ) {
-      if ( si[q] != -si[q + 1] ) {
-        si[q] = 0.0;
-        si[q + 1] = 0.0;
-      }
-    }
-    // compact to the front
-    const int cnt = ns - first;
-    for ( int q = 0; q < cnt; ++q ) {
-      sr[q] = sr[first + q];
-      si[q] = si[first + q];
-    }
-    wk.ibuf[3 * kMsMaxBulges] = cnt;
-  }
-  g.sync();
-  return wk.ibuf[3 * kMsMaxBulges];
+  return ms_arrange_shifts( g, sr, si, ks, ns, ns, wk );
 }
 
 #if defined( __CUDACC__ )
@@ -751,6 +766,68 @@ PB_D void ms_chase_chain( const G& g, bool wantt, bool wantz, int n, int l, int 
   }
 }
 
+// ---- aggressive early deflation on the trailing jw x jw window of the active block [ktop..kbot] -----------
+// nd_out: eigenvalues deflated (now final in wr/wi, H split below row kbot - nd); ns_out: shift candidates left in
+// wk.sr / wk.si (arranged in pairs, at most `keep`).
+template <class G>
+PB_D void ms_aed( const G& g, bool wantt, bool wantz, int n, int ktop, int kbot, int jw, int keep, double* H, int ldh, double* wr,
+                  double* wi, int iloz, int ihiz, double* Z, int ldz, const MsqrCfg& cfg, const MsqrWork& wk, int* nd_out,
+                  int* ns_out ) {
+  const int t = g.tid(), nt = g.size();
+  const int kwtop = kbot - jw + 1;
+  const int ldw = wk.ldw;
+  const double s = ( kwtop > ktop ) ? PB_H( kwtop, kwtop - 1 ) : 0.0;
+  ms_load_window( g, H, ldh, kwtop, jw, wk.Hw, ldw );
+  for ( int q = t; q < jw * jw; q += nt ) {
+    const int c = q / jw, r = q - c * jw;
+    wk.U[r + c * ldw] = ( r == c ) ? 1.0 : 0.0;
+  }
+  if ( t == 0 ) wk.ibuf[3 * kMsMaxBulges + 11] += 1;
+  g.sync();
+  int* out = wk.ibuf + 3 * kMsMaxBulges + 8;
+  double* er = wk.tile;            // eigenvalues of the window (2 jw doubles), then 2 jw doubles of scratch
+  double* ei = wk.tile + jw;
+  bool warp_done = false;
+#if defined( __CUDACC__ )
+  if constexpr ( G::kIsCta ) {
+    // a window of <= 48 rows keeps one warp busy at best: warp 0 runs it with warp-level barriers only
+    if ( ( threadIdx.x >> 5 ) == 0 ) aed_window( WarpGroup(), jw, wk.Hw, ldw, wk.U, ldw, s, er, ei, wk.tile + 2 * jw, out );
+    __syncthreads();
+    warp_done = true;
+  }
+#endif
+  if ( !warp_done ) aed_window( g, jw, wk.Hw, ldw, wk.U, ldw, s, er, ei, wk.tile + 2 * jw, out );
+  g.sync();
+  const int ns = out[0], infqr = out[1], changed = out[2];
+  PB_CHECK_UNIFORM( g, ns * 4 + changed, "aed result" );
+  if ( infqr != 0 ) {  // the window's own QR iteration failed: nothing was written back, no shifts from here
+    *nd_out = 0;
+    *ns_out = 0;
+    return;
+  }
+  // deflated eigenvalues are final
+  for ( int q = ns + t; q < jw; q += nt ) {
+    wr[kwtop + q] = er[q];
+    wi[kwtop + q] = ei[q];
+  }
+  if ( t == 0 ) wk.ibuf[3 * kMsMaxBulges + 12] += jw - ns;
+  // shift candidates: eigenvalues of the undeflated part
+  int nshift = 0;
+  if ( ns >= 2 ) nshift = ms_arrange_shifts( g, er, ei, 0, ns, keep, wk );
+  else g.sync();
+  if ( changed ) {
+    if ( t == 0 && kwtop > ktop ) PB_H( kwtop, kwtop - 1 ) = s * wk.U[0];
+    for ( int q = t; q < jw * jw; q += nt ) {
+      const int c = q / jw, r = q - c * jw;
+      if ( r - c <= 1 ) PB_H( kwtop + r, kwtop + c ) = wk.Hw[r + c * ldw];
+    }
+    g.sync();
+    ms_update_strips( g, wantt, wantz, n, ktop, kbot, kwtop, jw, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, 0, wk.U );
+  }
+  *nd_out = jw - ns;
+  *ns_out = nshift;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Driver. H upper Hessenberg in rows/cols ilo..ihi (isolated eigenvalues outside are the caller's
 // business, as in pb::lahqr). Returns 0 or LAPACK's info (i+1: eigenvalues i+1..ihi converged).
@@ -789,12 +866,46 @@ PB_D int hqr_multishift( const G& g, bool wantt, bool wantz, int n, int ilo, int
       continue;
     }
     if ( ++it > itmax ) return kbot + 1;
-    if ( t == 0 ) wk.ibuf[3 * kMsMaxBulges + 1] += 1;
-    nodefl += 1;
     // the shift block is factored inside the U buffer, hence ns <= W
     const int nshift_cfg = imin( cfg.nshift > 0 ? cfg.nshift : 2 * cfg.nb * cfg.nchains, 2 * cfg.nb * cfg.nchains );
-    const int nshift_want = imin( imin( nshift_cfg, cfg.W & ~1 ), ( ( m - 1 ) / 3 ) * 2 );
-    const int ns = ms_compute_shifts( g, ktop, kbot, H, ldh, imax( 2, nshift_want & ~1 ), ( nodefl % 6 ) == 0, wk );
+    int ns_aed = 0;
+    if ( cfg.aed > 0 ) {
+      const int jw = imin( imin( cfg.aed, cfg.W - 1 ), m );
+      int nd = 0;
+      ms_aed( g, wantt, wantz, n, ktop, kbot, jw, nshift_cfg, H, ldh, wr, wi, iloz, ihiz, Z, ldz, cfg, wk, &nd, &ns_aed );
+      PB_CHECK_UNIFORM( g, nd * 100 + ns_aed, "aed nd/ns" );
+      g.tick( kTickMsAed );
+      if ( nd > 0 ) {
+        kbot -= nd;
+        nodefl = 0;
+        // enough deflations (LAPACK's nibble = 14 %), or what is left is a small block: no sweep this time
+        if ( 100 * nd > 14 * jw || kbot - ktop + 1 <= cfg.ws_small ) {
+          if ( t == 0 ) wk.ibuf[3 * kMsMaxBulges + 13] += 1;
+          continue;
+        }
+      }
+    }
+    const int mm = kbot - ktop + 1;
+    if ( t == 0 ) wk.ibuf[3 * kMsMaxBulges + 1] += 1;
+    nodefl += 1;
+    const int nshift_want = imax( 2, imin( imin( nshift_cfg, cfg.W & ~1 ), ( ( mm - 1 ) / 3 ) * 2 ) & ~1 );
+    int ns;
+    const bool exceptional = ( nodefl % 6 ) == 0;
+    if ( !exceptional && ns_aed >= imax( 2, nshift_want / 2 ) ) {
+      // AED left enough shift candidates in wk.sr / wk.si (the smallest moduli are at the end)
+      ns = imin( ns_aed, nshift_want );
+      if ( ns < ns_aed ) {
+        g.sync();
+        if ( t == 0 )
+          for ( int q = 0; q < ns; ++q ) {
+            wk.sr[q] = wk.sr[ns_aed - ns + q];
+            wk.si[q] = wk.si[ns_aed - ns + q];
+          }
+        g.sync();
+      }
+    } else {
+      ns = ms_compute_shifts( g, ktop, kbot, H, ldh, nshift_want, exceptional, wk );
+    }
     PB_CHECK_UNIFORM( g, ns, "ns" );
     g.tick( kTickMsShifts );
     // chains of nb bulges; with fewer computed shifts than chains * 2 nb the set is reused cyclically

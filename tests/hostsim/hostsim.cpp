@@ -218,7 +218,7 @@ struct MsBuffers {
   MsBuffers( const pb::MsqrCfg& c ) {
     const int ldw = c.W | 1, ldt = c.tl | 1;
     d.assign( pb::msqr_work_doubles( c, ldw, ldt ) + 64, 0.0 );
-    i.assign( 3 * pb::kMsMaxBulges + 8, 0 );
+    i.assign( pb::kMsIbufInts, 0 );
     double* p = d.data();
     wk.Hw = p; p += pb::ms_even( (size_t)c.W * ldw );
     wk.U = p; p += pb::ms_even( (size_t)c.W * ldw );
@@ -232,21 +232,27 @@ struct MsBuffers {
   }
 };
 
-int g_ms_counters[8];
+// block reordering of the AED step (pb_aed.cuh): move the block at ifst up to ilst, Q accumulated
+int hs_trexc_up( int n, double* T, double* Q, int ifst, int ilst ) {
+  pb::HostGroup g;
+  return pb::aed_trexc_up( g, n, T, n, Q, n, n, ifst, ilst );
+}
+
+int g_ms_counters[16];
 int hs_msqr( int wantt, int wantz, int n, int ilo, int ihi, double* H, double* wr, double* wi, double* Z, int nb, int W,
              int ws_small, int tl, int nchains ) {
   pb::HostGroup g;
-  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains % 100, nchains / 100 };
+  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains % 100, ( nchains / 100 ) % 100, nchains / 10000 };
   MsBuffers buf( c );
   const int r = pb::hqr_multishift( g, wantt != 0, wantz != 0, n, ilo, ihi, H, n, wr, wi, 0, n - 1, Z, n, c, buf.wk );
-  for ( int k = 0; k < 8; ++k ) g_ms_counters[k] = buf.i[3 * pb::kMsMaxBulges + k];
+  for ( int k = 0; k < 16; ++k ) g_ms_counters[k] = buf.i[3 * pb::kMsMaxBulges + k];
   return r;
 }
 const int* hs_ms_counters() { return g_ms_counters; }
 
 int ht_msqr( int nt, int wantt, int wantz, int n, int ilo, int ihi, double* H, double* wr, double* wi, double* Z, int nb,
              int W, int ws_small, int tl, int nchains ) {
-  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains % 100, nchains / 100 };
+  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains % 100, ( nchains / 100 ) % 100, nchains / 10000 };
   MsBuffers buf( c );
   return run_threads( nt, [&]( const ThreadGroup& g ) {
     return pb::hqr_multishift( g, wantt != 0, wantz != 0, n, ilo, ihi, H, n, wr, wi, 0, n - 1, Z, n, c, buf.wk );
@@ -258,7 +264,7 @@ int hs_geev_ms( int n, double* A, double* wr, double* wi, int wantvr, double* V,
   pb::HostGroup g;
   std::vector<double> dw( 5 * n + 5 );
   std::vector<int> iw( 2 * n + 2 );
-  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains % 100, nchains / 100 };
+  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains % 100, ( nchains / 100 ) % 100, nchains / 10000 };
   MsBuffers buf( c );
   return pb::geev_group( g, n, A, n, wr, wi, false, (double*)nullptr, n, wantvr != 0, V, n, dw.data(), iw.data(), pb::QrMultishift{ c, buf.wk } );
 }
@@ -267,7 +273,7 @@ int ht_geev_ms( int nt, int n, double* A, double* wr, double* wi, int wantvr, do
                 int nchains ) {
   std::vector<double> dw( 5 * n + 5 );
   std::vector<int> iw( 2 * n + 2 );
-  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains % 100, nchains / 100 };
+  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains % 100, ( nchains / 100 ) % 100, nchains / 10000 };
   MsBuffers buf( c );
   return run_threads( nt, [&]( const ThreadGroup& g ) {
     return pb::geev_group( g, n, A, n, wr, wi, false, (double*)nullptr, n, wantvr != 0, V, n, dw.data(), iw.data(), pb::QrMultishift{ c, buf.wk } );

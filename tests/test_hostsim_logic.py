@@ -76,7 +76,10 @@ def _hessenberg_case(n, seed, sparse=False):
     return B, ilo, ihi, np.asfortranarray(np.triu(H, -1)), Hj, Q
 
 
-MS_CONFIGS = [(8, 49, 48, 128, 1), (8, 49, 48, 256, 2), (4, 17, 16, 7, 1), (2, 10, 6, 5, 3), (16, 97, 64, 64, 1)]
+# last entry: chains + 100 * shifts per sweep + 10000 * AED window order (0 = no AED)
+MS_CONFIGS = [(8, 49, 48, 128, 1), (8, 49, 48, 256, 2), (4, 17, 16, 7, 1), (2, 10, 6, 5, 3), (16, 97, 64, 64, 1),
+              (8, 49, 48, 128, 2 + 100 * 32 + 10000 * 48), (4, 17, 16, 7, 1 + 10000 * 16), (2, 10, 6, 5, 3 + 10000 * 9),
+              (8, 49, 20, 64, 2 + 10000 * 30)]
 
 
 @pytest.mark.parametrize("n", [10, 49, 50, 80, 130, 200])
@@ -102,6 +105,75 @@ def test_multishift_qr_matches_lapack_dhseqr(hs, n, cfg):
                 for k in np.nonzero(sub)[0]:  # standardised 2x2 blocks (dlanv2), never two in a row
                     assert T[k, k] == T[k + 1, k + 1] and T[k, k + 1] * T[k + 1, k] < 0
                     assert k + 1 >= n - 1 or sub[k + 1] == 0
+
+
+def test_block_swaps_match_lapack_dtrexc(hs):
+    """pb::aed_trexc_up (dtrexc/dlaexc restated, pb_aed.cuh) against LAPACK: same eigenvalue order, orthogonal
+    accumulated factor, similarity preserved."""
+    from scipy.linalg import schur
+    rng = np.random.default_rng(123)
+    moved = 0
+    for n in (2, 3, 5, 8, 13, 24, 48):
+        for trial in range(6):
+            A = rng.standard_normal((n, n))
+            if trial >= 4:
+                A = np.triu(A)  # real spectrum: 1x1 blocks only
+            T, Q = schur(A, output="real")
+            T = np.asfortranarray(T); Q = np.asfortranarray(Q)
+            starts = [k for k in range(n) if k == 0 or T[k, k - 1] == 0]
+            for ifst in starts[1:]:
+                for ilst in starts:
+                    if ilst >= ifst:
+                        continue
+                    T2, Q2 = T.copy(order="F"), Q.copy(order="F")
+                    at = hs.hs_trexc_up(n, dp(T2), dp(Q2), ifst, ilst)
+                    assert at == ilst
+                    assert np.abs(np.tril(T2, -2)).max() == 0 if n > 2 else True
+                    sub = np.diag(T2, -1)
+                    for k in np.nonzero(sub)[0]:
+                        assert T2[k, k] == T2[k + 1, k + 1] and T2[k, k + 1] * T2[k + 1, k] < 0
+                        assert k + 1 >= n - 1 or sub[k + 1] == 0
+                    nrm = max(1.0, np.abs(A).max())
+                    assert np.abs(Q2 @ T2 @ Q2.T - A).max() <= 1e-13 * nrm * n
+                    assert np.abs(Q2.T @ Q2 - np.eye(n)).max() <= 1e-13 * n
+                    # the moved block's eigenvalue(s) now sit at ilst; the blocks it passed keep their relative order
+                    def blocks(M):
+                        out, k = [], 0
+                        while k < n:
+                            if k + 1 < n and M[k + 1, k] != 0:
+                                out.append(complex(M[k, k], np.sqrt(abs(M[k, k + 1] * M[k + 1, k])))); k += 2
+                            else:
+                                out.append(complex(M[k, k], 0.0)); k += 1
+                        return out
+                    b0, b2 = blocks(T), blocks(T2)
+                    i0, i1 = starts.index(ifst), starts.index(ilst)
+                    want = b0[:i1] + [b0[i0]] + b0[i1:i0] + b0[i0 + 1:]
+                    assert len(want) == len(b2)
+                    assert np.abs(np.array(want) - np.array(b2)).max() <= 1e-10 * nrm * n
+                    moved += 1
+    assert moved > 200
+
+
+def test_aed_reduces_sweeps(hs):
+    """AED (pb_aed.cuh) must deflate most eigenvalues and at least halve the number of sweeps at n = 256."""
+    n = 256
+    B, ilo, ihi, H, Hj, Q = _hessenberg_case(n, 9)
+    hs.hs_ms_counters.restype = ctypes.POINTER(ctypes.c_int)
+    T0, wr0, wi0, Z0, info0 = ls.dhseqr(H, ilo, ihi, Z=Q)
+    sweeps = {}
+    for aed in (0, 48):
+        H2, Z2 = Hj.copy(order="F"), Q.copy(order="F")
+        wr, wi = np.zeros(n), np.zeros(n)
+        assert hs.hs_msqr(1, 1, n, ilo - 1, ihi - 1, dp(H2), dp(wr), dp(wi), dp(Z2), 8, 49, 48, 128, 2 + 100 * 32 + 10000 * aed) == 0
+        c = hs.hs_ms_counters()
+        sweeps[aed] = c[1]
+        if aed:
+            assert c[12] >= n // 2
+        nrm = max(1.0, np.linalg.norm(B, 2))
+        assert po.match_eigenvalues(wr + 1j * wi, wr0 + 1j * wi0) <= 1e-9 * nrm
+        T = np.triu(H2, -1)
+        assert np.abs(Z2 @ T @ Z2.T - B).max() <= 1e-12 * nrm * n
+    assert 2 * sweeps[48] <= sweeps[0]
 
 
 def test_multishift_geev_pipeline(hs):
@@ -211,7 +283,7 @@ from oracle import lapack_stages as ls, paladin_oracle as po
 hs = ctypes.CDLL(%r)
 dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
 rng = np.random.default_rng(1)
-for n, nt, (nb, W, wss, tl, nch) in [(30, 4, (2, 10, 6, 5, 2)), (40, 3, (3, 14, 8, 6, 1)), (26, 5, (2, 11, 7, 4, 3))]:
+for n, nt, (nb, W, wss, tl, nch) in [(30, 4, (2, 10, 6, 5, 2)), (40, 3, (3, 14, 8, 6, 1)), (26, 5, (2, 11, 7, 4, 3)), (44, 4, (2, 13, 8, 6, 2 + 10000 * 12)), (36, 5, (3, 14, 6, 5, 1 + 10000 * 9))]:
     A = rng.standard_normal((n, n))
     for wantvr in (0, 1):
         A2 = np.array(A, order='F'); wr = np.zeros(n); wi = np.zeros(n); V = np.zeros((n, n), order='F')
