@@ -13,7 +13,7 @@ _LIB = None
 NUM_STAGES = 8
 STAGE_NAMES = ("scatter", "balance", "hessenberg", "qr", "vectors", "small", "generic", "mid")
 PHASE_NAMES = ("balance", "hessenberg", "form_q", "qr_total", "trevc", "bak_normalise", "vec_gemm", "", "ms_scan", "ms_shifts",
-               "ms_chase", "ms_strips", "ms_small", "ms_small_u", "", "")
+               "ms_chase", "ms_strips", "ms_small", "ms_small_u", "ms_aed_window", "ms_aed_update")
 
 _c_int_p = ctypes.POINTER(ctypes.c_int)
 _c_i64_p = ctypes.POINTER(ctypes.c_int64)

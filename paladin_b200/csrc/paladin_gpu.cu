@@ -177,7 +177,11 @@ __global__ void __launch_bounds__( kGenericThreads ) geev_cta_kernel( BatchView 
 constexpr int kMidThreads = 256;
 constexpr int kNumTicks = 16;
 
-__host__ __device__ inline pb::MsqrCfg mid_cfg() { return pb::MsqrCfg{ 8, pb::kStripW, pb::kStripW - 1, 128, 2, 32, pb::kStripW - 1 }; }
+// AED window without block reordering (pb::aed_window). Its order is set per matrix (mid_aed_order): measured on B200,
+// 592 x n=512: QR stage 392 ms without AED, 263 / 271 / 277 ms with windows of 32 / 40 / 48 rows; 148 x n=1024: 682 ms
+// without, 402 / 410 ms with 32 / 48 (the strips grow with n, the window's own QR iteration does not).
+__host__ __device__ inline pb::MsqrCfg mid_cfg() { return pb::MsqrCfg{ 8, pb::kStripW, pb::kStripW - 1, 128, 2, 32, 32, 0 }; }
+__host__ __device__ inline int mid_aed_order( int n ) { return n <= 1024 ? 32 : pb::kStripW - 1; }
 
 constexpr int kMidMaxFusedN = 1024;  // warp-level kernels keep a matrix column in 32 * MAXCH registers per warp
 constexpr int kMidMaxBigN = 4608;    // streaming variants: 6 n + 64 doubles of shared memory
@@ -198,6 +202,7 @@ struct MidArgs {
   double* xwork;   // slots of xn_max^2 doubles for the triangular eigenvector factor
   size_t xslot;    // doubles per slot
   int xn_max;      // largest order a slot can hold (larger matrices use the in-place path)
+  int aed, aed_moves;  // tuning overrides of mid_cfg() (PALADIN_GPU_AED, PALADIN_GPU_AED_MOVES); -1 = default
 };
 
 __device__ __forceinline__ void mid_pointers( const BatchView& bv, int id, int n, double*& A, double*& V, double*& wr, double*& wi,
@@ -300,7 +305,10 @@ __global__ void __launch_bounds__( kMidThreads, 2 ) mid_qr_kernel( MidArgs a ) {
   extern __shared__ double smem[];
   __shared__ double red[64];
   __shared__ long long lstats[kNumTicks];
-  const pb::MsqrCfg c = mid_cfg();
+  pb::MsqrCfg c = mid_cfg();
+  c.aed = mid_aed_order( a.bv.n[a.ids[blockIdx.x]] );
+  if ( a.aed >= 0 ) c.aed = a.aed;
+  if ( a.aed_moves >= 0 ) c.aed_moves = a.aed_moves;
   const int ldw = c.W | 1, ldt = c.tl | 1;
   pb::MsqrWork wk;
   double* p = smem;
@@ -918,6 +926,10 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
       ma.xwork = b->d_xwork;
       ma.xslot = b->xslot;
       ma.xn_max = b->xn_max;
+      static const int env_aed = std::getenv( "PALADIN_GPU_AED" ) ? std::atoi( std::getenv( "PALADIN_GPU_AED" ) ) : -1;
+      static const int env_moves = std::getenv( "PALADIN_GPU_AED_MOVES" ) ? std::atoi( std::getenv( "PALADIN_GPU_AED_MOVES" ) ) : -1;
+      ma.aed = std::min( env_aed, pb::kStripW - 1 );
+      ma.aed_moves = env_moves;
       PB_CUDA( cudaMemsetAsync( b->d_stats, 0, sizeof( long long ) * kNumTicks, st ) );
       PB_CUDA( cudaMemsetAsync( b->d_counter, 0, sizeof( int ), st ) );
       const size_t s2 = qr_smem_bytes(), s3 = vec_smem_bytes( g.nmax );

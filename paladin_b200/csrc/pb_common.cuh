@@ -103,6 +103,59 @@ struct WarpGroup {
   PB_D void tick( int ) const {}
 };
 
+// the first nw warps of a CTA, synchronised by named barrier 1 (the CTA's other warps must not use that barrier
+// meanwhile); red points at >= 2 * nw doubles of shared scratch. A 32..48-row problem in shared memory offers 48-way
+// parallelism in each of its three update loops: three warps run them side by side where one warp needs two passes.
+struct WarpsGroup {
+  static constexpr bool kIsCta = false;
+  int nw;
+  double* red;
+  PB_D int tid() const { return threadIdx.x; }
+  PB_D int size() const { return 32 * nw; }
+  PB_D void sync() const { asm volatile( "bar.sync 1, %0;" ::"r"( 32 * nw ) : "memory" ); }
+  PB_D double sum( double x ) const {
+    x = warp_sum( x );
+    sync();
+    if ( ( threadIdx.x & 31 ) == 0 ) red[threadIdx.x >> 5] = x;
+    sync();
+    double t = 0.0;
+    for ( int i = 0; i < nw; ++i ) t += red[i];
+    return t;
+  }
+  PB_D double max( double x ) const {
+    x = warp_max( x );
+    sync();
+    if ( ( threadIdx.x & 31 ) == 0 ) red[threadIdx.x >> 5] = x;
+    sync();
+    double t = red[0];
+    for ( int i = 1; i < nw; ++i ) t = fmax( t, red[i] );
+    return t;
+  }
+  PB_D int imax_( int x ) const {
+    x = warp_imax( x );
+    int* ired = reinterpret_cast<int*>( red );
+    sync();
+    if ( ( threadIdx.x & 31 ) == 0 ) ired[threadIdx.x >> 5] = x;
+    sync();
+    int t = ired[0];
+    for ( int i = 1; i < nw; ++i ) t = ::max( t, ired[i] );
+    return t;
+  }
+  PB_D int imin_( int x ) const { return -imax_( -x ); }
+  PB_D int isum( int x ) const {
+    x = warp_isum( x );
+    int* ired = reinterpret_cast<int*>( red );
+    sync();
+    if ( ( threadIdx.x & 31 ) == 0 ) ired[threadIdx.x >> 5] = x;
+    sync();
+    int t = 0;
+    for ( int i = 0; i < nw; ++i ) t += ired[i];
+    return t;
+  }
+  PB_D bool any( bool x ) const { return imax_( x ? 1 : 0 ) != 0; }
+  PB_D void tick( int ) const {}
+};
+
 // whole thread block; red points at >= 64 doubles of shared scratch owned by the group
 struct CtaGroup {
   static constexpr bool kIsCta = true;

@@ -35,11 +35,11 @@ namespace pb {
 constexpr int kMsMaxBulges = 16;
 // ints of MsqrWork::ibuf: kpos, kfirst, kcount (kMsMaxBulges each), then
 //   +0 shift count  +1 sweeps  +2 windows  +3 small solves  +4 scratch  +5 steady-state windows  +6 strip work queue
-//   +8..+10 AED results (ns, lahqr code, changed)  +11 AED calls  +12 eigenvalues deflated by AED  +13 sweeps skipped
+//   +8..+11 AED results (ns, lahqr code, changed, shifts valid)  +12 eigenvalues deflated by AED  +13 sweeps skipped  +14 AED calls
 constexpr int kMsIbufInts = 3 * kMsMaxBulges + 16;
 constexpr int kReflStride = 6;  // w2, w3, t1, t2, t3, pad  (three 16-byte loads)
 // phase-profile slots (CtaGroup::tick)
-constexpr int kTickMsScan = 8, kTickMsShifts = 9, kTickMsChase = 10, kTickMsStrips = 11, kTickMsSmall = 12, kTickMsSmallU = 13, kTickMsAed = 14;
+constexpr int kTickMsScan = 8, kTickMsShifts = 9, kTickMsChase = 10, kTickMsStrips = 11, kTickMsSmall = 12, kTickMsSmallU = 13, kTickMsAed = 14, kTickMsAedU = 15;
 
 struct MsqrCfg {
   int nb;        // bulges per chain, <= kMsMaxBulges
@@ -49,6 +49,7 @@ struct MsqrCfg {
   int nchains;   // chains (of nb bulges) per sweep
   int nshift;    // shifts computed per sweep (<= 2*nb*nchains); chains beyond nshift/(2 nb) reuse them cyclically
   int aed = 0;   // order of the aggressive-early-deflation window (<= W - 1); 0 = no AED
+  int aed_moves = 1 << 20;  // undeflatable blocks an AED step may reorder (see pb::aed_window)
 };
 
 // on-chip work space (shared memory on the device)
@@ -103,6 +104,24 @@ PB_D int ms_find_split( const G& g, int ilo, int ihi, int lo, int hi, const doub
 }
 
 constexpr int kWinBatch = 8;
+// warps that run the in-window dense problems (pb::WarpsGroup): Schur factorisations with vectors have three 48-wide
+// loops per Francis step, the eigenvalue-only shift computation two
+// (measured at n = 512, two CTAs per SM: 1 warp 263 ms per 592 matrices, 3/2 warps 275 ms -- the Francis step is bound by
+// the latency of its reflector, not by its loops, and a named barrier costs more than __syncwarp)
+#ifndef PB_SMALL_WARPS
+#define PB_SMALL_WARPS 1
+#endif
+#ifndef PB_SHIFT_WARPS
+#define PB_SHIFT_WARPS 1
+#endif
+constexpr int kSmallWarps = PB_SMALL_WARPS, kShiftWarps = PB_SHIFT_WARPS;
+#if defined( __CUDACC__ )
+template <int NW>
+__device__ __forceinline__ auto small_group( double* red ) {
+  if constexpr ( NW == 1 ) return WarpGroup();
+  else return WarpsGroup{ NW, red };
+}
+#endif
 
 // ---- window <-> global ----------------------------------------------------------------------------
 // Only the band r - c <= 3 is meaningful below the diagonal (Hessenberg + parked bulges); whatever else
@@ -317,9 +336,9 @@ PB_D int ms_small_solve( const G& g, bool wantt, bool wantz, int n, int l, int i
   bool warp_done = false;
 #if defined( __CUDACC__ )
   if constexpr ( G::kIsCta ) {
-    // a block of <= 48 rows keeps one warp busy at best: warp 0 runs it with warp-level barriers only
-    if ( ( threadIdx.x >> 5 ) == 0 ) {
-      const int r = lahqr( WarpGroup(), acc, acc, m, 0, m - 1, wk.Hw, ldw, wr + l, wi + l, 0, m - 1, wk.U, ldw );
+    // a block of <= 48 rows keeps a few warps busy at best: they run it behind their own named barrier
+    if ( ( threadIdx.x >> 5 ) < kSmallWarps ) {
+      const int r = lahqr( small_group<kSmallWarps>( g.red ), acc, acc, m, 0, m - 1, wk.Hw, ldw, wr + l, wi + l, 0, m - 1, wk.U, ldw );
       if ( threadIdx.x == 0 ) wk.ibuf[3 * kMsMaxBulges + 4] = r;
     }
     __syncthreads();
@@ -425,9 +444,9 @@ PB_D int ms_compute_shifts( const G& g, int l, int i, const double* H, int ldh, 
     bool warp_done = false;
 #if defined( __CUDACC__ )
     if constexpr ( G::kIsCta ) {
-      // a 2nb x 2nb problem keeps one warp busy at best: run it on warp 0 with warp-level barriers only
-      if ( ( threadIdx.x >> 5 ) == 0 ) {
-        const int r = lahqr<WarpGroup, true>( WarpGroup(), false, false, ns, 0, ns - 1, S, ldw, sr, si, 0, ns - 1, (double*)nullptr, 1 );
+      // a 2nb x 2nb problem keeps two warps busy at best: they run it behind their own named barrier
+      if ( ( threadIdx.x >> 5 ) < kShiftWarps ) {
+        const int r = lahqr<decltype( small_group<kShiftWarps>( g.red ) ), true>( small_group<kShiftWarps>( g.red ), false, false, ns, 0, ns - 1, S, ldw, sr, si, 0, ns - 1, (double*)nullptr, 1 );
         if ( threadIdx.x == 0 ) wk.ibuf[3 * kMsMaxBulges + 4] = r;
       }
       __syncthreads();
@@ -766,6 +785,14 @@ PB_D void ms_chase_chain( const G& g, bool wantt, bool wantz, int n, int l, int 
   }
 }
 
+#if defined( __CUDACC__ )
+// kept out of line: the window code has its own register allocation and stack frame, the sweep code around it keeps its own
+__device__ __noinline__ void aed_window_warps( double* red, int jw, int max_moves, double* T, int ldt, double* V, int ldv, double s,
+                                               double* sr, double* si, double* work, int* out ) {
+  aed_window( small_group<kSmallWarps>( red ), jw, max_moves, T, ldt, V, ldv, s, sr, si, work, out );
+}
+#endif
+
 // ---- aggressive early deflation on the trailing jw x jw window of the active block [ktop..kbot] -----------
 // nd_out: eigenvalues deflated (now final in wr/wi, H split below row kbot - nd); ns_out: shift candidates left in
 // wk.sr / wk.si (arranged in pairs, at most `keep`).
@@ -782,7 +809,7 @@ PB_D void ms_aed( const G& g, bool wantt, bool wantz, int n, int ktop, int kbot,
     const int c = q / jw, r = q - c * jw;
     wk.U[r + c * ldw] = ( r == c ) ? 1.0 : 0.0;
   }
-  if ( t == 0 ) wk.ibuf[3 * kMsMaxBulges + 11] += 1;
+  if ( t == 0 ) wk.ibuf[3 * kMsMaxBulges + 14] += 1;
   g.sync();
   int* out = wk.ibuf + 3 * kMsMaxBulges + 8;
   double* er = wk.tile;            // eigenvalues of the window (2 jw doubles), then 2 jw doubles of scratch
@@ -790,16 +817,17 @@ PB_D void ms_aed( const G& g, bool wantt, bool wantz, int n, int ktop, int kbot,
   bool warp_done = false;
 #if defined( __CUDACC__ )
   if constexpr ( G::kIsCta ) {
-    // a window of <= 48 rows keeps one warp busy at best: warp 0 runs it with warp-level barriers only
-    if ( ( threadIdx.x >> 5 ) == 0 ) aed_window( WarpGroup(), jw, wk.Hw, ldw, wk.U, ldw, s, er, ei, wk.tile + 2 * jw, out );
+    // a window of <= 48 rows keeps a few warps busy at best: they run it behind their own named barrier
+    if ( ( threadIdx.x >> 5 ) < kSmallWarps ) aed_window_warps( g.red, jw, cfg.aed_moves, wk.Hw, ldw, wk.U, ldw, s, er, ei, wk.tile + 2 * jw, out );
     __syncthreads();
     warp_done = true;
   }
 #endif
-  if ( !warp_done ) aed_window( g, jw, wk.Hw, ldw, wk.U, ldw, s, er, ei, wk.tile + 2 * jw, out );
+  if ( !warp_done ) aed_window( g, jw, cfg.aed_moves, wk.Hw, ldw, wk.U, ldw, s, er, ei, wk.tile + 2 * jw, out );
   g.sync();
   const int ns = out[0], infqr = out[1], changed = out[2];
   PB_CHECK_UNIFORM( g, ns * 4 + changed, "aed result" );
+  g.tick( kTickMsAed );
   if ( infqr != 0 ) {  // the window's own QR iteration failed: nothing was written back, no shifts from here
     *nd_out = 0;
     *ns_out = 0;
@@ -813,7 +841,7 @@ PB_D void ms_aed( const G& g, bool wantt, bool wantz, int n, int ktop, int kbot,
   if ( t == 0 ) wk.ibuf[3 * kMsMaxBulges + 12] += jw - ns;
   // shift candidates: eigenvalues of the undeflated part
   int nshift = 0;
-  if ( ns >= 2 ) nshift = ms_arrange_shifts( g, er, ei, 0, ns, keep, wk );
+  if ( ns >= 2 && out[3] != 0 ) nshift = ms_arrange_shifts( g, er, ei, 0, ns, keep, wk );
   else g.sync();
   if ( changed ) {
     if ( t == 0 && kwtop > ktop ) PB_H( kwtop, kwtop - 1 ) = s * wk.U[0];
@@ -874,7 +902,7 @@ PB_D int hqr_multishift( const G& g, bool wantt, bool wantz, int n, int ilo, int
       int nd = 0;
       ms_aed( g, wantt, wantz, n, ktop, kbot, jw, nshift_cfg, H, ldh, wr, wi, iloz, ihiz, Z, ldz, cfg, wk, &nd, &ns_aed );
       PB_CHECK_UNIFORM( g, nd * 100 + ns_aed, "aed nd/ns" );
-      g.tick( kTickMsAed );
+      g.tick( kTickMsAedU );
       if ( nd > 0 ) {
         kbot -= nd;
         nodefl = 0;

@@ -343,10 +343,20 @@ PB_D void orghr( const G& g, int n, int ilo, int ihi, const double* A, int lda, 
 // ------------------------------------------------------------------------------------------------
 // FASTREFL: generate the 3-element reflectors with larfg3_fast (one sqrt, two reciprocals) instead of the
 // rescaling dlarfg3; used where the result only steers the iteration (shift computation).
-template <class G, bool FASTREFL = false>
+// HOOK: called (by every thread, after a barrier) each time the bottom block [l..i] of the active part has converged;
+// when it returns true the iteration stops and -(l+1) is returned: rows/columns l.. are in Schur form, the rest is
+// still upper Hessenberg (used by the early-deflation window, pb_aed.cuh).
+struct LahqrNoHook {
+  static constexpr bool kActive = false;
+  PB_HD bool operator()( int, int ) const { return false; }
+};
+template <class G, bool FASTREFL = false, class HOOK = LahqrNoHook>
 PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, double* H, int ldh,
-                double* wr, double* wi, int iloz, int ihiz, double* Z, int ldz ) {
+                double* wr, double* wi, int iloz, int ihiz, double* Z, int ldz, const HOOK& hook = HOOK() ) {
   const int t = g.tid(), nt = g.size();
+  // the Schur-vector loops start half a group away from the column loops they follow: in a group wider than the
+  // block both run side by side
+  const int tz = ( t + nt / 2 ) % nt;
   if ( n == 0 || ihi < ilo ) return 0;
   if ( ilo == ihi ) {
     if ( t == 0 ) {
@@ -508,6 +518,10 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
       g.sync();  // every thread has finished reading H for the shift vector before the sweep writes
       // ---- double-shift QR sweep ----
       for ( int k = m; k <= i - 1; ++k ) {
+#ifdef PB_AED_COUNT
+        PB_AED_COUNT( wantt ? 1 : 2 );
+        if ( k == m ) PB_AED_COUNT( 3 );
+#endif
         const int nr = imin( 3, i - k + 1 );
         double a0, a1, a2 = 0.0, t1;
         if ( k > m ) {
@@ -552,7 +566,7 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
             PB_H( j, k + 2 ) -= sum * t3;
           }
           if ( wantz ) {
-            for ( int j = iloz + t; j <= ihiz; j += nt ) {
+            for ( int j = iloz + tz; j <= ihiz; j += nt ) {
               const double sum = PB_Z( j, k ) + w2 * PB_Z( j, k + 1 ) + w3 * PB_Z( j, k + 2 );
               PB_Z( j, k ) -= sum * t1;
               PB_Z( j, k + 1 ) -= sum * t2;
@@ -573,7 +587,7 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
             PB_H( j, k + 1 ) -= sum * t2;
           }
           if ( wantz ) {
-            for ( int j = iloz + t; j <= ihiz; j += nt ) {
+            for ( int j = iloz + tz; j <= ihiz; j += nt ) {
               const double sum = PB_Z( j, k ) + w2 * PB_Z( j, k + 1 );
               PB_Z( j, k ) -= sum * t1;
               PB_Z( j, k + 1 ) -= sum * t2;
@@ -619,7 +633,7 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
         }
       }
       if ( wantz ) {
-        for ( int j = iloz + t; j <= ihiz; j += nt ) {
+        for ( int j = iloz + tz; j <= ihiz; j += nt ) {
           const double x = PB_Z( j, i - 1 ), y = PB_Z( j, i );
           PB_Z( j, i - 1 ) = cs * x + sn * y;
           PB_Z( j, i ) = cs * y - sn * x;
@@ -627,6 +641,9 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
       }
     }
     g.sync();
+    if ( HOOK::kActive ) {
+      if ( hook( l, i ) ) return -( l + 1 );
+    }
     kdefl = 0;
     i = l - 1;
   }
