@@ -16,6 +16,7 @@
 #include "../../include/paladin_gpu.h"
 #include "pb_geev.cuh"
 #include "pb_hess.cuh"
+#include "pb_coop.cuh"
 #include "pb_vecs.cuh"
 #include "pb_scatter.cuh"
 
@@ -295,18 +296,92 @@ __global__ void __launch_bounds__( pb::kHessThreads, ( MAXCH == 16 ? 2 : 1 ) ) m
   stats_end( a.stats, lstats );
 }
 
+
+// ---- stage 1 for large matrices (kMidMaxFusedN < n <= kMidMaxBigN): groups of S cooperating CTAs, one matrix per group
+// at a time (pb_coop.cuh); cooperative launch, one CTA per SM ------------------------------------------------------------
+struct CoopArgs {
+  unsigned* bars;  // 2 words per group, 2 more for the whole grid
+  double* ypart;   // S * nmax doubles per group
+  double* yz;      // 2 * nmax doubles per group
+  int S, G, nmax;
+};
+
+__global__ void __launch_bounds__( pb::kHessThreads, 1 ) big_prep_kernel( MidArgs a, CoopArgs ca ) {
+  extern __shared__ double smem[];
+  __shared__ double red[64];
+  __shared__ long long lstats[kNumTicks];
+  const int group = blockIdx.x / ca.S, rank = blockIdx.x % ca.S;
+  const pb::CoopGroup cg{ ca.bars + 2 * group, ca.S, rank };
+  pb::CtaGroup g{ red };
+  stats_begin( g, rank == 0 ? a.stats : nullptr, lstats );
+  double* ypart = ca.ypart + (size_t)group * ca.S * ca.nmax;
+  double* yz = ca.yz + (size_t)group * 2 * ca.nmax;
+  // scale check and balancing: one CTA per matrix (a few passes over it), all matrices of the launch side by side
+  for ( int k = blockIdx.x; k < a.count; k += gridDim.x ) {
+    const int id = a.ids[k];
+    const int n = a.bv.n[id];
+    double *A, *V, *wr, *wi, *dw;
+    int* iw;
+    mid_pointers( a.bv, id, n, A, V, wr, wi, dw, iw );
+    pb::GeevScaling sc;
+    int ilo = 0, ihi = n - 1, info = 0;
+    if ( !pb::geev_prologue( g, n, A, n, sc, &ilo, &ihi, dw + n, iw ) ) {
+      info = PALADIN_GPU_INFO_NONFINITE;
+      sc.scalea = false;
+      sc.anrm = 0.0;
+      sc.cscale = 1.0;
+    }
+    if ( threadIdx.x == 0 ) {
+      MidMeta m;
+      m.ilo = ilo;
+      m.ihi = ihi;
+      m.info = info;
+      m.scalea = sc.scalea ? 1 : 0;
+      m.anrm = sc.anrm;
+      m.cscale = sc.cscale;
+      a.meta[id] = m;
+      a.bv.info[id] = info;
+    }
+    __syncthreads();
+  }
+  pb::coop_sync( pb::CoopGroup{ ca.bars + 2 * ca.G, (int)gridDim.x, (int)blockIdx.x } );
+  g.tick( pb::kTickBalance );
+  for ( int k = group; k < a.count; k += ca.G ) {
+    const int id = a.ids[k];
+    const int n = a.bv.n[id];
+    double *A, *V, *wr, *wi, *dw;
+    int* iw;
+    mid_pointers( a.bv, id, n, A, V, wr, wi, dw, iw );
+    double* tau = dw;
+    const int4 mi = __ldcg( reinterpret_cast<const int4*>( &a.meta[id] ) );
+    const int ilo = mi.x, ihi = mi.y, info = mi.z;
+    if ( info == 0 ) {
+      pb::coop_hess( cg, n, ilo, ihi, A, n, tau, smem, ypart, yz );
+      pb::coop_sync( cg );
+      g.tick( pb::kTickHess );
+      if ( a.bv.wantvr || a.bv.wantvl ) pb::coop_form_q( cg, n, ilo, ihi, A, n, tau, V, n, smem );
+      if ( rank == 0 ) pb::geev_isolated_eigenvalues( g, n, ilo, ihi, A, n, wr, wi );
+    }
+    pb::coop_sync( cg );
+    g.tick( pb::kTickOrghr );
+  }
+  stats_end( rank == 0 ? a.stats : nullptr, lstats );
+}
+
 // ---- stage 2: QR iteration (windowed multishift sweeps) --------------------------------------------------
 inline size_t qr_smem_bytes() {
   const pb::MsqrCfg c = mid_cfg();
   return sizeof( double ) * pb::msqr_work_doubles( c, c.W | 1, c.tl | 1 ) + sizeof( int ) * pb::kMsIbufInts;
 }
 
+// CLUSTER: launched with a thread-block cluster per matrix (large matrices, few of them): rank 0 runs the iteration and
+// shares the strip updates of its steady-state windows with the other CTAs of the cluster (pb::ms_cluster_helper)
+template <bool CLUSTER>
 __global__ void __launch_bounds__( kMidThreads, 2 ) mid_qr_kernel( MidArgs a ) {
   extern __shared__ double smem[];
   __shared__ double red[64];
   __shared__ long long lstats[kNumTicks];
   pb::MsqrCfg c = mid_cfg();
-  c.aed = mid_aed_order( a.bv.n[a.ids[blockIdx.x]] );
   if ( a.aed >= 0 ) c.aed = a.aed;
   if ( a.aed_moves >= 0 ) c.aed_moves = a.aed_moves;
   const int ldw = c.W | 1, ldt = c.tl | 1;
@@ -322,17 +397,32 @@ __global__ void __launch_bounds__( kMidThreads, 2 ) mid_qr_kernel( MidArgs a ) {
   wk.ldw = ldw;
   wk.ldt = ldt;
   if ( threadIdx.x < pb::kMsIbufInts ) wk.ibuf[threadIdx.x] = 0;
-  const int id = a.ids[blockIdx.x];
+  int mat = blockIdx.x;
+  if constexpr ( CLUSTER ) {
+    cooperative_groups::cluster_group cl = cooperative_groups::this_cluster();
+    wk.csize = (int)cl.num_blocks();
+    wk.crank = (int)cl.block_rank();
+    mat = blockIdx.x / wk.csize;
+  }
+  const int id = a.ids[mat];
   const int n = a.bv.n[id];
+  if ( a.aed < 0 ) c.aed = mid_aed_order( n );
   pb::CtaGroup g{ red };
-  stats_begin( g, a.stats, lstats );
+  stats_begin( g, wk.crank == 0 ? a.stats : nullptr, lstats );
   const MidMeta m = a.meta[id];
-  if ( m.info != 0 ) return;
+  if ( m.info != 0 ) return;  // (the whole cluster)
   double *A, *V, *wr, *wi, *dw;
   int* iw;
   mid_pointers( a.bv, id, n, A, V, wr, wi, dw, iw );
   const bool wantz = a.bv.wantvr != 0 || a.bv.wantvl != 0;
+  if constexpr ( CLUSTER ) {
+    if ( wk.crank != 0 ) {
+      pb::ms_cluster_helper( wantz, wantz, n, A, n, 0, n - 1, V, n, c, wk );
+      return;
+    }
+  }
   const int info = pb::hqr_multishift( g, wantz, wantz, n, m.ilo, m.ihi, A, n, wr, wi, 0, n - 1, V, n, c, wk );
+  if constexpr ( CLUSTER ) pb::ms_cluster_release( wk );
   __syncthreads();
   g.tick( pb::kTickQr );
   pb::GeevScaling sc{ m.scalea != 0, m.anrm, m.cscale };
@@ -341,7 +431,7 @@ __global__ void __launch_bounds__( kMidThreads, 2 ) mid_qr_kernel( MidArgs a ) {
     a.meta[id].info = info;
     a.bv.info[id] = info;
   }
-  stats_end( a.stats, lstats );
+  stats_end( wk.crank == 0 ? a.stats : nullptr, lstats );
 }
 
 // ---- stage 3: eigenvectors (persistent CTAs, one work slot each) -----------------------------------------
@@ -430,6 +520,43 @@ __global__ void __launch_bounds__( pb::kVecThreads, 2 ) mid_vec_kernel( MidArgs 
   stats_end( a.stats, lstats );
 }
 
+
+// ---- stage 3 for large matrices: every matrix is shared by P CTAs; the three steps are separate launches (the kernel
+// boundary is the barrier between "all solves done" -> GEMM -> normalise). STEP 0: triangular solves, 1: first GEMM,
+// 2: second GEMM (both sides wanted), 3: un-balance + normalise ------------------------------------------------------------
+template <int STEP>
+__global__ void __launch_bounds__( pb::kVecThreads, 2 ) big_vec_kernel( MidArgs a, int P ) {
+  extern __shared__ double smem[];
+  int* perm = reinterpret_cast<int*>( smem + pb::vecs_gemm_smem_doubles() );
+  const int k = blockIdx.x / P, part = blockIdx.x % P;
+  const int id = a.ids[k];
+  const int n = a.bv.n[id];
+  const MidMeta m = a.meta[id];
+  if ( m.info != 0 ) return;
+  double *A, *V, *wr, *wi, *dw;
+  int* iw;
+  mid_pointers( a.bv, id, n, A, V, wr, wi, dw, iw );
+  double* scale = dw + n;
+  double* cnorm = dw + 2 * n;
+  const bool wantvr = a.bv.wantvr != 0, wantvl = a.bv.wantvl != 0;
+  double* VLout = wantvl ? a.bv.VL + a.bv.a_off[id] : nullptr;
+  double* X = a.xwork + (size_t)k * a.xslot;
+  double* Y = X + (size_t)n * n + 16;
+  if constexpr ( STEP == 0 ) {
+    if ( wantvr ) pb::vecs_solve( n, A, n, X, n, cnorm, false, part, P );
+    if ( wantvl ) pb::vecs_solve( n, A, n, wantvr ? Y : X, n, cnorm, true, part, P );
+  } else if constexpr ( STEP == 1 ) {
+    if ( wantvr ) pb::vecs_gemm( n, V, n, X, n, A, n, smem, false, part, P );  // A <- Z X
+    else pb::vecs_gemm( n, V, n, X, n, A, n, smem, true, part, P );            // A <- Z Y
+  } else if constexpr ( STEP == 2 ) {
+    pb::vecs_gemm( n, V, n, Y, n, X, n, smem, true, part, P );                 // X <- Z Y (X is free again)
+  } else {
+    if ( wantvr ) pb::vecs_finish_big( n, m.ilo, m.ihi, scale, wi, A, n, V, n, perm, false, part, P );
+    __syncthreads();
+    if ( wantvl ) pb::vecs_finish_big( n, m.ilo, m.ihi, scale, wi, wantvr ? X : A, n, VLout, n, perm, true, part, P );
+  }
+}
+
 struct StageTimer {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   bool used = false;
@@ -465,6 +592,10 @@ struct paladin_gpu_batch {
   double* d_xwork = nullptr;
   size_t xslot = 0;
   int xslots = 0, xn_max = 0;
+  // cooperative stage 1 of large matrices
+  unsigned* d_coop_bars = nullptr;
+  double *d_coop_ypart = nullptr, *d_coop_yz = nullptr;
+  int coop_S = 0, coop_G = 0, coop_nmax = 0;
   std::vector<Group> groups;
   StageTimer st[PALADIN_GPU_NUM_STAGES];
   bool scattered = false;
@@ -481,6 +612,7 @@ void free_batch( paladin_gpu_batch* b ) {
   cudaFree( b->d_coo_i ); cudaFree( b->d_coo_j ); cudaFree( b->d_coo_v );
   cudaFree( b->d_A ); cudaFree( b->d_V ); cudaFree( b->d_VL ); cudaFree( b->d_wr ); cudaFree( b->d_wi ); cudaFree( b->d_dwork );
   cudaFree( b->d_stats ); cudaFree( b->d_meta ); cudaFree( b->d_counter ); cudaFree( b->d_xwork );
+  cudaFree( b->d_coop_bars ); cudaFree( b->d_coop_ypart ); cudaFree( b->d_coop_yz );
   cudaFree( b->d_info ); cudaFree( b->d_iwork ); cudaFree( b->d_flags ); cudaFree( b->d_ids ); cudaFree( b->d_chunks );
   for ( auto& s : b->st ) {
     if ( s.e0 ) cudaEventDestroy( s.e0 );
@@ -743,6 +875,24 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
       A( dev_alloc( &b->d_xwork, b->xslot * b->xslots ) );
     }
   }
+  {
+    // scratch of the cooperative Hessenberg stage: the largest matrix that takes it fixes the group size
+    int nbigmax = 0;
+    for ( int k = 0; k < count; ++k )
+      if ( n[k] > kMidMaxFusedN && n[k] <= kMidMaxBigN ) nbigmax = std::max( nbigmax, n[k] );
+    static const bool no_coop = std::getenv( "PALADIN_GPU_NO_COOP" ) != nullptr;
+    if ( nbigmax > 0 && !no_coop ) {
+      b->coop_G = nbigmax > 2048 ? 1 : ( nbigmax > 1400 ? 2 : 4 );
+      if ( const char* env = std::getenv( "PALADIN_GPU_COOP_GROUPS" ) ) b->coop_G = std::max( 1, std::atoi( env ) );
+      b->coop_S = std::max( 1, c.sm_count / b->coop_G );
+      b->coop_nmax = nbigmax;
+      A( dev_alloc( &b->d_coop_bars, 2 * (size_t)b->coop_G + 2 ) );
+      A( dev_alloc( &b->d_coop_ypart, (size_t)b->coop_G * b->coop_S * nbigmax ) );
+      A( dev_alloc( &b->d_coop_yz, (size_t)b->coop_G * 2 * nbigmax ) );
+      if ( rc == PALADIN_GPU_OK && cudaMemset( b->d_coop_bars, 0, sizeof( unsigned ) * ( 2 * b->coop_G + 2 ) ) != cudaSuccess )
+        rc = fail( PALADIN_GPU_ECUDA, "cudaMemset failed" );
+    }
+  }
   if ( rc != PALADIN_GPU_OK ) {
     free_batch( b );
     return rc;
@@ -935,7 +1085,8 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
       const size_t s2 = qr_smem_bytes(), s3 = vec_smem_bytes( g.nmax );
       PB_CUDA( cudaFuncSetAttribute( mid_prep_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem_bytes( 512 ) ) );
       PB_CUDA( cudaFuncSetAttribute( mid_prep_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem_bytes( 1024 ) ) );
-      PB_CUDA( cudaFuncSetAttribute( mid_qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2 ) );
+      PB_CUDA( cudaFuncSetAttribute( mid_qr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2 ) );
+      PB_CUDA( cudaFuncSetAttribute( mid_qr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2 ) );
       PB_CUDA( cudaFuncSetAttribute( mid_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3 ) );
       stage_begin( b, PALADIN_GPU_STAGE_HESSENBERG, st );
       {
@@ -950,11 +1101,27 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
         nbig = std::min( nbig, cnt );
         nmid = std::min( nmid, cnt );
         int launches = 0;
-        if ( nbig > 0 ) {
+        int nhuge = 0;  // [0, nhuge): beyond the streaming kernels (n > kMidMaxBigN)
+        for ( int q = 0; q < nbig; ++q )
+          if ( b->n[b->ids[g.first + q]] > kMidMaxBigN ) nhuge = q + 1;
+        if ( b->coop_S > 0 && nbig > nhuge ) {
+          // large matrices: groups of cooperating CTAs, one matrix per group at a time
+          MidArgs mc = ma;
+          mc.ids = ids + nhuge;
+          mc.count = nbig - nhuge;
+          CoopArgs ca{ b->d_coop_bars, b->d_coop_ypart, b->d_coop_yz, b->coop_S, b->coop_G, b->coop_nmax };
+          const size_t sc = sizeof( double ) * pb::coop_hess_smem_doubles( b->coop_nmax, b->coop_S );
+          PB_CUDA( cudaFuncSetAttribute( big_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc ) );
+          void* kargs[] = { &mc, &ca };
+          PB_CUDA( cudaLaunchCooperativeKernel( (const void*)big_prep_kernel, dim3( b->coop_S * b->coop_G ), dim3( pb::kHessThreads ), kargs, sc, st ) );
+          ++launches;
+        }
+        const int n0 = ( b->coop_S > 0 ) ? nhuge : nbig;  // what is left for the one-CTA streaming / unblocked kernel
+        if ( n0 > 0 ) {
           MidArgs m0 = ma;
           const size_t sbig = sizeof( double ) * pb::hess_big_smem_doubles( std::min( g.nmax, kMidMaxBigN ) );
           PB_CUDA( cudaFuncSetAttribute( mid_prep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbig ) );
-          mid_prep_kernel<0><<<nbig, pb::kHessThreads, sbig, st>>>( m0 );
+          mid_prep_kernel<0><<<n0, pb::kHessThreads, sbig, st>>>( m0 );
           ++launches;
         }
         if ( nmid > nbig ) {
@@ -972,12 +1139,80 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
         stage_end( b, PALADIN_GPU_STAGE_HESSENBERG, st, launches );
       }
       stage_begin( b, PALADIN_GPU_STAGE_QR, st );
-      mid_qr_kernel<<<cnt, kMidThreads, s2, st>>>( ma );
-      stage_end( b, PALADIN_GPU_STAGE_QR, st, 1 );
+      {
+        // large matrices ([0, nqbig) of the size-sorted list) get a thread-block cluster each when they are few: the
+        // leader's strip updates are shared by the cluster
+        int nqbig = 0;
+        for ( int q = 0; q < cnt; ++q )
+          if ( b->n[b->ids[g.first + q]] > kMidMaxFusedN ) nqbig = q + 1;
+        const int slots = 2 * c.sm_count;
+        int csize = nqbig == 0 ? 1 : ( 16 * nqbig <= slots ? 16 : ( 8 * nqbig <= slots ? 8 : ( 4 * nqbig <= slots ? 4 : ( 2 * nqbig <= slots ? 2 : 1 ) ) ) );
+        static const int env_cluster = std::getenv( "PALADIN_GPU_CLUSTER" ) ? std::atoi( std::getenv( "PALADIN_GPU_CLUSTER" ) ) : 0;
+        if ( env_cluster > 0 ) csize = env_cluster;
+        int launches = 0;
+        if ( csize > 1 && nqbig > 0 ) {
+          if ( csize > 8 ) PB_CUDA( cudaFuncSetAttribute( mid_qr_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1 ) );
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3( nqbig * csize );
+          cfg.blockDim = dim3( kMidThreads );
+          cfg.dynamicSmemBytes = s2;
+          cfg.stream = st;
+          cudaLaunchAttribute attr[1];
+          attr[0].id = cudaLaunchAttributeClusterDimension;
+          attr[0].val.clusterDim.x = csize;
+          attr[0].val.clusterDim.y = 1;
+          attr[0].val.clusterDim.z = 1;
+          cfg.attrs = attr;
+          cfg.numAttrs = 1;
+          PB_CUDA( cudaLaunchKernelEx( &cfg, mid_qr_kernel<true>, ma ) );
+          ++launches;
+        } else {
+          nqbig = 0;
+        }
+        if ( cnt > nqbig ) {
+          MidArgs mq = ma;
+          mq.ids = ids + nqbig;
+          mq.count = cnt - nqbig;
+          mid_qr_kernel<false><<<cnt - nqbig, kMidThreads, s2, st>>>( mq );
+          ++launches;
+        }
+        stage_end( b, PALADIN_GPU_STAGE_QR, st, launches );
+      }
       if ( wantvr || wantvl ) {
         stage_begin( b, PALADIN_GPU_STAGE_VECTORS, st );
-        mid_vec_kernel<<<std::max( 1, std::min( cnt, b->xslots ) ), pb::kVecThreads, s3, st>>>( ma );
-        stage_end( b, PALADIN_GPU_STAGE_VECTORS, st, 1 );
+        int launches = 0;
+        // large matrices first ([0, nvbig) of the size-sorted list): each one shared by P CTAs, `xslots` of them at a time
+        int nvbig = 0;
+        for ( int q = 0; q < cnt; ++q )
+          if ( b->n[b->ids[g.first + q]] > kMidMaxFusedN ) nvbig = q + 1;
+        static const bool no_bigvec = std::getenv( "PALADIN_GPU_NO_COOP" ) != nullptr;
+        if ( no_bigvec ) nvbig = 0;
+        if ( nvbig > 0 ) {
+          PB_CUDA( cudaFuncSetAttribute( big_vec_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3 ) );
+          PB_CUDA( cudaFuncSetAttribute( big_vec_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3 ) );
+          PB_CUDA( cudaFuncSetAttribute( big_vec_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3 ) );
+          PB_CUDA( cudaFuncSetAttribute( big_vec_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3 ) );
+          for ( int q0 = 0; q0 < nvbig; q0 += b->xslots ) {
+            const int nq = std::min( b->xslots, nvbig - q0 );
+            const int P = std::max( 1, std::min( 64, ( 4 * c.sm_count ) / nq ) );
+            MidArgs mv = ma;
+            mv.ids = ids + q0;
+            mv.count = nq;
+            big_vec_kernel<0><<<nq * P, pb::kVecThreads, s3, st>>>( mv, P );
+            big_vec_kernel<1><<<nq * P, pb::kVecThreads, s3, st>>>( mv, P );
+            if ( wantvr && wantvl ) big_vec_kernel<2><<<nq * P, pb::kVecThreads, s3, st>>>( mv, P );
+            big_vec_kernel<3><<<nq * P, pb::kVecThreads, s3, st>>>( mv, P );
+            launches += ( wantvr && wantvl ) ? 4 : 3;
+          }
+        }
+        if ( cnt > nvbig ) {
+          MidArgs mv = ma;
+          mv.ids = ids + nvbig;
+          mv.count = cnt - nvbig;
+          mid_vec_kernel<<<std::max( 1, std::min( cnt - nvbig, b->xslots ) ), pb::kVecThreads, s3, st>>>( mv );
+          ++launches;
+        }
+        stage_end( b, PALADIN_GPU_STAGE_VECTORS, st, launches );
       }
       PB_CUDA( cudaGetLastError() );
       continue;

@@ -29,6 +29,9 @@
 #include "pb_small.cuh"
 #include "pb_strips.cuh"
 #include "pb_aed.cuh"
+#if defined( __CUDACC__ )
+#include <cooperative_groups.h>
+#endif
 
 namespace pb {
 
@@ -36,7 +39,7 @@ constexpr int kMsMaxBulges = 16;
 // ints of MsqrWork::ibuf: kpos, kfirst, kcount (kMsMaxBulges each), then
 //   +0 shift count  +1 sweeps  +2 windows  +3 small solves  +4 scratch  +5 steady-state windows  +6 strip work queue
 //   +8..+11 AED results (ns, lahqr code, changed, shifts valid)  +12 eigenvalues deflated by AED  +13 sweeps skipped  +14 AED calls
-constexpr int kMsIbufInts = 3 * kMsMaxBulges + 16;
+constexpr int kMsIbufInts = 3 * kMsMaxBulges + 16 + 8;
 constexpr int kReflStride = 6;  // w2, w3, t1, t2, t3, pad  (three 16-byte loads)
 // phase-profile slots (CtaGroup::tick)
 constexpr int kTickMsScan = 8, kTickMsShifts = 9, kTickMsChase = 10, kTickMsStrips = 11, kTickMsSmall = 12, kTickMsSmallU = 13, kTickMsAed = 14, kTickMsAedU = 15;
@@ -63,7 +66,14 @@ struct MsqrWork {
   double* si;     //                     (imaginary parts)
   int* ibuf;      // kMsIbufInts ints: kpos, kfirst, kcount, counters
   int ldw, ldt;
+  // thread-block cluster that shares the strip updates of this matrix (device, large matrices): the leader (rank 0)
+  // runs the whole iteration, the others wait in ms_cluster_helper for its commands
+  int csize = 1, crank = 0;
 };
+
+// command block the leader publishes in its ibuf (read by the helpers through distributed shared memory)
+constexpr int kMsCmd = 3 * kMsMaxBulges + 16;  // cmd (0 = exit, 1 = strips of a steady-state window), ws, wlen, l, i
+constexpr int kMsCmdInts = 8;
 
 PB_HD size_t ms_even( size_t x ) { return ( x + 1 ) & ~(size_t)1; }  // keeps every sub-buffer 16-byte aligned
 PB_HD size_t msqr_work_doubles( const MsqrCfg& c, int ldw, int ldt ) {
@@ -770,8 +780,17 @@ PB_D void ms_chase_chain( const G& g, bool wantt, bool wantz, int n, int l, int 
       // steady-state windows only (about five in six); the others take the tile path below
       if ( cfg.W == kStripW && cfg.nb == kStripNB && cfg.tl >= 16 * ( g.size() >> 5 ) &&
            strip_window_is_regular( nbulges, wlen, ws, kfirst, kcount ) ) {
+        if ( wk.csize > 1 ) {
+          // hand the window to the cluster: command + reflectors are read from this CTA's shared memory
+          if ( t == 0 ) {
+            int* cmd = wk.ibuf + kMsCmd;
+            cmd[0] = 1; cmd[1] = ws; cmd[2] = wlen; cmd[3] = l; cmd[4] = i;
+          }
+          cooperative_groups::this_cluster().sync();
+        }
         ms_strips_regs( wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, wk.refl, wk.tile, wk.ldt,
-                        wk.ibuf + 3 * kMsMaxBulges + 6 );
+                        wk.ibuf + 3 * kMsMaxBulges + 6, 0, wk.csize );
+        if ( wk.csize > 1 ) cooperative_groups::this_cluster().sync();
       } else {
         ms_update_strips( g, wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, nbulges, (const double*)nullptr );
       }
@@ -855,6 +874,42 @@ PB_D void ms_aed( const G& g, bool wantt, bool wantz, int n, int ktop, int kbot,
   *nd_out = jw - ns;
   *ns_out = nshift;
 }
+
+#if defined( __CUDACC__ )
+// ---- cluster helpers (ranks 1..csize-1): strips of the leader's steady-state windows -------------------------------------
+__device__ inline void ms_cluster_helper( bool wantt, bool wantz, int n, double* H, int ldh, int iloz, int ihiz, double* Z, int ldz,
+                                          const MsqrCfg& cfg, const MsqrWork& wk ) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  const int* lcmd = cluster.map_shared_rank( wk.ibuf + kMsCmd, 0 );
+  const double* lrefl = cluster.map_shared_rank( wk.refl, 0 );
+  const int nrefl = cfg.nb * cfg.W * kReflStride;
+  for ( ;; ) {
+    cluster.sync();
+    const int cmd = lcmd[0];
+    if ( cmd == 0 ) {
+      cluster.sync();  // the leader's shared memory stays alive until every helper has read the command
+      return;
+    }
+    const int ws = lcmd[1], wlen = lcmd[2], l = lcmd[3], i = lcmd[4];
+    for ( int q = threadIdx.x; q < nrefl / 2; q += blockDim.x )
+      reinterpret_cast<double2*>( wk.refl )[q] = reinterpret_cast<const double2*>( lrefl )[q];
+    if ( threadIdx.x == 0 ) wk.ibuf[3 * kMsMaxBulges + 6] = 0;
+    __syncthreads();
+    ms_strips_regs( wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, wk.refl, wk.tile, wk.ldt,
+                    wk.ibuf + 3 * kMsMaxBulges + 6, wk.crank, wk.csize );
+    cluster.sync();
+  }
+}
+// leader: releases the helpers for good
+__device__ inline void ms_cluster_release( const MsqrWork& wk ) {
+  if ( wk.csize <= 1 ) return;
+  __syncthreads();
+  if ( threadIdx.x == 0 ) wk.ibuf[kMsCmd] = 0;
+  cooperative_groups::this_cluster().sync();
+  cooperative_groups::this_cluster().sync();
+}
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // Driver. H upper Hessenberg in rows/cols ilo..ihi (isolated eigenvalues outside are the caller's

@@ -142,9 +142,11 @@ __device__ __forceinline__ void prefetch_l2( const void* p ) { asm volatile( "pr
 
 // Steady-state windows only. counter: one int of shared memory, zeroed by the caller before the CTA barrier that
 // precedes this call (work queue of the row batches).
+// crank / csize: this CTA is one of csize (a thread-block cluster, pb_msqr.cuh) that share the strips of the window:
+// right-strip batches and row batches are dealt round-robin to the CTAs; counter is CTA-local either way.
 __device__ inline void ms_strips_regs( bool wantt, bool wantz, int n, int l, int i, int ws, int wlen, double* __restrict__ H,
                                        int ldh, int iloz, int ihiz, double* __restrict__ Z, int ldz, const double* refl,
-                                       double* tile, int ldt, int* counter ) {
+                                       double* tile, int ldt, int* counter, int crank = 0, int csize = 1 ) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   const int we = ws + wlen - 1;
   const int i1 = wantt ? 0 : l, i2 = wantt ? n - 1 : i;
@@ -155,11 +157,12 @@ __device__ inline void ms_strips_regs( bool wantt, bool wantz, int n, int l, int
   // (slice w/2 spans the 16-line slices of warps w and w+1; odd warps never use theirs here), then lane = column.
   if ( ( warp & 1 ) == 0 ) {
     double* wt = tile + 32 * ( warp >> 1 );
-    for ( int bt = warp >> 1; bt < bright; bt += ( nwarps + 1 ) >> 1 ) {
+    const int rstride = ( ( nwarps + 1 ) >> 1 ) * csize;
+    for ( int bt = ( warp >> 1 ) + crank * ( ( nwarps + 1 ) >> 1 ); bt < bright; bt += rstride ) {
       const int j0 = we + 1 + 32 * bt;
       const int nl = imin( 32, i2 - j0 + 1 );
       if ( lane < nl ) {  // L2 prefetch of the next batch of this warp
-        const int jn = j0 + 32 * ( ( nwarps + 1 ) >> 1 ) + lane;
+        const int jn = j0 + 32 * rstride + lane;
         if ( jn <= i2 ) {
           const double* col = H + (size_t)jn * ldh + ws;
 #pragma unroll
@@ -222,13 +225,13 @@ __device__ inline void ms_strips_regs( bool wantt, bool wantz, int n, int l, int
   for ( ;; ) {
     int bt = 0;
     if ( lane == 0 ) bt = atomicAdd( counter, 1 );
-    bt = __shfl_sync( 0xffffffffu, bt, 0 );
+    bt = crank + csize * __shfl_sync( 0xffffffffu, bt, 0 );
     if ( bt >= nrow_batches ) break;
     double* M;
     int ldm, r0, nl;
     row_batch( bt, M, ldm, r0, nl );
     {  // L2 prefetch of a batch a few positions ahead in the queue
-      const int bn = bt + nwarps;
+      const int bn = bt + nwarps * csize;
       if ( bn < nrow_batches ) {
         double* Mn;
         int ldn, rn, nn;

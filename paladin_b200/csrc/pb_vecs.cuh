@@ -24,8 +24,12 @@ constexpr int kVecWarps = kVecThreads / 32;
 // ---- 1. triangular solves ---------------------------------------------------------------------------
 // X(:, ki) (real) or X(:, ki-1), X(:, ki) (pair, real and imaginary parts) <- eigenvector of T; entries
 // below the block are zeroed so that the GEMM may treat X as dense.
-__device__ inline void vecs_solve( int n, const double* T, int ldt, double* X, int ldx, double* cnorm, bool left ) {
+// part / nparts: this CTA is one of nparts that share the matrix (large matrices, big_vec_kernel): it takes every
+// nparts-th group of kVecWarps blocks; every part computes the (identical) column norms itself.
+__device__ inline void vecs_solve( int n, const double* T, int ldt, double* X, int ldx, double* cnorm, bool left, int part = 0,
+                                   int nparts = 1 ) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int stride = kVecWarps * nparts, mine = part * kVecWarps + warp;
   // column 1-norms of the strictly upper part (warp per column, lanes along rows)
   for ( int j = warp; j < n; j += kVecWarps ) {
     double s = 0.0;
@@ -41,7 +45,7 @@ __device__ inline void vecs_solve( int n, const double* T, int ldt, double* X, i
     int ki = n - 1;
     while ( ki >= 0 ) {
       const bool cplx = ( ki > 0 && T[ki + (size_t)( ki - 1 ) * ldt] != 0.0 );
-      if ( ( blk % kVecWarps ) == warp ) {
+      if ( ( blk % stride ) == mine ) {
         if ( !cplx ) {
           double* xr = X + (size_t)ki * ldx;
           trevc_right_solve( g, n, T, ldt, ki, false, cnorm, xr, xr );
@@ -63,7 +67,7 @@ __device__ inline void vecs_solve( int n, const double* T, int ldt, double* X, i
     int ki = 0;
     while ( ki < n ) {
       const bool cplx = ( ki < n - 1 && T[( ki + 1 ) + (size_t)ki * ldt] != 0.0 );
-      if ( ( blk % kVecWarps ) == warp ) {
+      if ( ( blk % stride ) == mine ) {
         double* xr = X + (size_t)ki * ldx;
         double* xi = cplx ? X + (size_t)( ki + 1 ) * ldx : xr;
         trevc_left_solve( g, n, T, ldt, ki, cplx, cnorm, xr, xi );
@@ -94,7 +98,7 @@ __device__ __forceinline__ void dmma_m8n8k4( double& c0, double& c1, double a, d
 // C (n x n, ldc) = Z (n x n, ldz) * X (n x n, ldx); column block [c0, c0+BN) of X is zero below row c0+BN
 // lower = true: X is lower (quasi-)triangular (left eigenvectors): column block [n0, n0+BN) is zero above row n0-1
 __device__ inline void vecs_gemm( int n, const double* __restrict__ Z, int ldz, const double* __restrict__ X, int ldx,
-                                  double* __restrict__ C, int ldc, double* sm, bool lower ) {
+                                  double* __restrict__ C, int ldc, double* sm, bool lower, int part = 0, int nparts = 1 ) {
   double* As = sm;                                 // [BK][LdA]
   double* Bs = sm + (size_t)kGemmBK * kGemmLdA;    // [BN][LdB]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -104,6 +108,7 @@ __device__ inline void vecs_gemm( int n, const double* __restrict__ Z, int ldz, 
     const int kend = lower ? n : imin( n, n0 + kGemmBN + 1 );
     const int kbeg = lower ? ( imax( 0, n0 - 1 ) / kGemmBK ) * kGemmBK : 0;
     for ( int m0 = 0; m0 < n; m0 += kGemmBM ) {
+      if ( nparts > 1 && ( ( n0 / kGemmBN ) * ( ( n + kGemmBM - 1 ) / kGemmBM ) + m0 / kGemmBM ) % nparts != part ) continue;
       double acc[4][4][2];
 #pragma unroll
       for ( int i = 0; i < 4; ++i )
@@ -289,8 +294,9 @@ __device__ void vecs_finish( int n, int ilo, int ihi, const double* scale, const
 
 // any n: the same un-balance + normalise with the column(s) streamed from memory in several passes (L2 hits)
 __device__ inline void vecs_finish_big( int n, int ilo, int ihi, const double* scale, const double* wi, const double* __restrict__ C,
-                                        int ldc, double* __restrict__ V, int ldv, int* perm, bool left ) {
+                                        int ldc, double* __restrict__ V, int ldv, int* perm, bool left, int part = 0, int nparts = 1 ) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int stride = kVecWarps * nparts, mine = part * kVecWarps + warp;
   if ( tid == 0 ) {
     for ( int r = 0; r < n; ++r ) perm[r] = r;
     for ( int ii = 0; ii < n; ++ii ) {
@@ -309,7 +315,7 @@ __device__ inline void vecs_finish_big( int n, int ilo, int ihi, const double* s
   int c = 0;
   while ( c < n ) {
     const bool pair = ( wi[c] > 0.0 && c + 1 < n );
-    if ( ( blk % kVecWarps ) == warp ) {
+    if ( ( blk % stride ) == mine ) {
       const double* ca = C + (size_t)c * ldc;
       const double* cb = C + (size_t)( pair ? c + 1 : c ) * ldc;
       auto rowscale = [&]( int src ) {

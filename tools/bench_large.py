@@ -19,6 +19,7 @@ def run(n, count, job="V"):
     ms = b.timer_stop()
     wr, wi, vr, info = b.download()
     st = b.stage_ms()
+    cyc = b.phase_cycles()
     b.destroy()
     A = vals[0].reshape((n, n), order="F")
     V = vr[:nn].reshape((n, n), order="F")
@@ -35,7 +36,11 @@ def run(n, count, job="V"):
     print("n=%d count=%d: %.1f ms -> %.2f decomp/s, info %s, max residual/(n eps ||A||) %.2f, trace err %.1e, stages %s" % (
         n, count, ms, count / ms * 1e3, info.tolist(), max(res) / (n * 2.2e-16 * np.linalg.norm(A, 2)), tr,
         {k_: round(v_[0], 1) for k_, v_ in st.items() if v_[0] > 0}), flush=True)
+    print("   phase Mcycles (summed over recording CTAs):", {k_: round(v_ / 1e6, 1) for k_, v_ in cyc.items() if v_}, flush=True)
 
 if __name__ == "__main__":
-    run(1536, 8)
-    run(3072, 4)
+    cases = [(1536, 8), (3072, 4)]
+    if len(sys.argv) > 1:
+        cases = [tuple(int(x) for x in a.split("x")) for a in sys.argv[1:]]
+    for n, count in cases:
+        run(n, count)
