@@ -417,7 +417,7 @@ __global__ void __launch_bounds__( kMidThreads, 2 ) mid_qr_kernel( MidArgs a ) {
   const bool wantz = a.bv.wantvr != 0 || a.bv.wantvl != 0;
   if constexpr ( CLUSTER ) {
     if ( wk.crank != 0 ) {
-      pb::ms_cluster_helper( wantz, wantz, n, A, n, 0, n - 1, V, n, c, wk );
+      pb::ms_cluster_helper( g, wantz, wantz, n, A, n, 0, n - 1, V, n, c, wk );
       return;
     }
   }

@@ -21,6 +21,14 @@
 #define PB_HD inline
 #endif
 
+// Loads of matrix data that another CTA of a thread-block cluster may have written (pb_msqr.cuh): straight from L2, never
+// through the L1 / read-only path (a `const __restrict__` pointer would otherwise allow ld.global.nc).
+#if defined(__CUDA_ARCH__)
+#define PB_LDCG( ptr ) __ldcg( ptr )
+#else
+#define PB_LDCG( ptr ) ( *( ptr ) )
+#endif
+
 // Uniformity checks of group-wide control values: compiled only into the threaded host simulator
 // (tests/hostsim defines PB_CHECK_UNIFORM as a call into its barrier), nothing on the device.
 #ifndef PB_CHECK_UNIFORM

@@ -35,6 +35,9 @@
 
 namespace pb {
 
+// H entries another CTA of the cluster may have updated are read through L2
+#define PB_HLD( i, j ) PB_LDCG( &PB_H( i, j ) )
+
 constexpr int kMsMaxBulges = 16;
 // ints of MsqrWork::ibuf: kpos, kfirst, kcount (kMsMaxBulges each), then
 //   +0 shift count  +1 sweeps  +2 windows  +3 small solves  +4 scratch  +5 steady-state windows  +6 strip work queue
@@ -86,21 +89,21 @@ PB_D int ms_find_split( const G& g, int ilo, int ihi, int lo, int hi, const doub
   const int t = g.tid(), nt = g.size();
   int kfound = lo;
   for ( int k = hi - t; k > lo; k -= nt ) {
-    const double hkk1 = fabs( PB_H( k, k - 1 ) );
+    const double hkk1 = fabs( PB_HLD( k, k - 1 ) );
     bool small = false;
     if ( hkk1 <= smlnum ) {
       small = true;
     } else {
-      double tst = fabs( PB_H( k - 1, k - 1 ) ) + fabs( PB_H( k, k ) );
+      double tst = fabs( PB_HLD( k - 1, k - 1 ) ) + fabs( PB_HLD( k, k ) );
       if ( tst == 0.0 ) {
-        if ( k - 2 >= ilo ) tst += fabs( PB_H( k - 1, k - 2 ) );
-        if ( k + 1 <= ihi ) tst += fabs( PB_H( k + 1, k ) );
+        if ( k - 2 >= ilo ) tst += fabs( PB_HLD( k - 1, k - 2 ) );
+        if ( k + 1 <= ihi ) tst += fabs( PB_HLD( k + 1, k ) );
       }
       if ( hkk1 <= kUlp * tst ) {
-        const double hk1k = fabs( PB_H( k - 1, k ) );
+        const double hk1k = fabs( PB_HLD( k - 1, k ) );
         const double ab = dmax( hkk1, hk1k ), ba = dmin( hkk1, hk1k );
-        const double dd = fabs( PB_H( k - 1, k - 1 ) - PB_H( k, k ) );
-        const double aa = dmax( fabs( PB_H( k, k ) ), dd ), bb = dmin( fabs( PB_H( k, k ) ), dd );
+        const double dd = fabs( PB_HLD( k - 1, k - 1 ) - PB_HLD( k, k ) );
+        const double aa = dmax( fabs( PB_HLD( k, k ) ), dd ), bb = dmin( fabs( PB_HLD( k, k ) ), dd );
         const double s = aa + ab;
         if ( ba * ( ab / s ) <= dmax( smlnum, kUlp * ( bb * ( aa / s ) ) ) ) small = true;
       }
@@ -146,7 +149,7 @@ PB_D void ms_load_window( const G& g, const double* __restrict__ H, int ldh, int
     for ( int u = 0; u < kWinBatch; ++u ) {
       const int q = imin( q0 + u * nt, total - 1 );
       const int c = q / wlen, r = q - c * wlen;
-      v[u] = PB_H( ws + r, ws + c );
+      v[u] = PB_HLD( ws + r, ws + c );
     }
 #pragma unroll
     for ( int u = 0; u < kWinBatch; ++u ) {
@@ -192,11 +195,11 @@ PB_D void ms_tile_load( const G& g, int kind, const double* __restrict__ M, int 
       if ( kind == 0 ) {
         line = q / wlen;
         pos = q - line * wlen;
-        v[u] = M[( ws + pos ) + (size_t)( l0 + line ) * ldm];
+        v[u] = PB_LDCG( &M[( ws + pos ) + (size_t)( l0 + line ) * ldm] );
       } else {
         pos = q / nl;
         line = q - pos * nl;
-        v[u] = M[( l0 + line ) + (size_t)( ws + pos ) * ldm];
+        v[u] = PB_LDCG( &M[( l0 + line ) + (size_t)( ws + pos ) * ldm] );
       }
       dst[u] = pos * ldt + line;
     }
@@ -285,7 +288,7 @@ PB_D void ms_tile_apply_u( const G& g, int nl, int m, const double* U, int ldu, 
 template <class G>
 PB_D void ms_update_strips( const G& g, bool wantt, bool wantz, int n, int l, int i, int ws, int wlen, double* H, int ldh,
                             int iloz, int ihiz, double* Z, int ldz, const MsqrCfg& cfg, const MsqrWork& wk, int nbulges,
-                            const double* U ) {
+                            const double* U, int crank = 0, int csize = 1 ) {
   const int we = ws + wlen - 1;
   const int i1 = wantt ? 0 : l, i2 = wantt ? n - 1 : i;
   const int* kfirst = wk.ibuf + kMsMaxBulges;
@@ -302,7 +305,7 @@ PB_D void ms_update_strips( const G& g, bool wantt, bool wantz, int n, int l, in
       M = Z; ldm = ldz; kind = 1; lo = iloz; hi = ihiz;
     }
     const int tl = ( U == nullptr ) ? cfg.tl : cfg.tl / 2;
-    for ( int l0 = lo; l0 <= hi; l0 += tl ) {
+    for ( int l0 = lo + crank * tl; l0 <= hi; l0 += tl * csize ) {
       const int nl = imin( tl, hi - l0 + 1 );
       ms_tile_load( g, kind, M, ldm, ws, wlen, l0, nl, wk.tile, wk.ldt );
       if ( U == nullptr ) {
@@ -316,6 +319,39 @@ PB_D void ms_update_strips( const G& g, bool wantt, bool wantz, int n, int l, in
   }
 }
 
+#if defined( __CUDACC__ )
+// ---- leader side of the cluster hand-off: publish a command, meet the helpers (they copy what they need from this
+// CTA's shared memory), and meet them again when everybody's share is done (pb::ms_cluster_helper) ------------------------
+// cmd 1: strips of a steady-state window (register path); 2: x <- U^T x with wk.U; 3: recorded reflectors, tile path
+__device__ __forceinline__ void ms_cluster_post( const MsqrWork& wk, int cmd, int ws, int wlen, int l, int i, int nbulges ) {
+  if ( threadIdx.x == 0 ) {
+    int* c = wk.ibuf + kMsCmd;
+    c[0] = cmd; c[1] = ws; c[2] = wlen; c[3] = l; c[4] = i; c[5] = nbulges;
+  }
+  cooperative_groups::this_cluster().sync();
+}
+__device__ __forceinline__ void ms_cluster_join() { cooperative_groups::this_cluster().sync(); }
+#endif
+
+// the off-window update of one window / block, shared with the cluster when there is one
+template <class G>
+PB_D void ms_update_strips_shared( const G& g, bool wantt, bool wantz, int n, int l, int i, int ws, int wlen, double* H, int ldh,
+                                   int iloz, int ihiz, double* Z, int ldz, const MsqrCfg& cfg, const MsqrWork& wk, int nbulges,
+                                   const double* U ) {
+#if defined( __CUDACC__ )
+  if constexpr ( G::kIsCta ) {
+    if ( wk.csize > 1 ) {
+      ms_cluster_post( wk, U != nullptr ? 2 : 3, ws, wlen, l, i, nbulges );
+      ms_update_strips( g, wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, nbulges, U, 0, wk.csize );
+      ms_cluster_join();
+      return;
+    }
+  }
+#endif
+  ms_update_strips( g, wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, nbulges, U );
+}
+
+
 // ---- finish a small diagonal block [l..i] (order <= W) inside the window ---------------------------
 // Returns 0 or the lahqr failure index (global, 1-based like LAPACK's info).
 template <class G>
@@ -325,7 +361,7 @@ PB_D int ms_small_solve( const G& g, bool wantt, bool wantz, int n, int l, int i
   const int m = i - l + 1;
   if ( m == 1 ) {
     if ( t == 0 ) {
-      wr[i] = PB_H( i, i );
+      wr[i] = PB_HLD( i, i );
       wi[i] = 0.0;
     }
     g.sync();
@@ -368,7 +404,7 @@ PB_D int ms_small_solve( const G& g, bool wantt, bool wantz, int n, int l, int i
     else if ( r - c <= 3 ) PB_H( l + r, l + c ) = 0.0;
   }
   g.sync();
-  ms_update_strips( g, wantt, wantz, n, l, i, l, m, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, 0, wk.U );
+  ms_update_strips_shared( g, wantt, wantz, n, l, i, l, m, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, 0, wk.U );
   g.tick( kTickMsSmallU );
   return 0;
 }
@@ -434,8 +470,8 @@ PB_D int ms_compute_shifts( const G& g, int l, int i, const double* H, int ldh, 
     if ( t == 0 ) {
       for ( int q = ns - 1; q >= 1; q -= 2 ) {
         const int r = i - ( ns - 1 - q );  // row of H matched with shift q
-        const double ss = fabs( PB_H( r, r - 1 ) ) + fabs( PB_H( r - 1, r - 2 ) );
-        double aa = 0.75 * ss + PB_H( r, r ), bb = ss, cc = -0.4375 * ss, dd = aa;
+        const double ss = fabs( PB_HLD( r, r - 1 ) ) + fabs( PB_HLD( r - 1, r - 2 ) );
+        double aa = 0.75 * ss + PB_HLD( r, r ), bb = ss, cc = -0.4375 * ss, dd = aa;
         double cs, sn;
         dlanv2( aa, bb, cc, dd, sr[q - 1], si[q - 1], sr[q], si[q], cs, sn );
       }
@@ -447,7 +483,7 @@ PB_D int ms_compute_shifts( const G& g, int l, int i, const double* H, int ldh, 
     const int r0 = i - ns + 1;
     for ( int q = t; q < ns * ns; q += nt ) {
       const int c = q / ns, r = q - c * ns;
-      S[r + c * ldw] = ( r - c <= 1 ) ? PB_H( r0 + r, r0 + c ) : 0.0;
+      S[r + c * ldw] = ( r - c <= 1 ) ? PB_HLD( r0 + r, r0 + c ) : 0.0;
     }
     g.sync();
     int inf = 0;
@@ -471,7 +507,7 @@ PB_D int ms_compute_shifts( const G& g, int l, int i, const double* H, int ldh, 
     if ( ns - ks < 2 ) {
       // fall back on the trailing 2x2 block
       if ( t == 0 ) {
-        double aa = PB_H( i - 1, i - 1 ), bb = PB_H( i - 1, i ), cc = PB_H( i, i - 1 ), dd = PB_H( i, i );
+        double aa = PB_HLD( i - 1, i - 1 ), bb = PB_HLD( i - 1, i ), cc = PB_HLD( i, i - 1 ), dd = PB_HLD( i, i );
         double cs, sn;
         dlanv2( aa, bb, cc, dd, sr[ns - 2], si[ns - 2], sr[ns - 1], si[ns - 1], cs, sn );
       }
@@ -780,19 +816,13 @@ PB_D void ms_chase_chain( const G& g, bool wantt, bool wantz, int n, int l, int 
       // steady-state windows only (about five in six); the others take the tile path below
       if ( cfg.W == kStripW && cfg.nb == kStripNB && cfg.tl >= 16 * ( g.size() >> 5 ) &&
            strip_window_is_regular( nbulges, wlen, ws, kfirst, kcount ) ) {
-        if ( wk.csize > 1 ) {
-          // hand the window to the cluster: command + reflectors are read from this CTA's shared memory
-          if ( t == 0 ) {
-            int* cmd = wk.ibuf + kMsCmd;
-            cmd[0] = 1; cmd[1] = ws; cmd[2] = wlen; cmd[3] = l; cmd[4] = i;
-          }
-          cooperative_groups::this_cluster().sync();
-        }
+        // hand the window to the cluster: command + reflectors are read from this CTA's shared memory
+        if ( wk.csize > 1 ) ms_cluster_post( wk, 1, ws, wlen, l, i, nbulges );
         ms_strips_regs( wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, wk.refl, wk.tile, wk.ldt,
                         wk.ibuf + 3 * kMsMaxBulges + 6, 0, wk.csize );
-        if ( wk.csize > 1 ) cooperative_groups::this_cluster().sync();
+        if ( wk.csize > 1 ) ms_cluster_join();
       } else {
-        ms_update_strips( g, wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, nbulges, (const double*)nullptr );
+        ms_update_strips_shared( g, wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, nbulges, (const double*)nullptr );
       }
     } else
 #endif
@@ -822,7 +852,7 @@ PB_D void ms_aed( const G& g, bool wantt, bool wantz, int n, int ktop, int kbot,
   const int t = g.tid(), nt = g.size();
   const int kwtop = kbot - jw + 1;
   const int ldw = wk.ldw;
-  const double s = ( kwtop > ktop ) ? PB_H( kwtop, kwtop - 1 ) : 0.0;
+  const double s = ( kwtop > ktop ) ? PB_HLD( kwtop, kwtop - 1 ) : 0.0;
   ms_load_window( g, H, ldh, kwtop, jw, wk.Hw, ldw );
   for ( int q = t; q < jw * jw; q += nt ) {
     const int c = q / jw, r = q - c * jw;
@@ -869,7 +899,7 @@ PB_D void ms_aed( const G& g, bool wantt, bool wantz, int n, int ktop, int kbot,
       if ( r - c <= 1 ) PB_H( kwtop + r, kwtop + c ) = wk.Hw[r + c * ldw];
     }
     g.sync();
-    ms_update_strips( g, wantt, wantz, n, ktop, kbot, kwtop, jw, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, 0, wk.U );
+    ms_update_strips_shared( g, wantt, wantz, n, ktop, kbot, kwtop, jw, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, 0, wk.U );
   }
   *nd_out = jw - ns;
   *ns_out = nshift;
@@ -877,8 +907,8 @@ PB_D void ms_aed( const G& g, bool wantt, bool wantz, int n, int ktop, int kbot,
 
 #if defined( __CUDACC__ )
 // ---- cluster helpers (ranks 1..csize-1): strips of the leader's steady-state windows -------------------------------------
-__device__ inline void ms_cluster_helper( bool wantt, bool wantz, int n, double* H, int ldh, int iloz, int ihiz, double* Z, int ldz,
-                                          const MsqrCfg& cfg, const MsqrWork& wk ) {
+__device__ inline void ms_cluster_helper( const CtaGroup& g, bool wantt, bool wantz, int n, double* H, int ldh, int iloz, int ihiz,
+                                          double* Z, int ldz, const MsqrCfg& cfg, const MsqrWork& wk ) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   const int* lcmd = cluster.map_shared_rank( wk.ibuf + kMsCmd, 0 );
@@ -891,13 +921,28 @@ __device__ inline void ms_cluster_helper( bool wantt, bool wantz, int n, double*
       cluster.sync();  // the leader's shared memory stays alive until every helper has read the command
       return;
     }
-    const int ws = lcmd[1], wlen = lcmd[2], l = lcmd[3], i = lcmd[4];
-    for ( int q = threadIdx.x; q < nrefl / 2; q += blockDim.x )
-      reinterpret_cast<double2*>( wk.refl )[q] = reinterpret_cast<const double2*>( lrefl )[q];
-    if ( threadIdx.x == 0 ) wk.ibuf[3 * kMsMaxBulges + 6] = 0;
-    __syncthreads();
-    ms_strips_regs( wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, wk.refl, wk.tile, wk.ldt,
-                    wk.ibuf + 3 * kMsMaxBulges + 6, wk.crank, wk.csize );
+    const int ws = lcmd[1], wlen = lcmd[2], l = lcmd[3], i = lcmd[4], nbulges = lcmd[5];
+    if ( cmd == 2 ) {
+      const double* lU = cluster.map_shared_rank( wk.U, 0 );
+      for ( int q = threadIdx.x; q < wlen * wk.ldw; q += blockDim.x ) wk.U[q] = lU[q];
+      __syncthreads();
+      ms_update_strips( g, wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, 0, wk.U, wk.crank, wk.csize );
+    } else {
+      for ( int q = threadIdx.x; q < nrefl / 2; q += blockDim.x )
+        reinterpret_cast<double2*>( wk.refl )[q] = reinterpret_cast<const double2*>( lrefl )[q];
+      if ( cmd == 3 ) {
+        const int* lk = cluster.map_shared_rank( wk.ibuf + kMsMaxBulges, 0 );
+        if ( threadIdx.x < 2 * kMsMaxBulges ) wk.ibuf[kMsMaxBulges + threadIdx.x] = lk[threadIdx.x];
+      }
+      if ( threadIdx.x == 0 ) wk.ibuf[3 * kMsMaxBulges + 6] = 0;
+      __syncthreads();
+      if ( cmd == 1 )
+        ms_strips_regs( wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, wk.refl, wk.tile, wk.ldt,
+                        wk.ibuf + 3 * kMsMaxBulges + 6, wk.crank, wk.csize );
+      else
+        ms_update_strips( g, wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, nbulges, (const double*)nullptr,
+                          wk.crank, wk.csize );
+    }
     cluster.sync();
   }
 }

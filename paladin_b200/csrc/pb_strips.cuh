@@ -175,8 +175,8 @@ __device__ inline void ms_strips_regs( bool wantt, bool wantz, int n, int l, int
         for ( int u = 0; u < 8; ++u ) {
           const int cc = imin( c0 + u, nl - 1 );
           const double* col = H + (size_t)( j0 + cc ) * ldh + ws;
-          v0[u] = col[lane];
-          v1[u] = col[imin( 32 + lane, kStripW - 1 )];
+          v0[u] = __ldcg( col + lane );
+          v1[u] = __ldcg( col + imin( 32 + lane, kStripW - 1 ) );
         }
 #pragma unroll
         for ( int u = 0; u < 8; ++u ) {
@@ -199,8 +199,8 @@ __device__ inline void ms_strips_regs( bool wantt, bool wantz, int n, int l, int
       __syncwarp();
       for ( int cc = 0; cc < nl; ++cc ) {
         double* col = H + (size_t)( j0 + cc ) * ldh + ws;
-        col[lane] = wt[lane * ldt + cc];
-        if ( 32 + lane < kStripW ) col[32 + lane] = wt[( 32 + lane ) * ldt + cc];
+        __stcg( col + lane, wt[lane * ldt + cc] );
+        if ( 32 + lane < kStripW ) __stcg( col + 32 + lane, wt[( 32 + lane ) * ldt + cc] );
       }
       __syncwarp();
     }

@@ -188,6 +188,37 @@ def test_sizes_across_kernel_variants(pg):
         _check_eigs(po.dense_matrix(*m), wr, wi, VR, inf, True)
 
 
+@pytest.mark.parametrize("jobvr,sizes", [("V", [1100, 1300, 2100]), ("N", [1290, 1537]), ("V", [1030] * 5 + [1500])])
+def test_large_matrices_cooperative_path(pg, jobvr, sizes):
+    """n > 1024: Hessenberg + Q on groups of cooperating CTAs (1, 2 or 4 groups by the largest order), QR strips shared
+    by a thread-block cluster (16, 8, ... CTAs by the number of large matrices), eigenvectors shared by many CTAs."""
+    mats = _random_mats(sizes, 29)
+    # one matrix with isolated eigenvalues (balancing permutes: ilo > 1, ihi < n) and a badly scaled row / column
+    n0 = sizes[0]
+    rng = np.random.default_rng(77)
+    B = rng.standard_normal((n0, n0))
+    B[5, :] = 0.0
+    B[5, 5] = 3.0
+    B[:, 40] = 0.0
+    B[40, 40] = -2.0
+    B[:, 7] *= 1e6
+    B[9, :] *= 1e-5
+    jj, ii = np.meshgrid(np.arange(1, n0 + 1, dtype=np.int32), np.arange(1, n0 + 1, dtype=np.int32))
+    mats[0] = (n0, ii.T.reshape(-1).copy(), jj.T.reshape(-1).copy(), np.ascontiguousarray(B.T).reshape(-1))
+    res, info = pg.geev_batch(*_concat(mats), jobvr=jobvr)
+    for k, (m, (wr, wi, VR), inf) in enumerate(zip(mats, res, info)):
+        A = po.dense_matrix(*m)
+        if k == 0:
+            assert inf == 0
+            wr0, wi0, _, _, _ = po.dgeev(A, right=False)
+            # graded matrix: the achievable accuracy is LAPACK's own, relative to the (huge) norm
+            assert po.match_eigenvalues(po.eigenvalues(wr, wi), po.eigenvalues(wr0, wi0)) <= EIG_TOL * max(1.0, np.linalg.norm(A, 2))
+            if jobvr == "V":
+                assert po.backward_error(A, wr, wi, VR) <= BACKWARD_TOL
+        else:
+            _check_eigs(A, wr, wi, VR, inf, jobvr == "V")
+
+
 def test_n512_full_decomposition(pg):
     mats = _random_mats([512, 512], 3)
     res, info = pg.geev_batch(*_concat(mats), jobvr="V")
