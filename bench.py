@@ -334,7 +334,7 @@ def ours(args):
             traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) / tj["matrices_per_launch"] * B
         if qr_ms > 0:
             achieved = B * qr_flops / (qr_ms * 1e-3) / 1e12
-            kernel_name = "mid_qr_kernel (windowed multishift QR, CTA per matrix)"
+            kernel_name = "mid_qr_kernel (windowed multishift QR with early deflation, CTA per matrix)"
         else:  # n <= 64: everything runs in the fused warp-per-matrix kernel
             achieved = B * flops / (solve_ms * 1e-3) / 1e12
             kernel_name = "geev_warp_kernel (all stages)"

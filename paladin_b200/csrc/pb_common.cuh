@@ -399,9 +399,21 @@ PB_HD void larfg3_fast( int n, double& a0, double& a1, double& a2, double& t1 ) 
     t1 = 0.0;
     return;
   }
+#if defined( __CUDA_ARCH__ )
+  // one reciprocal square root and one reciprocal on the critical path (the Francis step is bound by this latency):
+  // norm = |x| , beta = -sign(a0) norm, tau = (beta - a0) / beta = 1 + |a0| / norm, v = x / (a0 - beta) = sign(a0) x / (|a0| + norm)
+  const double nn = a0 * a0 + xn2;
+  const double rn = rsqrt( nn );
+  const double nrm = nn * rn;
+  const double aa = fabs( a0 );
+  const double rs = dsign( 1.0 / ( aa + nrm ), a0 );
+  const double beta = -dsign( nrm, a0 );
+  t1 = 1.0 + aa * rn;
+#else
   const double beta = -dsign( sqrt( a0 * a0 + xn2 ), a0 );
   const double rb = 1.0 / beta, rs = 1.0 / ( a0 - beta );
   t1 = ( beta - a0 ) * rb;
+#endif
   a1 *= rs;
   a2 *= rs;
   a0 = beta;

@@ -56,6 +56,8 @@ struct MsqrCfg {
   int nshift;    // shifts computed per sweep (<= 2*nb*nchains); chains beyond nshift/(2 nb) reuse them cyclically
   int aed = 0;   // order of the aggressive-early-deflation window (<= W - 1); 0 = no AED
   int aed_moves = 1 << 20;  // undeflatable blocks an AED step may reorder (see pb::aed_window)
+  int spec_shifts = 0;      // 1: the shifts of the next sweep are computed from the block as it is BEFORE the AED step
+                            // (on the device: by another warp, while the AED window is being factored)
 };
 
 // on-chip work space (shared memory on the device)
@@ -996,7 +998,12 @@ PB_D int hqr_multishift( const G& g, bool wantt, bool wantz, int n, int ilo, int
     if ( ++it > itmax ) return kbot + 1;
     // the shift block is factored inside the U buffer, hence ns <= W
     const int nshift_cfg = imin( cfg.nshift > 0 ? cfg.nshift : 2 * cfg.nb * cfg.nchains, 2 * cfg.nb * cfg.nchains );
-    int ns_aed = 0;
+    int ns_aed = 0, ns_spec = 0;
+    if ( cfg.aed > 0 && cfg.aed_moves == 0 && cfg.spec_shifts != 0 && ( ( nodefl + 1 ) % 6 ) != 0 ) {
+      const int want0 = imax( 2, imin( imin( nshift_cfg, cfg.W & ~1 ), ( ( m - 1 ) / 3 ) * 2 ) & ~1 );
+      ns_spec = ms_compute_shifts( g, ktop, kbot, H, ldh, want0, false, wk );
+      g.tick( kTickMsShifts );
+    }
     if ( cfg.aed > 0 ) {
       const int jw = imin( imin( cfg.aed, cfg.W - 1 ), m );
       int nd = 0;
@@ -1028,6 +1035,18 @@ PB_D int hqr_multishift( const G& g, bool wantt, bool wantz, int n, int ilo, int
           for ( int q = 0; q < ns; ++q ) {
             wk.sr[q] = wk.sr[ns_aed - ns + q];
             wk.si[q] = wk.si[ns_aed - ns + q];
+          }
+        g.sync();
+      }
+    } else if ( !exceptional && ns_spec >= 2 ) {
+      // speculative shifts (eigenvalues of the trailing block before the AED step): keep the smallest moduli
+      ns = imin( ns_spec, nshift_want );
+      if ( ns < ns_spec ) {
+        g.sync();
+        if ( t == 0 )
+          for ( int q = 0; q < ns; ++q ) {
+            wk.sr[q] = wk.sr[ns_spec - ns + q];
+            wk.si[q] = wk.si[ns_spec - ns + q];
           }
         g.sync();
       }
