@@ -600,6 +600,8 @@ struct paladin_gpu_batch {
   StageTimer st[PALADIN_GPU_NUM_STAGES];
   bool scattered = false;
   cudaStream_t stream = nullptr;             // every batch owns its stream: batches of one device overlap
+  cudaStream_t stream2 = nullptr;            // side stream: the QR kernel of the smaller matrices runs next to the clusters
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t t0 = nullptr, t1 = nullptr;    // stopwatch (paladin_gpu_batch_timer_*)
 };
 
@@ -621,6 +623,9 @@ void free_batch( paladin_gpu_batch* b ) {
   if ( b->t0 ) cudaEventDestroy( b->t0 );
   if ( b->t1 ) cudaEventDestroy( b->t1 );
   if ( b->stream ) cudaStreamDestroy( b->stream );
+  if ( b->stream2 ) cudaStreamDestroy( b->stream2 );
+  if ( b->ev_fork ) cudaEventDestroy( b->ev_fork );
+  if ( b->ev_join ) cudaEventDestroy( b->ev_join );
   delete b;
 }
 
@@ -882,12 +887,12 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
       if ( n[k] > kMidMaxFusedN && n[k] <= kMidMaxBigN ) nbigmax = std::max( nbigmax, n[k] );
     static const bool no_coop = std::getenv( "PALADIN_GPU_NO_COOP" ) != nullptr;
     if ( nbigmax > 0 && !no_coop ) {
-      b->coop_G = nbigmax > 2048 ? 1 : ( nbigmax > 1400 ? 2 : 4 );
-      if ( const char* env = std::getenv( "PALADIN_GPU_COOP_GROUPS" ) ) b->coop_G = std::max( 1, std::atoi( env ) );
-      b->coop_S = std::max( 1, c.sm_count / b->coop_G );
+      // groups per launch are chosen per size class at solve time (1, 2 or 4); the scratch covers every choice
+      b->coop_G = 4;
+      b->coop_S = c.sm_count;
       b->coop_nmax = nbigmax;
       A( dev_alloc( &b->d_coop_bars, 2 * (size_t)b->coop_G + 2 ) );
-      A( dev_alloc( &b->d_coop_ypart, (size_t)b->coop_G * b->coop_S * nbigmax ) );
+      A( dev_alloc( &b->d_coop_ypart, (size_t)c.sm_count * nbigmax ) );
       A( dev_alloc( &b->d_coop_yz, (size_t)b->coop_G * 2 * nbigmax ) );
       if ( rc == PALADIN_GPU_OK && cudaMemset( b->d_coop_bars, 0, sizeof( unsigned ) * ( 2 * b->coop_G + 2 ) ) != cudaSuccess )
         rc = fail( PALADIN_GPU_ECUDA, "cudaMemset failed" );
@@ -903,7 +908,10 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
   }
   cudaEventCreate( &b->t0 );
   cudaEventCreate( &b->t1 );
-  if ( cudaStreamCreateWithFlags( &b->stream, cudaStreamNonBlocking ) != cudaSuccess ) {
+  cudaEventCreateWithFlags( &b->ev_fork, cudaEventDisableTiming );
+  cudaEventCreateWithFlags( &b->ev_join, cudaEventDisableTiming );
+  if ( cudaStreamCreateWithFlags( &b->stream, cudaStreamNonBlocking ) != cudaSuccess ||
+       cudaStreamCreateWithFlags( &b->stream2, cudaStreamNonBlocking ) != cudaSuccess ) {
     free_batch( b );
     return fail( PALADIN_GPU_ECUDA, "cudaStreamCreate failed" );
   }
@@ -1105,16 +1113,35 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
         for ( int q = 0; q < nbig; ++q )
           if ( b->n[b->ids[g.first + q]] > kMidMaxBigN ) nhuge = q + 1;
         if ( b->coop_S > 0 && nbig > nhuge ) {
-          // large matrices: groups of cooperating CTAs, one matrix per group at a time
-          MidArgs mc = ma;
-          mc.ids = ids + nhuge;
-          mc.count = nbig - nhuge;
-          CoopArgs ca{ b->d_coop_bars, b->d_coop_ypart, b->d_coop_yz, b->coop_S, b->coop_G, b->coop_nmax };
-          const size_t sc = sizeof( double ) * pb::coop_hess_smem_doubles( b->coop_nmax, b->coop_S );
-          PB_CUDA( cudaFuncSetAttribute( big_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc ) );
-          void* kargs[] = { &mc, &ca };
-          PB_CUDA( cudaLaunchCooperativeKernel( (const void*)big_prep_kernel, dim3( b->coop_S * b->coop_G ), dim3( pb::kHessThreads ), kargs, sc, st ) );
-          ++launches;
+          // large matrices: groups of cooperating CTAs, one matrix per group at a time. The size-sorted list is cut into
+          // classes: all SMs on one matrix above n = 2048, two groups down to 1400, four groups below.
+          static const int env_groups = std::getenv( "PALADIN_GPU_COOP_GROUPS" ) ? std::max( 1, std::atoi( std::getenv( "PALADIN_GPU_COOP_GROUPS" ) ) ) : 0;
+          int q0 = nhuge;
+          while ( q0 < nbig ) {
+            const int nfirst = b->n[b->ids[g.first + q0]];
+            int G = nfirst > 2048 ? 1 : ( nfirst > 1400 ? 2 : 4 );
+            int q1 = q0;
+            while ( q1 < nbig ) {
+              const int nq = b->n[b->ids[g.first + q1]];
+              if ( ( nq > 2048 ? 1 : ( nq > 1400 ? 2 : 4 ) ) != G ) break;
+              ++q1;
+            }
+            if ( env_groups > 0 ) {
+              G = std::min( env_groups, 4 );
+              q1 = nbig;
+            }
+            const int S = std::max( 1, c.sm_count / G );
+            MidArgs mc = ma;
+            mc.ids = ids + q0;
+            mc.count = q1 - q0;
+            CoopArgs ca{ b->d_coop_bars, b->d_coop_ypart, b->d_coop_yz, S, G, b->coop_nmax };
+            const size_t sc = sizeof( double ) * pb::coop_hess_smem_doubles( nfirst, S );
+            PB_CUDA( cudaFuncSetAttribute( big_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc ) );
+            void* kargs[] = { &mc, &ca };
+            PB_CUDA( cudaLaunchCooperativeKernel( (const void*)big_prep_kernel, dim3( S * G ), dim3( pb::kHessThreads ), kargs, sc, st ) );
+            ++launches;
+            q0 = q1;
+          }
         }
         const int n0 = ( b->coop_S > 0 ) ? nhuge : nbig;  // what is left for the one-CTA streaming / unblocked kernel
         if ( n0 > 0 ) {
@@ -1150,6 +1177,12 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
         static const int env_cluster = std::getenv( "PALADIN_GPU_CLUSTER" ) ? std::atoi( std::getenv( "PALADIN_GPU_CLUSTER" ) ) : 0;
         if ( env_cluster > 0 ) csize = env_cluster;
         int launches = 0;
+        const bool fork = csize > 1 && nqbig > 0 && cnt > nqbig;
+        if ( fork ) {
+          // the smaller matrices do not wait for the clusters: their kernel goes to the side stream
+          PB_CUDA( cudaEventRecord( b->ev_fork, st ) );
+          PB_CUDA( cudaStreamWaitEvent( b->stream2, b->ev_fork, 0 ) );
+        }
         if ( csize > 1 && nqbig > 0 ) {
           if ( csize > 8 ) PB_CUDA( cudaFuncSetAttribute( mid_qr_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1 ) );
           cudaLaunchConfig_t cfg = {};
@@ -1173,8 +1206,12 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
           MidArgs mq = ma;
           mq.ids = ids + nqbig;
           mq.count = cnt - nqbig;
-          mid_qr_kernel<false><<<cnt - nqbig, kMidThreads, s2, st>>>( mq );
+          mid_qr_kernel<false><<<cnt - nqbig, kMidThreads, s2, fork ? b->stream2 : st>>>( mq );
           ++launches;
+        }
+        if ( fork ) {
+          PB_CUDA( cudaEventRecord( b->ev_join, b->stream2 ) );
+          PB_CUDA( cudaStreamWaitEvent( st, b->ev_join, 0 ) );
         }
         stage_end( b, PALADIN_GPU_STAGE_QR, st, launches );
       }
