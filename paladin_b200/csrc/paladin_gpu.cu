@@ -299,6 +299,7 @@ __global__ void __launch_bounds__( pb::kHessThreads, ( MAXCH == 16 ? 2 : 1 ) ) m
 
 // ---- stage 1 for large matrices (kMidMaxFusedN < n <= kMidMaxBigN): groups of S cooperating CTAs, one matrix per group
 // at a time (pb_coop.cuh); cooperative launch, one CTA per SM ------------------------------------------------------------
+constexpr int kCoopMaxGroups = 16;
 struct CoopArgs {
   unsigned* bars;  // 2 words per group, 2 more for the whole grid
   double* ypart;   // S * nmax doubles per group
@@ -600,8 +601,8 @@ struct paladin_gpu_batch {
   StageTimer st[PALADIN_GPU_NUM_STAGES];
   bool scattered = false;
   cudaStream_t stream = nullptr;             // every batch owns its stream: batches of one device overlap
-  cudaStream_t stream2 = nullptr;            // side stream: the QR kernel of the smaller matrices runs next to the clusters
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t side[3] = { nullptr, nullptr, nullptr };  // side streams: the QR launches of the size classes run side by side
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = { nullptr, nullptr, nullptr };
   cudaEvent_t t0 = nullptr, t1 = nullptr;    // stopwatch (paladin_gpu_batch_timer_*)
 };
 
@@ -623,9 +624,11 @@ void free_batch( paladin_gpu_batch* b ) {
   if ( b->t0 ) cudaEventDestroy( b->t0 );
   if ( b->t1 ) cudaEventDestroy( b->t1 );
   if ( b->stream ) cudaStreamDestroy( b->stream );
-  if ( b->stream2 ) cudaStreamDestroy( b->stream2 );
+  for ( int q = 0; q < 3; ++q ) {
+    if ( b->side[q] ) cudaStreamDestroy( b->side[q] );
+    if ( b->ev_join[q] ) cudaEventDestroy( b->ev_join[q] );
+  }
   if ( b->ev_fork ) cudaEventDestroy( b->ev_fork );
-  if ( b->ev_join ) cudaEventDestroy( b->ev_join );
   delete b;
 }
 
@@ -888,7 +891,7 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
     static const bool no_coop = std::getenv( "PALADIN_GPU_NO_COOP" ) != nullptr;
     if ( nbigmax > 0 && !no_coop ) {
       // groups per launch are chosen per size class at solve time (1, 2 or 4); the scratch covers every choice
-      b->coop_G = 4;
+      b->coop_G = kCoopMaxGroups;
       b->coop_S = c.sm_count;
       b->coop_nmax = nbigmax;
       A( dev_alloc( &b->d_coop_bars, 2 * (size_t)b->coop_G + 2 ) );
@@ -909,9 +912,12 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
   cudaEventCreate( &b->t0 );
   cudaEventCreate( &b->t1 );
   cudaEventCreateWithFlags( &b->ev_fork, cudaEventDisableTiming );
-  cudaEventCreateWithFlags( &b->ev_join, cudaEventDisableTiming );
-  if ( cudaStreamCreateWithFlags( &b->stream, cudaStreamNonBlocking ) != cudaSuccess ||
-       cudaStreamCreateWithFlags( &b->stream2, cudaStreamNonBlocking ) != cudaSuccess ) {
+  bool side_ok = true;
+  for ( int q = 0; q < 3; ++q ) {
+    cudaEventCreateWithFlags( &b->ev_join[q], cudaEventDisableTiming );
+    side_ok = side_ok && cudaStreamCreateWithFlags( &b->side[q], cudaStreamNonBlocking ) == cudaSuccess;
+  }
+  if ( cudaStreamCreateWithFlags( &b->stream, cudaStreamNonBlocking ) != cudaSuccess || !side_ok ) {
     free_batch( b );
     return fail( PALADIN_GPU_ECUDA, "cudaStreamCreate failed" );
   }
@@ -1119,15 +1125,20 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
           int q0 = nhuge;
           while ( q0 < nbig ) {
             const int nfirst = b->n[b->ids[g.first + q0]];
-            int G = nfirst > 2048 ? 1 : ( nfirst > 1400 ? 2 : 4 );
+            const int kind = nfirst > 2048 ? 0 : ( nfirst > 1400 ? 1 : 2 );
             int q1 = q0;
             while ( q1 < nbig ) {
               const int nq = b->n[b->ids[g.first + q1]];
-              if ( ( nq > 2048 ? 1 : ( nq > 1400 ? 2 : 4 ) ) != G ) break;
+              if ( ( nq > 2048 ? 0 : ( nq > 1400 ? 1 : 2 ) ) != kind ) break;
               ++q1;
             }
+            // a single matrix takes all SMs (latency); a class with many matrices is better off with more, smaller
+            // groups (throughput: the per-column barriers and reductions cost the same whatever the group size)
+            const int ncls = q1 - q0;
+            int G = kind == 0 ? ( ncls >= 8 ? 4 : ( ncls >= 4 ? 2 : 1 ) )
+                              : ( kind == 1 ? ( ncls >= 16 ? 8 : ( ncls >= 4 ? 4 : 2 ) ) : ( ncls >= 32 ? 16 : ( ncls >= 8 ? 8 : 4 ) ) );
             if ( env_groups > 0 ) {
-              G = std::min( env_groups, 4 );
+              G = std::min( env_groups, kCoopMaxGroups );
               q1 = nbig;
             }
             const int S = std::max( 1, c.sm_count / G );
@@ -1172,46 +1183,80 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
         int nqbig = 0;
         for ( int q = 0; q < cnt; ++q )
           if ( b->n[b->ids[g.first + q]] > kMidMaxFusedN ) nqbig = q + 1;
-        const int slots = 2 * c.sm_count;
-        int csize = nqbig == 0 ? 1 : ( 16 * nqbig <= slots ? 16 : ( 8 * nqbig <= slots ? 8 : ( 4 * nqbig <= slots ? 4 : ( 2 * nqbig <= slots ? 2 : 1 ) ) ) );
-        static const int env_cluster = std::getenv( "PALADIN_GPU_CLUSTER" ) ? std::atoi( std::getenv( "PALADIN_GPU_CLUSTER" ) ) : 0;
-        if ( env_cluster > 0 ) csize = env_cluster;
-        int launches = 0;
-        const bool fork = csize > 1 && nqbig > 0 && cnt > nqbig;
-        if ( fork ) {
-          // the smaller matrices do not wait for the clusters: their kernel goes to the side stream
-          PB_CUDA( cudaEventRecord( b->ev_fork, st ) );
-          PB_CUDA( cudaStreamWaitEvent( b->stream2, b->ev_fork, 0 ) );
+        // cluster size per size class of the sorted list (n > 2048: 16, > 1400: 8, else 4 CTAs), halved together until the
+        // clusters fit the 2 x SM-count resident CTAs (one and a half times: the tail of a class may queue); every class
+        // is its own launch on its own stream, the remaining matrices (one CTA each) run next to them
+        const int slots = 3 * c.sm_count;
+        struct QrClass { int first, count, csize; };
+        QrClass cls[3] = { { 0, 0, 16 }, { 0, 0, 8 }, { 0, 0, 4 } };
+        for ( int q = 0; q < nqbig; ++q ) {
+          const int nq = b->n[b->ids[g.first + q]];
+          QrClass& k = cls[nq > 2048 ? 0 : ( nq > 1400 ? 1 : 2 )];
+          if ( k.count == 0 ) k.first = q;
+          k.count += 1;
         }
-        if ( csize > 1 && nqbig > 0 ) {
-          if ( csize > 8 ) PB_CUDA( cudaFuncSetAttribute( mid_qr_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1 ) );
+        static const int env_cluster = std::getenv( "PALADIN_GPU_CLUSTER" ) ? std::atoi( std::getenv( "PALADIN_GPU_CLUSTER" ) ) : 0;
+        for ( ;; ) {
+          int demand = 0;
+          for ( const QrClass& k : cls ) demand += k.count * k.csize;
+          if ( demand <= slots ) break;
+          bool any = false;
+          for ( QrClass& k : cls )
+            if ( k.csize > 1 ) {
+              k.csize /= 2;
+              any = true;
+            }
+          if ( !any ) break;
+        }
+        if ( env_cluster > 0 )
+          for ( QrClass& k : cls ) k.csize = env_cluster;
+        int launches = 0, nclustered = 0, nside = 0;
+        PB_CUDA( cudaEventRecord( b->ev_fork, st ) );
+        for ( const QrClass& k : cls ) {
+          if ( k.count == 0 || k.csize <= 1 ) continue;
+          if ( k.first != nclustered ) break;  // (classes are contiguous prefixes of the sorted list)
+          cudaStream_t sq = st;
+          if ( nside > 0 ) {
+            sq = b->side[nside - 1];
+            PB_CUDA( cudaStreamWaitEvent( sq, b->ev_fork, 0 ) );
+          }
+          if ( k.csize > 8 ) PB_CUDA( cudaFuncSetAttribute( mid_qr_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1 ) );
+          MidArgs mq = ma;
+          mq.ids = ids + k.first;
+          mq.count = k.count;
           cudaLaunchConfig_t cfg = {};
-          cfg.gridDim = dim3( nqbig * csize );
+          cfg.gridDim = dim3( k.count * k.csize );
           cfg.blockDim = dim3( kMidThreads );
           cfg.dynamicSmemBytes = s2;
-          cfg.stream = st;
+          cfg.stream = sq;
           cudaLaunchAttribute attr[1];
           attr[0].id = cudaLaunchAttributeClusterDimension;
-          attr[0].val.clusterDim.x = csize;
+          attr[0].val.clusterDim.x = k.csize;
           attr[0].val.clusterDim.y = 1;
           attr[0].val.clusterDim.z = 1;
           cfg.attrs = attr;
           cfg.numAttrs = 1;
-          PB_CUDA( cudaLaunchKernelEx( &cfg, mid_qr_kernel<true>, ma ) );
+          PB_CUDA( cudaLaunchKernelEx( &cfg, mid_qr_kernel<true>, mq ) );
           ++launches;
-        } else {
-          nqbig = 0;
+          ++nside;
+          nclustered = k.first + k.count;
         }
-        if ( cnt > nqbig ) {
+        if ( cnt > nclustered ) {
+          cudaStream_t sq = st;
+          if ( nside > 0 ) {
+            sq = b->side[nside - 1];
+            PB_CUDA( cudaStreamWaitEvent( sq, b->ev_fork, 0 ) );
+          }
           MidArgs mq = ma;
-          mq.ids = ids + nqbig;
-          mq.count = cnt - nqbig;
-          mid_qr_kernel<false><<<cnt - nqbig, kMidThreads, s2, fork ? b->stream2 : st>>>( mq );
+          mq.ids = ids + nclustered;
+          mq.count = cnt - nclustered;
+          mid_qr_kernel<false><<<cnt - nclustered, kMidThreads, s2, sq>>>( mq );
           ++launches;
+          ++nside;
         }
-        if ( fork ) {
-          PB_CUDA( cudaEventRecord( b->ev_join, b->stream2 ) );
-          PB_CUDA( cudaStreamWaitEvent( st, b->ev_join, 0 ) );
+        for ( int q = 0; q + 1 < nside; ++q ) {
+          PB_CUDA( cudaEventRecord( b->ev_join[q], b->side[q] ) );
+          PB_CUDA( cudaStreamWaitEvent( st, b->ev_join[q], 0 ) );
         }
         stage_end( b, PALADIN_GPU_STAGE_QR, st, launches );
       }

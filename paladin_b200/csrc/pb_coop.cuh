@@ -214,11 +214,21 @@ __device__ inline void coop_hess( const CoopGroup& cg, int n, int ilo, int ihi, 
     {
       const int rows_per = ( nrow + S - 1 ) / S;
       const int r0 = rank * rows_per, r1 = imin( nrow, r0 + rows_per );
-      for ( int r = r0 + warp; r < r1; r += kHessWarps ) {
-        double s = 0.0;
-        for ( int p = lane; p < S; p += 32 ) s += __ldcg( ypart + (size_t)p * n + r );
-        s = warp_sum( s );
-        if ( lane == 0 ) __stcg( yfull + r, s );
+      if ( S > 32 ) {
+        // few rows, many partial vectors: a warp per row, lanes over the partials
+        for ( int r = r0 + warp; r < r1; r += kHessWarps ) {
+          double s = 0.0;
+          for ( int p = lane; p < S; p += 32 ) s += __ldcg( ypart + (size_t)p * n + r );
+          s = warp_sum( s );
+          if ( lane == 0 ) __stcg( yfull + r, s );
+        }
+      } else {
+        // many rows, few partial vectors: a thread per row (coalesced), the S loads of a row in flight together
+        for ( int r = r0 + tid; r < r1; r += kHessThreads ) {
+          double s = 0.0;
+          for ( int p = 0; p < S; ++p ) s += __ldcg( ypart + (size_t)p * n + r );
+          __stcg( yfull + r, s );
+        }
       }
     }
     coop_sync( cg );
