@@ -299,7 +299,12 @@ __global__ void __launch_bounds__( pb::kHessThreads, ( MAXCH == 16 ? 2 : 1 ) ) m
 
 // ---- stage 1 for large matrices (kMidMaxFusedN < n <= kMidMaxBigN): groups of S cooperating CTAs, one matrix per group
 // at a time (pb_coop.cuh); cooperative launch, one CTA per SM ------------------------------------------------------------
-constexpr int kCoopMaxGroups = 16;
+constexpr int kCoopMaxGroups = 37;
+// smallest order that takes the cooperative stage 1 (tuning: PALADIN_GPU_COOP_MIN_N)
+inline int coop_min_n() {
+  static const int v = std::getenv( "PALADIN_GPU_COOP_MIN_N" ) ? std::max( 64, std::atoi( std::getenv( "PALADIN_GPU_COOP_MIN_N" ) ) ) : kMidMaxFusedN;
+  return v;
+}
 struct CoopArgs {
   unsigned* bars;  // 2 words per group, 2 more for the whole grid
   double* ypart;   // S * nmax doubles per group
@@ -887,7 +892,7 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
     // scratch of the cooperative Hessenberg stage: the largest matrix that takes it fixes the group size
     int nbigmax = 0;
     for ( int k = 0; k < count; ++k )
-      if ( n[k] > kMidMaxFusedN && n[k] <= kMidMaxBigN ) nbigmax = std::max( nbigmax, n[k] );
+      if ( n[k] > coop_min_n() && n[k] <= kMidMaxBigN ) nbigmax = std::max( nbigmax, n[k] );
     static const bool no_coop = std::getenv( "PALADIN_GPU_NO_COOP" ) != nullptr;
     if ( nbigmax > 0 && !no_coop ) {
       // groups per launch are chosen per size class at solve time (1, 2 or 4); the scratch covers every choice
@@ -1109,11 +1114,11 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
         int nbig = 0, nmid = 0;
         for ( int q = 0; q < g.count; ++q ) {
           const int nq = b->n[b->ids[g.first + q]];
-          if ( nq > kMidMaxFusedN ) nbig = q + 1;
+          if ( nq > ( b->coop_S > 0 ? coop_min_n() : kMidMaxFusedN ) ) nbig = q + 1;
           if ( nq > 512 ) nmid = q + 1;
         }
         nbig = std::min( nbig, cnt );
-        nmid = std::min( nmid, cnt );
+        nmid = std::max( std::min( nmid, cnt ), nbig );
         int launches = 0;
         int nhuge = 0;  // [0, nhuge): beyond the streaming kernels (n > kMidMaxBigN)
         for ( int q = 0; q < nbig; ++q )

@@ -11,7 +11,9 @@
 //   * column j (brought up to date) and its reflector are computed REDUNDANTLY by every CTA from the same data in the
 //     same order, hence bit-identical everywhere: no barrier between reflector generation and the sweep;
 //   * in the sweep a thread owns rows t, t+256, ...: accumulators of (A v)(r) live in registers, (A^T v)(c) is one
-//     shuffle reduction per warp and column -- no shared-memory atomics;
+//     shuffle reduction per warp and column -- no shared-memory atomics (measured and rejected: double-buffering the
+//     column batches in registers, 1026 vs 910 ms per 8 matrices of 3072^2; groups of 4 CTAs for n = 512, 387 vs 133 ms
+//     per 592 matrices for the one-CTA fused kernel: the per-column barriers and reductions dominate small groups);
 //   * the per-CTA partial sums of A v are combined by a deterministic reduce-scatter through global memory:
 //     two group barriers per column (sense-reversing counter in global memory, co-residency guaranteed by the
 //     cooperative launch).
