@@ -1140,8 +1140,10 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
             // a single matrix takes all SMs (latency); a class with many matrices is better off with more, smaller
             // groups (throughput: the per-column barriers and reductions cost the same whatever the group size)
             const int ncls = q1 - q0;
-            int G = kind == 0 ? ( ncls >= 8 ? 4 : ( ncls >= 4 ? 2 : 1 ) )
-                              : ( kind == 1 ? ( ncls >= 16 ? 8 : ( ncls >= 4 ? 4 : 2 ) ) : ( ncls >= 32 ? 16 : ( ncls >= 8 ? 8 : 4 ) ) );
+            // (3072^2 x 8: 910 ms with 4 groups of 37; the sweep of a small group is bound by its SMs' L2 bandwidth, the
+            // fixed per-column cost is amortised over more columns per CTA)
+            const int gmin = kind == 0 ? 1 : ( kind == 1 ? 2 : 4 );
+            int G = std::min( std::max( ncls, gmin ), std::max( 1, c.sm_count / 8 ) );
             if ( env_groups > 0 ) {
               G = std::min( env_groups, kCoopMaxGroups );
               q1 = nbig;

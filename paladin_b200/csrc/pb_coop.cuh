@@ -255,49 +255,112 @@ __device__ inline void coop_hess( const CoopGroup& cg, int n, int ilo, int ihi, 
   }
 }
 
-// explicit Q, columns dealt round-robin to the CTAs of the group, warps take the CTA's columns round-robin; one
-// reflector per sweep staged in shared memory (sm: n doubles), two passes over the live part of each column (L2)
+// explicit Q, columns dealt round-robin to the CTAs of the group, warps take the CTA's columns round-robin. The
+// reflectors are applied kCoopQGroup at a time in compact WY form, H(jlo) ... H(jhi) = I - V T V^T (dlarft forward /
+// columnwise): V (4 vectors, zero outside their support) and T are staged in shared memory (sm: 4 n + 64 doubles), a
+// column then needs two passes over its live part per GROUP instead of per reflector (u = V^T q; q -= V (T u)).
+constexpr int kCoopQGroup = 4;
+
 __device__ inline void coop_form_q( const CoopGroup& cg, int n, int ilo, int ihi, const double* A, int lda, const double* tau,
                                     double* Q, int ldq, double* sm ) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int S = cg.size, rank = cg.rank;
-  double* vs = sm;
+  double* vs = sm;                          // kCoopQGroup x n
+  double* red = sm + kCoopQGroup * n;       // 64 doubles of reduction scratch
+  __shared__ double Ts[kCoopQGroup * kCoopQGroup];
   for ( int c = rank + warp * S; c < n; c += kHessWarps * S )
     for ( int r = lane; r < n; r += 32 ) __stcg( Q + r + (size_t)c * ldq, ( r == c ) ? 1.0 : 0.0 );
   __syncthreads();
-  for ( int j = ihi - 2; j >= ilo; --j ) {
-    const double tj = __ldcg( tau + j );
-    if ( tj == 0.0 ) continue;
-    for ( int r = j + 1 + tid; r <= ihi; r += kHessThreads ) vs[r] = ( r == j + 1 ) ? 1.0 : __ldcg( A + r + (size_t)j * lda );
+  for ( int jhi = ihi - 2; jhi >= ilo; jhi -= kCoopQGroup ) {
+    const int ng = imin( kCoopQGroup, jhi - ilo + 1 );
+    const int jlo = jhi - ng + 1;
+    // stage the group's vectors (ascending reflector index), rows jlo+1..ihi
+    for ( int g = 0; g < kCoopQGroup; ++g ) {
+      const int j = jlo + g;
+      for ( int r = jlo + 1 + tid; r <= ihi; r += kHessThreads )
+        vs[g * n + r] = ( g >= ng || r <= j ) ? 0.0 : ( r == j + 1 ? 1.0 : __ldcg( A + r + (size_t)j * lda ) );
+    }
     __syncthreads();
-    const int nr = ihi - j;  // rows j+1..ihi
-    // this CTA's columns in j+1..ihi: c = rank (mod S); its oi-th column overall goes to warp oi % warps
-    int oi = ( j + 1 - rank + S - 1 ) / S;
+    // T: T(i,i) = tau_i, T(0:i, i) = -tau_i T(0:i,0:i) (V(:,0:i)^T v_i)
+    double gram[kCoopQGroup][kCoopQGroup];
+#pragma unroll
+    for ( int a = 0; a < kCoopQGroup; ++a )
+#pragma unroll
+      for ( int b = 0; b < kCoopQGroup; ++b ) gram[a][b] = 0.0;
+#pragma unroll
+    for ( int b = 1; b < kCoopQGroup; ++b )
+#pragma unroll
+      for ( int a = 0; a < b; ++a ) {
+        double p = 0.0;
+        if ( b < ng )
+          for ( int r = jlo + 1 + tid; r <= ihi; r += kHessThreads ) p += vs[a * n + r] * vs[b * n + r];
+        gram[a][b] = cta_sum( p, red );
+      }
+    if ( tid == 0 ) {
+      double T[kCoopQGroup][kCoopQGroup];
+      for ( int a = 0; a < kCoopQGroup; ++a )
+        for ( int b = 0; b < kCoopQGroup; ++b ) T[a][b] = 0.0;
+      for ( int i = 0; i < ng; ++i ) {
+        const double ti = __ldcg( tau + jlo + i );
+        T[i][i] = ti;
+        for ( int a = 0; a < i; ++a ) {
+          double acc = 0.0;
+          for ( int b = a; b < i; ++b ) acc += T[a][b] * gram[b][i];
+          T[a][i] = -ti * acc;
+        }
+      }
+      for ( int a = 0; a < kCoopQGroup; ++a )
+        for ( int b = 0; b < kCoopQGroup; ++b ) Ts[a * kCoopQGroup + b] = T[a][b];
+    }
+    __syncthreads();
+    const int nr = ihi - jlo;  // rows jlo+1..ihi
+    // this CTA's columns in jlo+1..ihi: c = rank (mod S); its oi-th column overall goes to warp oi % warps
+    int oi = ( jlo + 1 - rank + S - 1 ) / S;
     if ( oi < 0 ) oi = 0;
     oi += ( warp - ( oi % kHessWarps ) + kHessWarps ) % kHessWarps;
     for ( int c = rank + oi * S; c <= ihi; c += kHessWarps * S ) {
-      double* col = Q + (size_t)c * ldq + ( j + 1 );
-      const double* v = vs + ( j + 1 );
-      double w = 0.0;
+      double* col = Q + (size_t)c * ldq + ( jlo + 1 );
+      const double* v = vs + ( jlo + 1 );
+      double u[kCoopQGroup];
+#pragma unroll
+      for ( int g = 0; g < kCoopQGroup; ++g ) u[g] = 0.0;
       for ( int r0 = 0; r0 < nr; r0 += 256 ) {
         double q[8];
 #pragma unroll
-        for ( int u = 0; u < 8; ++u ) q[u] = __ldcg( col + imin( r0 + lane + 32 * u, nr - 1 ) );
+        for ( int k = 0; k < 8; ++k ) q[k] = __ldcg( col + imin( r0 + lane + 32 * k, nr - 1 ) );
 #pragma unroll
-        for ( int u = 0; u < 8; ++u ) {
-          const int r = r0 + lane + 32 * u;
-          w += ( r < nr ) ? v[imin( r, nr - 1 )] * q[u] : 0.0;
+        for ( int k = 0; k < 8; ++k ) {
+          const int r = r0 + lane + 32 * k;
+          if ( r < nr ) {
+#pragma unroll
+            for ( int g = 0; g < kCoopQGroup; ++g ) u[g] += v[g * n + r] * q[k];
+          }
         }
       }
-      w = warp_sum( w ) * tj;
+#pragma unroll
+      for ( int g = 0; g < kCoopQGroup; ++g ) u[g] = warp_sum( u[g] );
+      double w[kCoopQGroup];
+#pragma unroll
+      for ( int a = 0; a < kCoopQGroup; ++a ) {
+        double acc = 0.0;
+#pragma unroll
+        for ( int b = 0; b < kCoopQGroup; ++b )
+          if ( b >= a ) acc += Ts[a * kCoopQGroup + b] * u[b];
+        w[a] = acc;
+      }
       for ( int r0 = 0; r0 < nr; r0 += 256 ) {
         double q[8];
 #pragma unroll
-        for ( int u = 0; u < 8; ++u ) q[u] = __ldcg( col + imin( r0 + lane + 32 * u, nr - 1 ) );
+        for ( int k = 0; k < 8; ++k ) q[k] = __ldcg( col + imin( r0 + lane + 32 * k, nr - 1 ) );
 #pragma unroll
-        for ( int u = 0; u < 8; ++u ) {
-          const int r = r0 + lane + 32 * u;
-          if ( r < nr ) __stcg( col + r, q[u] - w * v[r] );
+        for ( int k = 0; k < 8; ++k ) {
+          const int r = r0 + lane + 32 * k;
+          if ( r < nr ) {
+            double x = q[k];
+#pragma unroll
+            for ( int g = 0; g < kCoopQGroup; ++g ) x -= v[g * n + r] * w[g];
+            __stcg( col + r, x );
+          }
         }
       }
     }
