@@ -300,6 +300,13 @@ __global__ void __launch_bounds__( pb::kHessThreads, ( MAXCH == 16 ? 2 : 1 ) ) m
 // ---- stage 1 for large matrices (kMidMaxFusedN < n <= kMidMaxBigN): groups of S cooperating CTAs, one matrix per group
 // at a time (pb_coop.cuh); cooperative launch, one CTA per SM ------------------------------------------------------------
 constexpr int kCoopMaxGroups = 37;
+// smallest order whose eigenvector stage runs as three grid-wide launches instead of the persistent one-CTA-per-matrix
+// kernel (tuning: PALADIN_GPU_BIGVEC_MIN_N). Measured on B200, vectors stage per step: 1184 x n=200 9.9 -> 7.3 ms,
+// 592 x n=512 51.8 -> 35.2 ms, 148 x n=1024 154 -> 63.5 ms: the solves run at twice the warps per SM.
+inline int bigvec_min_n() {
+  static const int v = std::getenv( "PALADIN_GPU_BIGVEC_MIN_N" ) ? std::max( 64, std::atoi( std::getenv( "PALADIN_GPU_BIGVEC_MIN_N" ) ) ) : 64;
+  return v;
+}
 // smallest order that takes the cooperative stage 1 (tuning: PALADIN_GPU_COOP_MIN_N)
 inline int coop_min_n() {
   static const int v = std::getenv( "PALADIN_GPU_COOP_MIN_N" ) ? std::max( 64, std::atoi( std::getenv( "PALADIN_GPU_COOP_MIN_N" ) ) ) : kMidMaxFusedN;
@@ -530,8 +537,9 @@ __global__ void __launch_bounds__( pb::kVecThreads, 2 ) mid_vec_kernel( MidArgs 
 // ---- stage 3 for large matrices: every matrix is shared by P CTAs; the three steps are separate launches (the kernel
 // boundary is the barrier between "all solves done" -> GEMM -> normalise). STEP 0: triangular solves, 1: first GEMM,
 // 2: second GEMM (both sides wanted), 3: un-balance + normalise ------------------------------------------------------------
+// (the solves are latency bound -- one dependent chain per warp -- and run at four CTAs per SM / 64 registers)
 template <int STEP>
-__global__ void __launch_bounds__( pb::kVecThreads, 2 ) big_vec_kernel( MidArgs a, int P ) {
+__global__ void __launch_bounds__( pb::kVecThreads, STEP == 0 ? 4 : 2 ) big_vec_kernel( MidArgs a, int P ) {
   extern __shared__ double smem[];
   int* perm = reinterpret_cast<int*>( smem + pb::vecs_gemm_smem_doubles() );
   const int k = blockIdx.x / P, part = blockIdx.x % P;
@@ -557,9 +565,16 @@ __global__ void __launch_bounds__( pb::kVecThreads, 2 ) big_vec_kernel( MidArgs 
   } else if constexpr ( STEP == 2 ) {
     pb::vecs_gemm( n, V, n, Y, n, X, n, smem, true, part, P );                 // X <- Z Y (X is free again)
   } else {
-    if ( wantvr ) pb::vecs_finish_big( n, m.ilo, m.ihi, scale, wi, A, n, V, n, perm, false, part, P );
-    __syncthreads();
-    if ( wantvl ) pb::vecs_finish_big( n, m.ilo, m.ihi, scale, wi, wantvr ? X : A, n, VLout, n, perm, true, part, P );
+    for ( int side = 0; side < 2; ++side ) {
+      const bool left = side == 1;
+      if ( left ? !wantvl : !wantvr ) continue;
+      const double* src = ( left && wantvr ) ? X : A;
+      double* dst = left ? VLout : V;
+      if ( n <= 512 ) pb::vecs_finish<16>( n, m.ilo, m.ihi, scale, wi, src, n, dst, n, perm, left, part, P );
+      else if ( n <= kMidMaxFusedN ) pb::vecs_finish<32>( n, m.ilo, m.ihi, scale, wi, src, n, dst, n, perm, left, part, P );
+      else pb::vecs_finish_big( n, m.ilo, m.ihi, scale, wi, src, n, dst, n, perm, left, part, P );
+      __syncthreads();
+    }
   }
 }
 
@@ -884,7 +899,7 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
       b->xslot = ( (size_t)nmax * nmax + 16 ) * ( jobvr == 'V' && jobvl == 'V' ? 2 : 1 ) + 528;
       const size_t budget = (size_t)24 << 30;
       const int by_mem = (int)std::max<size_t>( 1, budget / ( b->xslot * sizeof( double ) ) );
-      b->xslots = std::max( 1, std::min( std::min( nmid, 2 * c.sm_count ), by_mem ) );
+      b->xslots = std::max( 1, std::min( std::min( nmid, bigvec_min_n() < kMidMaxFusedN ? nmid : 2 * c.sm_count ), by_mem ) );
       A( dev_alloc( &b->d_xwork, b->xslot * b->xslots ) );
     }
   }
@@ -1273,7 +1288,7 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
         // large matrices first ([0, nvbig) of the size-sorted list): each one shared by P CTAs, `xslots` of them at a time
         int nvbig = 0;
         for ( int q = 0; q < cnt; ++q )
-          if ( b->n[b->ids[g.first + q]] > kMidMaxFusedN ) nvbig = q + 1;
+          if ( b->n[b->ids[g.first + q]] > bigvec_min_n() ) nvbig = q + 1;
         static const bool no_bigvec = std::getenv( "PALADIN_GPU_NO_COOP" ) != nullptr;
         if ( no_bigvec ) nvbig = 0;
         if ( nvbig > 0 ) {

@@ -177,8 +177,9 @@ __device__ inline void vecs_gemm( int n, const double* __restrict__ Z, int ldz, 
 // perm: n ints of shared/global scratch (final row of each source row after dgebak's swaps)
 template <int MAXCH>
 __device__ void vecs_finish( int n, int ilo, int ihi, const double* scale, const double* wi, const double* __restrict__ C,
-                             int ldc, double* __restrict__ V, int ldv, int* perm, bool left ) {
+                             int ldc, double* __restrict__ V, int ldv, int* perm, bool left, int part = 0, int nparts = 1 ) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int stride = kVecWarps * nparts, mine = part * kVecWarps + warp;
   // dgebak 'B','R': rows ilo..ihi are scaled, then row swaps are applied for i = ilo-1..0 and ihi+1..n-1.
   // dest[p] = row where source row p ends up.
   if ( tid == 0 ) {
@@ -201,7 +202,7 @@ __device__ void vecs_finish( int n, int ilo, int ihi, const double* scale, const
   int c = 0;
   while ( c < n ) {
     const bool pair = ( wi[c] > 0.0 && c + 1 < n );
-    if ( ( blk % kVecWarps ) == warp ) {
+    if ( ( blk % stride ) == mine ) {
       double a[MAXCH], b[MAXCH];
       // position-major: element k of this lane is destination row r = lane + 32 k, read from source row perm[r]
 #pragma unroll
