@@ -387,6 +387,9 @@ inline size_t qr_smem_bytes() {
   return sizeof( double ) * pb::msqr_work_doubles( c, c.W | 1, c.tl | 1 ) + sizeof( int ) * pb::kMsIbufInts;
 }
 
+// (measured and rejected: four 128-thread CTAs per SM -- window inside the tile buffer, U and reflectors sharing a buffer,
+// two bulges per warp in the chase: 45 KB per CTA -- QR stage 407 ms per 592 matrices of n=512 against 271 ms with two
+// 256-thread CTAs; the same 16 warps per SM either way, and the chase slows down by more than the window phases gain)
 // CLUSTER: launched with a thread-block cluster per matrix (large matrices, few of them): rank 0 runs the iteration and
 // shares the strip updates of its steady-state windows with the other CTAs of the cluster (pb::ms_cluster_helper)
 template <bool CLUSTER>
