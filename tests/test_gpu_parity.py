@@ -9,6 +9,7 @@ conjugate-aware matching with error <= 1e-9 * max(1, ||A||); with vectors
 """
 import glob
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -18,6 +19,7 @@ from oracle import paladin_oracle as po
 pytestmark = pytest.mark.gpu
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EIG_TOL = 1e-9
 BACKWARD_TOL = 100.0
 
@@ -217,6 +219,38 @@ def test_large_matrices_cooperative_path(pg, jobvr, sizes):
                 assert po.backward_error(A, wr, wi, VR) <= BACKWARD_TOL
         else:
             _check_eigs(A, wr, wi, VR, inf, jobvr == "V")
+
+
+@pytest.mark.parametrize("env", [{"PALADIN_GPU_CLUSTER": "2"}, {"PALADIN_GPU_CLUSTER": "4"}, {"PALADIN_GPU_CLUSTER": "8"},
+                                 {"PALADIN_GPU_CLUSTER": "16", "PALADIN_GPU_COOP_GROUPS": "1"},
+                                 {"PALADIN_GPU_COOP_GROUPS": "4"}, {"PALADIN_GPU_COOP_GROUPS": "16", "PALADIN_GPU_AED": "48"},
+                                 {"PALADIN_GPU_NO_COOP": "1", "PALADIN_GPU_CLUSTER": "1", "PALADIN_GPU_AED": "0"},
+                                 {"PALADIN_GPU_AED_MOVES": "1000", "PALADIN_GPU_BIGVEC_MIN_N": "4000"}])
+def test_tuning_overrides_keep_parity(env):
+    """Every cluster size, cooperative group count and AED variant the launcher can choose (forced through the tuning
+    environment variables, which are read once per process) gives the same spectra within tolerance."""
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+import paladin_b200 as pg
+from oracle import paladin_oracle as po
+sizes = [300, 1100, 1350]
+mats = [(n,) + po.random_dense_coo(n, [61, q]) for q, n in enumerate(sizes)]
+n = np.array([m[0] for m in mats], dtype=np.int32)
+off = np.concatenate([[0], np.cumsum([len(m[3]) for m in mats])]).astype(np.int64)
+res, info = pg.geev_batch(n, off, np.concatenate([m[1] for m in mats]), np.concatenate([m[2] for m in mats]),
+                          np.concatenate([m[3] for m in mats]), jobvr="V")
+assert not info.any(), info
+for m, (wr, wi, VR) in zip(mats, res):
+    A = po.dense_matrix(*m)
+    wr0, wi0, _, _, _ = po.dgeev(A, right=False)
+    assert po.match_eigenvalues(po.eigenvalues(wr, wi), po.eigenvalues(wr0, wi0)) <= 1e-9 * max(1.0, np.linalg.norm(A, 2))
+    assert po.backward_error(A, wr, wi, VR) <= 100.0
+print("OK")
+""" % ROOT
+    import subprocess
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, **env), timeout=600)
+    assert "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
 def test_n512_full_decomposition(pg):
