@@ -203,7 +203,7 @@ struct MidArgs {
   double* xwork;   // slots of xn_max^2 doubles for the triangular eigenvector factor
   size_t xslot;    // doubles per slot
   int xn_max;      // largest order a slot can hold (larger matrices use the in-place path)
-  int aed, aed_moves;  // tuning overrides of mid_cfg() (PALADIN_GPU_AED, PALADIN_GPU_AED_MOVES); -1 = default
+  int aed, aed_moves, nibble;  // tuning overrides of mid_cfg() (PALADIN_GPU_AED, _AED_MOVES, _AED_NIBBLE); -1 = default
 };
 
 __device__ __forceinline__ void mid_pointers( const BatchView& bv, int id, int n, double*& A, double*& V, double*& wr, double*& wi,
@@ -400,6 +400,7 @@ __global__ void __launch_bounds__( kMidThreads, 2 ) mid_qr_kernel( MidArgs a ) {
   pb::MsqrCfg c = mid_cfg();
   if ( a.aed >= 0 ) c.aed = a.aed;
   if ( a.aed_moves >= 0 ) c.aed_moves = a.aed_moves;
+  if ( a.nibble >= 0 ) c.nibble = a.nibble;
   const int ldw = c.W | 1, ldt = c.tl | 1;
   pb::MsqrWork wk;
   double* p = smem;
@@ -1117,6 +1118,8 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
       static const int env_moves = std::getenv( "PALADIN_GPU_AED_MOVES" ) ? std::atoi( std::getenv( "PALADIN_GPU_AED_MOVES" ) ) : -1;
       ma.aed = std::min( env_aed, pb::kStripW - 1 );
       ma.aed_moves = env_moves;
+      static const int env_nibble = std::getenv( "PALADIN_GPU_AED_NIBBLE" ) ? std::atoi( std::getenv( "PALADIN_GPU_AED_NIBBLE" ) ) : -1;
+      ma.nibble = env_nibble;
       PB_CUDA( cudaMemsetAsync( b->d_stats, 0, sizeof( long long ) * kNumTicks, st ) );
       PB_CUDA( cudaMemsetAsync( b->d_counter, 0, sizeof( int ), st ) );
       const size_t s2 = qr_smem_bytes(), s3 = vec_smem_bytes( g.nmax );

@@ -56,6 +56,7 @@ struct MsqrCfg {
   int nshift;    // shifts computed per sweep (<= 2*nb*nchains); chains beyond nshift/(2 nb) reuse them cyclically
   int aed = 0;   // order of the aggressive-early-deflation window (<= W - 1); 0 = no AED
   int aed_moves = 1 << 20;  // undeflatable blocks an AED step may reorder (see pb::aed_window)
+  int nibble = 14;          // a sweep is skipped when AED deflated more than nibble % of its window (LAPACK: 14)
   int spec_shifts = 0;      // 1: the shifts of the next sweep are computed from the block as it is BEFORE the AED step
                             // (on the device: by another warp, while the AED window is being factored)
 };
@@ -1014,7 +1015,7 @@ PB_D int hqr_multishift( const G& g, bool wantt, bool wantz, int n, int ilo, int
         kbot -= nd;
         nodefl = 0;
         // enough deflations (LAPACK's nibble = 14 %), or what is left is a small block: no sweep this time
-        if ( 100 * nd > 14 * jw || kbot - ktop + 1 <= cfg.ws_small ) {
+        if ( 100 * nd > cfg.nibble * jw || kbot - ktop + 1 <= cfg.ws_small ) {
           if ( t == 0 ) wk.ibuf[3 * kMsMaxBulges + 13] += 1;
           continue;
         }
