@@ -129,6 +129,17 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b );
  * wr/wi: sum n[k] doubles; vl/vr: sum n[k]^2 doubles (NULL when not computed); info: count ints. */
 int paladin_gpu_batch_download( paladin_gpu_batch* b, double* wr, double* wi, double* vl, double* vr, int* info );
 
+/* The write filter of the reference's eigenvector writers (reference src/spectrum-util.hpp:134-196) evaluated on the device,
+ * after paladin_gpu_batch_solve: for every eigenvalue index c of matrix k the complex vector the reference unpacks for it
+ * (reference src/paladin.hpp:256-333: (re, 0), (re, +im) for the first eigenvalue of a conjugate pair, (re, -im) for the
+ * second) is scanned once:
+ *   max2[sum n[0..k) + c] = max_r |x_r|^2         (std::norm of the largest element, src/spectrum-util.hpp:175-176)
+ *   kept[k]              = number of entries of all n[k] vectors with |x_r|^2 > threshold * max2   (the nnz of the header line)
+ * Products and sums are rounded separately (no fused multiply-add), so both agree bit for bit with the host evaluation.
+ * side: 'R' or 'L' (the batch must have been created with the matching job). max2: sum n[k] doubles, kept: count values;
+ * matrices with info != 0 get kept = 0. */
+int paladin_gpu_batch_vector_filter( paladin_gpu_batch* b, char side, double threshold, double* max2, long long* kept );
+
 /* Device time of each stage of the most recent scatter/solve, in milliseconds, measured with CUDA
  * events on the library's own stream. ms must hold PALADIN_GPU_NUM_STAGES floats. launches (may be
  * NULL) receives the number of kernel launches of each stage. */
@@ -142,7 +153,8 @@ int paladin_gpu_batch_timer_stop( paladin_gpu_batch* b, float* ms );
 /* Phase profile of the most recent CTA-per-matrix solve: SM cycles summed over all CTAs, 16 slots
  * (0 balance, 1 Hessenberg, 2 form Q, 3 QR remainder, 4 eigenvectors of T, 5 un-balance + normalise, 6 back-transform GEMM,
  *  8 deflation scans, 9 shift computation, 10 in-window bulge chasing, 11 strip updates by recorded
- *  reflectors, 12 small-block solves, 13 strip updates by small U). Diagnostic only. */
+ *  reflectors, 12 small-block solves, 13 strip updates by small U, 14 early-deflation window, 15 its off-window update).
+ * Diagnostic only. */
 int paladin_gpu_batch_phase_cycles( paladin_gpu_batch* b, long long* cycles );
 
 int paladin_gpu_batch_destroy( paladin_gpu_batch* b );

@@ -63,6 +63,8 @@ def lib():
                                              ctypes.c_void_p, ctypes.c_void_p]
     L.paladin_gpu_batch_stage_ms.argtypes = [ctypes.c_void_p, _c_flt_p, _c_int_p]
     L.paladin_gpu_batch_destroy.argtypes = [ctypes.c_void_p]
+    L.paladin_gpu_batch_vector_filter.argtypes = [ctypes.c_void_p, ctypes.c_char, ctypes.c_double, ctypes.c_void_p,
+                                                  ctypes.c_void_p]
     L.paladin_gpu_batch_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]
     L.paladin_gpu_batch_timer_start.argtypes = [ctypes.c_void_p]
     L.paladin_gpu_batch_timer_stop.argtypes = [ctypes.c_void_p, _c_flt_p]
@@ -170,6 +172,13 @@ class Batch:
                                                 _ptr(vr) if self.jobvr == "V" else None, _ptr(info)))
         self.vl = vl  # left vectors of the last download (None unless jobvl == 'V')
         return wr, wi, vr, info
+
+    def vector_filter(self, side="R", threshold=1e-3):
+        """-> (max |x|^2 per eigenvalue index, entries kept per matrix) of the reference's eigenvector writer, on the device."""
+        max2 = np.zeros(self.total_n)
+        kept = np.zeros(self.count, dtype=np.int64)
+        _check(lib().paladin_gpu_batch_vector_filter(self._h, side.encode(), float(threshold), _ptr(max2), _ptr(kept)))
+        return max2, kept
 
     def stage_ms(self):
         ms = (ctypes.c_float * NUM_STAGES)()

@@ -582,6 +582,56 @@ __global__ void __launch_bounds__( pb::kVecThreads, STEP == 0 ? 4 : 2 ) big_vec_
   }
 }
 
+// ---- eigenvector write filter (reference src/spectrum-util.hpp:134-196): per eigenvalue index the largest |x|^2 of the
+// unpacked complex vector and the number of entries above threshold * that. One warp per column. -----------------------
+__global__ void __launch_bounds__( 256 ) vector_filter_kernel( BatchView bv, const double* vecs, double threshold, double* max2,
+                                                               unsigned long long* kept, int count ) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int k = blockIdx.y;
+  if ( k >= count ) return;
+  const int n = bv.n[k];
+  const int c = blockIdx.x * 8 + warp;
+  if ( c >= n || bv.info[k] != 0 ) return;
+  const double* wi = bv.wi + bv.w_off[k];
+  // the reference decides "pair" sequentially (skipNext, src/paladin.hpp:257-289): replay it up to column c
+  int role = 0;  // 0 real, 1 first of a pair, 2 second of a pair
+  {
+    bool second = false;
+    for ( int q = 0; q <= c; ++q ) {
+      if ( second ) {
+        role = 2;
+        second = false;
+      } else {
+        const bool pair = ( q + 1 < n ) && ( wi[q] == -wi[q + 1] ) && ( wi[q] != 0.0 );
+        role = pair ? 1 : 0;
+        second = pair;
+      }
+    }
+  }
+  const double* V = vecs + bv.a_off[k];
+  const double* re = V + (size_t)( role == 2 ? c - 1 : c ) * n;
+  const double* im = role == 0 ? nullptr : V + (size_t)( role == 2 ? c : c + 1 ) * n;
+  double mx = 0.0;
+  for ( int r = lane; r < n; r += 32 ) {
+    const double x = re[r], y = im ? im[r] : 0.0;
+    const double nrm = __dadd_rn( __dmul_rn( x, x ), __dmul_rn( y, y ) );
+    mx = nrm > mx ? nrm : mx;
+  }
+  mx = pb::warp_max( mx );
+  const double cut = __dmul_rn( threshold, mx );
+  int cnt = 0;
+  for ( int r = lane; r < n; r += 32 ) {
+    const double x = re[r], y = im ? im[r] : 0.0;
+    const double nrm = __dadd_rn( __dmul_rn( x, x ), __dmul_rn( y, y ) );
+    cnt += ( nrm > cut ) ? 1 : 0;
+  }
+  cnt = pb::warp_isum( cnt );
+  if ( lane == 0 ) {
+    max2[bv.w_off[k] + c] = mx;
+    atomicAdd( kept + k, (unsigned long long)cnt );
+  }
+}
+
 struct StageTimer {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   bool used = false;
@@ -1373,6 +1423,45 @@ int paladin_gpu_batch_download( paladin_gpu_batch* b, double* wr, double* wi, do
     }
   }
   PB_CUDA( cudaStreamSynchronize( st ) );
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_batch_vector_filter( paladin_gpu_batch* b, char side, double threshold, double* max2, long long* kept ) {
+  if ( !b || !max2 || !kept ) return fail( PALADIN_GPU_EINVAL, "bad arguments" );
+  if ( side != 'R' && side != 'L' ) return fail( PALADIN_GPU_EINVAL, "side must be 'R' or 'L'" );
+  const double* vecs = side == 'R' ? b->d_V : b->d_VL;
+  if ( ( side == 'R' ? b->jobvr : b->jobvl ) != 'V' || !vecs ) return fail( PALADIN_GPU_EINVAL, "the batch holds no vectors of that side" );
+  PB_CUDA( cudaSetDevice( b->device ) );
+  if ( b->count == 0 ) return PALADIN_GPU_OK;
+  cudaStream_t st = b->stream;
+  double* d_max2 = nullptr;
+  unsigned long long* d_kept = nullptr;
+  PB_TRY( dev_alloc( &d_max2, (size_t)b->total_n ) );
+  if ( dev_alloc( &d_kept, (size_t)b->count ) != PALADIN_GPU_OK ) {
+    cudaFree( d_max2 );
+    return PALADIN_GPU_ENOMEM;
+  }
+  int nmax = 0;
+  for ( int k = 0; k < b->count; ++k ) nmax = std::max( nmax, b->n[k] );
+  cudaError_t e = cudaMemsetAsync( d_max2, 0, sizeof( double ) * std::max<int64_t>( b->total_n, 1 ), st );
+  if ( e == cudaSuccess ) e = cudaMemsetAsync( d_kept, 0, sizeof( unsigned long long ) * b->count, st );
+  if ( e == cudaSuccess && nmax > 0 ) {
+    BatchView bv = batch_view( b );
+    // (grid.y is limited to 65535 matrices per launch)
+    for ( int k0 = 0; k0 < b->count && e == cudaSuccess; k0 += 65535 ) {
+      BatchView bk = bv;
+      bk.n += k0; bk.a_off += k0; bk.w_off += k0; bk.info += k0;
+      const int cnt = std::min( 65535, b->count - k0 );
+      vector_filter_kernel<<<dim3( ( nmax + 7 ) / 8, cnt ), 256, 0, st>>>( bk, vecs, threshold, d_max2, d_kept + k0, cnt );
+      e = cudaGetLastError();
+    }
+  }
+  if ( e == cudaSuccess && b->total_n ) e = cudaMemcpyAsync( max2, d_max2, sizeof( double ) * b->total_n, cudaMemcpyDeviceToHost, st );
+  if ( e == cudaSuccess ) e = cudaMemcpyAsync( kept, d_kept, sizeof( long long ) * b->count, cudaMemcpyDeviceToHost, st );
+  if ( e == cudaSuccess ) e = cudaStreamSynchronize( st );
+  cudaFree( d_max2 );
+  cudaFree( d_kept );
+  if ( e != cudaSuccess ) return fail( PALADIN_GPU_ECUDA, cudaGetErrorString( e ) );
   return PALADIN_GPU_OK;
 }
 

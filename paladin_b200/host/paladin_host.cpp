@@ -206,57 +206,69 @@ inline int run_pod( int device, const std::vector<std::string>& pod, const Optio
         next = std::async( std::launch::async, parse_batch, std::cref( pod ), firsts[bi + 1],
                            std::min<std::size_t>( o.batch, pod.size() - firsts[bi + 1] ), parse_threads );
       const std::size_t count = cur.count, first = cur.first;
-      auto wr = std::make_shared<std::vector<std::vector<double>>>( count );
-      auto wi = std::make_shared<std::vector<std::vector<double>>>( count );
-      auto vr = std::make_shared<std::vector<std::vector<double>>>( count );
-      auto vl = std::make_shared<std::vector<std::vector<double>>>( count );
-      std::vector<double*> pwr( count ), pwi( count ), pvr( count, nullptr ), pvl( count, nullptr );
+      // results of the whole batch, concatenated (the staged C-ABI): eigenvalue offsets woff, vector offsets voff
+      auto woff = std::make_shared<std::vector<std::size_t>>( count + 1, 0 );
+      auto voff = std::make_shared<std::vector<std::size_t>>( count + 1, 0 );
       for ( std::size_t k = 0; k < count; ++k ) {
         const std::size_t nk = static_cast<std::size_t>( cur.n[k] );
-        ( *wr )[k].assign( nk, 0.0 );
-        ( *wi )[k].assign( nk, 0.0 );
-        if ( o.right ) ( *vr )[k].assign( nk * nk, 0.0 );
-        if ( o.left ) ( *vl )[k].assign( nk * nk, 0.0 );
-        pwr[k] = ( *wr )[k].data();
-        pwi[k] = ( *wi )[k].data();
-        pvr[k] = o.right ? ( *vr )[k].data() : nullptr;
-        pvl[k] = o.left ? ( *vl )[k].data() : nullptr;
+        ( *woff )[k + 1] = ( *woff )[k] + nk;
+        ( *voff )[k + 1] = ( *voff )[k] + nk * nk;
       }
+      const std::size_t tn = ( *woff )[count], tnn = ( *voff )[count];
+      auto wr = std::make_shared<std::vector<double>>( tn, 0.0 );
+      auto wi = std::make_shared<std::vector<double>>( tn, 0.0 );
+      auto vr = std::make_shared<std::vector<double>>( o.right ? tnn : 0, 0.0 );
+      auto vl = std::make_shared<std::vector<double>>( o.left ? tnn : 0, 0.0 );
+      // write filter of the eigenvector files, evaluated on the device (paladin_gpu_batch_vector_filter)
+      auto max2r = std::make_shared<std::vector<double>>( o.right ? tn : 0, 0.0 );
+      auto max2l = std::make_shared<std::vector<double>>( o.left ? tn : 0, 0.0 );
+      auto keptr = std::make_shared<std::vector<long long>>( o.right ? count : 0, 0 );
+      auto keptl = std::make_shared<std::vector<long long>>( o.left ? count : 0, 0 );
       auto info = std::make_shared<std::vector<int>>( count, 0 );
       const auto t_eig = clock::now();
-      const int rc = paladin_gpu_geev_batch( device, static_cast<int>( count ), cur.n.data(), cur.off.data(), cur.ci.data(),
-                                             cur.cj.data(), cur.cv.data(), jobvl, jobvr, pwr.data(), pwi.data(), pvl.data(),
-                                             pvr.data(), info->data() );
+      paladin_gpu_batch* gb = nullptr;
+      int rc = paladin_gpu_batch_create( device, static_cast<int>( count ), cur.n.data(), cur.off.data(), jobvl, jobvr, &gb );
+      if ( rc == PALADIN_GPU_OK ) rc = paladin_gpu_batch_upload( gb, cur.ci.data() + cur.off[0], cur.cj.data() + cur.off[0], cur.cv.data() + cur.off[0] );
+      if ( rc == PALADIN_GPU_OK ) rc = paladin_gpu_batch_scatter( gb );
+      if ( rc == PALADIN_GPU_OK ) rc = paladin_gpu_batch_solve( gb );
+      if ( rc == PALADIN_GPU_OK && o.right && count > 0 ) rc = paladin_gpu_batch_vector_filter( gb, 'R', o.threshold, max2r->data(), keptr->data() );
+      if ( rc == PALADIN_GPU_OK && o.left && count > 0 ) rc = paladin_gpu_batch_vector_filter( gb, 'L', o.threshold, max2l->data(), keptl->data() );
+      if ( rc == PALADIN_GPU_OK )
+        rc = paladin_gpu_batch_download( gb, wr->data(), wi->data(), o.left ? vl->data() : nullptr, o.right ? vr->data() : nullptr, info->data() );
+      paladin_gpu_batch_destroy( gb );
       times.eig += std::chrono::duration<double>( clock::now() - t_eig ).count();
       if ( rc != PALADIN_GPU_OK ) {
-        std::cerr << "paladin_gpu_geev_batch failed on device " << device << ": " << paladin_gpu_last_error() << '\n';
+        std::cerr << "the GPU eigensolver failed on device " << device << ": " << paladin_gpu_last_error() << '\n';
         return -1;
       }
       if ( rep != 0 ) continue;  // like the reference, only the first repeat produces output
       if ( writer.valid() ) failures += writer.get();
       auto ns = std::make_shared<std::vector<int>>( cur.n );
-      writer = std::async( std::launch::async, [&pod, &o, first, count, ns, wr, wi, vr, vl, info]() {
+      writer = std::async( std::launch::async, [&pod, &o, first, count, ns, woff, voff, wr, wi, vr, vl, max2r, max2l, keptr, keptl, info]() {
         int bad = 0;
         for ( std::size_t k = 0; k < count; ++k ) {
           const int nk = ( *ns )[k];
-          if ( ( *info )[k] != 0 ) {
+          const bool ok = ( *info )[k] == 0;
+          if ( !ok ) {
             ++bad;
             std::cerr << "warning: " << pod[first + k] << ": info = " << ( *info )[k] << '\n';
           }
           SpectralDecomposition s( nk, o.threshold );
-          s.unpack( nk, ( *wr )[k].data(), ( *wi )[k].data(), o.right && ( *info )[k] == 0 ? ( *vr )[k].data() : nullptr,
-                    o.left && ( *info )[k] == 0 ? ( *vl )[k].data() : nullptr );
+          s.unpack( nk, wr->data() + ( *woff )[k], wi->data() + ( *woff )[k], o.right && ok ? vr->data() + ( *voff )[k] : nullptr,
+                    o.left && ok ? vl->data() + ( *voff )[k] : nullptr );
           std::string text;
           s.write_eigenvalues( text );
           write_file( pod[first + k] + ".spectrum", text );
           if ( o.left ) {
             text.clear();
-            s.write_left_eigenvectors( text );
+            if ( ok ) s.write_left_eigenvectors( text, max2l->data() + ( *woff )[k], ( *keptl )[k] );
+            else s.write_left_eigenvectors( text );
             write_file( pod[first + k] + ".leftvecs", text );
           }
           if ( o.right ) {
             text.clear();
-            s.write_right_eigenvectors( text );
+            if ( ok ) s.write_right_eigenvectors( text, max2r->data() + ( *woff )[k], ( *keptr )[k] );
+            else s.write_right_eigenvectors( text );
             write_file( pod[first + k] + ".rightvecs", text );
           }
         }

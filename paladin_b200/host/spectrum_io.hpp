@@ -89,18 +89,30 @@ class SpectralDecomposition {
     }
   }
 
-  void write_right_eigenvectors( std::string& out ) const { write_vectors( out, rightEigenvectors_ ); }
-  void write_left_eigenvectors( std::string& out ) const { write_vectors( out, leftEigenvectors_ ); }
+  // max2 / kept: the filter pass of the writer (largest |x|^2 per vector, number of entries kept) when it has already
+  // been evaluated on the device (paladin_gpu_batch_vector_filter); nullptr = evaluate it here
+  void write_right_eigenvectors( std::string& out, const double* max2 = nullptr, long long kept = 0 ) const {
+    write_vectors( out, rightEigenvectors_, max2, kept );
+  }
+  void write_left_eigenvectors( std::string& out, const double* max2 = nullptr, long long kept = 0 ) const {
+    write_vectors( out, leftEigenvectors_, max2, kept );
+  }
 
  private:
-  void write_vectors( std::string& out, const std::vector<std::vector<std::complex<double>>>& vecs ) const {
+  void write_vectors( std::string& out, const std::vector<std::vector<std::complex<double>>>& vecs, const double* max2,
+                      long long kept_in ) const {
     const int n = size();
     std::vector<double> biggest( vecs.size(), 0.0 );
     long kept = 0;
-    for ( std::size_t v = 0; v < vecs.size(); ++v ) {
-      for ( const auto& x : vecs[v] ) biggest[v] = std::norm( x ) > biggest[v] ? std::norm( x ) : biggest[v];
-      for ( const auto& x : vecs[v] )
-        if ( std::norm( x ) > vectorWriteThreshold_ * biggest[v] ) ++kept;
+    if ( max2 != nullptr && !vecs.empty() ) {
+      for ( std::size_t v = 0; v < vecs.size(); ++v ) biggest[v] = max2[v];
+      kept = static_cast<long>( kept_in );
+    } else {
+      for ( std::size_t v = 0; v < vecs.size(); ++v ) {
+        for ( const auto& x : vecs[v] ) biggest[v] = std::norm( x ) > biggest[v] ? std::norm( x ) : biggest[v];
+        for ( const auto& x : vecs[v] )
+          if ( std::norm( x ) > vectorWriteThreshold_ * biggest[v] ) ++kept;
+      }
     }
     out += "%%MatrixMarket matrix coordinate complex general\n";
     append_number( out, static_cast<long>( n ) );

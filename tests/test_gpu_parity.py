@@ -366,6 +366,39 @@ def test_left_eigenvectors(pg, sides):
     assert inf == 0 and po.left_backward_error(A, wr, wi, VL) <= BACKWARD_TOL and po.backward_error(A, wr, wi, VR) <= BACKWARD_TOL
 
 
+@pytest.mark.parametrize("threshold", [1e-3, 0.3, 0.0])
+def test_vector_write_filter_on_device_is_bit_exact(pg, threshold):
+    """paladin_gpu_batch_vector_filter against the reference writer's own pass (src/spectrum-util.hpp:134-196): largest
+    |x|^2 per unpacked vector and number of entries above threshold * that, identical to the last bit."""
+    sizes = [1, 2, 5, 33, 64, 100, 300, 600]
+    mats = _random_mats(sizes, 57)
+    n, off, ii, jj, vv = _concat(mats)
+    b = pg.Batch(n, off, jobvl="V", jobvr="V")
+    b.upload(ii, jj, vv)
+    b.scatter()
+    b.solve()
+    got = {side: b.vector_filter(side, threshold) for side in ("R", "L")}
+    wr, wi, vr, info = b.download()
+    vl = b.vl
+    b.destroy()
+    assert not info.any()
+    wo, vo = 0, 0
+    for k, nk in enumerate(sizes):
+        for side, packed in (("R", vr), ("L", vl)):
+            V = packed[vo:vo + nk * nk].reshape((nk, nk), order="F")
+            parts = po.unpack_parts(wr[wo:wo + nk], wi[wo:wo + nk], V)
+            assert len(parts) == nk
+            kept = 0
+            for c, (re, im) in enumerate(parts):
+                nrm = re * re + im * im          # two roundings per product-sum, like std::norm on the host
+                m = nrm.max()
+                assert got[side][0][wo + c] == m, (nk, side, c)
+                kept += int((nrm > threshold * m).sum())
+            assert got[side][1][k] == kept, (nk, side)
+        wo += nk
+        vo += nk * nk
+
+
 def test_nonfinite_input_flagged(pg):
     A = np.ones((5, 5))
     A[2, 2] = np.nan
