@@ -245,7 +245,7 @@ int g_ms_counters[16];
 int hs_msqr( int wantt, int wantz, int n, int ilo, int ihi, double* H, double* wr, double* wi, double* Z, int nb, int W,
              int ws_small, int tl, int nchains ) {
   pb::HostGroup g;
-  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains % 100, ( nchains / 100 ) % 100, nchains / 10000, g_aed_moves, g_spec_shifts };
+  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains % 100, ( nchains / 100 ) % 100, nchains / 10000, g_aed_moves, 14, g_spec_shifts };
   MsBuffers buf( c );
   const int r = pb::hqr_multishift( g, wantt != 0, wantz != 0, n, ilo, ihi, H, n, wr, wi, 0, n - 1, Z, n, c, buf.wk );
   for ( int k = 0; k < 16; ++k ) g_ms_counters[k] = buf.i[3 * pb::kMsMaxBulges + k];
@@ -258,7 +258,7 @@ const int* hs_ms_counters() { return g_ms_counters; }
 
 int ht_msqr( int nt, int wantt, int wantz, int n, int ilo, int ihi, double* H, double* wr, double* wi, double* Z, int nb,
              int W, int ws_small, int tl, int nchains ) {
-  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains % 100, ( nchains / 100 ) % 100, nchains / 10000, g_aed_moves, g_spec_shifts };
+  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains % 100, ( nchains / 100 ) % 100, nchains / 10000, g_aed_moves, 14, g_spec_shifts };
   MsBuffers buf( c );
   return run_threads( nt, [&]( const ThreadGroup& g ) {
     return pb::hqr_multishift( g, wantt != 0, wantz != 0, n, ilo, ihi, H, n, wr, wi, 0, n - 1, Z, n, c, buf.wk );
@@ -270,7 +270,7 @@ int hs_geev_ms( int n, double* A, double* wr, double* wi, int wantvr, double* V,
   pb::HostGroup g;
   std::vector<double> dw( 5 * n + 5 );
   std::vector<int> iw( 2 * n + 2 );
-  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains % 100, ( nchains / 100 ) % 100, nchains / 10000, g_aed_moves, g_spec_shifts };
+  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains % 100, ( nchains / 100 ) % 100, nchains / 10000, g_aed_moves, 14, g_spec_shifts };
   MsBuffers buf( c );
   return pb::geev_group( g, n, A, n, wr, wi, false, (double*)nullptr, n, wantvr != 0, V, n, dw.data(), iw.data(), pb::QrMultishift{ c, buf.wk } );
 }
@@ -279,7 +279,7 @@ int ht_geev_ms( int nt, int n, double* A, double* wr, double* wi, int wantvr, do
                 int nchains ) {
   std::vector<double> dw( 5 * n + 5 );
   std::vector<int> iw( 2 * n + 2 );
-  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains % 100, ( nchains / 100 ) % 100, nchains / 10000, g_aed_moves, g_spec_shifts };
+  pb::MsqrCfg c{ nb, W, ws_small, tl, nchains % 100, ( nchains / 100 ) % 100, nchains / 10000, g_aed_moves, 14, g_spec_shifts };
   MsBuffers buf( c );
   return run_threads( nt, [&]( const ThreadGroup& g ) {
     return pb::geev_group( g, n, A, n, wr, wi, false, (double*)nullptr, n, wantvr != 0, V, n, dw.data(), iw.data(), pb::QrMultishift{ c, buf.wk } );
