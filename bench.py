@@ -232,7 +232,9 @@ def ours(args):
         batch.solve()
 
     # e2e: the step's matrices go through the C-ABI as two half batches driven by two host threads; every batch owns
-    # a stream, so the copies of one half run under the kernels of the other
+    # a stream, so the copies of one half run under the kernels of the other. Over K steps each thread streams its
+    # half K times (upload, scatter, solve, download per step, results of every step land in host memory); the threads
+    # are joined once, at the end of the K steps, like the batches of the paladin-gpu executable.
     halves = []
     if B >= 2:
         h0 = B // 2
@@ -247,14 +249,19 @@ def ours(args):
         hb.download(out_wr.array[lo * n:hi * n], out_wi.array[lo * n:hi * n],
                     out_vr.array[lo * nn:hi * nn] if job == "V" else None, out_info.array[lo:hi])
 
-    def step_e2e():
+    def steps_e2e(k):
         if not halves:
-            batch.upload(pi.array, pj.array, pv.array)
-            batch.scatter()
-            batch.solve()
-            batch.download(out_wr.array, out_wi.array, out_vr.array if job == "V" else None, out_info.array)
+            for _ in range(k):
+                batch.upload(pi.array, pj.array, pv.array)
+                batch.scatter()
+                batch.solve()
+                batch.download(out_wr.array, out_wi.array, out_vr.array if job == "V" else None, out_info.array)
             return
-        th = [threading.Thread(target=run_half, args=h) for h in halves]
+
+        def stream_half(hb, lo, hi):
+            for _ in range(k):
+                run_half(hb, lo, hi)
+        th = [threading.Thread(target=stream_half, args=h) for h in halves]
         for t_ in th:
             t_.start()
         for t_ in th:
@@ -298,12 +305,10 @@ def ours(args):
             assert r < 100.0, "bench residual check failed: %g" % r
 
     # ---- e2e: host buffers through the C-ABI ----
-    for _ in range(max(1, args.warmup // 2)):
-        step_e2e()
+    steps_e2e(max(1, args.warmup // 2))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
+    steps_e2e(args.steps)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")

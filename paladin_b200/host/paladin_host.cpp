@@ -11,6 +11,7 @@
 // Built twice: as the executable paladin-gpu and (with -DPALADIN_HOST_LIBRARY) as libpaladin_host.so, whose
 // extern "C" hooks let tests/ drive the parser, balancer and writers without a GPU.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstring>
@@ -36,6 +37,7 @@ struct Options {
   std::string listing = "no matrices given!", rootdir = ".", dump_partition;
   int repeats = 1, gpus = -1, batch = 256;
   bool showdist = false, right = false, left = false;
+  bool dynamic = false;  // --dynamic: GPUs pull batches of the sorted list from a shared queue (default: the reference's static pods)
   LoadPredictor measure = LoadPredictor::NUMNONZEROS;
   double threshold = 1.0e-3;
 };
@@ -66,11 +68,12 @@ inline Options parse_options( int argc, char* argv[], bool quiet ) {
   o.gpus = std::stoi( clp.getValue( "gpus", "-1" ) );
   o.batch = std::max( 1, std::stoi( clp.getValue( "batch", "256" ) ) );
   o.dump_partition = clp.getValue( "dump-partition", "" );
+  o.dynamic = clp.checkExists( "dynamic" );
   if ( !quiet ) {
     bool bad = false;
     for ( const auto& k : clp.get_keys() ) {
       static const char* known[] = { "listing", "repeats", "showdist", "measure", "rootdir", "left", "right",
-                                     "write-threshold", "gpus", "batch", "dump-partition" };
+                                     "write-threshold", "gpus", "batch", "dump-partition", "dynamic" };
       if ( std::none_of( std::begin( known ), std::end( known ), [&]( const char* s ) { return k == s; } ) ) {
         std::cout << "\n-- POTENTIAL ERROR: key " << k << " is not a recognized option!";
         bad = true;
@@ -78,7 +81,7 @@ inline Options parse_options( int argc, char* argv[], bool quiet ) {
     }
     if ( bad )
       std::cout << "\n-- Allowable keys: listing, repeats, showdist, measure, rootdir, left, right, write-threshold, "
-                   "gpus, batch, dump-partition\n\n";
+                   "gpus, batch, dump-partition, dynamic\n\n";
   }
   return o;
 }
@@ -111,6 +114,13 @@ inline Plan make_plan( const Options& o, int pods ) {
     p.measures.push_back( e.second );
   }
   return p;
+}
+
+// --dynamic: consecutive batches of the sorted list, (first, count)
+inline std::vector<std::pair<std::size_t, std::size_t>> dynamic_chunks( std::size_t total, std::size_t batch ) {
+  std::vector<std::pair<std::size_t, std::size_t>> chunks;
+  for ( std::size_t first = 0; first < total; first += batch ) chunks.emplace_back( first, std::min( batch, total - first ) );
+  return chunks;
 }
 
 inline void write_file( const std::string& path, const std::string& text ) {
@@ -325,6 +335,46 @@ inline int host_main( int argc, char* argv[] ) {
   if ( !o.dump_partition.empty() ) {
     std::ofstream out( o.dump_partition );
     for ( std::size_t s = 0; s < plan.paths.size(); ++s ) out << s << " " << plan.colour[s] << " " << plan.paths[s] << '\n';
+    return 0;
+  }
+  if ( o.dynamic ) {
+    // SURVEY.md 8(f) rank 4, behind a flag: the static colouring balances the reference's cost model (nnz, n^3, ...), which
+    // is not what a matrix costs on a GPU. Here the sorted list (largest measure first) is cut into batches and every GPU
+    // thread takes the next batch when it is done with its own. The output files do not depend on who computed them.
+    const std::vector<std::pair<std::size_t, std::size_t>> chunks = dynamic_chunks( plan.paths.size(), static_cast<std::size_t>( o.batch ) );
+    std::cout << "dynamic balancing: " << chunks.size() << " batches of up to " << o.batch << " matrices on " << pods << " GPUs" << '\n';
+    std::atomic<std::size_t> next_chunk( 0 );
+    std::vector<PodTimes> dtimes( pods );
+    std::vector<int> dstatus( pods, 0 );
+    std::vector<std::size_t> taken( pods, 0 );
+    std::vector<std::thread> dworkers;
+    const int dparse = std::max( 1, static_cast<int>( std::thread::hardware_concurrency() ) / pods - 1 );
+    for ( int r = 0; r < pods; ++r )
+      dworkers.emplace_back( [&, r] {
+        const auto t0 = std::chrono::steady_clock::now();
+        for ( ;; ) {
+          const std::size_t c = next_chunk.fetch_add( 1 );
+          if ( c >= chunks.size() ) break;
+          const std::vector<std::string> part( plan.paths.begin() + chunks[c].first, plan.paths.begin() + chunks[c].first + chunks[c].second );
+          PodTimes t;
+          const int st = run_pod( r, part, o, t, dparse );
+          if ( st < 0 ) {
+            dstatus[r] = st;
+            break;
+          }
+          dstatus[r] += st;
+          dtimes[r].read += t.read;
+          dtimes[r].eig += t.eig;
+          taken[r] += chunks[c].second;
+        }
+        dtimes[r].total = std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count() / o.repeats;
+      } );
+    for ( auto& w : dworkers ) w.join();
+    for ( int r = 0; r < pods; ++r ) {
+      std::cout << "pod " << r << ": " << taken[r] << " matrices" << '\n';
+      if ( dstatus[r] < 0 ) return 4;
+    }
+    display_timings( dtimes, o.repeats );
     return 0;
   }
   std::vector<std::vector<std::string>> pod( pods );

@@ -462,7 +462,8 @@ def test_staged_api_and_stage_timers(pg):
 # ---------------------------------------------------------------------------------------------------
 # (d) the drop-in executable: reference CLI, listing and output files, GPUs as pods
 # ---------------------------------------------------------------------------------------------------
-def test_paladin_gpu_executable_reproduces_ctest_goldens(pg, tmp_path):
+@pytest.mark.parametrize("extra", [[], ["--dynamic", "--batch=2"]])
+def test_paladin_gpu_executable_reproduces_ctest_goldens(pg, tmp_path, extra):
     import shutil
     import subprocess
     from paladin_b200 import host
@@ -474,7 +475,8 @@ def test_paladin_gpu_executable_reproduces_ctest_goldens(pg, tmp_path):
         if not os.path.exists(lst):  # fixtures keep one listing per suite
             lst = sorted(glob.glob(os.path.join(dst, "listing*")))[-1]
         # exactly the reference's ctest invocation (test/compare_spectra.cmake:8-13): --left --right
-        r = subprocess.run([host.exe_path(), "--listing=" + lst, "--rootdir=" + str(dst), "--left", "--right", "--gpus=1", "--showdist"],
+        # extra = --dynamic: batches of the sorted list pulled from a shared queue instead of the static pods; same files
+        r = subprocess.run([host.exe_path(), "--listing=" + lst, "--rootdir=" + str(dst), "--left", "--right", "--gpus=1", "--showdist"] + extra,
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         assert "load imbalance" in r.stdout
