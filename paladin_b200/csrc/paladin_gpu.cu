@@ -203,6 +203,8 @@ struct MidArgs {
   double* xwork;   // slots of xn_max^2 doubles for the triangular eigenvector factor
   size_t xslot;    // doubles per slot
   int xn_max;      // largest order a slot can hold (larger matrices use the in-place path)
+  int64_t xhalf;   // > 0: the three-launch path addresses X like the dense matrices (xwork + a_off[id]); the second factor
+                   // (both sides wanted) lives xhalf doubles further
   int aed, aed_moves, nibble;  // tuning overrides of mid_cfg() (PALADIN_GPU_AED, _AED_MOVES, _AED_NIBBLE); -1 = default
 };
 
@@ -543,10 +545,12 @@ __global__ void __launch_bounds__( pb::kVecThreads, 2 ) mid_vec_kernel( MidArgs 
 // 2: second GEMM (both sides wanted), 3: un-balance + normalise ------------------------------------------------------------
 // (the solves are latency bound -- one dependent chain per warp -- and run at four CTAs per SM / 64 registers)
 template <int STEP>
-__global__ void __launch_bounds__( pb::kVecThreads, STEP == 0 ? 4 : 2 ) big_vec_kernel( MidArgs a, int P ) {
+__global__ void __launch_bounds__( pb::kVecThreads, STEP == 0 ? 4 : 2 ) big_vec_kernel( MidArgs a, const int4* items ) {
   extern __shared__ double smem[];
   int* perm = reinterpret_cast<int*>( smem + pb::vecs_gemm_smem_doubles() );
-  const int k = blockIdx.x / P, part = blockIdx.x % P;
+  // work item = (matrix of the group, part, parts of that matrix): a matrix is shared by a number of CTAs proportional to n^3
+  const int4 item = items[blockIdx.x];
+  const int k = item.x, part = item.y, P = item.z;
   const int id = a.ids[k];
   const int n = a.bv.n[id];
   const MidMeta m = a.meta[id];
@@ -558,8 +562,8 @@ __global__ void __launch_bounds__( pb::kVecThreads, STEP == 0 ? 4 : 2 ) big_vec_
   double* cnorm = dw + 2 * n;
   const bool wantvr = a.bv.wantvr != 0, wantvl = a.bv.wantvl != 0;
   double* VLout = wantvl ? a.bv.VL + a.bv.a_off[id] : nullptr;
-  double* X = a.xwork + (size_t)k * a.xslot;
-  double* Y = X + (size_t)n * n + 16;
+  double* X = a.xhalf > 0 ? a.xwork + a.bv.a_off[id] : a.xwork + (size_t)k * a.xslot;
+  double* Y = a.xhalf > 0 ? X + a.xhalf : X + (size_t)n * n + 16;
   if constexpr ( STEP == 0 ) {
     if ( wantvr ) pb::vecs_solve( n, A, n, X, n, cnorm, false, part, P );
     if ( wantvl ) pb::vecs_solve( n, A, n, wantvr ? Y : X, n, cnorm, true, part, P );
@@ -667,6 +671,9 @@ struct paladin_gpu_batch {
   double* d_xwork = nullptr;
   size_t xslot = 0;
   int xslots = 0, xn_max = 0;
+  int64_t xhalf = 0;
+  int4* d_vec_items = nullptr;               // work items of the three-launch eigenvector stage
+  int n_vec_items = 0;
   // cooperative stage 1 of large matrices
   unsigned* d_coop_bars = nullptr;
   double *d_coop_ypart = nullptr, *d_coop_yz = nullptr;
@@ -689,7 +696,7 @@ void free_batch( paladin_gpu_batch* b ) {
   cudaFree( b->d_coo_i ); cudaFree( b->d_coo_j ); cudaFree( b->d_coo_v );
   cudaFree( b->d_A ); cudaFree( b->d_V ); cudaFree( b->d_VL ); cudaFree( b->d_wr ); cudaFree( b->d_wi ); cudaFree( b->d_dwork );
   cudaFree( b->d_stats ); cudaFree( b->d_meta ); cudaFree( b->d_counter ); cudaFree( b->d_xwork );
-  cudaFree( b->d_coop_bars ); cudaFree( b->d_coop_ypart ); cudaFree( b->d_coop_yz );
+  cudaFree( b->d_coop_bars ); cudaFree( b->d_coop_ypart ); cudaFree( b->d_coop_yz ); cudaFree( b->d_vec_items );
   cudaFree( b->d_info ); cudaFree( b->d_iwork ); cudaFree( b->d_flags ); cudaFree( b->d_ids ); cudaFree( b->d_chunks );
   for ( auto& s : b->st ) {
     if ( s.e0 ) cudaEventDestroy( s.e0 );
@@ -950,11 +957,35 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
       // one slot holds the triangular factor(s) of the largest matrix (two when both sides are wanted); at most two
       // resident CTAs per SM, at most 24 GB in total (fewer slots for very large matrices)
       b->xn_max = nmax;
-      b->xslot = ( (size_t)nmax * nmax + 16 ) * ( jobvr == 'V' && jobvl == 'V' ? 2 : 1 ) + 528;
-      const size_t budget = (size_t)24 << 30;
-      const int by_mem = (int)std::max<size_t>( 1, budget / ( b->xslot * sizeof( double ) ) );
-      b->xslots = std::max( 1, std::min( std::min( nmid, bigvec_min_n() < kMidMaxFusedN ? nmid : 2 * c.sm_count ), by_mem ) );
-      A( dev_alloc( &b->d_xwork, b->xslot * b->xslots ) );
+      if ( bigvec_min_n() <= kSmallMax ) {
+        // every matrix of the group takes the three-launch path: X is laid out like the dense matrices themselves
+        b->xhalf = b->total_nn + 16;
+        b->xslots = nmid;
+        // work items: parts per matrix proportional to n^3, about four items per SM in total, at most 64 per matrix
+        for ( const auto& g : b->groups ) {
+          if ( g.kind != 1 ) continue;
+          double total = 0.0;
+          for ( int q = 0; q < g.count; ++q ) total += std::pow( (double)n[b->ids[g.first + q]], 3.0 );
+          const double unit = std::max( 1.0, total / ( 4.0 * c.sm_count ) );
+          std::vector<int4> items;
+          for ( int q = 0; q < g.count; ++q ) {
+            const double w = std::pow( (double)n[b->ids[g.first + q]], 3.0 );
+            const int parts = std::max( 1, std::min( 64, (int)std::ceil( w / unit - 1e-9 ) ) );
+            for ( int p2 = 0; p2 < parts; ++p2 ) items.push_back( make_int4( q, p2, parts, 0 ) );
+          }
+          b->n_vec_items = (int)items.size();
+          A( dev_alloc( &b->d_vec_items, items.size() ) );
+          if ( rc == PALADIN_GPU_OK && cudaMemcpy( b->d_vec_items, items.data(), sizeof( int4 ) * items.size(), cudaMemcpyHostToDevice ) != cudaSuccess )
+            rc = fail( PALADIN_GPU_ECUDA, "cudaMemcpy failed" );
+        }
+        A( dev_alloc( &b->d_xwork, (size_t)b->xhalf * ( jobvr == 'V' && jobvl == 'V' ? 2 : 1 ) ) );
+      } else {
+        b->xslot = ( (size_t)nmax * nmax + 16 ) * ( jobvr == 'V' && jobvl == 'V' ? 2 : 1 ) + 528;
+        const size_t budget = (size_t)24 << 30;
+        const int by_mem = (int)std::max<size_t>( 1, budget / ( b->xslot * sizeof( double ) ) );
+        b->xslots = std::max( 1, std::min( std::min( nmid, 2 * c.sm_count ), by_mem ) );
+        A( dev_alloc( &b->d_xwork, b->xslot * b->xslots ) );
+      }
     }
   }
   {
@@ -1164,6 +1195,7 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
       ma.xwork = b->d_xwork;
       ma.xslot = b->xslot;
       ma.xn_max = b->xn_max;
+      ma.xhalf = b->xhalf;
       static const int env_aed = std::getenv( "PALADIN_GPU_AED" ) ? std::atoi( std::getenv( "PALADIN_GPU_AED" ) ) : -1;
       static const int env_moves = std::getenv( "PALADIN_GPU_AED_MOVES" ) ? std::atoi( std::getenv( "PALADIN_GPU_AED_MOVES" ) ) : -1;
       ma.aed = std::min( env_aed, pb::kStripW - 1 );
@@ -1345,24 +1377,42 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
         int nvbig = 0;
         for ( int q = 0; q < cnt; ++q )
           if ( b->n[b->ids[g.first + q]] > bigvec_min_n() ) nvbig = q + 1;
-        static const bool no_bigvec = std::getenv( "PALADIN_GPU_NO_COOP" ) != nullptr;
-        if ( no_bigvec ) nvbig = 0;
         if ( nvbig > 0 ) {
           PB_CUDA( cudaFuncSetAttribute( big_vec_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3 ) );
           PB_CUDA( cudaFuncSetAttribute( big_vec_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3 ) );
           PB_CUDA( cudaFuncSetAttribute( big_vec_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3 ) );
           PB_CUDA( cudaFuncSetAttribute( big_vec_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3 ) );
-          for ( int q0 = 0; q0 < nvbig; q0 += b->xslots ) {
-            const int nq = std::min( b->xslots, nvbig - q0 );
-            const int P = std::max( 1, std::min( 64, ( 4 * c.sm_count ) / nq ) );
+          if ( b->d_vec_items != nullptr && nvbig == cnt && !any_bad ) {
+            // every matrix of the group, parts proportional to n^3 (work items built at batch_create)
             MidArgs mv = ma;
-            mv.ids = ids + q0;
-            mv.count = nq;
-            big_vec_kernel<0><<<nq * P, pb::kVecThreads, s3, st>>>( mv, P );
-            big_vec_kernel<1><<<nq * P, pb::kVecThreads, s3, st>>>( mv, P );
-            if ( wantvr && wantvl ) big_vec_kernel<2><<<nq * P, pb::kVecThreads, s3, st>>>( mv, P );
-            big_vec_kernel<3><<<nq * P, pb::kVecThreads, s3, st>>>( mv, P );
+            const int ni = b->n_vec_items;
+            big_vec_kernel<0><<<ni, pb::kVecThreads, s3, st>>>( mv, b->d_vec_items );
+            big_vec_kernel<1><<<ni, pb::kVecThreads, s3, st>>>( mv, b->d_vec_items );
+            if ( wantvr && wantvl ) big_vec_kernel<2><<<ni, pb::kVecThreads, s3, st>>>( mv, b->d_vec_items );
+            big_vec_kernel<3><<<ni, pb::kVecThreads, s3, st>>>( mv, b->d_vec_items );
             launches += ( wantvr && wantvl ) ? 4 : 3;
+          } else {
+            // uniform parts (tuning paths, filtered id lists): items built on the fly
+            for ( int q0 = 0; q0 < nvbig; q0 += b->xslots ) {
+              const int nq = std::min( b->xslots, nvbig - q0 );
+              const int P = std::max( 1, std::min( 64, ( 4 * c.sm_count ) / nq ) );
+              std::vector<int4> items;
+              for ( int q = 0; q < nq; ++q )
+                for ( int p2 = 0; p2 < P; ++p2 ) items.push_back( make_int4( q, p2, P, 0 ) );
+              int4* d_items = nullptr;
+              PB_TRY( dev_alloc( &d_items, items.size() ) );
+              PB_CUDA( cudaMemcpyAsync( d_items, items.data(), sizeof( int4 ) * items.size(), cudaMemcpyHostToDevice, st ) );
+              MidArgs mv = ma;
+              mv.ids = ids + q0;
+              mv.count = nq;
+              big_vec_kernel<0><<<nq * P, pb::kVecThreads, s3, st>>>( mv, d_items );
+              big_vec_kernel<1><<<nq * P, pb::kVecThreads, s3, st>>>( mv, d_items );
+              if ( wantvr && wantvl ) big_vec_kernel<2><<<nq * P, pb::kVecThreads, s3, st>>>( mv, d_items );
+              big_vec_kernel<3><<<nq * P, pb::kVecThreads, s3, st>>>( mv, d_items );
+              launches += ( wantvr && wantvl ) ? 4 : 3;
+              PB_CUDA( cudaStreamSynchronize( st ) );
+              cudaFree( d_items );
+            }
           }
         }
         if ( cnt > nvbig ) {
