@@ -1246,7 +1246,14 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
             // (3072^2 x 8: 910 ms with 4 groups of 37; the sweep of a small group is bound by its SMs' L2 bandwidth, the
             // fixed per-column cost is amortised over more columns per CTA)
             const int gmin = kind == 0 ? 1 : ( kind == 1 ? 2 : 4 );
-            int G = std::min( std::max( ncls, gmin ), std::max( 1, c.sm_count / 8 ) );
+            const int gcap = std::max( 1, c.sm_count / 8 );
+            int G = std::min( std::max( ncls, gmin ), gcap );
+            if ( ncls > G ) {
+              // several rounds: the same number of rounds with as few (hence as large) groups as possible, so that the last
+              // round is not mostly idle (23 matrices: 12 groups of 12 CTAs instead of 18 + 5 on groups of 8)
+              const int rounds = ( ncls + G - 1 ) / G;
+              G = ( ncls + rounds - 1 ) / rounds;
+            }
             if ( env_groups > 0 ) {
               G = std::min( env_groups, kCoopMaxGroups );
               q1 = nbig;
