@@ -543,7 +543,9 @@ __global__ void __launch_bounds__( pb::kVecThreads, 2 ) mid_vec_kernel( MidArgs 
 // ---- stage 3 for large matrices: every matrix is shared by P CTAs; the three steps are separate launches (the kernel
 // boundary is the barrier between "all solves done" -> GEMM -> normalise). STEP 0: triangular solves, 1: first GEMM,
 // 2: second GEMM (both sides wanted), 3: un-balance + normalise ------------------------------------------------------------
-// (the solves are latency bound -- one dependent chain per warp -- and run at four CTAs per SM / 64 registers)
+// (the solves are latency bound -- one dependent chain per warp -- and run at four CTAs per SM / 64 registers; measured
+// and rejected at 592 x n=512: the vector being solved in shared memory, 64 KB per CTA hence three CTAs per SM, 48.3 ms
+// against 34.8 ms; L1 prefetch of the next columns of T, no change: warps in flight are what counts)
 template <int STEP>
 __global__ void __launch_bounds__( pb::kVecThreads, STEP == 0 ? 4 : 2 ) big_vec_kernel( MidArgs a, const int4* items ) {
   extern __shared__ double smem[];
