@@ -253,6 +253,42 @@ print("OK")
     assert "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+def test_bench_sized_step_properties(pg):
+    """One bench-sized step of BASELINE.json configs[2] (592 distinct dense N(0,1) 512 x 512 matrices, default_rng([3, k]),
+    eigenvalues + right eigenvectors) checked through size-independent properties: info == 0, sum of eigenvalues = trace,
+    sum of |lambda|^2 <= ||A||_F^2 (Schur), conjugate pairs adjacent with +imag first, unit-norm vectors, and the
+    backward error of a sample of matrices."""
+    n, count = 512, 592
+    nn = n * n
+    ii = np.tile(np.arange(1, n + 1, dtype=np.int32), n)
+    jj = np.repeat(np.arange(1, n + 1, dtype=np.int32), n)
+    vals = np.empty(count * nn)
+    for k in range(count):
+        vals[k * nn:(k + 1) * nn] = np.random.default_rng([3, k]).standard_normal(nn)
+    b = pg.Batch(np.full(count, n, dtype=np.int32), np.arange(count + 1, dtype=np.int64) * nn, jobvr="V")
+    b.upload(np.tile(ii, count), np.tile(jj, count), vals)
+    b.scatter()
+    b.solve()
+    wr, wi, vr, info = b.download()
+    b.destroy()
+    assert not info.any()
+    for k in range(count):
+        A = vals[k * nn:(k + 1) * nn].reshape((n, n), order="F")
+        lr, li = wr[k * n:(k + 1) * n], wi[k * n:(k + 1) * n]
+        assert abs(lr.sum() - np.trace(A)) <= 1e-9 * np.sqrt(n) * n
+        assert abs(li.sum()) <= 1e-9 * n
+        assert (lr ** 2 + li ** 2).sum() <= (A ** 2).sum() * (1 + 1e-12)
+        pos = np.nonzero(li > 0)[0]
+        assert np.all(li[pos + 1] == -li[pos]) and np.all(lr[pos + 1] == lr[pos])
+        assert (li > 0).sum() == (li < 0).sum()
+    for k in range(0, count, 74):
+        A = vals[k * nn:(k + 1) * nn].reshape((n, n), order="F")
+        V = vr[k * nn:(k + 1) * nn].reshape((n, n), order="F")
+        assert po.backward_error(A, wr[k * n:(k + 1) * n], wi[k * n:(k + 1) * n], V) <= BACKWARD_TOL
+        nrm = np.linalg.norm(np.array(po.unpack(wr[k * n:(k + 1) * n], wi[k * n:(k + 1) * n], V)), axis=1)
+        assert np.allclose(nrm, 1.0, atol=1e-12)
+
+
 def test_n512_full_decomposition(pg):
     mats = _random_mats([512, 512], 3)
     res, info = pg.geev_batch(*_concat(mats), jobvr="V")
