@@ -257,7 +257,8 @@ __global__ void __launch_bounds__( pb::kHessThreads, ( MAXCH == 16 ? 2 : 1 ) ) m
   double* scale = dw + n;
   pb::GeevScaling sc;
   int ilo = 0, ihi = n - 1, info = 0;
-  if ( !pb::geev_prologue( g, n, A, n, sc, &ilo, &ihi, scale, iw ) ) {
+  // (the dynamic shared memory is free until the reduction starts: row / column sums of the balancing sweeps)
+  if ( !pb::geev_prologue( g, n, A, n, sc, &ilo, &ihi, scale, iw, MAXCH > 0 || n <= kMidMaxBigN ? smem : nullptr ) ) {
     info = PALADIN_GPU_INFO_NONFINITE;
     sc.scalea = false;
     sc.anrm = 0.0;
@@ -340,7 +341,7 @@ __global__ void __launch_bounds__( pb::kHessThreads, 1 ) big_prep_kernel( MidArg
     mid_pointers( a.bv, id, n, A, V, wr, wi, dw, iw );
     pb::GeevScaling sc;
     int ilo = 0, ihi = n - 1, info = 0;
-    if ( !pb::geev_prologue( g, n, A, n, sc, &ilo, &ihi, dw + n, iw ) ) {
+    if ( !pb::geev_prologue( g, n, A, n, sc, &ilo, &ihi, dw + n, iw, smem ) ) {
       info = PALADIN_GPU_INFO_NONFINITE;
       sc.scalea = false;
       sc.anrm = 0.0;

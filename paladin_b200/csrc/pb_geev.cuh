@@ -89,7 +89,7 @@ struct GeevScaling {
 
 template <class G>
 PB_D bool geev_prologue( const G& g, int n, double* A, int lda, GeevScaling& sc, int* ilo, int* ihi, double* scale,
-                         int* iwork ) {
+                         int* iwork, double* work4n = nullptr ) {
   const int t = g.tid(), nt = g.size();
   double anrm = 0.0;
   bool bad = false;
@@ -115,7 +115,7 @@ PB_D bool geev_prologue( const G& g, int n, double* A, int lda, GeevScaling& sc,
     sc.cscale = bignum0;
   }
   if ( sc.scalea ) lascl( g, anrm, sc.cscale, n, n, A, lda );
-  gebal( g, n, A, lda, ilo, ihi, scale, iwork );
+  gebal( g, n, A, lda, ilo, ihi, scale, iwork, work4n );
   g.sync();
   return true;
 }

@@ -148,6 +148,26 @@ void hs_gebal( int n, double* A, int* ilo, int* ihi, double* scale ) {
   std::vector<int> icnt( 2 * n + 2 );
   pb::gebal( g, n, A, n, ilo, ihi, scale, icnt.data() );
 }
+// with the 4 n doubles of work: precomputed row / column sums (used from 128 active rows on)
+void hs_gebal_work( int n, double* A, int* ilo, int* ihi, double* scale ) {
+  pb::HostGroup g;
+  std::vector<int> icnt( 2 * n + 2 );
+  std::vector<double> work( 4 * n + 4 );
+  pb::gebal( g, n, A, n, ilo, ihi, scale, icnt.data(), work.data() );
+}
+int ht_gebal_work( int nt, int n, double* A, int* ilo, int* ihi, double* scale ) {
+  std::vector<int> icnt( 2 * n + 2 );
+  std::vector<double> work( 4 * n + 4 );
+  return run_threads( nt, [&]( const ThreadGroup& g ) {
+    int lo = 0, hi = 0;
+    pb::gebal( g, n, A, n, &lo, &hi, scale, icnt.data(), work.data() );
+    if ( g.tid() == 0 ) {
+      *ilo = lo;
+      *ihi = hi;
+    }
+    return 0;
+  } );
+}
 
 void hs_gehd2( int n, int ilo, int ihi, double* A, double* tau ) {
   pb::HostGroup g;

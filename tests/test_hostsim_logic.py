@@ -223,6 +223,38 @@ def test_left_eigenvectors_match_lapack(hs):
         assert po.backward_error(A, w1, w2, VR) <= 100 and po.left_backward_error(A, w1, w2, VL) <= 100
 
 
+def test_balancing_with_precomputed_sums_matches_lapack(hs):
+    """pb::gebal with its work array (row / column sums of a sweep taken in two coalesced passes until the first rescaling,
+    used by the prep kernels from 128 active rows on) against LAPACK dgebal: same ilo/ihi, same power-of-two scale
+    factors, same balanced matrix -- for inputs that need no scaling, one rescaling, and many."""
+    rng = np.random.default_rng(12)
+    for n in (130, 200, 300):
+        for kind in range(4):
+            A = rng.standard_normal((n, n))
+            if kind == 1:
+                A[:, 7] *= 1e6
+            elif kind == 2:
+                A *= np.outer(2.0 ** rng.integers(-20, 20, n), 2.0 ** rng.integers(-20, 20, n))
+            elif kind == 3:
+                A[rng.random((n, n)) < 0.97] = 0      # isolated rows / columns: ilo > 1, ihi < n
+                A[:, 3] *= 1e5
+            A = np.asfortranarray(A)
+            B, ilo, ihi, sc = ls.dgebal(A)
+            for threaded in (False, True):
+                A2 = A.copy(order="F")
+                ilo2, ihi2, sc2 = ctypes.c_int(), ctypes.c_int(), np.zeros(n)
+                if threaded:
+                    hs.ht_gebal_work(4, n, dp(A2), ctypes.byref(ilo2), ctypes.byref(ihi2), dp(sc2))
+                else:
+                    hs.hs_gebal_work(n, dp(A2), ctypes.byref(ilo2), ctypes.byref(ihi2), dp(sc2))
+                assert (ilo2.value, ihi2.value) == (ilo - 1, ihi - 1), (n, kind)
+                scl = sc.copy()
+                for k in list(range(0, ilo - 1)) + list(range(ihi, n)):
+                    scl[k] -= 1
+                assert np.array_equal(scl, sc2), (n, kind, threaded)
+                assert np.array_equal(B, A2), (n, kind, threaded)
+
+
 def test_stage_functions_match_lapack(hs):
     rng = np.random.default_rng(3)
     for n in (6, 20, 50):
@@ -310,6 +342,11 @@ for n, nt in [(1, 3), (2, 3), (3, 4), (7, 4), (12, 3), (20, 5)]:
             assert info == 0
             assert po.match_eigenvalues(wr + 1j * wi, wr0 + 1j * wi0) <= 1e-9 * max(1, np.linalg.norm(A, 2))
             if wantvr: assert po.backward_error(A, wr, wi, V) <= 100
+import ctypes as _ct
+for n, nt in [(140, 4)]:
+    A = np.asfortranarray(rng.standard_normal((n, n))); A[:, 5] *= 1e4
+    lo, hi, sc = _ct.c_int(), _ct.c_int(), np.zeros(n)
+    hs.ht_gebal_work(nt, n, dp(A), _ct.byref(lo), _ct.byref(hi), dp(sc))
 print('DONE')
 """ % (os.path.dirname(HERE), so)
     env = dict(os.environ, LD_PRELOAD=tsan_rt, TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 exitcode=0")
