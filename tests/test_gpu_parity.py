@@ -289,6 +289,17 @@ def test_bench_sized_step_properties(pg):
         assert np.allclose(nrm, 1.0, atol=1e-12)
 
 
+@pytest.mark.parametrize("jobvr", ["N", "V"])
+def test_dispatch_boundaries(pg, jobvr):
+    """Orders on both sides of every dispatch threshold of the launcher: warp path <= 64, 16- / 32-chunk fused Hessenberg
+    at 512, cooperative groups + clusters + AED window 48 above 1024, group / cluster size classes at 1400 and 2048."""
+    sizes = [63, 64, 65, 66, 511, 512, 513, 1023, 1024, 1025, 1400, 1401] + ([2048, 2049] if jobvr == "N" else [2049])
+    mats = _random_mats(sizes, 71)
+    res, info = pg.geev_batch(*_concat(mats), jobvr=jobvr)
+    for m, (wr, wi, VR), inf in zip(mats, res, info):
+        _check_eigs(po.dense_matrix(*m), wr, wi, VR, inf, jobvr == "V")
+
+
 def test_n512_full_decomposition(pg):
     mats = _random_mats([512, 512], 3)
     res, info = pg.geev_batch(*_concat(mats), jobvr="V")
