@@ -205,6 +205,7 @@ struct MidArgs {
   int xn_max;      // largest order a slot can hold (larger matrices use the in-place path)
   int64_t xhalf;   // > 0: the three-launch path addresses X like the dense matrices (xwork + a_off[id]); the second factor
                    // (both sides wanted) lives xhalf doubles further
+  int refl_global;  // clusters: reflectors through global memory (L2) instead of the leader's shared memory
   int aed, aed_moves, nibble;  // tuning overrides of mid_cfg() (PALADIN_GPU_AED, _AED_MOVES, _AED_NIBBLE); -1 = default
 };
 
@@ -436,6 +437,8 @@ __global__ void __launch_bounds__( kMidThreads, 2 ) mid_qr_kernel( MidArgs a ) {
   mid_pointers( a.bv, id, n, A, V, wr, wi, dw, iw );
   const bool wantz = a.bv.wantvr != 0 || a.bv.wantvl != 0;
   if constexpr ( CLUSTER ) {
+    // (tau, scale | 3 n doubles free until the eigenvector stage: the reflectors of a window, 2352 doubles, for n >= 784)
+    if ( a.refl_global && 3 * n >= c.nb * c.W * pb::kReflStride ) wk.gscratch = dw + 2 * n;
     if ( wk.crank != 0 ) {
       pb::ms_cluster_helper( g, wantz, wantz, n, A, n, 0, n - 1, V, n, c, wk );
       return;
@@ -1205,6 +1208,8 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
       ma.aed_moves = env_moves;
       static const int env_nibble = std::getenv( "PALADIN_GPU_AED_NIBBLE" ) ? std::atoi( std::getenv( "PALADIN_GPU_AED_NIBBLE" ) ) : -1;
       ma.nibble = env_nibble;
+      static const int env_rg = std::getenv( "PALADIN_GPU_REFL_GLOBAL" ) ? std::atoi( std::getenv( "PALADIN_GPU_REFL_GLOBAL" ) ) : 1;  // 3072^2 x 2, clusters of 16: QR stage 1373 -> 1275 ms
+      ma.refl_global = env_rg;
       PB_CUDA( cudaMemsetAsync( b->d_stats, 0, sizeof( long long ) * kNumTicks, st ) );
       PB_CUDA( cudaMemsetAsync( b->d_counter, 0, sizeof( int ), st ) );
       const size_t s2 = qr_smem_bytes(), s3 = vec_smem_bytes( g.nmax );

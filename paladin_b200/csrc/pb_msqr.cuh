@@ -75,6 +75,9 @@ struct MsqrWork {
   // thread-block cluster that shares the strip updates of this matrix (device, large matrices): the leader (rank 0)
   // runs the whole iteration, the others wait in ms_cluster_helper for its commands
   int csize = 1, crank = 0;
+  double* gscratch = nullptr;  // optional global scratch (>= nb * W * kReflStride doubles): the leader publishes the recorded
+                               // reflectors there and the helpers read them through L2 instead of all pulling them out of
+                               // the leader's shared memory
 };
 
 // command block the leader publishes in its ibuf (read by the helpers through distributed shared memory)
@@ -327,6 +330,11 @@ PB_D void ms_update_strips( const G& g, bool wantt, bool wantz, int n, int l, in
 // CTA's shared memory), and meet them again when everybody's share is done (pb::ms_cluster_helper) ------------------------
 // cmd 1: strips of a steady-state window (register path); 2: x <- U^T x with wk.U; 3: recorded reflectors, tile path
 __device__ __forceinline__ void ms_cluster_post( const MsqrWork& wk, int cmd, int ws, int wlen, int l, int i, int nbulges ) {
+  if ( wk.gscratch != nullptr && cmd != 2 ) {
+    const int nrefl2 = kStripNB * kStripW * kReflStride / 2;
+    for ( int q = threadIdx.x; q < nrefl2; q += blockDim.x )
+      __stcg( reinterpret_cast<double2*>( wk.gscratch ) + q, reinterpret_cast<const double2*>( wk.refl )[q] );
+  }
   if ( threadIdx.x == 0 ) {
     int* c = wk.ibuf + kMsCmd;
     c[0] = cmd; c[1] = ws; c[2] = wlen; c[3] = l; c[4] = i; c[5] = nbulges;
@@ -931,8 +939,13 @@ __device__ inline void ms_cluster_helper( const CtaGroup& g, bool wantt, bool wa
       __syncthreads();
       ms_update_strips( g, wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, 0, wk.U, wk.crank, wk.csize );
     } else {
-      for ( int q = threadIdx.x; q < nrefl / 2; q += blockDim.x )
-        reinterpret_cast<double2*>( wk.refl )[q] = reinterpret_cast<const double2*>( lrefl )[q];
+      if ( wk.gscratch != nullptr ) {
+        for ( int q = threadIdx.x; q < nrefl / 2; q += blockDim.x )
+          reinterpret_cast<double2*>( wk.refl )[q] = __ldcg( reinterpret_cast<const double2*>( wk.gscratch ) + q );
+      } else {
+        for ( int q = threadIdx.x; q < nrefl / 2; q += blockDim.x )
+          reinterpret_cast<double2*>( wk.refl )[q] = reinterpret_cast<const double2*>( lrefl )[q];
+      }
       if ( cmd == 3 ) {
         const int* lk = cluster.map_shared_rank( wk.ibuf + kMsMaxBulges, 0 );
         if ( threadIdx.x < 2 * kMsMaxBulges ) wk.ibuf[kMsMaxBulges + threadIdx.x] = lk[threadIdx.x];

@@ -222,7 +222,7 @@ def test_large_matrices_cooperative_path(pg, jobvr, sizes):
 
 
 @pytest.mark.parametrize("env", [{"PALADIN_GPU_CLUSTER": "2"}, {"PALADIN_GPU_CLUSTER": "4"}, {"PALADIN_GPU_CLUSTER": "8"},
-                                 {"PALADIN_GPU_CLUSTER": "16", "PALADIN_GPU_COOP_GROUPS": "1"},
+                                 {"PALADIN_GPU_CLUSTER": "16", "PALADIN_GPU_COOP_GROUPS": "1", "PALADIN_GPU_REFL_GLOBAL": "0"},
                                  {"PALADIN_GPU_COOP_GROUPS": "4"}, {"PALADIN_GPU_COOP_GROUPS": "16", "PALADIN_GPU_AED": "48"},
                                  {"PALADIN_GPU_NO_COOP": "1", "PALADIN_GPU_CLUSTER": "1", "PALADIN_GPU_AED": "0"},
                                  {"PALADIN_GPU_AED_MOVES": "1000", "PALADIN_GPU_BIGVEC_MIN_N": "4000"}])
