@@ -438,7 +438,11 @@ __global__ void __launch_bounds__( kMidThreads, 2 ) mid_qr_kernel( MidArgs a ) {
   const bool wantz = a.bv.wantvr != 0 || a.bv.wantvl != 0;
   if constexpr ( CLUSTER ) {
     // (tau, scale | 3 n doubles free until the eigenvector stage: the reflectors of a window, 2352 doubles, for n >= 784)
-    if ( a.refl_global && 3 * n >= c.nb * c.W * pb::kReflStride ) wk.gscratch = dw + 2 * n;
+    if ( a.refl_global && 3 * n >= c.nb * c.W * pb::kReflStride + 1 ) {
+      wk.gscratch = dw + 2 * n;
+      if ( reinterpret_cast<uintptr_t>( wk.gscratch ) & 15 ) wk.gscratch += 1;  // read and written as double2
+    }
+    wk.overlap = a.refl_global >= 2 ? 0 : 1;  // PALADIN_GPU_REFL_GLOBAL=2: published reflectors, blocking hand-off
     if ( wk.crank != 0 ) {
       pb::ms_cluster_helper( g, wantz, wantz, n, A, n, 0, n - 1, V, n, c, wk );
       return;

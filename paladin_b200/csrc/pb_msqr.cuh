@@ -75,6 +75,7 @@ struct MsqrWork {
   // thread-block cluster that shares the strip updates of this matrix (device, large matrices): the leader (rank 0)
   // runs the whole iteration, the others wait in ms_cluster_helper for its commands
   int csize = 1, crank = 0;
+  int overlap = 1;             // cluster: the leader chases the next window while the helpers finish the strips (needs gscratch)
   double* gscratch = nullptr;  // optional global scratch (>= nb * W * kReflStride doubles): the leader publishes the recorded
                                // reflectors there and the helpers read them through L2 instead of all pulling them out of
                                // the leader's shared memory
@@ -674,6 +675,7 @@ PB_D void ms_chase_chain( const G& g, bool wantt, bool wantz, int n, int l, int 
   for ( int b = t; b < nbulges; b += nt ) kpos[b] = l;
   g.sync();
   int ws = l;
+  bool pending = false;  // cluster: the helpers may still be working on the strips of the previous window
   for ( ;; ) {
     // all bulges gone?
     int first_live = -1, last_live = -1;
@@ -827,12 +829,28 @@ PB_D void ms_chase_chain( const G& g, bool wantt, bool wantz, int n, int l, int 
       // steady-state windows only (about five in six); the others take the tile path below
       if ( cfg.W == kStripW && cfg.nb == kStripNB && cfg.tl >= 16 * ( g.size() >> 5 ) &&
            strip_window_is_regular( nbulges, wlen, ws, kfirst, kcount ) ) {
-        // hand the window to the cluster: command + reflectors are read from this CTA's shared memory
-        if ( wk.csize > 1 ) ms_cluster_post( wk, 1, ws, wlen, l, i, nbulges );
+        // hand the window to the cluster. With the reflectors published in global memory the leader does not wait for the
+        // helpers: it takes its own share -- which holds the right-strip batches 0..3, i.e. every column the next window
+        // can reach -- and goes on to chase the next window while the helpers finish this one; they are joined before the
+        // next hand-off (or at the end of the chain).
+        if ( wk.csize > 1 ) {
+          if ( pending ) {
+            ms_cluster_join();
+            pending = false;
+          }
+          ms_cluster_post( wk, 1, ws, wlen, l, i, nbulges );
+        }
         ms_strips_regs( wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, wk.refl, wk.tile, wk.ldt,
-                        wk.ibuf + 3 * kMsMaxBulges + 6, 0, wk.csize );
-        if ( wk.csize > 1 ) ms_cluster_join();
+                        wk.ibuf + 3 * kMsMaxBulges + 6, 0, wk.csize, wk.csize > 2 && wk.gscratch != nullptr && wk.overlap != 0 );
+        if ( wk.csize > 1 ) {
+          if ( wk.gscratch != nullptr && wk.overlap ) pending = true;
+          else ms_cluster_join();
+        }
       } else {
+        if ( pending ) {
+          ms_cluster_join();
+          pending = false;
+        }
         ms_update_strips_shared( g, wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, nbulges, (const double*)nullptr );
       }
     } else
@@ -843,6 +861,12 @@ PB_D void ms_chase_chain( const G& g, bool wantt, bool wantz, int n, int l, int 
     g.sync();
     g.tick( kTickMsStrips );
   }
+#if defined( __CUDACC__ )
+  if constexpr ( G::kIsCta ) {
+    if ( pending ) ms_cluster_join();
+  }
+#endif
+  (void)pending;
 }
 
 #if defined( __CUDACC__ )
@@ -954,7 +978,7 @@ __device__ inline void ms_cluster_helper( const CtaGroup& g, bool wantt, bool wa
       __syncthreads();
       if ( cmd == 1 )
         ms_strips_regs( wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, wk.refl, wk.tile, wk.ldt,
-                        wk.ibuf + 3 * kMsMaxBulges + 6, wk.crank, wk.csize );
+                        wk.ibuf + 3 * kMsMaxBulges + 6, wk.crank, wk.csize, wk.csize > 2 && wk.gscratch != nullptr && wk.overlap != 0 );
       else
         ms_update_strips( g, wantt, wantz, n, l, i, ws, wlen, H, ldh, iloz, ihiz, Z, ldz, cfg, wk, nbulges, (const double*)nullptr,
                           wk.crank, wk.csize );

@@ -146,8 +146,19 @@ __device__ __forceinline__ void prefetch_l2( const void* p ) { asm volatile( "pr
 // right-strip batches and row batches are dealt round-robin to the CTAs; counter is CTA-local either way.
 __device__ inline void ms_strips_regs( bool wantt, bool wantz, int n, int l, int i, int ws, int wlen, double* __restrict__ H,
                                        int ldh, int iloz, int ihiz, double* __restrict__ Z, int ldz, const double* refl,
-                                       double* tile, int ldt, int* counter, int crank = 0, int csize = 1 ) {
+                                       double* tile, int ldt, int* counter, int crank = 0, int csize = 1, bool lookahead = false ) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  // lookahead (overlapped cluster hand-off): the leader only takes right-strip batches 0 and 1 -- every column the next
+  // window can reach -- and leaves the rest of the window's strips to the other csize - 1 CTAs
+  const int rfirst = lookahead ? 2 : 0;
+  if ( lookahead ) {
+    if ( crank == 0 ) {
+      csize = 0;  // (marks the leader below)
+    } else {
+      crank -= 1;
+      csize -= 1;
+    }
+  }
   const int we = ws + wlen - 1;
   const int i1 = wantt ? 0 : l, i2 = wantt ? n - 1 : i;
   const int nright = imax( 0, i2 - we ), nup = imax( 0, ws - i1 ), nz = wantz ? ( ihiz - iloz + 1 ) : 0;
@@ -157,8 +168,9 @@ __device__ inline void ms_strips_regs( bool wantt, bool wantz, int n, int l, int
   // (slice w/2 spans the 16-line slices of warps w and w+1; odd warps never use theirs here), then lane = column.
   if ( ( warp & 1 ) == 0 ) {
     double* wt = tile + 32 * ( warp >> 1 );
-    const int rstride = ( ( nwarps + 1 ) >> 1 ) * csize;
-    for ( int bt = ( warp >> 1 ) + crank * ( ( nwarps + 1 ) >> 1 ); bt < bright; bt += rstride ) {
+    const int rstride = csize > 0 ? ( ( nwarps + 1 ) >> 1 ) * csize : ( 1 << 20 );
+    const int rlimit = csize > 0 ? bright : imin( bright, 2 );
+    for ( int bt = ( csize > 0 ? rfirst + ( warp >> 1 ) + crank * ( ( nwarps + 1 ) >> 1 ) : ( warp >> 1 ) ); bt < rlimit; bt += rstride ) {
       const int j0 = we + 1 + 32 * bt;
       const int nl = imin( 32, i2 - j0 + 1 );
       if ( lane < nl ) {  // L2 prefetch of the next batch of this warp
@@ -208,7 +220,7 @@ __device__ inline void ms_strips_regs( bool wantt, bool wantz, int n, int l, int
   // ---- rows of the strip above the window and of Z: lane = row, every access is a contiguous 256-byte segment;
   // batches are handed out through a shared counter (odd warps start here at once, even warps join after their
   // share of the right strip)
-  const int nrow_batches = bup + bz;
+  const int nrow_batches = csize > 0 ? bup + bz : 0;
   auto row_batch = [&]( int bt, double*& M, int& ldm, int& r0, int& nl ) {
     if ( bt < bup ) {
       M = H;
