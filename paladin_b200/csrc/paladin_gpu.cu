@@ -323,7 +323,7 @@ struct CoopArgs {
   int S, G, nmax;
 };
 
-__global__ void __launch_bounds__( pb::kHessThreads, 1 ) big_prep_kernel( MidArgs a, CoopArgs ca ) {
+__global__ void __launch_bounds__( pb::kCoopThreads, 1 ) big_prep_kernel( MidArgs a, CoopArgs ca ) {
   extern __shared__ double smem[];
   __shared__ double red[64];
   __shared__ long long lstats[kNumTicks];
@@ -1278,7 +1278,7 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
             const size_t sc = sizeof( double ) * pb::coop_hess_smem_doubles( nfirst, S );
             PB_CUDA( cudaFuncSetAttribute( big_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc ) );
             void* kargs[] = { &mc, &ca };
-            PB_CUDA( cudaLaunchCooperativeKernel( (const void*)big_prep_kernel, dim3( S * G ), dim3( pb::kHessThreads ), kargs, sc, st ) );
+            PB_CUDA( cudaLaunchCooperativeKernel( (const void*)big_prep_kernel, dim3( S * G ), dim3( pb::kCoopThreads ), kargs, sc, st ) );
             ++launches;
             q0 = q1;
           }

@@ -52,15 +52,42 @@ __device__ __forceinline__ void coop_sync( const CoopGroup& cg ) {
   __syncthreads();
 }
 
-constexpr int kCoopMaxK = 18;  // rows per thread: n <= 256 * kCoopMaxK = 4608
+// 512 threads per CTA (one CTA per SM): twice the loads in flight of the 256-thread kernels -- the column sweep of a small
+// group is bound by how much memory traffic one SM keeps in flight
+constexpr int kCoopThreads = 512;
+constexpr int kCoopWarps = kCoopThreads / 32;
+constexpr int kCoopMaxK = 9;  // rows per thread: n <= 512 * kCoopMaxK = 4608
+
+__device__ __forceinline__ double coop_cta_sum( double x, double* red ) {
+  x = warp_sum( x );
+  const int w = threadIdx.x >> 5;
+  __syncthreads();
+  if ( ( threadIdx.x & 31 ) == 0 ) red[w] = x;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for ( int i = 0; i < kCoopWarps; ++i ) t += red[i];
+  return t;
+}
+__device__ __forceinline__ double coop_cta_max( double x, double* red ) {
+  x = warp_max( x );
+  const int w = threadIdx.x >> 5;
+  __syncthreads();
+  if ( ( threadIdx.x & 31 ) == 0 ) red[w] = x;
+  __syncthreads();
+  double t = red[0];
+#pragma unroll
+  for ( int i = 1; i < kCoopWarps; ++i ) t = fmax( t, red[i] );
+  return t;
+}
 
 // shared memory (doubles): vprev, ypp, vcur, zpp, ycur (also column j), zcur : 6 n ; red: 64 ; zw: warps x (n / S + 2)
-__host__ __device__ inline size_t coop_hess_smem_doubles( int n, int S ) { return (size_t)6 * n + 64 + (size_t)kHessWarps * ( n / S + 2 ); }
+__host__ __device__ inline size_t coop_hess_smem_doubles( int n, int S ) { return (size_t)6 * n + 64 + (size_t)kCoopWarps * ( n / S + 2 ); }
 
 // One sweep over this CTA's columns c0, c0 + S, ... (ncols of them): applies the rank-2 update of the previous step,
-// accumulates (A v)(r) for the thread's rows r = tid + 256 k in registers and (A^T v)(c) per column. Columns are taken CB
+// accumulates (A v)(r) for the thread's rows r = tid + 512 k in registers and (A^T v)(c) per column. Columns are taken CB
 // at a time with all their loads issued before the first store, so that CB * K loads per thread are in flight (a
-// column-at-a-time loop exposes one L2 round trip per column). K rows per thread: n <= 256 K.
+// column-at-a-time loop exposes one L2 round trip per column). K rows per thread: n <= 512 K.
 template <int K, int CB>
 __device__ __forceinline__ void coop_sweep( int nrow, int S, int c0, int ncols, int ihi, bool have_prev, double* A, int lda,
                                             const double* vprev, const double* ypp, const double* vcur, const double* zpp, double* zw,
@@ -75,7 +102,7 @@ __device__ __forceinline__ void coop_sweep( int nrow, int S, int c0, int ncols, 
     for ( int b = 0; b < CB; ++b ) {
       const double* col = A + (size_t)( c0 + imin( ci0 + b, ncols - 1 ) * S ) * lda;
 #pragma unroll
-      for ( int k = 0; k < K; ++k ) a[b][k] = __ldcg( col + imin( tid + kHessThreads * k, nrow - 1 ) );
+      for ( int k = 0; k < K; ++k ) a[b][k] = __ldcg( col + imin( tid + kCoopThreads * k, nrow - 1 ) );
     }
 #pragma unroll
     for ( int b = 0; b < CB; ++b ) {
@@ -87,7 +114,7 @@ __device__ __forceinline__ void coop_sweep( int nrow, int S, int c0, int ncols, 
         double zsum = 0.0;
 #pragma unroll
         for ( int k = 0; k < K; ++k ) {
-          const int r = tid + kHessThreads * k;
+          const int r = tid + kCoopThreads * k;
           if ( r < nrow ) {
             const double x = a[b][k] - ( vprev[r] * zc + ypp[r] * vpc );
             yacc[k] += x * vcc;
@@ -102,7 +129,7 @@ __device__ __forceinline__ void coop_sweep( int nrow, int S, int c0, int ncols, 
   }
 #pragma unroll
   for ( int k = 0; k < K; ++k ) {
-    const int r = tid + kHessThreads * k;
+    const int r = tid + kCoopThreads * k;
     if ( r < nrow ) __stcg( ymine + r, yacc[k] );
   }
 }
@@ -124,15 +151,15 @@ __device__ inline void coop_hess( const CoopGroup& cg, int n, int ilo, int ihi, 
   double* yfull = yz;
   double* zfull = yz + n;
   const int nrow = ihi + 1;
-  const int kcnt = ( nrow + kHessThreads - 1 ) / kHessThreads;
-  for ( int r = tid; r < n; r += kHessThreads ) {
+  const int kcnt = ( nrow + kCoopThreads - 1 ) / kCoopThreads;
+  for ( int r = tid; r < n; r += kCoopThreads ) {
     vprev[r] = 0.0;
     ypp[r] = 0.0;
     zpp[r] = 0.0;
     vcur[r] = 0.0;
   }
   if ( rank == 0 )
-    for ( int j = tid; j < n; j += kHessThreads )
+    for ( int j = tid; j < n; j += kCoopThreads )
       if ( j < ilo || j >= ihi ) tau[j] = 0.0;
   __syncthreads();
   bool have_prev = false;
@@ -142,7 +169,7 @@ __device__ inline void coop_hess( const CoopGroup& cg, int n, int ilo, int ihi, 
     {
       const double zj = zpp[j];
       const double* src = A + (size_t)j * lda;
-      for ( int r = tid; r < nrow; r += kHessThreads ) colj[r] = __ldcg( src + r ) - ( vprev[r] * zj + ypp[r] );
+      for ( int r = tid; r < nrow; r += kCoopThreads ) colj[r] = __ldcg( src + r ) - ( vprev[r] * zj + ypp[r] );
     }
     __syncthreads();
     // (b) reflector from column j, rows j+1..ihi
@@ -150,17 +177,17 @@ __device__ inline void coop_hess( const CoopGroup& cg, int n, int ilo, int ihi, 
     {
       const double alpha = colj[j + 1];
       double mx = 0.0;
-      for ( int r = j + 2 + tid; r <= ihi; r += kHessThreads ) mx = fmax( mx, fabs( colj[r] ) );
-      mx = cta_max( mx, red );
+      for ( int r = j + 2 + tid; r <= ihi; r += kCoopThreads ) mx = fmax( mx, fabs( colj[r] ) );
+      mx = coop_cta_max( mx, red );
       beta = alpha;
       double sc = 0.0;
       if ( mx != 0.0 ) {
         double ss = 0.0;
-        for ( int r = j + 2 + tid; r <= ihi; r += kHessThreads ) {
+        for ( int r = j + 2 + tid; r <= ihi; r += kCoopThreads ) {
           const double x = colj[r] / mx;
           ss += x * x;
         }
-        double xnorm = mx * sqrt( cta_sum( ss, red ) );
+        double xnorm = mx * sqrt( coop_cta_sum( ss, red ) );
         double al = alpha;
         beta = -dsign( dlapy2( al, xnorm ), al );
         const double safmin = kSafmin / kEps;
@@ -184,7 +211,7 @@ __device__ inline void coop_hess( const CoopGroup& cg, int n, int ilo, int ihi, 
       __syncthreads();
       const bool owner = ( j % S ) == rank;
       double* dst = A + (size_t)j * lda;
-      for ( int r = tid; r < n; r += kHessThreads ) {
+      for ( int r = tid; r < n; r += kCoopThreads ) {
         double v = 0.0;
         if ( r == j + 1 ) v = 1.0;
         else if ( r >= j + 2 && r <= ihi ) v = colj[r] * sc;
@@ -201,15 +228,15 @@ __device__ inline void coop_hess( const CoopGroup& cg, int n, int ilo, int ihi, 
       c0 += ( rank - m + S ) % S;
     }
     const int ncols = ( c0 < n ) ? ( n - 1 - c0 ) / S + 1 : 0;
-    if ( kcnt <= 6 ) coop_sweep<6, 8>( nrow, S, c0, ncols, ihi, have_prev, A, lda, vprev, ypp, vcur, zpp, zw, maxc, ypart + (size_t)rank * n );
-    else if ( kcnt <= 12 ) coop_sweep<12, 4>( nrow, S, c0, ncols, ihi, have_prev, A, lda, vprev, ypp, vcur, zpp, zw, maxc, ypart + (size_t)rank * n );
-    else coop_sweep<18, 2>( nrow, S, c0, ncols, ihi, have_prev, A, lda, vprev, ypp, vcur, zpp, zw, maxc, ypart + (size_t)rank * n );
+    if ( kcnt <= 3 ) coop_sweep<3, 8>( nrow, S, c0, ncols, ihi, have_prev, A, lda, vprev, ypp, vcur, zpp, zw, maxc, ypart + (size_t)rank * n );
+    else if ( kcnt <= 6 ) coop_sweep<6, 4>( nrow, S, c0, ncols, ihi, have_prev, A, lda, vprev, ypp, vcur, zpp, zw, maxc, ypart + (size_t)rank * n );
+    else coop_sweep<9, 4>( nrow, S, c0, ncols, ihi, have_prev, A, lda, vprev, ypp, vcur, zpp, zw, maxc, ypart + (size_t)rank * n );
     __syncthreads();
     // (d) partial results to global memory, reduce-scatter over the group
-    for ( int ci = tid; ci < ncols; ci += kHessThreads ) {
+    for ( int ci = tid; ci < ncols; ci += kCoopThreads ) {
       double z = 0.0;
 #pragma unroll
-      for ( int w = 0; w < kHessWarps; ++w ) z += zw[w * maxc + ci];
+      for ( int w = 0; w < kCoopWarps; ++w ) z += zw[w * maxc + ci];
       __stcg( zfull + c0 + ci * S, z );
     }
     coop_sync( cg );
@@ -218,7 +245,7 @@ __device__ inline void coop_hess( const CoopGroup& cg, int n, int ilo, int ihi, 
       const int r0 = rank * rows_per, r1 = imin( nrow, r0 + rows_per );
       if ( S > 32 ) {
         // few rows, many partial vectors: a warp per row, lanes over the partials
-        for ( int r = r0 + warp; r < r1; r += kHessWarps ) {
+        for ( int r = r0 + warp; r < r1; r += kCoopWarps ) {
           double s = 0.0;
           for ( int p = lane; p < S; p += 32 ) s += __ldcg( ypart + (size_t)p * n + r );
           s = warp_sum( s );
@@ -226,7 +253,7 @@ __device__ inline void coop_hess( const CoopGroup& cg, int n, int ilo, int ihi, 
         }
       } else {
         // many rows, few partial vectors: a thread per row (coalesced), the S loads of a row in flight together
-        for ( int r = r0 + tid; r < r1; r += kHessThreads ) {
+        for ( int r = r0 + tid; r < r1; r += kCoopThreads ) {
           double s = 0.0;
           for ( int p = 0; p < S; ++p ) s += __ldcg( ypart + (size_t)p * n + r );
           __stcg( yfull + r, s );
@@ -235,16 +262,16 @@ __device__ inline void coop_hess( const CoopGroup& cg, int n, int ilo, int ihi, 
     }
     coop_sync( cg );
     double av = 0.0;
-    for ( int r = tid; r < n; r += kHessThreads ) {
+    for ( int r = tid; r < n; r += kCoopThreads ) {
       const double y = ( r < nrow ) ? __ldcg( yfull + r ) : 0.0;
       ycur[r] = y;
       zcur[r] = ( r > j ) ? __ldcg( zfull + r ) : 0.0;
       av += vcur[r] * y;
     }
-    const double alpha2 = cta_sum( av, red );
+    const double alpha2 = coop_cta_sum( av, red );
     const double half = 0.5 * tj * tj * alpha2;
     __syncthreads();
-    for ( int r = tid; r < n; r += kHessThreads ) {
+    for ( int r = tid; r < n; r += kCoopThreads ) {
       const double v = vcur[r];
       vprev[r] = v;
       ypp[r] = ( r < nrow ) ? tj * ycur[r] - half * v : 0.0;
@@ -268,7 +295,7 @@ __device__ inline void coop_form_q( const CoopGroup& cg, int n, int ilo, int ihi
   double* vs = sm;                          // kCoopQGroup x n
   double* red = sm + kCoopQGroup * n;       // 64 doubles of reduction scratch
   __shared__ double Ts[kCoopQGroup * kCoopQGroup];
-  for ( int c = rank + warp * S; c < n; c += kHessWarps * S )
+  for ( int c = rank + warp * S; c < n; c += kCoopWarps * S )
     for ( int r = lane; r < n; r += 32 ) __stcg( Q + r + (size_t)c * ldq, ( r == c ) ? 1.0 : 0.0 );
   __syncthreads();
   for ( int jhi = ihi - 2; jhi >= ilo; jhi -= kCoopQGroup ) {
@@ -277,7 +304,7 @@ __device__ inline void coop_form_q( const CoopGroup& cg, int n, int ilo, int ihi
     // stage the group's vectors (ascending reflector index), rows jlo+1..ihi
     for ( int g = 0; g < kCoopQGroup; ++g ) {
       const int j = jlo + g;
-      for ( int r = jlo + 1 + tid; r <= ihi; r += kHessThreads )
+      for ( int r = jlo + 1 + tid; r <= ihi; r += kCoopThreads )
         vs[g * n + r] = ( g >= ng || r <= j ) ? 0.0 : ( r == j + 1 ? 1.0 : __ldcg( A + r + (size_t)j * lda ) );
     }
     __syncthreads();
@@ -293,8 +320,8 @@ __device__ inline void coop_form_q( const CoopGroup& cg, int n, int ilo, int ihi
       for ( int a = 0; a < b; ++a ) {
         double p = 0.0;
         if ( b < ng )
-          for ( int r = jlo + 1 + tid; r <= ihi; r += kHessThreads ) p += vs[a * n + r] * vs[b * n + r];
-        gram[a][b] = cta_sum( p, red );
+          for ( int r = jlo + 1 + tid; r <= ihi; r += kCoopThreads ) p += vs[a * n + r] * vs[b * n + r];
+        gram[a][b] = coop_cta_sum( p, red );
       }
     if ( tid == 0 ) {
       double T[kCoopQGroup][kCoopQGroup];
@@ -317,8 +344,8 @@ __device__ inline void coop_form_q( const CoopGroup& cg, int n, int ilo, int ihi
     // this CTA's columns in jlo+1..ihi: c = rank (mod S); its oi-th column overall goes to warp oi % warps
     int oi = ( jlo + 1 - rank + S - 1 ) / S;
     if ( oi < 0 ) oi = 0;
-    oi += ( warp - ( oi % kHessWarps ) + kHessWarps ) % kHessWarps;
-    for ( int c = rank + oi * S; c <= ihi; c += kHessWarps * S ) {
+    oi += ( warp - ( oi % kCoopWarps ) + kCoopWarps ) % kCoopWarps;
+    for ( int c = rank + oi * S; c <= ihi; c += kCoopWarps * S ) {
       double* col = Q + (size_t)c * ldq + ( jlo + 1 );
       const double* v = vs + ( jlo + 1 );
       double u[kCoopQGroup];
