@@ -212,30 +212,29 @@ PB_D void gebal( const G& g, int n, double* A, int lda, int* ilo_out, int* ihi_o
     }
     for ( int i = k; i <= l; ++i ) {
       double cs = 0.0, rs = 0.0, ca = 0.0, ra = 0.0;
+      double c, r;
       if ( pre ) {
-        // thread 0 contributes the totals, everybody else the neutral element of the reductions below
-        if ( t == 0 ) {
-          cs = work[i];
-          rs = work[n + i];
-          ca = work[2 * n + i];
-          ra = work[3 * n + i];
-        }
+        // the totals of this sweep's pre-pass: every thread reads them, no reduction (and no barrier) per index
+        c = sqrt( work[i] ) * up;
+        r = sqrt( work[n + i] ) * up;
+        ca = work[2 * n + i];
+        ra = work[3 * n + i];
       } else {
-      for ( int r = k + t; r <= l; r += nt ) {
-        const double x = PB_A( r, i ) * down;
-        cs += x * x;
+        for ( int rr = k + t; rr <= l; rr += nt ) {
+          const double x = PB_A( rr, i ) * down;
+          cs += x * x;
+        }
+        for ( int cc = k + t; cc <= l; cc += nt ) {
+          const double x = PB_A( i, cc ) * down;
+          rs += x * x;
+        }
+        for ( int rr = t; rr <= l; rr += nt ) ca = dmax( ca, fabs( PB_A( rr, i ) ) );
+        for ( int cc = k + t; cc < n; cc += nt ) ra = dmax( ra, fabs( PB_A( i, cc ) ) );
+        c = sqrt( g.sum( cs ) ) * up;
+        r = sqrt( g.sum( rs ) ) * up;
+        ca = g.max( ca );
+        ra = g.max( ra );
       }
-      for ( int c = k + t; c <= l; c += nt ) {
-        const double x = PB_A( i, c ) * down;
-        rs += x * x;
-      }
-      for ( int r = t; r <= l; r += nt ) ca = dmax( ca, fabs( PB_A( r, i ) ) );
-      for ( int c = k + t; c < n; c += nt ) ra = dmax( ra, fabs( PB_A( i, c ) ) );
-      }
-      double c = sqrt( g.sum( cs ) ) * up;
-      double r = sqrt( g.sum( rs ) ) * up;
-      ca = g.max( ca );
-      ra = g.max( ra );
       if ( c == 0.0 || r == 0.0 ) continue;
       double gg = r / sclfac;
       double f = 1.0;
