@@ -358,6 +358,14 @@ def ours(args):
                    "peak": peaks["hbm_gbs"], "unit": "GB/s", "bytes_per_unit": 24 * nn}
         if scatter["achieved"]:
             scatter["frac"] = scatter["achieved"] / scatter["peak"]
+        # Hessenberg + explicit Q stage: one read + one write of the trailing matrix per column (8 n^3 bytes) plus the
+        # backward accumulation of Q (1.07 + 0.36 GB per 512^2 matrix, confirmed by ncu: 422 GB per 296)
+        hess_ms = stage_acc.get("hessenberg", 0.0) / args.steps
+        hess_bytes = (8.0 + (8.0 / 3.0 if job == "V" else 0.0)) * n ** 3
+        hessenberg = {"bound": "hbm", "achieved": B * hess_bytes / (hess_ms * 1e-3) / 1e9 if hess_ms > 0 else None,
+                      "peak": peaks["hbm_gbs"], "unit": "GB/s", "bytes_per_unit": hess_bytes}
+        if hessenberg["achieved"]:
+            hessenberg["frac"] = hessenberg["achieved"] / hessenberg["peak"]
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
@@ -378,7 +386,7 @@ def ours(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms},
             "gpu_launches": launches,
-            "roofline": roofline, "scatter_roofline": scatter, "cpu_baseline": cpu,
+            "roofline": roofline, "scatter_roofline": scatter, "hessenberg_roofline": hessenberg, "cpu_baseline": cpu,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage_acc.items() if v > 0},
             "phase_cycle_share": phase_share,
             "wall_ms_per_step": wall_ms / args.steps,
