@@ -398,6 +398,11 @@ def ours(args):
                       "peak": peaks["hbm_gbs"], "unit": "GB/s", "bytes_per_unit": hess_bytes}
         if hessenberg["achieved"]:
             hessenberg["frac"] = hessenberg["achieved"] / hessenberg["peak"]
+        hessenberg["traffic"] = None
+        if os.path.exists(tpath) and n == 512 and job == "V":
+            pj_ = json.load(open(tpath)).get("prep_r01z")
+            if pj_:  # ncu dram__bytes of mid_prep_kernel<16>, scaled to this launch's matrix count (L2 absorbs the rest)
+                hessenberg["traffic"] = (pj_["dram_bytes_read"] + pj_["dram_bytes_write"]) / pj_["matrices_per_launch"] * B
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
