@@ -6,7 +6,7 @@
 // A "pod" is an MPI rank in the reference and a GPU here: the balancer runs with numRanks = number of GPUs, every
 // pod is driven by one host thread, pods never exchange data (the reference's compute() has no communication
 // either). Extra keys: --gpus=N (default: all usable devices), --batch=B (matrices per library call),
-// --dump-partition=FILE (write the sorted listing with pod colours and exit; needs no GPU).
+// --inflight=K (batches of one GPU in flight at once, default 2), --dump-partition=FILE (write the sorted listing with pod colours and exit; needs no GPU).
 //
 // Built twice: as the executable paladin-gpu and (with -DPALADIN_HOST_LIBRARY) as libpaladin_host.so, whose
 // extern "C" hooks let tests/ drive the parser, balancer and writers without a GPU.
@@ -19,7 +19,9 @@
 #include <functional>
 #include <future>
 #include <iostream>
+#include <deque>
 #include <memory>
+#include <mutex>
 #include <sstream>
 #include <string>
 #include <thread>
@@ -36,6 +38,7 @@ namespace paladin {
 struct Options {
   std::string listing = "no matrices given!", rootdir = ".", dump_partition;
   int repeats = 1, gpus = -1, batch = 256;
+  int inflight = 2;  // --inflight=K: batches of one GPU whose library calls / writers may overlap (1 = strictly one after the other)
   bool showdist = false, right = false, left = false;
   bool dynamic = false;  // --dynamic: GPUs pull batches of the sorted list from a shared queue (default: the reference's static pods)
   LoadPredictor measure = LoadPredictor::NUMNONZEROS;
@@ -67,13 +70,14 @@ inline Options parse_options( int argc, char* argv[], bool quiet ) {
   o.threshold = std::stod( clp.getValue( "write-threshold", "1e-3" ) );
   o.gpus = std::stoi( clp.getValue( "gpus", "-1" ) );
   o.batch = std::max( 1, std::stoi( clp.getValue( "batch", "256" ) ) );
+  o.inflight = std::max( 1, std::stoi( clp.getValue( "inflight", "2" ) ) );
   o.dump_partition = clp.getValue( "dump-partition", "" );
   o.dynamic = clp.checkExists( "dynamic" );
   if ( !quiet ) {
     bool bad = false;
     for ( const auto& k : clp.get_keys() ) {
       static const char* known[] = { "listing", "repeats", "showdist", "measure", "rootdir", "left", "right",
-                                     "write-threshold", "gpus", "batch", "dump-partition", "dynamic" };
+                                     "write-threshold", "gpus", "batch", "dump-partition", "dynamic", "inflight" };
       if ( std::none_of( std::begin( known ), std::end( known ), [&]( const char* s ) { return k == s; } ) ) {
         std::cout << "\n-- POTENTIAL ERROR: key " << k << " is not a recognized option!";
         bad = true;
@@ -81,7 +85,7 @@ inline Options parse_options( int argc, char* argv[], bool quiet ) {
     }
     if ( bad )
       std::cout << "\n-- Allowable keys: listing, repeats, showdist, measure, rootdir, left, right, write-threshold, "
-                   "gpus, batch, dump-partition, dynamic\n\n";
+                   "gpus, batch, dump-partition, dynamic, inflight\n\n";
   }
   return o;
 }
@@ -193,100 +197,131 @@ inline ParsedBatch parse_batch( const std::vector<std::string>& pod, std::size_t
   return b;
 }
 
-// One pod = one GPU: parse (next batch, in the background) -> batched library call -> unpack + write (previous batch,
-// in the background). "read" = time spent parsing, "eig." = time inside the library, as in the reference's table;
-// because the stages overlap their sum can exceed "total".
+// One pod = one GPU: parse (next batch, in the background) -> batched library call -> unpack + write. Up to
+// --inflight batches are between their library call and the end of their writer at any time, each on a host thread of
+// its own: every batch owns a CUDA stream (include/paladin_gpu.h "Thread model"), so the copies and the HBM-bound
+// Hessenberg kernels of one batch run under the latency-bound QR kernels of another, and the text
+// writers of finished batches run beside both. The files do not depend on the schedule (one file set per matrix,
+// every matrix solved on its own). "read" = time spent parsing, "eig." = time inside the library, as in the
+// reference's table; because the stages overlap their sum can exceed "total".
 inline int run_pod( int device, const std::vector<std::string>& pod, const Options& o, PodTimes& times, int parse_threads ) {
   using clock = std::chrono::steady_clock;
   const auto t_start = clock::now();
   const char jobvr = o.right ? 'V' : 'N';
   const char jobvl = o.left ? 'V' : 'N';
   int failures = 0;
+  bool gpu_failed = false;
+  std::mutex mu;  // times.eig, std::cerr
   std::vector<std::size_t> firsts;
   for ( std::size_t first = 0; first < pod.size(); first += o.batch ) firsts.push_back( first );
-  for ( int rep = 0; rep < o.repeats; ++rep ) {
+
+  // library call + writers of one batch; returns the number of matrices with info != 0, -1 when the library failed
+  auto solve_and_write = [&]( std::shared_ptr<ParsedBatch> curp, bool write ) -> int {
+    const ParsedBatch& cur = *curp;
+    const std::size_t count = cur.count, first = cur.first;
+    // results of the whole batch, concatenated (the staged C-ABI): eigenvalue offsets woff, vector offsets voff
+    std::vector<std::size_t> woff( count + 1, 0 ), voff( count + 1, 0 );
+    for ( std::size_t k = 0; k < count; ++k ) {
+      const std::size_t nk = static_cast<std::size_t>( cur.n[k] );
+      woff[k + 1] = woff[k] + nk;
+      voff[k + 1] = voff[k] + nk * nk;
+    }
+    const std::size_t tn = woff[count], tnn = voff[count];
+    std::vector<double> wr( tn, 0.0 ), wi( tn, 0.0 ), vr( o.right ? tnn : 0, 0.0 ), vl( o.left ? tnn : 0, 0.0 );
+    // write filter of the eigenvector files, evaluated on the device (paladin_gpu_batch_vector_filter)
+    std::vector<double> max2r( o.right ? tn : 0, 0.0 ), max2l( o.left ? tn : 0, 0.0 );
+    std::vector<long long> keptr( o.right ? count : 0, 0 ), keptl( o.left ? count : 0, 0 );
+    std::vector<int> info( count, 0 );
+    const auto t_eig = clock::now();
+    paladin_gpu_batch* gb = nullptr;
+    int rc = paladin_gpu_batch_create( device, static_cast<int>( count ), cur.n.data(), cur.off.data(), jobvl, jobvr, &gb );
+    if ( rc == PALADIN_GPU_OK ) rc = paladin_gpu_batch_upload( gb, cur.ci.data() + cur.off[0], cur.cj.data() + cur.off[0], cur.cv.data() + cur.off[0] );
+    if ( rc == PALADIN_GPU_OK ) rc = paladin_gpu_batch_scatter( gb );
+    if ( rc == PALADIN_GPU_OK ) rc = paladin_gpu_batch_solve( gb );
+    if ( rc == PALADIN_GPU_OK && o.right && count > 0 ) rc = paladin_gpu_batch_vector_filter( gb, 'R', o.threshold, max2r.data(), keptr.data() );
+    if ( rc == PALADIN_GPU_OK && o.left && count > 0 ) rc = paladin_gpu_batch_vector_filter( gb, 'L', o.threshold, max2l.data(), keptl.data() );
+    if ( rc == PALADIN_GPU_OK )
+      rc = paladin_gpu_batch_download( gb, wr.data(), wi.data(), o.left ? vl.data() : nullptr, o.right ? vr.data() : nullptr, info.data() );
+    const std::string why = rc == PALADIN_GPU_OK ? std::string() : std::string( paladin_gpu_last_error() );  // per-thread message
+    paladin_gpu_batch_destroy( gb );
+    {
+      std::lock_guard<std::mutex> lock( mu );
+      times.eig += std::chrono::duration<double>( clock::now() - t_eig ).count();
+      if ( rc != PALADIN_GPU_OK ) std::cerr << "the GPU eigensolver failed on device " << device << ": " << why << '\n';
+    }
+    if ( rc != PALADIN_GPU_OK ) return -1;
+    if ( !write ) return 0;  // like the reference, only the first repeat produces output
+    // unpack + text formatting: one matrix per worker at a time (the reference formats on all of its ranks at once; with
+    // vectors this stage costs far more host time per matrix than the GPU spends on the decomposition)
+    std::atomic<int> bad{ 0 };
+    std::atomic<std::size_t> cursor{ 0 };
+    auto write_some = [&]() {
+    for ( std::size_t k = cursor.fetch_add( 1 ); k < count; k = cursor.fetch_add( 1 ) ) {
+      const int nk = cur.n[k];
+      const bool ok = info[k] == 0;
+      if ( !ok ) {
+        ++bad;
+        std::lock_guard<std::mutex> lock( mu );
+        std::cerr << "warning: " << pod[first + k] << ": info = " << info[k] << '\n';
+      }
+      SpectralDecomposition s( nk, o.threshold );
+      s.unpack( nk, wr.data() + woff[k], wi.data() + woff[k], o.right && ok ? vr.data() + voff[k] : nullptr,
+                o.left && ok ? vl.data() + voff[k] : nullptr );
+      std::string text;
+      s.write_eigenvalues( text );
+      write_file( pod[first + k] + ".spectrum", text );
+      if ( o.left ) {
+        text.clear();
+        if ( ok ) s.write_left_eigenvectors( text, max2l.data() + woff[k], keptl[k] );
+        else s.write_left_eigenvectors( text );
+        write_file( pod[first + k] + ".leftvecs", text );
+      }
+      if ( o.right ) {
+        text.clear();
+        if ( ok ) s.write_right_eigenvectors( text, max2r.data() + woff[k], keptr[k] );
+        else s.write_right_eigenvectors( text );
+        write_file( pod[first + k] + ".rightvecs", text );
+      }
+    }
+    };
+    std::vector<std::thread> writers;
+    const std::size_t nw = std::min<std::size_t>( static_cast<std::size_t>( std::max( 1, parse_threads ) ), count );
+    for ( std::size_t w = 1; w < nw; ++w ) writers.emplace_back( write_some );
+    write_some();
+    for ( auto& w : writers ) w.join();
+    return bad.load();
+  };
+
+  std::deque<std::future<int>> flying;
+  auto land = [&]( std::size_t keep ) {
+    while ( flying.size() > keep ) {
+      const int r = flying.front().get();
+      flying.pop_front();
+      if ( r < 0 ) gpu_failed = true;
+      else failures += r;
+    }
+  };
+  for ( int rep = 0; rep < o.repeats && !gpu_failed; ++rep ) {
     std::future<ParsedBatch> next;
-    std::future<int> writer;
     if ( !firsts.empty() )
       next = std::async( std::launch::async, parse_batch, std::cref( pod ), firsts[0], std::min<std::size_t>( o.batch, pod.size() ), parse_threads );
     for ( std::size_t bi = 0; bi < firsts.size(); ++bi ) {
-      ParsedBatch cur = next.get();
-      times.read += cur.seconds;
+      auto cur = std::make_shared<ParsedBatch>( next.get() );
+      times.read += cur->seconds;
       if ( bi + 1 < firsts.size() )
         next = std::async( std::launch::async, parse_batch, std::cref( pod ), firsts[bi + 1],
                            std::min<std::size_t>( o.batch, pod.size() - firsts[bi + 1] ), parse_threads );
-      const std::size_t count = cur.count, first = cur.first;
-      // results of the whole batch, concatenated (the staged C-ABI): eigenvalue offsets woff, vector offsets voff
-      auto woff = std::make_shared<std::vector<std::size_t>>( count + 1, 0 );
-      auto voff = std::make_shared<std::vector<std::size_t>>( count + 1, 0 );
-      for ( std::size_t k = 0; k < count; ++k ) {
-        const std::size_t nk = static_cast<std::size_t>( cur.n[k] );
-        ( *woff )[k + 1] = ( *woff )[k] + nk;
-        ( *voff )[k + 1] = ( *voff )[k] + nk * nk;
+      land( static_cast<std::size_t>( o.inflight ) - 1 );
+      if ( gpu_failed ) {
+        if ( next.valid() ) next.wait();
+        break;
       }
-      const std::size_t tn = ( *woff )[count], tnn = ( *voff )[count];
-      auto wr = std::make_shared<std::vector<double>>( tn, 0.0 );
-      auto wi = std::make_shared<std::vector<double>>( tn, 0.0 );
-      auto vr = std::make_shared<std::vector<double>>( o.right ? tnn : 0, 0.0 );
-      auto vl = std::make_shared<std::vector<double>>( o.left ? tnn : 0, 0.0 );
-      // write filter of the eigenvector files, evaluated on the device (paladin_gpu_batch_vector_filter)
-      auto max2r = std::make_shared<std::vector<double>>( o.right ? tn : 0, 0.0 );
-      auto max2l = std::make_shared<std::vector<double>>( o.left ? tn : 0, 0.0 );
-      auto keptr = std::make_shared<std::vector<long long>>( o.right ? count : 0, 0 );
-      auto keptl = std::make_shared<std::vector<long long>>( o.left ? count : 0, 0 );
-      auto info = std::make_shared<std::vector<int>>( count, 0 );
-      const auto t_eig = clock::now();
-      paladin_gpu_batch* gb = nullptr;
-      int rc = paladin_gpu_batch_create( device, static_cast<int>( count ), cur.n.data(), cur.off.data(), jobvl, jobvr, &gb );
-      if ( rc == PALADIN_GPU_OK ) rc = paladin_gpu_batch_upload( gb, cur.ci.data() + cur.off[0], cur.cj.data() + cur.off[0], cur.cv.data() + cur.off[0] );
-      if ( rc == PALADIN_GPU_OK ) rc = paladin_gpu_batch_scatter( gb );
-      if ( rc == PALADIN_GPU_OK ) rc = paladin_gpu_batch_solve( gb );
-      if ( rc == PALADIN_GPU_OK && o.right && count > 0 ) rc = paladin_gpu_batch_vector_filter( gb, 'R', o.threshold, max2r->data(), keptr->data() );
-      if ( rc == PALADIN_GPU_OK && o.left && count > 0 ) rc = paladin_gpu_batch_vector_filter( gb, 'L', o.threshold, max2l->data(), keptl->data() );
-      if ( rc == PALADIN_GPU_OK )
-        rc = paladin_gpu_batch_download( gb, wr->data(), wi->data(), o.left ? vl->data() : nullptr, o.right ? vr->data() : nullptr, info->data() );
-      paladin_gpu_batch_destroy( gb );
-      times.eig += std::chrono::duration<double>( clock::now() - t_eig ).count();
-      if ( rc != PALADIN_GPU_OK ) {
-        std::cerr << "the GPU eigensolver failed on device " << device << ": " << paladin_gpu_last_error() << '\n';
-        return -1;
-      }
-      if ( rep != 0 ) continue;  // like the reference, only the first repeat produces output
-      if ( writer.valid() ) failures += writer.get();
-      auto ns = std::make_shared<std::vector<int>>( cur.n );
-      writer = std::async( std::launch::async, [&pod, &o, first, count, ns, woff, voff, wr, wi, vr, vl, max2r, max2l, keptr, keptl, info]() {
-        int bad = 0;
-        for ( std::size_t k = 0; k < count; ++k ) {
-          const int nk = ( *ns )[k];
-          const bool ok = ( *info )[k] == 0;
-          if ( !ok ) {
-            ++bad;
-            std::cerr << "warning: " << pod[first + k] << ": info = " << ( *info )[k] << '\n';
-          }
-          SpectralDecomposition s( nk, o.threshold );
-          s.unpack( nk, wr->data() + ( *woff )[k], wi->data() + ( *woff )[k], o.right && ok ? vr->data() + ( *voff )[k] : nullptr,
-                    o.left && ok ? vl->data() + ( *voff )[k] : nullptr );
-          std::string text;
-          s.write_eigenvalues( text );
-          write_file( pod[first + k] + ".spectrum", text );
-          if ( o.left ) {
-            text.clear();
-            if ( ok ) s.write_left_eigenvectors( text, max2l->data() + ( *woff )[k], ( *keptl )[k] );
-            else s.write_left_eigenvectors( text );
-            write_file( pod[first + k] + ".leftvecs", text );
-          }
-          if ( o.right ) {
-            text.clear();
-            if ( ok ) s.write_right_eigenvectors( text, max2r->data() + ( *woff )[k], ( *keptr )[k] );
-            else s.write_right_eigenvectors( text );
-            write_file( pod[first + k] + ".rightvecs", text );
-          }
-        }
-        return bad;
-      } );
+      flying.push_back( std::async( std::launch::async, solve_and_write, cur, rep == 0 ) );
     }
-    if ( writer.valid() ) failures += writer.get();
+    land( 0 );  // a repeat is timed as a whole
   }
+  land( 0 );
+  if ( gpu_failed ) return -1;
   times.total = std::chrono::duration<double>( clock::now() - t_start ).count() / o.repeats;
   times.read /= o.repeats;
   times.eig /= o.repeats;

@@ -509,7 +509,7 @@ def test_staged_api_and_stage_timers(pg):
 # ---------------------------------------------------------------------------------------------------
 # (d) the drop-in executable: reference CLI, listing and output files, GPUs as pods
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("extra", [[], ["--dynamic", "--batch=2"]])
+@pytest.mark.parametrize("extra", [[], ["--dynamic", "--batch=2"], ["--inflight=1", "--batch=1"], ["--inflight=3", "--batch=1"]])
 def test_paladin_gpu_executable_reproduces_ctest_goldens(pg, tmp_path, extra):
     import shutil
     import subprocess
@@ -523,6 +523,7 @@ def test_paladin_gpu_executable_reproduces_ctest_goldens(pg, tmp_path, extra):
             lst = sorted(glob.glob(os.path.join(dst, "listing*")))[-1]
         # exactly the reference's ctest invocation (test/compare_spectra.cmake:8-13): --left --right
         # extra = --dynamic: batches of the sorted list pulled from a shared queue instead of the static pods; same files
+        # extra = --inflight=K: K batches of a GPU between their library call and the end of their writers; same files
         r = subprocess.run([host.exe_path(), "--listing=" + lst, "--rootdir=" + str(dst), "--left", "--right", "--gpus=1", "--showdist"] + extra,
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
