@@ -11,6 +11,8 @@
 #ifndef PALADIN_GPU_HOST_SPECTRUM_IO_HPP_
 #define PALADIN_GPU_HOST_SPECTRUM_IO_HPP_
 
+#include <charconv>
+#include <cmath>
 #include <complex>
 #include <cstdio>
 #include <string>
@@ -73,12 +75,23 @@ class SpectralDecomposition {
   }
 
   // "%g" is what operator<<(double) prints at the default precision of 6 (the reference never changes it)
+  // std::to_chars( general, 6 ) is specified to give printf's "%.6g" characters and is about twice as fast as snprintf
+  // (compared on 2e7 random, denormal, short-decimal and tie values); non-finite values keep the printf spelling.
   static void append_number( std::string& out, double x ) {
     char buf[40];
+    if ( std::isfinite( x ) ) {
+      const std::to_chars_result r = std::to_chars( buf, buf + sizeof( buf ), x, std::chars_format::general, 6 );
+      out.append( buf, static_cast<std::size_t>( r.ptr - buf ) );
+      return;
+    }
     const int len = std::snprintf( buf, sizeof( buf ), "%g", x );
     out.append( buf, static_cast<std::size_t>( len ) );
   }
-  static void append_number( std::string& out, long x ) { out += std::to_string( x ); }
+  static void append_number( std::string& out, long x ) {
+    char buf[24];
+    const std::to_chars_result r = std::to_chars( buf, buf + sizeof( buf ), x );
+    out.append( buf, static_cast<std::size_t>( r.ptr - buf ) );
+  }
 
   void write_eigenvalues( std::string& out ) const {
     for ( const auto& ev : eigenvalues_ ) {
