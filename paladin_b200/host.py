@@ -48,6 +48,25 @@ def parse_mm(path):
     return n.value, nnz, ii, jj, vv
 
 
+def parse_batch(paths, threads=4):
+    """The executable's batch parser (paladin_host.cpp::parse_batch): files -> concatenated COO triplets."""
+    L = lib()
+    L.ph_parse_batch.restype = ctypes.c_longlong
+    L.ph_parse_batch.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong,
+                                 ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    blob = "\n".join(paths).encode()
+    total = L.ph_parse_batch(blob, len(paths), threads, None, None, 0, None, None, None)
+    if total < 0:
+        raise ValueError("cannot parse the batch")
+    n = np.zeros(len(paths), dtype=np.int32)
+    off = np.zeros(len(paths) + 1, dtype=np.int64)
+    ii = np.zeros(total, dtype=np.int32)
+    jj = np.zeros(total, dtype=np.int32)
+    vv = np.zeros(total, dtype=np.float64)
+    L.ph_parse_batch(blob, len(paths), threads, n.ctypes.data, off.ctypes.data, total, ii.ctypes.data, jj.ctypes.data, vv.ctypes.data)
+    return n, off, ii, jj, vv
+
+
 def measure(n, nnz, kind="nnz"):
     return lib().ph_measure(int(n), int(nnz), kind.encode())
 

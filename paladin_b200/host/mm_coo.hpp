@@ -118,11 +118,20 @@ inline double field_to_double( const char* p, const char* end ) {
 }  // namespace detail
 
 inline std::string slurp( const std::string& path ) {
-  std::ifstream in( path, std::ios::binary );
+  std::ifstream in( path, std::ios::binary | std::ios::ate );
   if ( !in ) throw std::runtime_error( "Couldn't open the matrix file, " + path );
-  std::ostringstream ss;
-  ss << in.rdbuf();
-  return ss.str();
+  const std::streamoff size = in.tellg();
+  if ( size < 0 ) {  // not seekable: stream it
+    in.clear();
+    std::ostringstream ss;
+    ss << in.rdbuf();
+    return ss.str();
+  }
+  std::string text( static_cast<std::size_t>( size ), '\0' );
+  in.seekg( 0 );
+  in.read( text.data(), size );
+  text.resize( static_cast<std::size_t>( in.gcount() ) );
+  return text;
 }
 
 // dimension and entry count from the size line only (what the load measures need)

@@ -157,20 +157,26 @@ inline ParsedBatch parse_batch( const std::vector<std::string>& pod, std::size_t
   const auto t0 = std::chrono::steady_clock::now();
   std::vector<CooMatrix> mats( count );
   std::vector<std::string> errors( count );
-  auto work = [&]( std::size_t lo, std::size_t hi ) {
-    for ( std::size_t k = lo; k < hi; ++k ) {
-      try {
-        mats[k] = read_coo_from_mm_file( pod[first + k] );
-      } catch ( const std::exception& e ) {
-        errors[k] = e.what();
-      }
-    }
-  };
+  // files are handed out one at a time (their sizes differ), and the concatenation of the triplets -- hundreds of MB
+  // per batch -- is spread over the same workers instead of being a serial tail
   const std::size_t nthreads = std::max<std::size_t>( 1, std::min<std::size_t>( threads, count ) );
-  std::vector<std::thread> pool;
-  for ( std::size_t w = 1; w < nthreads; ++w ) pool.emplace_back( work, count * w / nthreads, count * ( w + 1 ) / nthreads );
-  work( 0, count / nthreads );
-  for ( auto& th : pool ) th.join();
+  auto run_on_pool = [&]( const std::function<void( std::size_t )>& item ) {
+    std::atomic<std::size_t> cursor{ 0 };
+    auto loop = [&]() {
+      for ( std::size_t k = cursor.fetch_add( 1 ); k < count; k = cursor.fetch_add( 1 ) ) item( k );
+    };
+    std::vector<std::thread> pool;
+    for ( std::size_t w = 1; w < nthreads; ++w ) pool.emplace_back( loop );
+    loop();
+    for ( auto& th : pool ) th.join();
+  };
+  run_on_pool( [&]( std::size_t k ) {
+    try {
+      mats[k] = read_coo_from_mm_file( pod[first + k] );
+    } catch ( const std::exception& e ) {
+      errors[k] = e.what();
+    }
+  } );
   for ( const auto& e : errors )
     if ( !e.empty() ) {
       std::cerr << e << ", exiting!" << '\n';
@@ -188,11 +194,14 @@ inline ParsedBatch parse_batch( const std::vector<std::string>& pod, std::size_t
   b.ci.resize( b.off[count] );
   b.cj.resize( b.off[count] );
   b.cv.resize( b.off[count] );
-  for ( std::size_t k = 0; k < count; ++k ) {
+  run_on_pool( [&]( std::size_t k ) {
     std::copy( mats[k].row.begin(), mats[k].row.end(), b.ci.begin() + b.off[k] );
     std::copy( mats[k].col.begin(), mats[k].col.end(), b.cj.begin() + b.off[k] );
     std::copy( mats[k].val.begin(), mats[k].val.end(), b.cv.begin() + b.off[k] );
-  }
+    CooMatrix().row.swap( mats[k].row );
+    CooMatrix().col.swap( mats[k].col );
+    CooMatrix().val.swap( mats[k].val );
+  } );
   b.seconds = std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
   return b;
 }
@@ -451,6 +460,29 @@ int ph_parse_mm( const char* path, int* n, int cap, int* row, int* col, double* 
       std::copy( m.val.begin(), m.val.end(), val );
     }
     return m.nnz_;
+  } catch ( const std::exception& ) {
+    return -1;
+  }
+}
+
+// parse_batch over `count` newline-separated paths on `threads` workers; returns the total entry count (>= 0) or -1.
+// Call with null arrays first to size them; n[count], off[count + 1].
+long long ph_parse_batch( const char* paths, int count, int threads, int* n, long long* off, long long cap, int* row, int* col, double* val ) {
+  try {
+    std::vector<std::string> pod;
+    std::istringstream in( paths );
+    for ( std::string line; std::getline( in, line ); ) pod.push_back( line );
+    if ( static_cast<int>( pod.size() ) != count ) return -1;
+    const paladin::ParsedBatch b = paladin::parse_batch( pod, 0, pod.size(), threads );
+    const long long total = static_cast<long long>( b.off[pod.size()] );
+    if ( row && cap >= total ) {
+      std::copy( b.n.begin(), b.n.end(), n );
+      for ( std::size_t k = 0; k <= pod.size(); ++k ) off[k] = static_cast<long long>( b.off[k] );
+      std::copy( b.ci.begin(), b.ci.end(), row );
+      std::copy( b.cj.begin(), b.cj.end(), col );
+      std::copy( b.cv.begin(), b.cv.end(), val );
+    }
+    return total;
   } catch ( const std::exception& ) {
     return -1;
   }

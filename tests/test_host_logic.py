@@ -73,6 +73,20 @@ CTEST = sorted(glob.glob(os.path.join(GOLD, "ref_ctest", "*", "*.matrix")))
 RUNS = sorted(glob.glob(os.path.join(GOLD, "ref_run", "*.matrix")))
 
 
+@pytest.mark.parametrize("threads", [1, 3, 16])
+def test_batch_parser_concatenates_in_listing_order(ph, threads):
+    # the executable's threaded batch parser against the single-file reader, file by file and bit for bit
+    paths = (CTEST + RUNS) * 2
+    n, off, ii, jj, vv = ph.parse_batch(paths, threads)
+    assert off[0] == 0 and off[-1] == len(vv)
+    for k, p in enumerate(paths):
+        n1, nnz1, i1, j1, v1 = ph.parse_mm(p)
+        assert n[k] == n1 and off[k + 1] - off[k] == nnz1
+        sl = slice(off[k], off[k + 1])
+        assert np.array_equal(ii[sl], i1) and np.array_equal(jj[sl], j1)
+        assert v1.tobytes() == vv[sl].tobytes()
+
+
 @pytest.mark.parametrize("path", CTEST + RUNS, ids=lambda p: os.path.relpath(p, GOLD))
 def test_writers_byte_exact(ph, path):
     # eigen data from the oracle's dgeev, formatted by the product's writers, against the reference's own files
