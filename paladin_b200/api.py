@@ -28,7 +28,9 @@ class PaladinGpuError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "lib", "libpaladin_gpu.so")
+    # PALADIN_GPU_LIB: another build of the SAME library (tuning variants compiled with different -D switches, see
+    # tools/build_variants.sh); never a different implementation
+    return os.environ.get("PALADIN_GPU_LIB") or os.path.join(_HERE, "lib", "libpaladin_gpu.so")
 
 
 def lib():

@@ -50,6 +50,7 @@ struct DeviceCtx {
   int sm_count = 0;
   int max_smem_optin = 0;
   cudaEvent_t t0 = nullptr, t1 = nullptr;
+  bool attrs_set = false;  // per-function launch attributes raised to the device maximum (set_kernel_attributes)
 };
 
 DeviceCtx g_ctx[kMaxDevices];
@@ -207,6 +208,7 @@ struct MidArgs {
                    // (both sides wanted) lives xhalf doubles further
   int refl_global;  // clusters: reflectors through global memory (L2) instead of the leader's shared memory
   int aed, aed_moves, nibble;  // tuning overrides of mid_cfg() (PALADIN_GPU_AED, _AED_MOVES, _AED_NIBBLE); -1 = default
+  int itmax;                   // PALADIN_GPU_QR_ITMAX: cap on the QR sweeps of a matrix (0 = LAPACK's 30 * max(10, nh))
 };
 
 __device__ __forceinline__ void mid_pointers( const BatchView& bv, int id, int n, double*& A, double*& V, double*& wr, double*& wi,
@@ -405,6 +407,7 @@ __global__ void __launch_bounds__( kMidThreads, 2 ) mid_qr_kernel( MidArgs a ) {
   if ( a.aed >= 0 ) c.aed = a.aed;
   if ( a.aed_moves >= 0 ) c.aed_moves = a.aed_moves;
   if ( a.nibble >= 0 ) c.nibble = a.nibble;
+  c.itmax = a.itmax;
   const int ldw = c.W | 1, ldt = c.tl | 1;
   pb::MsqrWork wk;
   double* p = smem;
@@ -646,6 +649,38 @@ __global__ void __launch_bounds__( 256 ) vector_filter_kernel( BatchView bv, con
   }
 }
 
+// Per-function, per-device launch attributes are set ONCE (under the context mutex) to the largest dynamic shared-memory
+// size the device offers and never lowered: batches of one device are solved from several host threads
+// (paladin-gpu --inflight), and a set-then-launch pair with a batch-dependent size could be undercut by another thread
+// between the two calls.
+template <class K>
+cudaError_t raise_smem_limit( K kernel, int optin ) {
+  cudaFuncAttributes fa;
+  cudaError_t e = cudaFuncGetAttributes( &fa, kernel );
+  if ( e != cudaSuccess ) return e;
+  return cudaFuncSetAttribute( kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, optin - (int)fa.sharedSizeBytes );
+}
+
+int set_kernel_attributes( DeviceCtx& c ) {
+  if ( c.attrs_set ) return PALADIN_GPU_OK;
+  const int o = c.max_smem_optin;
+  PB_CUDA( raise_smem_limit( geev_warp_kernel, o ) );
+  PB_CUDA( raise_smem_limit( mid_prep_kernel<0>, o ) );
+  PB_CUDA( raise_smem_limit( mid_prep_kernel<16>, o ) );
+  PB_CUDA( raise_smem_limit( mid_prep_kernel<32>, o ) );
+  PB_CUDA( raise_smem_limit( big_prep_kernel, o ) );
+  PB_CUDA( raise_smem_limit( mid_qr_kernel<false>, o ) );
+  PB_CUDA( raise_smem_limit( mid_qr_kernel<true>, o ) );
+  PB_CUDA( cudaFuncSetAttribute( mid_qr_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1 ) );
+  PB_CUDA( raise_smem_limit( mid_vec_kernel, o ) );
+  PB_CUDA( raise_smem_limit( big_vec_kernel<0>, o ) );
+  PB_CUDA( raise_smem_limit( big_vec_kernel<1>, o ) );
+  PB_CUDA( raise_smem_limit( big_vec_kernel<2>, o ) );
+  PB_CUDA( raise_smem_limit( big_vec_kernel<3>, o ) );
+  c.attrs_set = true;
+  return PALADIN_GPU_OK;
+}
+
 struct StageTimer {
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   bool used = false;
@@ -668,7 +703,7 @@ struct paladin_gpu_batch {
   int *d_coo_i = nullptr, *d_coo_j = nullptr;
   double* d_coo_v = nullptr;
   double *d_A = nullptr, *d_V = nullptr, *d_VL = nullptr, *d_wr = nullptr, *d_wi = nullptr, *d_dwork = nullptr;
-  int *d_info = nullptr, *d_iwork = nullptr, *d_flags = nullptr, *d_ids = nullptr;
+  int *d_info = nullptr, *d_iwork = nullptr, *d_flags = nullptr, *d_ids = nullptr, *d_ids_f = nullptr;
   pb::ScatterChunk* d_chunks = nullptr;
   int nchunks = 0;
   // host-side plan
@@ -682,6 +717,8 @@ struct paladin_gpu_batch {
   size_t xslot = 0;
   int xslots = 0, xn_max = 0;
   int64_t xhalf = 0;
+  double* d_max2 = nullptr;                  // scratch of paladin_gpu_batch_vector_filter (allocated with the batch: no
+  unsigned long long* d_kept = nullptr;      // cudaMalloc / cudaFree -- device-wide synchronisations -- per call)
   int4* d_vec_items = nullptr;               // work items of the three-launch eigenvector stage
   int n_vec_items = 0;
   // cooperative stage 1 of large matrices
@@ -707,7 +744,7 @@ void free_batch( paladin_gpu_batch* b ) {
   cudaFree( b->d_A ); cudaFree( b->d_V ); cudaFree( b->d_VL ); cudaFree( b->d_wr ); cudaFree( b->d_wi ); cudaFree( b->d_dwork );
   cudaFree( b->d_stats ); cudaFree( b->d_meta ); cudaFree( b->d_counter ); cudaFree( b->d_xwork );
   cudaFree( b->d_coop_bars ); cudaFree( b->d_coop_ypart ); cudaFree( b->d_coop_yz ); cudaFree( b->d_vec_items );
-  cudaFree( b->d_info ); cudaFree( b->d_iwork ); cudaFree( b->d_flags ); cudaFree( b->d_ids ); cudaFree( b->d_chunks );
+  cudaFree( b->d_info ); cudaFree( b->d_iwork ); cudaFree( b->d_flags ); cudaFree( b->d_ids ); cudaFree( b->d_ids_f ); cudaFree( b->d_max2 ); cudaFree( b->d_kept ); cudaFree( b->d_chunks );
   for ( auto& s : b->st ) {
     if ( s.e0 ) cudaEventDestroy( s.e0 );
     if ( s.e1 ) cudaEventDestroy( s.e1 );
@@ -863,6 +900,7 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
   DeviceCtx& c = g_ctx[device];
   std::lock_guard<std::mutex> lk( c.mu );
   PB_CUDA( cudaSetDevice( device ) );
+  PB_TRY( set_kernel_attributes( c ) );
 
   paladin_gpu_batch* b = new paladin_gpu_batch;
   b->device = device;
@@ -951,7 +989,12 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
   A( dev_alloc( &b->d_info, count ) );
   A( dev_alloc( &b->d_flags, count ) );
   A( dev_alloc( &b->d_ids, b->ids.size() ) );
+  A( dev_alloc( &b->d_ids_f, b->ids.size() ) );
   A( dev_alloc( &b->d_chunks, chunks.size() ) );
+  if ( jobvr == 'V' || jobvl == 'V' ) {
+    A( dev_alloc( &b->d_max2, b->total_n ) );
+    A( dev_alloc( &b->d_kept, count ) );
+  }
   A( dev_alloc( &b->d_stats, kNumTicks ) );
   A( dev_alloc( &b->d_meta, count ) );
   A( dev_alloc( &b->d_counter, 1 ) );
@@ -1051,6 +1094,10 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
   H2D( b->d_chunks, chunks.data(), sizeof( pb::ScatterChunk ) * chunks.size() );
   if ( rc == PALADIN_GPU_OK ) {
     cudaError_t e = cudaMemsetAsync( b->d_info, 0, sizeof( int ) * std::max( count, 1 ), st );
+    // eigenvalues of matrices that are never solved (bad COO index, non-finite entry) read as NaN, not as whatever the
+    // allocation held before
+    if ( e == cudaSuccess ) e = cudaMemsetAsync( b->d_wr, 0xff, sizeof( double ) * std::max<int64_t>( b->total_n, 1 ), st );
+    if ( e == cudaSuccess ) e = cudaMemsetAsync( b->d_wi, 0xff, sizeof( double ) * std::max<int64_t>( b->total_n, 1 ), st );
     if ( e == cudaSuccess ) e = cudaStreamSynchronize( st );
     if ( e != cudaSuccess ) rc = fail( PALADIN_GPU_ECUDA, cudaGetErrorString( e ) );
   }
@@ -1168,24 +1215,25 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
   const bool wantvl = b->jobvl == 'V';
   bool any_bad = false;
   for ( int k = 0; k < b->count; ++k ) any_bad = any_bad || ( b->flags[k] & pb::kFlagBadIndex );
-  std::vector<int> ids_filtered;
+  std::vector<int> gid;  // ids of the group that are solved (size-sorted like the group itself)
   for ( const auto& g : b->groups ) {
     const int* ids = b->d_ids + g.first;
-    int cnt = g.count;
+    gid.assign( b->ids.begin() + g.first, b->ids.begin() + g.first + g.count );
     if ( any_bad ) {
-      // rare: drop matrices whose scatter failed; re-upload the filtered list of this group
-      ids_filtered.clear();
+      // rare: drop matrices whose scatter failed. The filtered list goes to a scratch copy of the id array (d_ids itself
+      // is never modified), and every class boundary below is derived from it.
+      gid.clear();
       for ( int q = 0; q < g.count; ++q )
-        if ( !( b->flags[b->ids[g.first + q]] & pb::kFlagBadIndex ) ) ids_filtered.push_back( b->ids[g.first + q] );
-      cnt = (int)ids_filtered.size();
-      if ( cnt ) PB_CUDA( cudaMemcpyAsync( b->d_ids + g.first, ids_filtered.data(), sizeof( int ) * cnt, cudaMemcpyHostToDevice, st ) );
+        if ( !( b->flags[b->ids[g.first + q]] & pb::kFlagBadIndex ) ) gid.push_back( b->ids[g.first + q] );
+      ids = b->d_ids_f + g.first;
+      if ( !gid.empty() ) PB_CUDA( cudaMemcpyAsync( b->d_ids_f + g.first, gid.data(), sizeof( int ) * gid.size(), cudaMemcpyHostToDevice, st ) );
       PB_CUDA( cudaStreamSynchronize( st ) );
     }
+    const int cnt = (int)gid.size();
     if ( cnt == 0 ) continue;
     if ( g.kind == 0 ) {
       const size_t smem = warp_smem_bytes( g.nmax, ( wantvr ? 1 : 0 ) + ( wantvl ? 1 : 0 ) );
       if ( smem <= (size_t)c.max_smem_optin ) {
-        PB_CUDA( cudaFuncSetAttribute( geev_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem ) );
         stage_begin( b, PALADIN_GPU_STAGE_SMALL, st );
         geev_warp_kernel<<<cnt, 32, smem, st>>>( bv, ids, g.nmax, g.nmax | 1 );
         stage_end( b, PALADIN_GPU_STAGE_SMALL, st, 1 );
@@ -1212,23 +1260,20 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
       ma.aed_moves = env_moves;
       static const int env_nibble = std::getenv( "PALADIN_GPU_AED_NIBBLE" ) ? std::atoi( std::getenv( "PALADIN_GPU_AED_NIBBLE" ) ) : -1;
       ma.nibble = env_nibble;
+      static const int env_itmax = std::getenv( "PALADIN_GPU_QR_ITMAX" ) ? std::max( 0, std::atoi( std::getenv( "PALADIN_GPU_QR_ITMAX" ) ) ) : 0;
+      ma.itmax = env_itmax;
       static const int env_rg = std::getenv( "PALADIN_GPU_REFL_GLOBAL" ) ? std::atoi( std::getenv( "PALADIN_GPU_REFL_GLOBAL" ) ) : 1;  // 3072^2 x 2, clusters of 16: QR stage 1373 -> 1275 ms
       ma.refl_global = env_rg;
       PB_CUDA( cudaMemsetAsync( b->d_stats, 0, sizeof( long long ) * kNumTicks, st ) );
       PB_CUDA( cudaMemsetAsync( b->d_counter, 0, sizeof( int ), st ) );
       const size_t s2 = qr_smem_bytes(), s3 = vec_smem_bytes( g.nmax );
-      PB_CUDA( cudaFuncSetAttribute( mid_prep_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem_bytes( 512 ) ) );
-      PB_CUDA( cudaFuncSetAttribute( mid_prep_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem_bytes( 1024 ) ) );
-      PB_CUDA( cudaFuncSetAttribute( mid_qr_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2 ) );
-      PB_CUDA( cudaFuncSetAttribute( mid_qr_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2 ) );
-      PB_CUDA( cudaFuncSetAttribute( mid_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3 ) );
       stage_begin( b, PALADIN_GPU_STAGE_HESSENBERG, st );
       {
         // the group's ids are sorted by decreasing n: [0, nbig) need the unblocked path, [nbig, nmid) the 32-chunk
         // kernel, the rest the 16-chunk kernel
         int nbig = 0, nmid = 0;
-        for ( int q = 0; q < g.count; ++q ) {
-          const int nq = b->n[b->ids[g.first + q]];
+        for ( int q = 0; q < cnt; ++q ) {
+          const int nq = b->n[gid[q]];
           if ( nq > ( b->coop_S > 0 ? coop_min_n() : kMidMaxFusedN ) ) nbig = q + 1;
           if ( nq > 512 ) nmid = q + 1;
         }
@@ -1237,18 +1282,18 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
         int launches = 0;
         int nhuge = 0;  // [0, nhuge): beyond the streaming kernels (n > kMidMaxBigN)
         for ( int q = 0; q < nbig; ++q )
-          if ( b->n[b->ids[g.first + q]] > kMidMaxBigN ) nhuge = q + 1;
+          if ( b->n[gid[q]] > kMidMaxBigN ) nhuge = q + 1;
         if ( b->coop_S > 0 && nbig > nhuge ) {
           // large matrices: groups of cooperating CTAs, one matrix per group at a time. The size-sorted list is cut into
           // classes: all SMs on one matrix above n = 2048, two groups down to 1400, four groups below.
           static const int env_groups = std::getenv( "PALADIN_GPU_COOP_GROUPS" ) ? std::max( 1, std::atoi( std::getenv( "PALADIN_GPU_COOP_GROUPS" ) ) ) : 0;
           int q0 = nhuge;
           while ( q0 < nbig ) {
-            const int nfirst = b->n[b->ids[g.first + q0]];
+            const int nfirst = b->n[gid[q0]];
             const int kind = nfirst > 2048 ? 0 : ( nfirst > 1400 ? 1 : 2 );
             int q1 = q0;
             while ( q1 < nbig ) {
-              const int nq = b->n[b->ids[g.first + q1]];
+              const int nq = b->n[gid[q1]];
               if ( ( nq > 2048 ? 0 : ( nq > 1400 ? 1 : 2 ) ) != kind ) break;
               ++q1;
             }
@@ -1276,7 +1321,6 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
             mc.count = q1 - q0;
             CoopArgs ca{ b->d_coop_bars, b->d_coop_ypart, b->d_coop_yz, S, G, b->coop_nmax };
             const size_t sc = sizeof( double ) * pb::coop_hess_smem_doubles( nfirst, S );
-            PB_CUDA( cudaFuncSetAttribute( big_prep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc ) );
             void* kargs[] = { &mc, &ca };
             PB_CUDA( cudaLaunchCooperativeKernel( (const void*)big_prep_kernel, dim3( S * G ), dim3( pb::kCoopThreads ), kargs, sc, st ) );
             ++launches;
@@ -1287,7 +1331,6 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
         if ( n0 > 0 ) {
           MidArgs m0 = ma;
           const size_t sbig = sizeof( double ) * pb::hess_big_smem_doubles( std::min( g.nmax, kMidMaxBigN ) );
-          PB_CUDA( cudaFuncSetAttribute( mid_prep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sbig ) );
           mid_prep_kernel<0><<<n0, pb::kHessThreads, sbig, st>>>( m0 );
           ++launches;
         }
@@ -1311,7 +1354,7 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
         // leader's strip updates are shared by the cluster
         int nqbig = 0;
         for ( int q = 0; q < cnt; ++q )
-          if ( b->n[b->ids[g.first + q]] > kMidMaxFusedN ) nqbig = q + 1;
+          if ( b->n[gid[q]] > kMidMaxFusedN ) nqbig = q + 1;
         // cluster size per size class of the sorted list (n > 2048: 16, > 1400: 8, else 4 CTAs), halved together until the
         // clusters fit the 2 x SM-count resident CTAs (one and a half times: the tail of a class may queue); every class
         // is its own launch on its own stream, the remaining matrices (one CTA each) run next to them
@@ -1319,7 +1362,7 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
         struct QrClass { int first, count, csize; };
         QrClass cls[3] = { { 0, 0, 16 }, { 0, 0, 8 }, { 0, 0, 4 } };
         for ( int q = 0; q < nqbig; ++q ) {
-          const int nq = b->n[b->ids[g.first + q]];
+          const int nq = b->n[gid[q]];
           QrClass& k = cls[nq > 2048 ? 0 : ( nq > 1400 ? 1 : 2 )];
           if ( k.count == 0 ) k.first = q;
           k.count += 1;
@@ -1349,7 +1392,6 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
             sq = b->side[nside - 1];
             PB_CUDA( cudaStreamWaitEvent( sq, b->ev_fork, 0 ) );
           }
-          if ( k.csize > 8 ) PB_CUDA( cudaFuncSetAttribute( mid_qr_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1 ) );
           MidArgs mq = ma;
           mq.ids = ids + k.first;
           mq.count = k.count;
@@ -1395,12 +1437,8 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
         // large matrices first ([0, nvbig) of the size-sorted list): each one shared by P CTAs, `xslots` of them at a time
         int nvbig = 0;
         for ( int q = 0; q < cnt; ++q )
-          if ( b->n[b->ids[g.first + q]] > bigvec_min_n() ) nvbig = q + 1;
+          if ( b->n[gid[q]] > bigvec_min_n() ) nvbig = q + 1;
         if ( nvbig > 0 ) {
-          PB_CUDA( cudaFuncSetAttribute( big_vec_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3 ) );
-          PB_CUDA( cudaFuncSetAttribute( big_vec_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3 ) );
-          PB_CUDA( cudaFuncSetAttribute( big_vec_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3 ) );
-          PB_CUDA( cudaFuncSetAttribute( big_vec_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3 ) );
           if ( b->d_vec_items != nullptr && nvbig == cnt && !any_bad ) {
             // every matrix of the group, parts proportional to n^3 (work items built at batch_create)
             MidArgs mv = ma;
@@ -1452,7 +1490,6 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
     PB_CUDA( cudaGetLastError() );
   }
   PB_CUDA( cudaStreamSynchronize( st ) );
-  if ( any_bad ) PB_CUDA( cudaMemcpy( b->d_ids, b->ids.data(), sizeof( int ) * b->ids.size(), cudaMemcpyHostToDevice ) );
   b->scattered = false;  // the dense matrices have been destroyed
   return PALADIN_GPU_OK;
 }
@@ -1503,13 +1540,8 @@ int paladin_gpu_batch_vector_filter( paladin_gpu_batch* b, char side, double thr
   PB_CUDA( cudaSetDevice( b->device ) );
   if ( b->count == 0 ) return PALADIN_GPU_OK;
   cudaStream_t st = b->stream;
-  double* d_max2 = nullptr;
-  unsigned long long* d_kept = nullptr;
-  PB_TRY( dev_alloc( &d_max2, (size_t)b->total_n ) );
-  if ( dev_alloc( &d_kept, (size_t)b->count ) != PALADIN_GPU_OK ) {
-    cudaFree( d_max2 );
-    return PALADIN_GPU_ENOMEM;
-  }
+  double* d_max2 = b->d_max2;
+  unsigned long long* d_kept = b->d_kept;
   int nmax = 0;
   for ( int k = 0; k < b->count; ++k ) nmax = std::max( nmax, b->n[k] );
   cudaError_t e = cudaMemsetAsync( d_max2, 0, sizeof( double ) * std::max<int64_t>( b->total_n, 1 ), st );
@@ -1528,8 +1560,6 @@ int paladin_gpu_batch_vector_filter( paladin_gpu_batch* b, char side, double thr
   if ( e == cudaSuccess && b->total_n ) e = cudaMemcpyAsync( max2, d_max2, sizeof( double ) * b->total_n, cudaMemcpyDeviceToHost, st );
   if ( e == cudaSuccess ) e = cudaMemcpyAsync( kept, d_kept, sizeof( long long ) * b->count, cudaMemcpyDeviceToHost, st );
   if ( e == cudaSuccess ) e = cudaStreamSynchronize( st );
-  cudaFree( d_max2 );
-  cudaFree( d_kept );
   if ( e != cudaSuccess ) return fail( PALADIN_GPU_ECUDA, cudaGetErrorString( e ) );
   return PALADIN_GPU_OK;
 }

@@ -59,6 +59,7 @@ struct MsqrCfg {
   int nibble = 14;          // a sweep is skipped when AED deflated more than nibble % of its window (LAPACK: 14)
   int spec_shifts = 0;      // 1: the shifts of the next sweep are computed from the block as it is BEFORE the AED step
                             // (on the device: by another warp, while the AED window is being factored)
+  int itmax = 0;            // > 0: cap on the number of sweeps (LAPACK: 30 * max(10, nh)); tests force info > 0 with it
 };
 
 // on-chip work space (shared memory on the device)
@@ -1013,7 +1014,7 @@ PB_D int hqr_multishift( const G& g, bool wantt, bool wantz, int n, int ilo, int
   g.sync();
   const int nh = ihi - ilo + 1;
   const double smlnum = kSafmin * ( (double)nh / kUlp );
-  const int itmax = 30 * imax( 10, nh );
+  const int itmax = cfg.itmax > 0 ? cfg.itmax : 30 * imax( 10, nh );
   int kbot = ihi;
   int it = 0, nodefl = 0;
   while ( kbot >= ilo ) {

@@ -271,8 +271,12 @@ inline int run_pod( int device, const std::vector<std::string>& pod, const Optio
       if ( !ok ) {
         ++bad;
         std::lock_guard<std::mutex> lock( mu );
-        std::cerr << "warning: " << pod[first + k] << ": info = " << info[k] << '\n';
+        std::cerr << "warning: " << pod[first + k] << ": info = " << info[k]
+                  << ( info[k] < 0 ? " (input rejected, no output files written)" : " (QR iteration did not converge, eigenvalues before that index are NaN)" ) << '\n';
       }
+      // info < 0: the library refused the input (COO index outside [1, n], non-finite entry) and computed nothing --
+      // there is no spectrum to write; the run ends with a non-zero exit status
+      if ( info[k] < 0 ) continue;
       SpectralDecomposition s( nk, o.threshold );
       s.unpack( nk, wr.data() + woff[k], wi.data() + woff[k], o.right && ok ? vr.data() + voff[k] : nullptr,
                 o.left && ok ? vl.data() + voff[k] : nullptr );
@@ -414,11 +418,17 @@ inline int host_main( int argc, char* argv[] ) {
         dtimes[r].total = std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count() / o.repeats;
       } );
     for ( auto& w : dworkers ) w.join();
+    int dfailed = 0;
     for ( int r = 0; r < pods; ++r ) {
       std::cout << "pod " << r << ": " << taken[r] << " matrices" << '\n';
       if ( dstatus[r] < 0 ) return 4;
+      dfailed += dstatus[r];
     }
     display_timings( dtimes, o.repeats );
+    if ( dfailed > 0 ) {
+      std::cerr << "paladin-gpu: " << dfailed << " matrices were rejected or did not converge (see the warnings above)\n";
+      return 5;
+    }
     return 0;
   }
   std::vector<std::vector<std::string>> pod( pods );
@@ -435,9 +445,16 @@ inline int host_main( int argc, char* argv[] ) {
   const int parse_threads = std::max( 1, static_cast<int>( std::thread::hardware_concurrency() ) / pods - 1 );
   for ( int r = 0; r < pods; ++r ) workers.emplace_back( [&, r] { status[r] = run_pod( r, pod[r], o, times[r], parse_threads ); } );
   for ( auto& w : workers ) w.join();
-  for ( int r = 0; r < pods; ++r )
+  int failed = 0;
+  for ( int r = 0; r < pods; ++r ) {
     if ( status[r] < 0 ) return 4;
+    failed += status[r];
+  }
   display_timings( times, o.repeats );
+  if ( failed > 0 ) {
+    std::cerr << "paladin-gpu: " << failed << " matrices were rejected or did not converge (see the warnings above)\n";
+    return 5;
+  }
   return 0;
 }
 

@@ -51,20 +51,41 @@ def _scatter_on_gpu(pg, mats):
     return out
 
 
-def _check_eigs(A, wr, wi, VR, info, want_vectors):
+ESCAPES = []   # (label, error, LAPACK sensitivity): every comparison that needed the ill-conditioned rule
+
+
+def _log_escape(label, err, sens, nrm):
+    ESCAPES.append((label, err, sens))
+    msg = "ill-conditioned rule used: %s err=%.3e sens=%.3e ||A||=%.3e" % (label, err, sens, nrm)
+    print(msg)
+    out = os.path.join(ROOT, "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, "parity_escapes.log"), "a") as f:
+            f.write(msg + "\n")
+
+
+def _eig_error_ok(A, wr, wi, wr0, wi0, label, allow_ill_conditioned):
+    """The plain bar of north_star: matched eigenvalue error <= 1e-9 * max(1, ||A||). Only with
+    allow_ill_conditioned=True (defective / structurally singular spectra, named at the call site) a miss may fall back on
+    what LAPACK's OWN answer moves by under a 1e-14 relative perturbation of A; every use is logged."""
+    nrm = max(1.0, np.linalg.norm(A, 2)) if A.shape[0] else 1.0
+    err = po.match_eigenvalues(po.eigenvalues(wr, wi), po.eigenvalues(wr0, wi0))
+    if err <= EIG_TOL * nrm:
+        return
+    assert allow_ill_conditioned, "%s: eigenvalue error %.3e > 1e-9 * %.3e" % (label, err, nrm)
+    E = np.random.default_rng(1).standard_normal(A.shape) * 1e-14 * nrm
+    wrp, wip, _, _, _ = po.dgeev(A + E)
+    sens = po.match_eigenvalues(po.eigenvalues(wrp, wip), po.eigenvalues(wr0, wi0))
+    _log_escape(label, err, sens, nrm)
+    assert err <= 100.0 * sens, "%s: eigenvalue error %.3e, LAPACK sensitivity %.3e (||A||=%.3e)" % (label, err, sens, nrm)
+
+
+def _check_eigs(A, wr, wi, VR, info, want_vectors, allow_ill_conditioned=False, label="?"):
     n = A.shape[0]
     assert info == 0
     wr0, wi0, _, VR0, info0 = po.dgeev(A, right=want_vectors)
     assert info0 == 0
-    nrm = max(1.0, np.linalg.norm(A, 2)) if n else 1.0
-    err = po.match_eigenvalues(po.eigenvalues(wr, wi), po.eigenvalues(wr0, wi0))
-    if err > EIG_TOL * nrm:
-        # defective / structurally singular spectra (sparse matrices with nilpotent parts): the eigenvalues themselves
-        # move by eps^(1/k). Accept what LAPACK's own answer moves by under a 1e-14 relative perturbation of A.
-        E = np.random.default_rng(1).standard_normal(A.shape) * 1e-14 * nrm
-        wrp, wip, _, _, _ = po.dgeev(A + E)
-        sens = po.match_eigenvalues(po.eigenvalues(wrp, wip), po.eigenvalues(wr0, wi0))
-        assert err <= 100.0 * sens, "eigenvalue error %.3e, LAPACK sensitivity %.3e (||A||=%.3e)" % (err, sens, nrm)
+    _eig_error_ok(A, wr, wi, wr0, wi0, label, allow_ill_conditioned)
     # pair convention consumed by the reference unpack loop (src/paladin.hpp:262-263)
     k = 0
     while k < n:
@@ -170,7 +191,8 @@ def test_small_path_matches_oracle(pg, jobvr, kind):
     res, info = pg.geev_batch(*_concat(mats), jobvr=jobvr)
     for m, (wr, wi, VR), inf in zip(mats, res, info):
         A = po.dense_matrix(*m)
-        _check_eigs(A, wr, wi, VR, inf, jobvr == "V")
+        # sparse random matrices have nilpotent parts (eigenvalues move by eps^(1/k)); dense N(0,1) must meet the plain bar
+        _check_eigs(A, wr, wi, VR, inf, jobvr == "V", allow_ill_conditioned=(kind == "sparse"), label="small %s n=%d" % (kind, m[0]))
 
 
 @pytest.mark.parametrize("jobvr", ["N", "V"])
@@ -381,13 +403,11 @@ def test_structured_matrices_through_the_multishift_aed_path(pg, n):
     for (name, A), (wr, wi, VR), inf in zip(cases.items(), res, info):
         assert inf == 0, name
         wr0, wi0, _, VR0, _ = po.dgeev(A, right=True)
-        nrm = max(1.0, np.linalg.norm(A, 2))
-        err = po.match_eigenvalues(po.eigenvalues(wr, wi), po.eigenvalues(wr0, wi0))
-        # ill-conditioned spectra (companion, repeated, rank one, graded, random Hessenberg -- LAPACK's own eigenvalues of
-        # the n = 600 Hessenberg case move by 1e-5 under a 1e-16 relative perturbation of the input): LAPACK itself is only
-        # accurate to eps * condition; the backward error below is the sharp test there
-        tol = EIG_TOL * nrm if name in ("symmetric", "skew", "orthogonal", "identity", "zero", "triangular") else 1e-4 * nrm
-        assert err <= tol, (name, err)
+        # well-conditioned spectra must meet the plain 1e-9 bar; the ill-conditioned ones (companion, repeated, rank one,
+        # graded, random Hessenberg: LAPACK's own eigenvalues move by up to 1e-5 under a 1e-14 perturbation) are held to
+        # 100 x LAPACK's measured sensitivity, and each use of that rule is logged. The backward error is the sharp test.
+        ill = name not in ("symmetric", "skew", "orthogonal", "identity", "zero", "triangular")
+        _eig_error_ok(A, wr, wi, wr0, wi0, "structured %s n=%d" % (name, n), ill)
         assert po.backward_error(A, wr, wi, VR) <= BACKWARD_TOL, name
 
 
@@ -453,6 +473,86 @@ def test_nonfinite_input_flagged(pg):
     assert info == -4
 
 
+def test_bench_matrices_match_oracle(pg):
+    """The 37 distinct matrices bench.py cycles through on rank 0 (bench.py synth_coo: default_rng([3, k]), n = 512, dense,
+    eigenvalues + right eigenvectors), every one compared eigenvalue by eigenvalue with LAPACK at the plain 1e-9 bar."""
+    mats = _random_mats([512] * 37, 3)
+    res, info = pg.geev_batch(*_concat(mats), jobvr="V")
+    for q, (m, (wr, wi, VR), inf) in enumerate(zip(mats, res, info)):
+        _check_eigs(po.dense_matrix(*m), wr, wi, VR, inf, True, label="bench matrix %d" % q)
+
+
+def test_n3072_full_decomposition(pg):
+    """BASELINE.json configs[4] (README-scale 3072 x 3072, --right): default_rng([5, k]), plain 1e-9 bar, backward error <= 100."""
+    mats = _random_mats([3072, 3072], 5)
+    res, info = pg.geev_batch(*_concat(mats), jobvr="V")
+    for q, (m, (wr, wi, VR), inf) in enumerate(zip(mats, res, info)):
+        _check_eigs(po.dense_matrix(*m), wr, wi, VR, inf, True, label="n=3072 matrix %d" % q)
+
+
+def test_mixed_batch_up_to_3072_matches_oracle(pg):
+    """BASELINE.json configs[3]: sizes log-uniform over the whole range 32...3072 (both ends forced), densities 1-100 %,
+    shuffled COO order; every size class of the launcher in one batch."""
+    rng = np.random.default_rng(405)
+    sizes = sorted(set(np.round(np.exp(rng.uniform(np.log(32), np.log(3072), size=14))).astype(int).tolist() + [32, 3072]))
+    mats = []
+    for q, n in enumerate(sizes):
+        dens = float(rng.uniform(0.01, 1.0)) if n < 3072 else 1.0
+        mats.append((n,) + po.random_sparse_coo(n, dens, [4, 100 + q]))
+    res, info = pg.geev_batch(*_concat(mats), jobvr="V")
+    for m, (wr, wi, VR), inf in zip(mats, res, info):
+        _check_eigs(po.dense_matrix(*m), wr, wi, VR, inf, True, allow_ill_conditioned=True, label="mixed-3072 n=%d" % m[0])
+
+
+def test_bad_index_in_mixed_group_keeps_the_others(pg):
+    """A rejected matrix (COO index outside [1, n]) inside a group that spans the CTA-path size classes (n > 64, > 512,
+    cooperative-sized): the remaining matrices are solved from the filtered id list, every class boundary included."""
+    sizes = [1100, 600, 520, 300, 100, 70]
+    mats = _random_mats(sizes, 91)
+    for bad in (0, 2, 5):
+        ms = list(mats)
+        n, ii, jj, vv = ms[bad]
+        ii = ii.copy()
+        ii[3] = n + 7
+        ms[bad] = (n, ii, jj, vv)
+        res, info = pg.geev_batch(*_concat(ms), jobvr="V")
+        assert info[bad] == -101
+        for q, (m, (wr, wi, VR), inf) in enumerate(zip(ms, res, info)):
+            if q == bad:
+                assert np.all(np.isnan(wr)) and np.all(np.isnan(wi))   # never a previous batch's eigenvalues
+                continue
+            _check_eigs(po.dense_matrix(*m), wr, wi, VR, inf, True, label="bad-index group n=%d" % m[0])
+
+
+def test_qr_nonconvergence_reports_info_and_partial_spectrum():
+    """info > 0 (LAPACK dgeev: the QR iteration failed; wr/wi[info..n) hold converged eigenvalues, no vectors). Forced with
+    the sweep cap PALADIN_GPU_QR_ITMAX (read once per process, hence the subprocess)."""
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+import paladin_b200 as pg
+from oracle import paladin_oracle as po
+n = 300
+m = (n,) + po.random_dense_coo(n, [62, 0])
+res, info = pg.geev_batch(np.array([n], dtype=np.int32), np.array([0, n * n], dtype=np.int64), m[1], m[2], m[3], jobvr="V")
+i = int(info[0])
+assert 0 < i <= n, i
+wr, wi, VR = res[0]
+A = po.dense_matrix(*m)
+wr0, wi0, _, _, _ = po.dgeev(A)
+ref = po.eigenvalues(wr0, wi0)
+got = po.eigenvalues(wr[i:], wi[i:])
+assert np.all(np.isfinite(got.real)) and np.all(np.isfinite(got.imag))
+# every converged eigenvalue is an eigenvalue of A (nearest-neighbour distance)
+d = np.abs(got[:, None] - ref[None, :]).min(axis=1) if len(got) else np.zeros(0)
+assert len(got) == 0 or d.max() <= 1e-9 * max(1.0, np.linalg.norm(A, 2)), d.max()
+print("OK", i, len(got))
+""" % ROOT
+    import subprocess
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=dict(os.environ, PALADIN_GPU_QR_ITMAX="6"), timeout=600)
+    assert "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
 # ---------------------------------------------------------------------------------------------------
 # (c) the reference's own golden files through the GPU path
 # ---------------------------------------------------------------------------------------------------
@@ -514,13 +614,12 @@ def test_paladin_gpu_executable_reproduces_ctest_goldens(pg, tmp_path, extra):
     import shutil
     import subprocess
     from paladin_b200 import host
-    for suite, listing in [("canonical-2x2", "listing1"), ("canonical-2x2", "listing2"), ("multiple-matrices", "listing")]:
+    for suite, listing in CTEST_LISTINGS:
         src = os.path.join(GOLD, "ref_ctest", suite)
         dst = tmp_path / (suite + "-" + listing)
         shutil.copytree(src, dst)
         lst = os.path.join(dst, listing)
-        if not os.path.exists(lst):  # fixtures keep one listing per suite
-            lst = sorted(glob.glob(os.path.join(dst, "listing*")))[-1]
+        assert os.path.exists(lst), lst
         # exactly the reference's ctest invocation (test/compare_spectra.cmake:8-13): --left --right
         # extra = --dynamic: batches of the sorted list pulled from a shared queue instead of the static pods; same files
         # extra = --inflight=K: K batches of a GPU between their library call and the end of their writers; same files
@@ -528,12 +627,68 @@ def test_paladin_gpu_executable_reproduces_ctest_goldens(pg, tmp_path, extra):
                            capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         assert "load imbalance" in r.stdout
-        for m in sorted(glob.glob(os.path.join(dst, "*.matrix"))):
-            if not os.path.exists(m + ".spectrum"):
-                continue  # not named by this listing
-            assert open(m + ".spectrum", "rb").read() == open(m + ".spectrum.exact", "rb").read(), m
-            assert open(m + ".rightvecs", "rb").read() == open(m + ".rightvecs.exact", "rb").read(), m
-            assert open(m + ".leftvecs", "rb").read() == open(m + ".leftvecs.exact", "rb").read(), m
+        assert _compare_listing_outputs(str(dst), lst) > 0
+
+
+# the reference's six ctest cases (test/CMakeLists.txt:15-20); the identity listings name the same file 1, 2 and 10 times
+CTEST_LISTINGS = [("identity-matrix", "10x10.listing1"), ("identity-matrix", "10x10.listing2"), ("identity-matrix", "10x10.listing10"),
+                  ("canonical-2x2", "listing1"), ("canonical-2x2", "listing2"), ("multiple-matrices", "listing")]
+
+
+def _compare_listing_outputs(rootdir, listing):
+    """test/compare_spectra.cmake:24-46: for every listing line, the three output files byte-equal to their .exact twins."""
+    checked = 0
+    for line in open(listing).read().split("\n"):
+        if not line:
+            break
+        m = os.path.join(rootdir, line)
+        for ext in (".spectrum", ".leftvecs", ".rightvecs"):
+            assert open(m + ext, "rb").read() == open(m + ext + ".exact", "rb").read(), m + ext
+            checked += 1
+    return checked
+
+
+def test_unmodified_reference_program_linked_against_the_gpu_library(pg, tmp_path):
+    """Link-level drop-in (INTEGRATION.md option A): the reference's own test program, compiled unmodified from
+    /root/reference/test/compute-and-write-eigenvalues.cpp with -Ddgeev_=paladin_gpu_dgeev_ and linked against
+    libpaladin_gpu.so (oracle/Makefile, target test-paladin-gpu), run exactly like the reference's ctest
+    (test/compare_spectra.cmake:8-13) at 1, 2 and 4 ranks of the MPI stand-in: 60 output files per rank count, byte for
+    byte."""
+    import shutil
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "test-paladin-gpu")
+    mpirun = os.path.join(ROOT, "oracle", "_ref", "shim_mpirun")
+    assert os.path.exists(exe) and os.path.exists(mpirun), "oracle/_ref/test-paladin-gpu is built by oracle/Makefile where /root/reference exists"
+    total = 0
+    for np_ in (1, 2, 4):
+        for suite, listing in CTEST_LISTINGS:
+            dst = tmp_path / ("np%d-%s-%s" % (np_, suite, listing))
+            shutil.copytree(os.path.join(GOLD, "ref_ctest", suite), dst)
+            lst = os.path.join(dst, listing)
+            r = subprocess.run([mpirun, "-np", str(np_), exe, "--listing=" + lst, "--rootdir=" + str(dst), "--left", "--right"],
+                               capture_output=True, text=True, timeout=600)
+            assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+            total += _compare_listing_outputs(str(dst), lst)
+    assert total == 3 * 3 * (1 + 2 + 10 + 4 + 8 + 25)   # 450 compares, as the reference ctest suite at 1, 2 and 4 ranks
+
+
+def test_executable_rejects_bad_index_file_with_nonzero_exit(pg, tmp_path):
+    """A malformed input (COO row index n + 1) must not produce a plausible-looking spectrum file and a success exit code."""
+    import subprocess
+    from paladin_b200 import host
+    n = 12
+    ii, jj, vv = po.random_dense_coo(n, [63, 0])
+    (tmp_path / "good.matrix").write_bytes(po.mm_text(n, ii, jj, vv)[:-1])
+    bad = ii.copy()
+    bad[5] = n + 1
+    (tmp_path / "bad.matrix").write_bytes(po.mm_text(n, bad, jj, vv)[:-1])
+    (tmp_path / "listing").write_text("good.matrix\nbad.matrix\ngood.matrix")
+    r = subprocess.run([host.exe_path(), "--listing=" + str(tmp_path / "listing"), "--rootdir=" + str(tmp_path), "--right", "--gpus=1"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 5, (r.returncode, r.stdout[-1000:], r.stderr[-1000:])
+    assert "info = -101" in r.stderr
+    assert os.path.exists(tmp_path / "good.matrix.spectrum") and os.path.exists(tmp_path / "good.matrix.rightvecs")
+    assert not os.path.exists(tmp_path / "bad.matrix.spectrum") and not os.path.exists(tmp_path / "bad.matrix.rightvecs")
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -550,7 +705,7 @@ def test_mixed_size_batch_matches_oracle(pg):
     res, info = pg.geev_batch(*_concat(mats), jobvr="V")
     for m, (wr, wi, VR), inf in zip(mats, res, info):
         A = po.dense_matrix(*m)
-        _check_eigs(A, wr, wi, VR, inf, True)
+        _check_eigs(A, wr, wi, VR, inf, True, allow_ill_conditioned=True, label="mixed sparse n=%d" % m[0])
 
 
 def test_executable_mixed_listing_all_measures(pg, tmp_path):
