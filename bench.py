@@ -714,7 +714,7 @@ def ours(args):
 
     if cx.rank == 0:
         cyc = res["phase_cycles"]
-        top = ("balance", "hessenberg", "form_q", "qr_total", "trevc", "bak_normalise")
+        top = ("balance", "hessenberg", "hess_update", "form_q", "qr_total", "trevc", "bak_normalise")
         tot = float(sum(cyc[k] for k in top)) or 1.0
         phase_share = {k: round(v / tot, 4) for k, v in cyc.items() if v}
         rf = rooflines(cx, res)

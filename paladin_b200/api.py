@@ -12,7 +12,7 @@ _LIB = None
 
 NUM_STAGES = 8
 STAGE_NAMES = ("scatter", "balance", "hessenberg", "qr", "vectors", "small", "generic", "mid")
-PHASE_NAMES = ("balance", "hessenberg", "form_q", "qr_total", "trevc", "bak_normalise", "vec_gemm", "", "ms_scan", "ms_shifts",
+PHASE_NAMES = ("balance", "hessenberg", "form_q", "qr_total", "trevc", "bak_normalise", "vec_gemm", "hess_update", "ms_scan", "ms_shifts",
                "ms_chase", "ms_strips", "ms_small", "ms_small_u", "ms_aed_window", "ms_aed_update")
 
 _c_int_p = ctypes.POINTER(ctypes.c_int)

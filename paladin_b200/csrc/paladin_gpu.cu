@@ -16,6 +16,7 @@
 #include "../../include/paladin_gpu.h"
 #include "pb_geev.cuh"
 #include "pb_hess.cuh"
+#include "pb_bhess.cuh"
 #include "pb_coop.cuh"
 #include "pb_vecs.cuh"
 #include "pb_scatter.cuh"
@@ -209,6 +210,15 @@ struct MidArgs {
   int refl_global;  // clusters: reflectors through global memory (L2) instead of the leader's shared memory
   int aed, aed_moves, nibble;  // tuning overrides of mid_cfg() (PALADIN_GPU_AED, _AED_MOVES, _AED_NIBBLE); -1 = default
   int itmax;                   // PALADIN_GPU_QR_ITMAX: cap on the QR sweeps of a matrix (0 = LAPACK's 30 * max(10, nh))
+  int spec_shifts;             // PALADIN_GPU_SPEC_SHIFTS: 0 = shifts after the AED step, 1 = before it, 2 = side by side with it (second warp)
+  // blocked Hessenberg reduction (pb_bhess.cuh): global scratch per matrix, tensor maps of A (2 id) and of the Schur-vector
+  // array (2 id + 1), and whether a matrix has them (even leading dimension, encoder succeeded)
+  double* hwork;
+  const int64_t* h_off;
+  const CUtensorMap* tmaps;
+  const int* tmap_ok;
+  int hess_tma;                // 0: stage the update tiles with plain loads (PALADIN_GPU_HESS=notma)
+  int formq_unblocked;         // 1: explicit Q by the register-resident unblocked accumulation (pb::form_q) instead of the block reflectors
 };
 
 __device__ __forceinline__ void mid_pointers( const BatchView& bv, int id, int n, double*& A, double*& V, double*& wr, double*& wi,
@@ -283,6 +293,70 @@ __global__ void __launch_bounds__( pb::kHessThreads, ( MAXCH == 16 ? 2 : 1 ) ) m
         if ( n <= kMidMaxBigN ) pb::form_q_big( n, ilo, ihi, A, n, tau, V, n, smem );
         else pb::orghr( g, n, ilo, ihi, A, n, tau, V, n );
       }
+    }
+    __syncthreads();
+    g.tick( pb::kTickOrghr );
+    pb::geev_isolated_eigenvalues( g, n, ilo, ihi, A, n, wr, wi );
+  }
+  if ( threadIdx.x == 0 ) {
+    MidMeta m;
+    m.ilo = ilo;
+    m.ihi = ihi;
+    m.info = info;
+    m.scalea = sc.scalea ? 1 : 0;
+    m.anrm = sc.anrm;
+    m.cscale = sc.cscale;
+    a.meta[id] = m;
+    a.bv.info[id] = info;
+  }
+  stats_end( a.stats, lstats );
+}
+
+
+// ---- stage 1, blocked: scale check, balancing, dlahr2-panel Hessenberg reduction with DMMA / TMA-staged trailing updates,
+// blocked explicit Q (pb_bhess.cuh). MAXCH = 16: n <= 512, two CTAs per SM; MAXCH = 32: n <= 1024 -----------------------
+inline size_t bprep_smem_bytes( int nmax ) { return sizeof( double ) * pb::bh_smem_doubles( nmax ); }
+
+template <int MAXCH>
+__global__ void __launch_bounds__( pb::kBhThreads, ( MAXCH == 16 ? 2 : 1 ) ) mid_prep_blocked_kernel( MidArgs a ) {
+  extern __shared__ __align__( 128 ) double smem[];
+  __shared__ double red[64];
+  __shared__ long long lstats[kNumTicks];
+  __shared__ __align__( 8 ) uint64_t bars[2];
+  const int id = a.ids[blockIdx.x];
+  const int n = a.bv.n[id];
+  pb::CtaGroup g{ red };
+  stats_begin( g, a.stats, lstats );
+  if ( threadIdx.x == 0 ) {
+    pb::bh_mbar_init( &bars[0], 1 );
+    pb::bh_mbar_init( &bars[1], 1 );
+    asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" );
+  }
+  __syncthreads();
+  double *A, *V, *wr, *wi, *dw;
+  int* iw;
+  mid_pointers( a.bv, id, n, A, V, wr, wi, dw, iw );
+  double* tau = dw;
+  double* scale = dw + n;
+  pb::GeevScaling sc;
+  int ilo = 0, ihi = n - 1, info = 0;
+  if ( !pb::geev_prologue( g, n, A, n, sc, &ilo, &ihi, scale, iw, smem ) ) {
+    info = PALADIN_GPU_INFO_NONFINITE;
+    sc.scalea = false;
+    sc.anrm = 0.0;
+    sc.cscale = 1.0;
+  } else {
+    g.tick( pb::kTickBalance );
+    __syncthreads();
+    pb::BhSmem sh = pb::bh_carve( smem, n, bars );
+    const bool tma = a.hess_tma != 0 && a.tmap_ok[id] != 0;
+    double* scratch = a.hwork + a.h_off[id];
+    pb::bh_gehrd<MAXCH>( g, n, ilo, ihi, A, n, tau, scratch, tma ? a.tmaps + 2 * (size_t)id : nullptr, sh );
+    __syncthreads();
+    g.tick( pb::kTickHess );
+    if ( a.bv.wantvr || a.bv.wantvl ) {
+      if ( a.formq_unblocked ) pb::form_q<MAXCH>( n, ilo, ihi, A, n, tau, V, n, smem );
+      else pb::bh_form_q( n, ilo, ihi, A, n, V, n, scratch, tma ? a.tmaps + 2 * (size_t)id + 1 : nullptr, sh );
     }
     __syncthreads();
     g.tick( pb::kTickOrghr );
@@ -408,6 +482,7 @@ __global__ void __launch_bounds__( kMidThreads, 2 ) mid_qr_kernel( MidArgs a ) {
   if ( a.aed_moves >= 0 ) c.aed_moves = a.aed_moves;
   if ( a.nibble >= 0 ) c.nibble = a.nibble;
   c.itmax = a.itmax;
+  c.spec_shifts = a.spec_shifts;
   const int ldw = c.W | 1, ldt = c.tl | 1;
   pb::MsqrWork wk;
   double* p = smem;
@@ -668,6 +743,8 @@ int set_kernel_attributes( DeviceCtx& c ) {
   PB_CUDA( raise_smem_limit( mid_prep_kernel<0>, o ) );
   PB_CUDA( raise_smem_limit( mid_prep_kernel<16>, o ) );
   PB_CUDA( raise_smem_limit( mid_prep_kernel<32>, o ) );
+  PB_CUDA( raise_smem_limit( mid_prep_blocked_kernel<16>, o ) );
+  PB_CUDA( raise_smem_limit( mid_prep_blocked_kernel<32>, o ) );
   PB_CUDA( raise_smem_limit( big_prep_kernel, o ) );
   PB_CUDA( raise_smem_limit( mid_qr_kernel<false>, o ) );
   PB_CUDA( raise_smem_limit( mid_qr_kernel<true>, o ) );
@@ -717,6 +794,11 @@ struct paladin_gpu_batch {
   size_t xslot = 0;
   int xslots = 0, xn_max = 0;
   int64_t xhalf = 0;
+  // blocked Hessenberg reduction (64 < n <= 1024): scratch, its offsets, tensor maps (A, Schur vectors) per matrix
+  double* d_hwork = nullptr;
+  int64_t* d_h_off = nullptr;
+  CUtensorMap* d_tmaps = nullptr;
+  int* d_tmap_ok = nullptr;
   double* d_max2 = nullptr;                  // scratch of paladin_gpu_batch_vector_filter (allocated with the batch: no
   unsigned long long* d_kept = nullptr;      // cudaMalloc / cudaFree -- device-wide synchronisations -- per call)
   int4* d_vec_items = nullptr;               // work items of the three-launch eigenvector stage
@@ -736,6 +818,33 @@ struct paladin_gpu_batch {
 
 namespace {
 
+// cuTensorMapEncodeTiled through the runtime's driver-entry-point query (nothing links libcuda). One map per dense
+// matrix: 2-D, column-major n x n doubles, box = kBhBoxRows rows x 1 column, no swizzle, zero fill out of bounds.
+typedef CUresult ( *EncodeTiledFn )( CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill );
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if ( cudaGetDriverEntryPoint( "cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q ) != cudaSuccess || q != cudaDriverEntryPointSuccess ) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>( p );
+  }();
+  return fn;
+}
+bool encode_matrix_map( CUtensorMap* map, double* base, int n ) {
+  EncodeTiledFn enc = tensor_map_encoder();
+  if ( !enc || ( n & 1 ) || ( reinterpret_cast<uintptr_t>( base ) & 15 ) ) return false;
+  const cuuint64_t gdim[2] = { (cuuint64_t)n, (cuuint64_t)n };
+  const cuuint64_t gstr[1] = { (cuuint64_t)n * sizeof( double ) };
+  const cuuint32_t box[2] = { (cuuint32_t)pb::kBhBoxRows, 1u };
+  const cuuint32_t estr[2] = { 1u, 1u };
+  return enc( map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE ) == CUDA_SUCCESS;
+}
+
 void free_batch( paladin_gpu_batch* b ) {
   if ( !b ) return;
   cudaSetDevice( b->device );
@@ -744,7 +853,8 @@ void free_batch( paladin_gpu_batch* b ) {
   cudaFree( b->d_A ); cudaFree( b->d_V ); cudaFree( b->d_VL ); cudaFree( b->d_wr ); cudaFree( b->d_wi ); cudaFree( b->d_dwork );
   cudaFree( b->d_stats ); cudaFree( b->d_meta ); cudaFree( b->d_counter ); cudaFree( b->d_xwork );
   cudaFree( b->d_coop_bars ); cudaFree( b->d_coop_ypart ); cudaFree( b->d_coop_yz ); cudaFree( b->d_vec_items );
-  cudaFree( b->d_info ); cudaFree( b->d_iwork ); cudaFree( b->d_flags ); cudaFree( b->d_ids ); cudaFree( b->d_ids_f ); cudaFree( b->d_max2 ); cudaFree( b->d_kept ); cudaFree( b->d_chunks );
+  cudaFree( b->d_info ); cudaFree( b->d_iwork ); cudaFree( b->d_flags ); cudaFree( b->d_hwork ); cudaFree( b->d_h_off ); cudaFree( b->d_tmaps ); cudaFree( b->d_tmap_ok );
+  cudaFree( b->d_ids ); cudaFree( b->d_ids_f ); cudaFree( b->d_max2 ); cudaFree( b->d_kept ); cudaFree( b->d_chunks );
   for ( auto& s : b->st ) {
     if ( s.e0 ) cudaEventDestroy( s.e0 );
     if ( s.e1 ) cudaEventDestroy( s.e1 );
@@ -998,6 +1108,35 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
   A( dev_alloc( &b->d_stats, kNumTicks ) );
   A( dev_alloc( &b->d_meta, count ) );
   A( dev_alloc( &b->d_counter, 1 ) );
+  {
+    // blocked Hessenberg reduction: per-matrix scratch (Y, V T, T of every panel) and TMA tensor maps of the dense matrix
+    // and of the Schur-vector array (box = 256 rows x 1 column of doubles; needs an even leading dimension)
+    std::vector<int64_t> h_off( count + 1, 0 );
+    for ( int k = 0; k < count; ++k )
+      h_off[k + 1] = h_off[k] + ( ( n[k] > kSmallMax && n[k] <= kMidMaxFusedN ) ? (int64_t)( ( pb::bh_scratch_doubles( n[k] ) + 1 ) & ~(size_t)1 ) : 0 );
+    if ( h_off[count] > 0 ) {
+      A( dev_alloc( &b->d_hwork, (size_t)h_off[count] ) );
+      A( dev_alloc( &b->d_h_off, count + 1 ) );
+      A( dev_alloc( &b->d_tmaps, 2 * (size_t)count ) );
+      A( dev_alloc( &b->d_tmap_ok, count ) );
+      if ( rc == PALADIN_GPU_OK ) {
+        std::vector<CUtensorMap> maps( 2 * (size_t)count );
+        std::vector<int> ok( count, 0 );
+        std::memset( maps.data(), 0, sizeof( CUtensorMap ) * maps.size() );
+        double* qbase = jobvr == 'V' ? b->d_V : ( jobvl == 'V' ? b->d_VL : nullptr );
+        for ( int k = 0; k < count; ++k ) {
+          if ( !( n[k] > kSmallMax && n[k] <= kMidMaxFusedN ) || ( n[k] & 1 ) ) continue;
+          bool good = encode_matrix_map( &maps[2 * (size_t)k], b->d_A + b->a_off[k], n[k] );
+          if ( good && qbase ) good = encode_matrix_map( &maps[2 * (size_t)k + 1], qbase + b->a_off[k], n[k] );
+          ok[k] = good ? 1 : 0;
+        }
+        if ( cudaMemcpy( b->d_h_off, h_off.data(), sizeof( int64_t ) * ( count + 1 ), cudaMemcpyHostToDevice ) != cudaSuccess ||
+             cudaMemcpy( b->d_tmaps, maps.data(), sizeof( CUtensorMap ) * maps.size(), cudaMemcpyHostToDevice ) != cudaSuccess ||
+             cudaMemcpy( b->d_tmap_ok, ok.data(), sizeof( int ) * count, cudaMemcpyHostToDevice ) != cudaSuccess )
+          rc = fail( PALADIN_GPU_ECUDA, "cudaMemcpy failed" );
+      }
+    }
+  }
   {
     // work slots of the eigenvector stage: two resident CTAs per SM at most
     int nmid = 0, nmax = 0;
@@ -1262,6 +1401,19 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
       ma.nibble = env_nibble;
       static const int env_itmax = std::getenv( "PALADIN_GPU_QR_ITMAX" ) ? std::max( 0, std::atoi( std::getenv( "PALADIN_GPU_QR_ITMAX" ) ) ) : 0;
       ma.itmax = env_itmax;
+      static const int env_spec = std::getenv( "PALADIN_GPU_SPEC_SHIFTS" ) ? std::atoi( std::getenv( "PALADIN_GPU_SPEC_SHIFTS" ) ) : 0;
+      ma.spec_shifts = env_spec;
+      // PALADIN_GPU_HESS: "fused" = the unblocked single-sweep kernel (pb_hess.cuh), "notma" = blocked, tiles staged by plain
+      // loads; default = blocked with TMA-staged tiles (odd orders always stage by plain loads)
+      static const std::string env_hess = std::getenv( "PALADIN_GPU_HESS" ) ? std::getenv( "PALADIN_GPU_HESS" ) : "";
+      const bool hess_blocked = env_hess != "fused" && b->d_hwork != nullptr;
+      ma.hwork = b->d_hwork;
+      ma.h_off = b->d_h_off;
+      ma.tmaps = b->d_tmaps;
+      ma.tmap_ok = b->d_tmap_ok;
+      ma.hess_tma = env_hess == "notma" ? 0 : 1;
+      static const bool env_formq_old = std::getenv( "PALADIN_GPU_FORMQ" ) != nullptr && std::string( std::getenv( "PALADIN_GPU_FORMQ" ) ) == "unblocked";
+      ma.formq_unblocked = env_formq_old ? 1 : 0;
       static const int env_rg = std::getenv( "PALADIN_GPU_REFL_GLOBAL" ) ? std::atoi( std::getenv( "PALADIN_GPU_REFL_GLOBAL" ) ) : 1;  // 3072^2 x 2, clusters of 16: QR stage 1373 -> 1275 ms
       ma.refl_global = env_rg;
       PB_CUDA( cudaMemsetAsync( b->d_stats, 0, sizeof( long long ) * kNumTicks, st ) );
@@ -1337,16 +1489,23 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
         if ( nmid > nbig ) {
           MidArgs m1 = ma;
           m1.ids = ids + nbig;
-          mid_prep_kernel<32><<<nmid - nbig, pb::kHessThreads, prep_smem_bytes( 1024 ), st>>>( m1 );
+          if ( hess_blocked ) mid_prep_blocked_kernel<32><<<nmid - nbig, pb::kBhThreads, bprep_smem_bytes( 1024 ), st>>>( m1 );
+          else mid_prep_kernel<32><<<nmid - nbig, pb::kHessThreads, prep_smem_bytes( 1024 ), st>>>( m1 );
           ++launches;
         }
         if ( cnt > nmid ) {
           MidArgs m2 = ma;
           m2.ids = ids + nmid;
-          mid_prep_kernel<16><<<cnt - nmid, pb::kHessThreads, prep_smem_bytes( 512 ), st>>>( m2 );
+          if ( hess_blocked ) mid_prep_blocked_kernel<16><<<cnt - nmid, pb::kBhThreads, bprep_smem_bytes( 512 ), st>>>( m2 );
+          else mid_prep_kernel<16><<<cnt - nmid, pb::kHessThreads, prep_smem_bytes( 512 ), st>>>( m2 );
           ++launches;
         }
         stage_end( b, PALADIN_GPU_STAGE_HESSENBERG, st, launches );
+      }
+      // debugging / tests: stop after stage 1 so that H (+ reflectors) and Q can be inspected (get_dense / download)
+      if ( std::getenv( "PALADIN_GPU_DEBUG_STOP_AFTER_PREP" ) != nullptr ) {
+        PB_CUDA( cudaGetLastError() );
+        continue;
       }
       stage_begin( b, PALADIN_GPU_STAGE_QR, st );
       {

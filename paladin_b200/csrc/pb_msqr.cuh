@@ -42,7 +42,7 @@ constexpr int kMsMaxBulges = 16;
 // ints of MsqrWork::ibuf: kpos, kfirst, kcount (kMsMaxBulges each), then
 //   +0 shift count  +1 sweeps  +2 windows  +3 small solves  +4 scratch  +5 steady-state windows  +6 strip work queue
 //   +8..+11 AED results (ns, lahqr code, changed, shifts valid)  +12 eigenvalues deflated by AED  +13 sweeps skipped  +14 AED calls
-constexpr int kMsIbufInts = 3 * kMsMaxBulges + 16 + 8;
+constexpr int kMsIbufInts = 3 * kMsMaxBulges + 16 + 8;  // (+15: result code of the speculative shift computation)
 constexpr int kReflStride = 6;  // w2, w3, t1, t2, t3, pad  (three 16-byte loads)
 // phase-profile slots (CtaGroup::tick)
 constexpr int kTickMsScan = 8, kTickMsShifts = 9, kTickMsChase = 10, kTickMsStrips = 11, kTickMsSmall = 12, kTickMsSmallU = 13, kTickMsAed = 14, kTickMsAedU = 15;
@@ -881,14 +881,28 @@ __device__ __noinline__ void aed_window_warps( double* red, int jw, int max_move
 // ---- aggressive early deflation on the trailing jw x jw window of the active block [ktop..kbot] -----------
 // nd_out: eigenvalues deflated (now final in wr/wi, H split below row kbot - nd); ns_out: shift candidates left in
 // wk.sr / wk.si (arranged in pairs, at most `keep`).
+// spec_ns > 0: the eigenvalues of the trailing spec_ns x spec_ns block AS IT IS BEFORE this AED step are computed as well
+// (speculative shifts of the next sweep; on the device by a second warp while the first one factors the AED window);
+// *spec_out receives how many of them are left in wk.sr / wk.si (arranged in pairs), 0 when the AED step itself left shifts.
 template <class G>
 PB_D void ms_aed( const G& g, bool wantt, bool wantz, int n, int ktop, int kbot, int jw, int keep, double* H, int ldh, double* wr,
                   double* wi, int iloz, int ihiz, double* Z, int ldz, const MsqrCfg& cfg, const MsqrWork& wk, int* nd_out,
-                  int* ns_out ) {
+                  int* ns_out, int spec_ns = 0, int* spec_out = nullptr ) {
   const int t = g.tid(), nt = g.size();
   const int kwtop = kbot - jw + 1;
   const int ldw = wk.ldw;
   const double s = ( kwtop > ktop ) ? PB_HLD( kwtop, kwtop - 1 ) : 0.0;
+  // speculative shift block: a copy of the trailing block in the strip-tile buffer, behind the AED scratch
+  double* S2 = wk.tile + 4 * cfg.W;
+  double* sr2 = S2 + (size_t)cfg.W * ldw;
+  double* si2 = sr2 + cfg.W;
+  if ( spec_ns > 0 ) {
+    const int r0 = kbot - spec_ns + 1;
+    for ( int q = t; q < spec_ns * spec_ns; q += nt ) {
+      const int c = q / spec_ns, r = q - c * spec_ns;
+      S2[r + c * ldw] = ( r - c <= 1 ) ? PB_HLD( r0 + r, r0 + c ) : 0.0;
+    }
+  }
   ms_load_window( g, H, ldh, kwtop, jw, wk.Hw, ldw );
   for ( int q = t; q < jw * jw; q += nt ) {
     const int c = q / jw, r = q - c * jw;
@@ -900,19 +914,30 @@ PB_D void ms_aed( const G& g, bool wantt, bool wantz, int n, int ktop, int kbot,
   double* er = wk.tile;            // eigenvalues of the window (2 jw doubles), then 2 jw doubles of scratch
   double* ei = wk.tile + jw;
   bool warp_done = false;
+  int spec_inf = 0;
 #if defined( __CUDACC__ )
   if constexpr ( G::kIsCta ) {
     // a window of <= 48 rows keeps a few warps busy at best: they run it behind their own named barrier
     if ( ( threadIdx.x >> 5 ) < kSmallWarps ) aed_window_warps( g.red, jw, cfg.aed_moves, wk.Hw, ldw, wk.U, ldw, s, er, ei, wk.tile + 2 * jw, out );
+    else if ( spec_ns > 0 && ( threadIdx.x >> 5 ) == kSmallWarps ) {
+      // the warp next to them: eigenvalues of the speculative shift block, side by side with the window
+      const int r = lahqr<WarpGroup, true>( WarpGroup(), false, false, spec_ns, 0, spec_ns - 1, S2, ldw, sr2, si2, 0, spec_ns - 1, (double*)nullptr, 1 );
+      if ( ( threadIdx.x & 31 ) == 0 ) wk.ibuf[3 * kMsMaxBulges + 15] = r;
+    }
     __syncthreads();
+    if ( spec_ns > 0 ) spec_inf = wk.ibuf[3 * kMsMaxBulges + 15];
     warp_done = true;
   }
 #endif
-  if ( !warp_done ) aed_window( g, jw, cfg.aed_moves, wk.Hw, ldw, wk.U, ldw, s, er, ei, wk.tile + 2 * jw, out );
+  if ( !warp_done ) {
+    if ( spec_ns > 0 ) spec_inf = lahqr<G, true>( g, false, false, spec_ns, 0, spec_ns - 1, S2, ldw, sr2, si2, 0, spec_ns - 1, (double*)nullptr, 1 );
+    aed_window( g, jw, cfg.aed_moves, wk.Hw, ldw, wk.U, ldw, s, er, ei, wk.tile + 2 * jw, out );
+  }
   g.sync();
   const int ns = out[0], infqr = out[1], changed = out[2];
   PB_CHECK_UNIFORM( g, ns * 4 + changed, "aed result" );
   g.tick( kTickMsAed );
+  if ( spec_out != nullptr ) *spec_out = 0;
   if ( infqr != 0 ) {  // the window's own QR iteration failed: nothing was written back, no shifts from here
     *nd_out = 0;
     *ns_out = 0;
@@ -927,6 +952,7 @@ PB_D void ms_aed( const G& g, bool wantt, bool wantz, int n, int ktop, int kbot,
   // shift candidates: eigenvalues of the undeflated part
   int nshift = 0;
   if ( ns >= 2 && out[3] != 0 ) nshift = ms_arrange_shifts( g, er, ei, 0, ns, keep, wk );
+  else if ( spec_ns > 0 && spec_out != nullptr && spec_ns - spec_inf >= 2 ) *spec_out = ms_arrange_shifts( g, sr2, si2, spec_inf, spec_ns, spec_ns, wk );
   else g.sync();
   if ( changed ) {
     if ( t == 0 && kwtop > ktop ) PB_H( kwtop, kwtop - 1 ) = s * wk.U[0];
@@ -1037,16 +1063,20 @@ PB_D int hqr_multishift( const G& g, bool wantt, bool wantz, int n, int ilo, int
     if ( ++it > itmax ) return kbot + 1;
     // the shift block is factored inside the U buffer, hence ns <= W
     const int nshift_cfg = imin( cfg.nshift > 0 ? cfg.nshift : 2 * cfg.nb * cfg.nchains, 2 * cfg.nb * cfg.nchains );
-    int ns_aed = 0, ns_spec = 0;
+    int ns_aed = 0, ns_spec = 0, spec_want = 0;
     if ( cfg.aed > 0 && cfg.aed_moves == 0 && cfg.spec_shifts != 0 && ( ( nodefl + 1 ) % 6 ) != 0 ) {
       const int want0 = imax( 2, imin( imin( nshift_cfg, cfg.W & ~1 ), ( ( m - 1 ) / 3 ) * 2 ) & ~1 );
-      ns_spec = ms_compute_shifts( g, ktop, kbot, H, ldh, want0, false, wk );
-      g.tick( kTickMsShifts );
+      if ( cfg.spec_shifts == 1 ) {
+        ns_spec = ms_compute_shifts( g, ktop, kbot, H, ldh, want0, false, wk );
+        g.tick( kTickMsShifts );
+      } else {
+        spec_want = imin( want0, m );  // side by side with the AED window (ms_aed)
+      }
     }
     if ( cfg.aed > 0 ) {
       const int jw = imin( imin( cfg.aed, cfg.W - 1 ), m );
       int nd = 0;
-      ms_aed( g, wantt, wantz, n, ktop, kbot, jw, nshift_cfg, H, ldh, wr, wi, iloz, ihiz, Z, ldz, cfg, wk, &nd, &ns_aed );
+      ms_aed( g, wantt, wantz, n, ktop, kbot, jw, nshift_cfg, H, ldh, wr, wi, iloz, ihiz, Z, ldz, cfg, wk, &nd, &ns_aed, spec_want, &ns_spec );
       PB_CHECK_UNIFORM( g, nd * 100 + ns_aed, "aed nd/ns" );
       g.tick( kTickMsAedU );
       if ( nd > 0 ) {

@@ -247,7 +247,8 @@ def test_large_matrices_cooperative_path(pg, jobvr, sizes):
                                  {"PALADIN_GPU_CLUSTER": "16", "PALADIN_GPU_COOP_GROUPS": "1", "PALADIN_GPU_REFL_GLOBAL": "0"},
                                  {"PALADIN_GPU_COOP_GROUPS": "4"}, {"PALADIN_GPU_COOP_GROUPS": "16", "PALADIN_GPU_AED": "48"},
                                  {"PALADIN_GPU_NO_COOP": "1", "PALADIN_GPU_CLUSTER": "1", "PALADIN_GPU_AED": "0"},
-                                 {"PALADIN_GPU_AED_MOVES": "1000", "PALADIN_GPU_BIGVEC_MIN_N": "4000"}])
+                                 {"PALADIN_GPU_AED_MOVES": "1000", "PALADIN_GPU_BIGVEC_MIN_N": "4000"},
+                                 {"PALADIN_GPU_HESS": "fused"}, {"PALADIN_GPU_HESS": "notma"}])
 def test_tuning_overrides_keep_parity(env):
     """Every cluster size, cooperative group count and AED variant the launcher can choose (forced through the tuning
     environment variables, which are read once per process) gives the same spectra within tolerance."""
@@ -256,7 +257,7 @@ import sys, numpy as np
 sys.path.insert(0, %r)
 import paladin_b200 as pg
 from oracle import paladin_oracle as po
-sizes = [300, 1100, 1350]
+sizes = [300, 700, 1100, 1350]
 mats = [(n,) + po.random_dense_coo(n, [61, q]) for q, n in enumerate(sizes)]
 n = np.array([m[0] for m in mats], dtype=np.int32)
 off = np.concatenate([[0], np.cumsum([len(m[3]) for m in mats])]).astype(np.int64)
@@ -471,6 +472,37 @@ def test_nonfinite_input_flagged(pg):
     A[2, 2] = np.nan
     wr, wi, VR, info = pg.dgeev(A)
     assert info == -4
+
+
+def test_blocked_hessenberg_factorisation(pg):
+    """Stage 1 alone (PALADIN_GPU_DEBUG_STOP_AFTER_PREP): the blocked reduction (dlahr2 panels, DMMA / TMA-staged trailing
+    updates) leaves H upper Hessenberg with Q^T A Q = H and Q orthogonal, for orders on both sides of every tile / box /
+    chunk boundary, odd orders (tiles staged without TMA) and a matrix whose balancing isolates eigenvalues."""
+    sizes = [65, 66, 96, 130, 200, 255, 256, 258, 300, 511, 512, 514, 600, 768, 1000, 1024]
+    mats = _random_mats(sizes, 93)
+    n, off, ii, jj, vv = _concat(mats)
+    os.environ["PALADIN_GPU_DEBUG_STOP_AFTER_PREP"] = "1"
+    try:
+        b = pg.Batch(n, off, jobvr="V")
+        b.upload(ii, jj, vv)
+        b.scatter()
+        b.solve()
+        Hs = [b.get_dense(k) for k in range(len(mats))]
+        wr, wi, vr, info = b.download()
+        b.destroy()
+    finally:
+        del os.environ["PALADIN_GPU_DEBUG_STOP_AFTER_PREP"]
+    o = 0
+    for m, Hraw in zip(mats, Hs):
+        nk = m[0]
+        A = po.dense_matrix(*m)
+        H = np.triu(Hraw.reshape((nk, nk), order="F"), -1)
+        Q = vr[o:o + nk * nk].reshape((nk, nk), order="F")
+        o += nk * nk
+        nrm = np.linalg.norm(A, 2)
+        assert np.linalg.norm(Q.T @ Q - np.eye(nk)) <= 1e-13 * nk, nk
+        # dense N(0,1): balancing neither permutes nor scales, so Q^T A Q = H holds for the input itself
+        assert np.linalg.norm(Q.T @ A @ Q - H) <= 1e-13 * nk * nrm, (nk, np.linalg.norm(Q.T @ A @ Q - H) / nrm)
 
 
 def test_bench_matrices_match_oracle(pg):
