@@ -658,19 +658,39 @@ def exe_entry(cx, args):
             names.append(nm)
         with open(os.path.join(tmp, "listing"), "w") as f:
             f.write("\n".join(names))
-        cmd = [ph.exe_path(), "--listing=" + os.path.join(tmp, "listing"), "--rootdir=" + tmp, "--right", "--gpus=1"]
-        t0 = time.perf_counter()
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=1800)
-        wall = time.perf_counter() - t0
-        if r.returncode != 0:
-            return {"value": None, "error": (r.stdout[-500:] + r.stderr[-500:])}
-        m = re.search(r"^max\t(\S+)\t(\S+)\t(\S+)", r.stdout, re.M)
-        total = float(m.group(3)) if m else wall
+        def run(extra):
+            cmd = [ph.exe_path(), "--listing=" + os.path.join(tmp, "listing"), "--rootdir=" + tmp, "--right", "--gpus=1"] + extra
+            t0 = time.perf_counter()
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=1800)
+            wall = time.perf_counter() - t0
+            if r.returncode != 0:
+                return None, wall, (r.stdout[-500:] + r.stderr[-500:])
+            m = re.search(r"^max\t(\S+)\t(\S+)\t(\S+)", r.stdout, re.M)
+            return (float(m.group(3)) if m else wall), wall, ""
+        total, wall, err = run([])
+        if total is None:
+            return {"value": None, "error": err}
         nbytes_in = sum(os.path.getsize(os.path.join(tmp, "d%d.matrix" % (k % distinct))) for k in range(count))
         nbytes_out = sum(os.path.getsize(os.path.join(tmp, nm + ext)) for nm in names for ext in (".spectrum", ".rightvecs"))
-        return {"value": count / total, "unit": UNIT, "matrices": count, "seconds": total, "wall_incl_listing_scan": wall,
-                "text_in_bytes": nbytes_in, "text_out_bytes": nbytes_out, "host_cores": os.cpu_count(),
-                "what": "paladin-gpu --right on %d MatrixMarket files of 512x512 -> .spectrum + .rightvecs (text in, text out)" % count}
+        out = {"value": count / total, "unit": UNIT, "matrices": count, "seconds": total, "wall_incl_listing_scan": wall,
+               "text_in_bytes": nbytes_in, "text_out_bytes": nbytes_out, "host_cores": os.cpu_count(),
+               "what": "paladin-gpu --right on %d MatrixMarket files of 512x512 -> .spectrum + .rightvecs (text in, text out); "
+                       "entry lines parsed and eigenvector files formatted on the GPU" % count}
+        # the same with parsing and formatting on the host cores (the round-1 path), on a sixth of the files
+        sub = max(1, count // 6)
+        with open(os.path.join(tmp, "listing_sub"), "w") as f:
+            f.write("\n".join(names[:sub]))
+
+        def run_sub():
+            cmd = [ph.exe_path(), "--listing=" + os.path.join(tmp, "listing_sub"), "--rootdir=" + tmp, "--right", "--gpus=1", "--host-text"]
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=1800)
+            m = re.search(r"^max\t(\S+)\t(\S+)\t(\S+)", r.stdout, re.M)
+            return float(m.group(3)) if (r.returncode == 0 and m) else None
+        t2 = run_sub()
+        if t2:
+            out["host_text_value"] = sub / t2
+            out["host_text_matrices"] = sub
+        return out
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
@@ -775,7 +795,7 @@ def main():
     ap.add_argument("--ref-per-rank", type=int, default=0, help="matrices per host core in the reference sample (0: 8 / 1 / 200 for 512v / 3072v / 64n)")
     ap.add_argument("--mixed-m", type=int, default=2048, help="matrices of the mixed batch (fixed total, strong scaling)")
     ap.add_argument("--ref-mixed-stride", type=int, default=64, help="the reference sample of the mixed batch takes every k-th matrix")
-    ap.add_argument("--exe-matrices", type=int, default=1184, help="matrices of the text-in/text-out executable leg (0 = skip)")
+    ap.add_argument("--exe-matrices", type=int, default=3552, help="matrices of the text-in/text-out executable leg (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="e2e: the step's matrices go through the C-ABI as this many batches, one host thread each")

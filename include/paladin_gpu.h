@@ -24,6 +24,7 @@
 #ifndef PALADIN_GPU_H_
 #define PALADIN_GPU_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -140,6 +141,48 @@ int paladin_gpu_batch_download( paladin_gpu_batch* b, double* wr, double* wi, do
  * matrices with info != 0 get kept = 0. */
 int paladin_gpu_batch_vector_filter( paladin_gpu_batch* b, char side, double threshold, double* max2, long long* kept );
 
+/* ---- the text ends of the path on the device (GPU-assisted MatrixMarket parse, GPU-side formatting) --------- */
+
+/* Alternative to paladin_gpu_batch_upload: the ENTRY LINES of every matrix as raw MatrixMarket text ("i j v\n", exactly as on
+ * disk, after the size line; reference reader src/square-matrix.hpp:101-117). text_off[count + 1] are byte offsets into
+ * `text` (host memory, ideally page-locked): matrix k's entry lines are text[text_off[k] .. text_off[k+1]). The device
+ * splits the lines and converts the fields with the values atoi / atoi / atof give (bit-exact); fields it cannot convert
+ * with certainty (hex floats, inf / nan, more than 19 significant digits, ...) are converted inside this call by the C
+ * library on the host. needs_host[k] (count ints, may be NULL) is set to 1 when matrix k has to go through the caller's own
+ * reader instead -- a line with fewer than two blanks, a field longer than the reference's buffers (5 / 5 / 31 characters),
+ * fewer lines than entries -- and its triplets are then expected through paladin_gpu_batch_upload_coo_one. */
+int paladin_gpu_batch_upload_text( paladin_gpu_batch* b, const char* text, const int64_t* text_off, int* needs_host );
+
+/* Streaming variant of the text upload: paladin_gpu_batch_text_begin reserves `total_bytes` of device text,
+ * paladin_gpu_batch_text_put copies a piece of it (any thread, any order, e.g. one file at a time out of a small page-locked
+ * staging buffer), and paladin_gpu_batch_upload_text called with text == NULL converts what has been placed (text_off[0]
+ * must then be 0). No batch-sized host buffer is needed. */
+int paladin_gpu_batch_text_begin( paladin_gpu_batch* b, size_t total_bytes );
+int paladin_gpu_batch_text_put( paladin_gpu_batch* b, size_t offset, const char* src, size_t bytes );
+
+/* Host -> device copy of the COO triplets of ONE matrix of the batch (nnz of that matrix values each). */
+int paladin_gpu_batch_upload_coo_one( paladin_gpu_batch* b, int k, const int* coo_i, const int* coo_j, const double* coo_v );
+
+/* Parity/debug: the COO triplets as they are on the device (total nnz values each; any pointer may be NULL). */
+int paladin_gpu_batch_get_coo( paladin_gpu_batch* b, int* coo_i, int* coo_j, double* coo_v );
+
+/* The BODY of the reference's eigenvector files (reference src/spectrum-util.hpp:134-196, everything after the "N N nnz"
+ * header line) formatted on the device, after paladin_gpu_batch_solve, for the matrices [first, first + count) of the batch:
+ * for every vector (index outermost) and row the line "row col re im\n" when |x|^2 > threshold * max |x|^2, numbers as
+ * operator<<(double) prints them (6 significant digits, "%g"). side: 'R' or 'L'. text: caller buffer of `cap` bytes (48
+ * bytes per vector component of the range always suffice; page-locked memory makes the copy a DMA); the body of matrix
+ * first + q is text[body_off[q] .. body_off[q+1]) (count + 1 offsets). kept[q] = number of lines = the nnz of the header
+ * line. needs_host[q] = 1 when a number of that matrix could not be rounded with certainty on the device (its body is then
+ * undefined and the caller formats that matrix from the downloaded vectors); matrices with info != 0 get empty bodies. */
+int paladin_gpu_batch_format_vectors( paladin_gpu_batch* b, char side, double threshold, int first, int count, char* text, size_t cap,
+                                      int64_t* body_off, long long* kept, int* needs_host );
+
+/* Streaming variant: paladin_gpu_batch_format_vectors called with text == NULL (range of at most 48 Mi vector components)
+ * leaves the formatted bodies on the device; this entry copies bytes [offset, offset + bytes) of them (the offsets are the
+ * body_off values of that call) to dst. A small page-locked staging buffer per writer thread is enough, whatever the batch
+ * holds. May be called from several threads at once for the same batch; the text stays valid until the next format call. */
+int paladin_gpu_batch_fetch_text( paladin_gpu_batch* b, size_t offset, size_t bytes, char* dst );
+
 /* Device time of each stage of the most recent scatter/solve, in milliseconds, measured with CUDA
  * events on the library's own stream. ms must hold PALADIN_GPU_NUM_STAGES floats. launches (may be
  * NULL) receives the number of kernel launches of each stage. */
@@ -151,9 +194,9 @@ int paladin_gpu_batch_timer_start( paladin_gpu_batch* b );
 int paladin_gpu_batch_timer_stop( paladin_gpu_batch* b, float* ms );
 
 /* Phase profile of the most recent CTA-per-matrix solve: SM cycles summed over all CTAs, 16 slots
- * (0 balance, 1 Hessenberg, 2 form Q, 3 QR remainder, 4 eigenvectors of T, 5 un-balance + normalise, 6 back-transform GEMM,
- *  8 deflation scans, 9 shift computation, 10 in-window bulge chasing, 11 strip updates by recorded
- *  reflectors, 12 small-block solves, 13 strip updates by small U, 14 early-deflation window, 15 its off-window update).
+ * (0 balance, 1 Hessenberg panels, 2 form Q, 3 QR remainder, 4 eigenvectors of T, 5 un-balance + normalise, 6 back-transform
+ *  GEMM, 7 Hessenberg trailing updates, 8 deflation scans, 9 shift computation, 10 in-window bulge chasing, 11 strip updates by
+ *  recorded reflectors, 12 small-block solves, 13 strip updates by small U, 14 early-deflation window, 15 its off-window update).
  * Diagnostic only. */
 int paladin_gpu_batch_phase_cycles( paladin_gpu_batch* b, long long* cycles );
 

@@ -67,6 +67,11 @@ def lib():
     L.paladin_gpu_batch_destroy.argtypes = [ctypes.c_void_p]
     L.paladin_gpu_batch_vector_filter.argtypes = [ctypes.c_void_p, ctypes.c_char, ctypes.c_double, ctypes.c_void_p,
                                                   ctypes.c_void_p]
+    L.paladin_gpu_batch_upload_text.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.paladin_gpu_batch_upload_coo_one.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.paladin_gpu_batch_get_coo.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.paladin_gpu_batch_format_vectors.argtypes = [ctypes.c_void_p, ctypes.c_char, ctypes.c_double, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                   ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     L.paladin_gpu_batch_phase_cycles.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_longlong)]
     L.paladin_gpu_batch_timer_start.argtypes = [ctypes.c_void_p]
     L.paladin_gpu_batch_timer_stop.argtypes = [ctypes.c_void_p, _c_flt_p]
@@ -146,6 +151,41 @@ class Batch:
     def upload(self, coo_i, coo_j, coo_v):
         assert coo_i.dtype == np.int32 and coo_j.dtype == np.int32 and coo_v.dtype == np.float64
         _check(lib().paladin_gpu_batch_upload(self._h, _ptr(coo_i), _ptr(coo_j), _ptr(coo_v)))
+
+    def upload_text(self, text, text_off):
+        """Raw MatrixMarket entry lines of the batch (bytes / uint8 array) -> COO on the device. Returns needs_host[count]."""
+        buf = np.frombuffer(text, dtype=np.uint8) if isinstance(text, (bytes, bytearray)) else np.ascontiguousarray(text, dtype=np.uint8)
+        off = np.ascontiguousarray(text_off, dtype=np.int64)
+        assert len(off) == self.count + 1
+        need = np.zeros(max(self.count, 1), dtype=np.int32)
+        _check(lib().paladin_gpu_batch_upload_text(self._h, ctypes.c_void_p(buf.ctypes.data) if len(buf) else None, _ptr(off), _ptr(need)))
+        return need[:self.count]
+
+    def upload_coo_one(self, k, coo_i, coo_j, coo_v):
+        coo_i = np.ascontiguousarray(coo_i, dtype=np.int32)
+        coo_j = np.ascontiguousarray(coo_j, dtype=np.int32)
+        coo_v = np.ascontiguousarray(coo_v, dtype=np.float64)
+        _check(lib().paladin_gpu_batch_upload_coo_one(self._h, int(k), _ptr(coo_i), _ptr(coo_j), _ptr(coo_v)))
+
+    def get_coo(self):
+        nnz = int(self.nnz_offsets[-1] - self.nnz_offsets[0])
+        i = np.zeros(nnz, dtype=np.int32)
+        j = np.zeros(nnz, dtype=np.int32)
+        v = np.zeros(nnz, dtype=np.float64)
+        _check(lib().paladin_gpu_batch_get_coo(self._h, _ptr(i), _ptr(j), _ptr(v)))
+        return i, j, v
+
+    def format_vectors(self, side="R", threshold=1e-3):
+        """-> (list of body bytes per matrix, kept[count], needs_host[count]) of the eigenvector files, formatted on the device."""
+        cap = 48 * max(self.total_nn, 1) + 64
+        text = np.zeros(cap, dtype=np.uint8)
+        off = np.zeros(self.count + 1, dtype=np.int64)
+        kept = np.zeros(max(self.count, 1), dtype=np.int64)
+        need = np.zeros(max(self.count, 1), dtype=np.int32)
+        _check(lib().paladin_gpu_batch_format_vectors(self._h, side.encode(), float(threshold), 0, self.count, _ptr(text), cap, _ptr(off), _ptr(kept),
+                                                      _ptr(need)))
+        bodies = [text[off[k]:off[k + 1]].tobytes() for k in range(self.count)]
+        return bodies, kept[:self.count], need[:self.count]
 
     def scatter(self):
         _check(lib().paladin_gpu_batch_scatter(self._h))

@@ -20,6 +20,7 @@
 #include "pb_coop.cuh"
 #include "pb_vecs.cuh"
 #include "pb_scatter.cuh"
+#include "pb_textio.cuh"
 
 namespace {
 
@@ -90,6 +91,14 @@ int ensure_ctx( int device ) {
     PB_CUDA( cudaDeviceGetAttribute( &c.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device ) );
     PB_CUDA( cudaEventCreate( &c.t0 ) );
     PB_CUDA( cudaEventCreate( &c.t1 ) );
+    {
+      // device memory of the batches comes from the stream-ordered allocator and is kept by its pool between batches:
+      // cudaMalloc / cudaFree synchronise the whole device, which stalls the OTHER batches in flight on it
+      cudaMemPool_t pool;
+      PB_CUDA( cudaDeviceGetDefaultMemPool( &pool, device ) );
+      unsigned long long keep = ~0ull;
+      PB_CUDA( cudaMemPoolSetAttribute( pool, cudaMemPoolAttrReleaseThreshold, &keep ) );
+    }
     c.ready = true;
   }
   return PALADIN_GPU_OK;
@@ -799,6 +808,19 @@ struct paladin_gpu_batch {
   int64_t* d_h_off = nullptr;
   CUtensorMap* d_tmaps = nullptr;
   int* d_tmap_ok = nullptr;
+  // text ends (pb_textio.cuh): raw MatrixMarket text of the batch and the parser's tables; formatter scratch
+  char* d_text = nullptr;
+  size_t text_cap = 0;
+  size_t text_resident = 0;                  // bytes placed with paladin_gpu_batch_text_begin / _put (upload_text with text == NULL parses them)
+  void* d_text_tables = nullptr;             // chunks, ranges, counters (one allocation)
+  size_t text_tables_cap = 0;
+  char *d_fmt_slots = nullptr, *d_fmt_out = nullptr;
+  unsigned char* d_fmt_lens = nullptr;
+  unsigned long long* d_fmt_bsum = nullptr;
+  long long* d_fmt_eoff = nullptr;           // e_off (count + 1), body_off (count + 1)
+  int* d_fmt_flags = nullptr;
+  long long fmt_cap_entries = 0;
+  size_t fmt_text_bytes = 0;                 // bytes of formatted text kept in d_fmt_out (paladin_gpu_batch_fetch_text)
   double* d_max2 = nullptr;                  // scratch of paladin_gpu_batch_vector_filter (allocated with the batch: no
   unsigned long long* d_kept = nullptr;      // cudaMalloc / cudaFree -- device-wide synchronisations -- per call)
   int4* d_vec_items = nullptr;               // work items of the three-launch eigenvector stage
@@ -817,6 +839,21 @@ struct paladin_gpu_batch {
 };
 
 namespace {
+
+// stream the calling thread's allocations are ordered on (the batch's own stream, set by every entry that allocates)
+thread_local cudaStream_t g_alloc_stream = nullptr;
+
+template <class T>
+int dev_alloc( T** p, size_t count ) {
+  *p = nullptr;
+  if ( count == 0 ) count = 1;
+  PB_CUDA( cudaMallocAsync( reinterpret_cast<void**>( p ), count * sizeof( T ), g_alloc_stream ) );
+  return PALADIN_GPU_OK;
+}
+inline void dev_free( void* p, cudaStream_t st ) {
+  if ( p ) cudaFreeAsync( p, st );
+}
+
 
 // cuTensorMapEncodeTiled through the runtime's driver-entry-point query (nothing links libcuda). One map per dense
 // matrix: 2-D, column-major n x n doubles, box = kBhBoxRows rows x 1 column, no swizzle, zero fill out of bounds.
@@ -848,13 +885,15 @@ bool encode_matrix_map( CUtensorMap* map, double* base, int n ) {
 void free_batch( paladin_gpu_batch* b ) {
   if ( !b ) return;
   cudaSetDevice( b->device );
-  cudaFree( b->d_n ); cudaFree( b->d_nnz_off ); cudaFree( b->d_a_off ); cudaFree( b->d_w_off );
-  cudaFree( b->d_coo_i ); cudaFree( b->d_coo_j ); cudaFree( b->d_coo_v );
-  cudaFree( b->d_A ); cudaFree( b->d_V ); cudaFree( b->d_VL ); cudaFree( b->d_wr ); cudaFree( b->d_wi ); cudaFree( b->d_dwork );
-  cudaFree( b->d_stats ); cudaFree( b->d_meta ); cudaFree( b->d_counter ); cudaFree( b->d_xwork );
-  cudaFree( b->d_coop_bars ); cudaFree( b->d_coop_ypart ); cudaFree( b->d_coop_yz ); cudaFree( b->d_vec_items );
-  cudaFree( b->d_info ); cudaFree( b->d_iwork ); cudaFree( b->d_flags ); cudaFree( b->d_hwork ); cudaFree( b->d_h_off ); cudaFree( b->d_tmaps ); cudaFree( b->d_tmap_ok );
-  cudaFree( b->d_ids ); cudaFree( b->d_ids_f ); cudaFree( b->d_max2 ); cudaFree( b->d_kept ); cudaFree( b->d_chunks );
+  dev_free( b->d_n, b->stream ); dev_free( b->d_nnz_off, b->stream ); dev_free( b->d_a_off, b->stream ); dev_free( b->d_w_off, b->stream );
+  dev_free( b->d_coo_i, b->stream ); dev_free( b->d_coo_j, b->stream ); dev_free( b->d_coo_v, b->stream );
+  dev_free( b->d_A, b->stream ); dev_free( b->d_V, b->stream ); dev_free( b->d_VL, b->stream ); dev_free( b->d_wr, b->stream ); dev_free( b->d_wi, b->stream ); dev_free( b->d_dwork, b->stream );
+  dev_free( b->d_stats, b->stream ); dev_free( b->d_meta, b->stream ); dev_free( b->d_counter, b->stream ); dev_free( b->d_xwork, b->stream );
+  dev_free( b->d_coop_bars, b->stream ); dev_free( b->d_coop_ypart, b->stream ); dev_free( b->d_coop_yz, b->stream ); dev_free( b->d_vec_items, b->stream );
+  dev_free( b->d_info, b->stream ); dev_free( b->d_iwork, b->stream ); dev_free( b->d_flags, b->stream ); dev_free( b->d_text, b->stream ); dev_free( b->d_text_tables, b->stream ); dev_free( b->d_fmt_slots, b->stream ); dev_free( b->d_fmt_out, b->stream ); dev_free( b->d_fmt_lens, b->stream );
+  dev_free( b->d_fmt_bsum, b->stream ); dev_free( b->d_fmt_eoff, b->stream ); dev_free( b->d_fmt_flags, b->stream );
+  dev_free( b->d_hwork, b->stream ); dev_free( b->d_h_off, b->stream ); dev_free( b->d_tmaps, b->stream ); dev_free( b->d_tmap_ok, b->stream );
+  dev_free( b->d_ids, b->stream ); dev_free( b->d_ids_f, b->stream ); dev_free( b->d_max2, b->stream ); dev_free( b->d_kept, b->stream ); dev_free( b->d_chunks, b->stream );
   for ( auto& s : b->st ) {
     if ( s.e0 ) cudaEventDestroy( s.e0 );
     if ( s.e1 ) cudaEventDestroy( s.e1 );
@@ -868,14 +907,6 @@ void free_batch( paladin_gpu_batch* b ) {
   }
   if ( b->ev_fork ) cudaEventDestroy( b->ev_fork );
   delete b;
-}
-
-template <class T>
-int dev_alloc( T** p, size_t count ) {
-  *p = nullptr;
-  if ( count == 0 ) count = 1;
-  PB_CUDA( cudaMalloc( reinterpret_cast<void**>( p ), count * sizeof( T ) ) );
-  return PALADIN_GPU_OK;
 }
 
 #define PB_TRY( expr )                    \
@@ -1013,6 +1044,11 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
   PB_TRY( set_kernel_attributes( c ) );
 
   paladin_gpu_batch* b = new paladin_gpu_batch;
+  if ( cudaStreamCreateWithFlags( &b->stream, cudaStreamNonBlocking ) != cudaSuccess ) {
+    delete b;
+    return fail( PALADIN_GPU_ECUDA, "cudaStreamCreate failed" );
+  }
+  g_alloc_stream = b->stream;
   b->device = device;
   b->count = count;
   b->jobvl = jobvl;
@@ -1023,6 +1059,7 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
   b->w_off.assign( count + 1, 0 );
   for ( int k = 0; k < count; ++k ) {
     if ( n[k] < 0 || nnz_offsets[k + 1] < nnz_offsets[k] || nnz_offsets[k + 1] - nnz_offsets[k] > 0x7fffffffLL ) {
+      cudaStreamDestroy( b->stream );
       delete b;
       return fail( PALADIN_GPU_EINVAL, "negative order or decreasing nnz_offsets at matrix " + std::to_string( k ) );
     }
@@ -1130,7 +1167,7 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
           if ( good && qbase ) good = encode_matrix_map( &maps[2 * (size_t)k + 1], qbase + b->a_off[k], n[k] );
           ok[k] = good ? 1 : 0;
         }
-        if ( cudaMemcpy( b->d_h_off, h_off.data(), sizeof( int64_t ) * ( count + 1 ), cudaMemcpyHostToDevice ) != cudaSuccess ||
+        if ( cudaStreamSynchronize( b->stream ) != cudaSuccess || cudaMemcpy( b->d_h_off, h_off.data(), sizeof( int64_t ) * ( count + 1 ), cudaMemcpyHostToDevice ) != cudaSuccess ||
              cudaMemcpy( b->d_tmaps, maps.data(), sizeof( CUtensorMap ) * maps.size(), cudaMemcpyHostToDevice ) != cudaSuccess ||
              cudaMemcpy( b->d_tmap_ok, ok.data(), sizeof( int ) * count, cudaMemcpyHostToDevice ) != cudaSuccess )
           rc = fail( PALADIN_GPU_ECUDA, "cudaMemcpy failed" );
@@ -1167,7 +1204,7 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
           }
           b->n_vec_items = (int)items.size();
           A( dev_alloc( &b->d_vec_items, items.size() ) );
-          if ( rc == PALADIN_GPU_OK && cudaMemcpy( b->d_vec_items, items.data(), sizeof( int4 ) * items.size(), cudaMemcpyHostToDevice ) != cudaSuccess )
+          if ( rc == PALADIN_GPU_OK && ( cudaStreamSynchronize( b->stream ) != cudaSuccess || cudaMemcpy( b->d_vec_items, items.data(), sizeof( int4 ) * items.size(), cudaMemcpyHostToDevice ) != cudaSuccess ) )
             rc = fail( PALADIN_GPU_ECUDA, "cudaMemcpy failed" );
         }
         A( dev_alloc( &b->d_xwork, (size_t)b->xhalf * ( jobvr == 'V' && jobvl == 'V' ? 2 : 1 ) ) );
@@ -1194,7 +1231,7 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
       A( dev_alloc( &b->d_coop_bars, 2 * (size_t)b->coop_G + 2 ) );
       A( dev_alloc( &b->d_coop_ypart, (size_t)c.sm_count * nbigmax ) );
       A( dev_alloc( &b->d_coop_yz, (size_t)b->coop_G * 2 * nbigmax ) );
-      if ( rc == PALADIN_GPU_OK && cudaMemset( b->d_coop_bars, 0, sizeof( unsigned ) * ( 2 * b->coop_G + 2 ) ) != cudaSuccess )
+      if ( rc == PALADIN_GPU_OK && ( cudaStreamSynchronize( b->stream ) != cudaSuccess || cudaMemset( b->d_coop_bars, 0, sizeof( unsigned ) * ( 2 * b->coop_G + 2 ) ) != cudaSuccess ) )
         rc = fail( PALADIN_GPU_ECUDA, "cudaMemset failed" );
     }
   }
@@ -1214,7 +1251,7 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
     cudaEventCreateWithFlags( &b->ev_join[q], cudaEventDisableTiming );
     side_ok = side_ok && cudaStreamCreateWithFlags( &b->side[q], cudaStreamNonBlocking ) == cudaSuccess;
   }
-  if ( cudaStreamCreateWithFlags( &b->stream, cudaStreamNonBlocking ) != cudaSuccess || !side_ok ) {
+  if ( !side_ok ) {
     free_batch( b );
     return fail( PALADIN_GPU_ECUDA, "cudaStreamCreate failed" );
   }
@@ -1344,6 +1381,7 @@ int paladin_gpu_batch_get_dense( paladin_gpu_batch* b, int k, double* out ) {
 int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
   if ( !b ) return fail( PALADIN_GPU_EINVAL, "null batch" );
   if ( !b->scattered ) return fail( PALADIN_GPU_EINVAL, "solve called before scatter / upload_dense" );
+  g_alloc_stream = b->stream;
   DeviceCtx& c = g_ctx[b->device];
   (void)c;
   PB_CUDA( cudaSetDevice( b->device ) );
@@ -1627,7 +1665,7 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
               big_vec_kernel<3><<<nq * P, pb::kVecThreads, s3, st>>>( mv, d_items );
               launches += ( wantvr && wantvl ) ? 4 : 3;
               PB_CUDA( cudaStreamSynchronize( st ) );
-              cudaFree( d_items );
+              dev_free( d_items, st );
             }
           }
         }
@@ -1720,6 +1758,351 @@ int paladin_gpu_batch_vector_filter( paladin_gpu_batch* b, char side, double thr
   if ( e == cudaSuccess ) e = cudaMemcpyAsync( kept, d_kept, sizeof( long long ) * b->count, cudaMemcpyDeviceToHost, st );
   if ( e == cudaSuccess ) e = cudaStreamSynchronize( st );
   if ( e != cudaSuccess ) return fail( PALADIN_GPU_ECUDA, cudaGetErrorString( e ) );
+  return PALADIN_GPU_OK;
+}
+
+// ---- text ends --------------------------------------------------------------------------------------------------------------
+int paladin_gpu_batch_text_begin( paladin_gpu_batch* b, size_t total_bytes ) {
+  if ( !b ) return fail( PALADIN_GPU_EINVAL, "null batch" );
+  PB_CUDA( cudaSetDevice( b->device ) );
+  cudaStream_t st = b->stream;
+  g_alloc_stream = st;
+  if ( b->text_cap < total_bytes + 64 ) {
+    dev_free( b->d_text, st );
+    b->d_text = nullptr;
+    b->text_cap = 0;
+    PB_CUDA( cudaMallocAsync( reinterpret_cast<void**>( &b->d_text ), total_bytes + 64, st ) );
+    b->text_cap = total_bytes + 64;
+  }
+  PB_CUDA( cudaMemsetAsync( b->d_text + total_bytes, '\n', 64, st ) );
+  PB_CUDA( cudaStreamSynchronize( st ) );
+  b->text_resident = total_bytes;
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_batch_text_put( paladin_gpu_batch* b, size_t offset, const char* src, size_t bytes ) {
+  if ( !b || ( bytes > 0 && !src ) ) return fail( PALADIN_GPU_EINVAL, "bad arguments" );
+  if ( offset + bytes > b->text_resident ) return fail( PALADIN_GPU_EINVAL, "range outside the text reserved with paladin_gpu_batch_text_begin" );
+  if ( bytes == 0 ) return PALADIN_GPU_OK;
+  PB_CUDA( cudaSetDevice( b->device ) );
+  PB_CUDA( cudaMemcpy( b->d_text + offset, src, bytes, cudaMemcpyHostToDevice ) );
+  return PALADIN_GPU_OK;
+}
+int paladin_gpu_batch_upload_text( paladin_gpu_batch* b, const char* text, const int64_t* text_off, int* needs_host ) {
+  if ( !b ) return fail( PALADIN_GPU_EINVAL, "null batch" );
+  if ( b->count > 0 && !text_off ) return fail( PALADIN_GPU_EINVAL, "null text offsets" );
+  const bool resident = text == nullptr;  // the text was placed on the device with paladin_gpu_batch_text_begin / _put
+  PB_CUDA( cudaSetDevice( b->device ) );
+  cudaStream_t st = b->stream;
+  g_alloc_stream = st;
+  const int count = b->count;
+  if ( needs_host )
+    for ( int k = 0; k < count; ++k ) needs_host[k] = 0;
+  if ( count == 0 ) return PALADIN_GPU_OK;
+  for ( int k = 0; k < count; ++k )
+    if ( text_off[k + 1] < text_off[k] ) return fail( PALADIN_GPU_EINVAL, "decreasing text offsets" );
+  const long long t0 = text_off[0];
+  const size_t total = (size_t)( text_off[count] - t0 );
+  if ( resident ) {
+    if ( t0 != 0 || total > b->text_resident ) return fail( PALADIN_GPU_EINVAL, "text offsets do not match the text placed on the device" );
+  } else {
+    if ( b->text_cap < total + 64 ) {
+      dev_free( b->d_text, st );
+      b->d_text = nullptr;
+      b->text_cap = 0;
+      PB_CUDA( cudaMallocAsync( reinterpret_cast<void**>( &b->d_text ), total + 64, st ) );
+      b->text_cap = total + 64;
+    }
+    if ( total ) PB_CUDA( cudaMemcpyAsync( b->d_text, text + t0, total, cudaMemcpyHostToDevice, st ) );
+    PB_CUDA( cudaMemsetAsync( b->d_text + total, '\n', 64, st ) );
+  }
+  // chunk table
+  std::vector<pb::TextChunk> chunks;
+  std::vector<long long> cfirst( count + 1, 0 ), tb( count ), te( count );
+  for ( int k = 0; k < count; ++k ) {
+    tb[k] = text_off[k] - t0;
+    te[k] = text_off[k + 1] - t0;
+    cfirst[k] = (long long)chunks.size();
+    int idx = 0;
+    for ( long long p = tb[k]; p < te[k]; p += pb::kTxtChunk )
+      chunks.push_back( pb::TextChunk{ k, idx++, p, (int)std::min<long long>( pb::kTxtChunk, te[k] - p ) } );
+  }
+  cfirst[count] = (long long)chunks.size();
+  const size_t nchunks = chunks.size();
+  // one allocation: chunks | chunk_first | t_begin | t_end | chunk_lines | needs_host | lines_found | n_fallback | fallback
+  auto up16 = []( size_t x ) { return ( x + 15 ) & ~(size_t)15; };
+  const size_t o_chunks = 0;
+  const size_t o_cfirst = o_chunks + up16( sizeof( pb::TextChunk ) * std::max<size_t>( nchunks, 1 ) );
+  const size_t o_tb = o_cfirst + up16( sizeof( long long ) * ( count + 1 ) );
+  const size_t o_te = o_tb + up16( sizeof( long long ) * count );
+  const size_t o_lines = o_te + up16( sizeof( long long ) * count );
+  const size_t o_need = o_lines + up16( sizeof( int ) * std::max<size_t>( nchunks, 1 ) );
+  const size_t o_found = o_need + up16( sizeof( int ) * count );
+  const size_t o_nfb = o_found + up16( sizeof( int ) * count );
+  const size_t o_fb = o_nfb + 16;
+  const size_t need = o_fb + sizeof( pb::TextFallback ) * (size_t)pb::kTxtMaxFallback;
+  if ( b->text_tables_cap < need ) {
+    dev_free( b->d_text_tables, st );
+    b->d_text_tables = nullptr;
+    b->text_tables_cap = 0;
+    PB_CUDA( cudaMallocAsync( &b->d_text_tables, need, st ) );
+    b->text_tables_cap = need;
+  }
+  char* tbl = reinterpret_cast<char*>( b->d_text_tables );
+  if ( nchunks ) PB_CUDA( cudaMemcpyAsync( tbl + o_chunks, chunks.data(), sizeof( pb::TextChunk ) * nchunks, cudaMemcpyHostToDevice, st ) );
+  PB_CUDA( cudaMemcpyAsync( tbl + o_cfirst, cfirst.data(), sizeof( long long ) * ( count + 1 ), cudaMemcpyHostToDevice, st ) );
+  PB_CUDA( cudaMemcpyAsync( tbl + o_tb, tb.data(), sizeof( long long ) * count, cudaMemcpyHostToDevice, st ) );
+  PB_CUDA( cudaMemcpyAsync( tbl + o_te, te.data(), sizeof( long long ) * count, cudaMemcpyHostToDevice, st ) );
+  PB_CUDA( cudaMemsetAsync( tbl + o_need, 0, o_fb - o_need, st ) );
+  pb::TextArgs ta;
+  ta.text = b->d_text;
+  ta.t_begin = reinterpret_cast<const long long*>( tbl + o_tb );
+  ta.t_end = reinterpret_cast<const long long*>( tbl + o_te );
+  ta.nnz_off = b->d_nnz_off;
+  ta.chunks = reinterpret_cast<const pb::TextChunk*>( tbl + o_chunks );
+  ta.chunk_first = reinterpret_cast<const long long*>( tbl + o_cfirst );
+  ta.chunk_lines = reinterpret_cast<int*>( tbl + o_lines );
+  ta.coo_i = b->d_coo_i;
+  ta.coo_j = b->d_coo_j;
+  ta.coo_v = b->d_coo_v;
+  ta.needs_host = reinterpret_cast<int*>( tbl + o_need );
+  ta.lines_found = reinterpret_cast<int*>( tbl + o_found );
+  ta.fallback = reinterpret_cast<pb::TextFallback*>( tbl + o_fb );
+  ta.n_fallback = reinterpret_cast<int*>( tbl + o_nfb );
+  if ( nchunks ) {
+    pb::text_count_kernel<<<(unsigned)nchunks, pb::kTxtThreads, 0, st>>>( ta );
+    pb::text_scan_kernel<<<count, 32, 0, st>>>( ta, count );
+    pb::text_parse_kernel<<<(unsigned)nchunks, pb::kTxtThreads, 0, st>>>( ta );
+  } else {
+    pb::text_scan_kernel<<<count, 32, 0, st>>>( ta, count );
+  }
+  PB_CUDA( cudaGetLastError() );
+  std::vector<int> need_h( count, 0 );
+  int nfb = 0;
+  PB_CUDA( cudaMemcpyAsync( need_h.data(), tbl + o_need, sizeof( int ) * count, cudaMemcpyDeviceToHost, st ) );
+  PB_CUDA( cudaMemcpyAsync( &nfb, tbl + o_nfb, sizeof( int ), cudaMemcpyDeviceToHost, st ) );
+  PB_CUDA( cudaStreamSynchronize( st ) );
+  if ( nfb > 0 ) {
+    // fields the device refused: the C library converts them (atoi / atoi / atof on the field, reference
+    // src/square-matrix.hpp:112-114), the results are patched into the device arrays
+    const int take = std::min( nfb, pb::kTxtMaxFallback );
+    std::vector<pb::TextFallback> fb( take );
+    PB_CUDA( cudaMemcpy( fb.data(), tbl + o_fb, sizeof( pb::TextFallback ) * take, cudaMemcpyDeviceToHost ) );
+    std::vector<long long> where;
+    std::vector<int> vi, vj;
+    std::vector<double> vv;
+    char line[112];
+    for ( const pb::TextFallback& f : fb ) {
+      if ( need_h[f.matrix] ) continue;
+      const char* p = resident ? line : text + t0 + f.offset;
+      const char* end = resident ? line : text + t0 + te[f.matrix];
+      if ( resident ) {
+        // the line itself comes back from the device (legal lines are at most 5 + 1 + 5 + 1 + 31 + 1 bytes)
+        const size_t nb = (size_t)std::min<long long>( (long long)sizeof( line ), te[f.matrix] - f.offset );
+        PB_CUDA( cudaMemcpy( line, b->d_text + f.offset, nb, cudaMemcpyDeviceToHost ) );
+        end = line + nb;
+      }
+      const char* fld[3];
+      size_t len[3];
+      for ( int part = 0; part < 3; ++part ) {
+        const char stop = part < 2 ? ' ' : '\n';
+        fld[part] = p;
+        while ( p < end && *p != stop ) ++p;
+        len[part] = (size_t)( p - fld[part] );
+        if ( p < end ) ++p;
+      }
+      char buf[3][40];
+      for ( int part = 0; part < 3; ++part ) {
+        const size_t l = std::min<size_t>( len[part], 39 );
+        std::memcpy( buf[part], fld[part], l );
+        buf[part][l] = '\0';
+      }
+      where.push_back( b->nnz_off[f.matrix] + f.line );
+      vi.push_back( std::atoi( buf[0] ) );
+      vj.push_back( std::atoi( buf[1] ) );
+      vv.push_back( std::atof( buf[2] ) );
+    }
+    const int np = (int)where.size();
+    if ( np > 0 ) {
+      long long* d_where = nullptr;
+      int *d_vi = nullptr, *d_vj = nullptr;
+      double* d_vv = nullptr;
+      int rc = dev_alloc( &d_where, np );
+      if ( rc == PALADIN_GPU_OK ) rc = dev_alloc( &d_vi, np );
+      if ( rc == PALADIN_GPU_OK ) rc = dev_alloc( &d_vj, np );
+      if ( rc == PALADIN_GPU_OK ) rc = dev_alloc( &d_vv, np );
+      cudaError_t e = cudaSuccess;
+      if ( rc == PALADIN_GPU_OK ) {
+        e = cudaMemcpy( d_where, where.data(), sizeof( long long ) * np, cudaMemcpyHostToDevice );
+        if ( e == cudaSuccess ) e = cudaMemcpy( d_vi, vi.data(), sizeof( int ) * np, cudaMemcpyHostToDevice );
+        if ( e == cudaSuccess ) e = cudaMemcpy( d_vj, vj.data(), sizeof( int ) * np, cudaMemcpyHostToDevice );
+        if ( e == cudaSuccess ) e = cudaMemcpy( d_vv, vv.data(), sizeof( double ) * np, cudaMemcpyHostToDevice );
+        if ( e == cudaSuccess ) {
+          pb::text_patch_kernel<<<( np + 255 ) / 256, 256, 0, st>>>( np, d_where, d_vi, d_vj, d_vv, b->d_coo_i, b->d_coo_j, b->d_coo_v );
+          e = cudaStreamSynchronize( st );
+        }
+      }
+      dev_free( d_where, st ); dev_free( d_vi, st ); dev_free( d_vj, st ); dev_free( d_vv, st );
+      if ( rc != PALADIN_GPU_OK ) return rc;
+      if ( e != cudaSuccess ) return fail( PALADIN_GPU_ECUDA, cudaGetErrorString( e ) );
+    }
+  }
+  if ( needs_host )
+    for ( int k = 0; k < count; ++k ) needs_host[k] = need_h[k];
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_batch_upload_coo_one( paladin_gpu_batch* b, int k, const int* coo_i, const int* coo_j, const double* coo_v ) {
+  if ( !b || k < 0 || k >= b->count ) return fail( PALADIN_GPU_EINVAL, "bad arguments" );
+  const int64_t nnz = b->nnz_off[k + 1] - b->nnz_off[k];
+  if ( nnz > 0 && ( !coo_i || !coo_j || !coo_v ) ) return fail( PALADIN_GPU_EINVAL, "null COO arrays" );
+  PB_CUDA( cudaSetDevice( b->device ) );
+  if ( nnz > 0 ) {
+    PB_CUDA( cudaMemcpyAsync( b->d_coo_i + b->nnz_off[k], coo_i, sizeof( int ) * nnz, cudaMemcpyHostToDevice, b->stream ) );
+    PB_CUDA( cudaMemcpyAsync( b->d_coo_j + b->nnz_off[k], coo_j, sizeof( int ) * nnz, cudaMemcpyHostToDevice, b->stream ) );
+    PB_CUDA( cudaMemcpyAsync( b->d_coo_v + b->nnz_off[k], coo_v, sizeof( double ) * nnz, cudaMemcpyHostToDevice, b->stream ) );
+  }
+  PB_CUDA( cudaStreamSynchronize( b->stream ) );
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_batch_get_coo( paladin_gpu_batch* b, int* coo_i, int* coo_j, double* coo_v ) {
+  if ( !b ) return fail( PALADIN_GPU_EINVAL, "null batch" );
+  PB_CUDA( cudaSetDevice( b->device ) );
+  if ( b->total_nnz > 0 ) {
+    if ( coo_i ) PB_CUDA( cudaMemcpyAsync( coo_i, b->d_coo_i, sizeof( int ) * b->total_nnz, cudaMemcpyDeviceToHost, b->stream ) );
+    if ( coo_j ) PB_CUDA( cudaMemcpyAsync( coo_j, b->d_coo_j, sizeof( int ) * b->total_nnz, cudaMemcpyDeviceToHost, b->stream ) );
+    if ( coo_v ) PB_CUDA( cudaMemcpyAsync( coo_v, b->d_coo_v, sizeof( double ) * b->total_nnz, cudaMemcpyDeviceToHost, b->stream ) );
+  }
+  PB_CUDA( cudaStreamSynchronize( b->stream ) );
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_batch_format_vectors( paladin_gpu_batch* b, char side, double threshold, int first, int count, char* text, size_t cap,
+                                      int64_t* body_off, long long* kept, int* needs_host ) {
+  if ( !b || !body_off || !kept || !needs_host ) return fail( PALADIN_GPU_EINVAL, "bad arguments" );
+  if ( side != 'R' && side != 'L' ) return fail( PALADIN_GPU_EINVAL, "side must be 'R' or 'L'" );
+  if ( first < 0 || count < 0 || first + count > b->count ) return fail( PALADIN_GPU_EINVAL, "matrix range outside the batch" );
+  const double* vecs = side == 'R' ? b->d_V : b->d_VL;
+  if ( ( side == 'R' ? b->jobvr : b->jobvl ) != 'V' || !vecs ) return fail( PALADIN_GPU_EINVAL, "the batch holds no vectors of that side" );
+  PB_CUDA( cudaSetDevice( b->device ) );
+  body_off[0] = 0;
+  if ( count == 0 ) return PALADIN_GPU_OK;
+  cudaStream_t st = b->stream;
+  g_alloc_stream = st;
+  // 1. the write filter: largest |x|^2 per vector, kept entries per matrix (bit-exact with the reference writer's first pass)
+  {
+    int nmax = 0;
+    for ( int k = first; k < first + count; ++k ) nmax = std::max( nmax, b->n[k] );
+    PB_CUDA( cudaMemsetAsync( b->d_kept + first, 0, sizeof( unsigned long long ) * count, st ) );
+    if ( nmax > 0 ) {
+      BatchView bv = batch_view( b );
+      for ( int k0 = first; k0 < first + count; k0 += 65535 ) {
+        BatchView bk = bv;
+        bk.n += k0; bk.a_off += k0; bk.w_off += k0; bk.info += k0;
+        const int cnt = std::min( 65535, first + count - k0 );
+        vector_filter_kernel<<<dim3( ( nmax + 7 ) / 8, cnt ), 256, 0, st>>>( bk, vecs, threshold, b->d_max2, b->d_kept + k0, cnt );
+      }
+      PB_CUDA( cudaGetLastError() );
+    }
+    PB_CUDA( cudaMemcpyAsync( kept, b->d_kept + first, sizeof( long long ) * count, cudaMemcpyDeviceToHost, st ) );
+  }
+  // 2. scratch of the formatter: groups of consecutive matrices with at most fmt_cap_entries vector components
+  const long long want_entries = 48LL << 20;
+  long long biggest = 0, range_entries = 0;
+  for ( int k = first; k < first + count; ++k ) {
+    biggest = std::max( biggest, (long long)b->n[k] * b->n[k] );
+    range_entries += (long long)b->n[k] * b->n[k];
+  }
+  const long long cap_entries = std::max( std::max( std::min( want_entries, range_entries ), biggest ), 1LL );
+  if ( b->fmt_cap_entries < cap_entries ) {
+    dev_free( b->d_fmt_slots, st ); dev_free( b->d_fmt_out, st ); dev_free( b->d_fmt_lens, st ); dev_free( b->d_fmt_bsum, st ); dev_free( b->d_fmt_eoff, st ); dev_free( b->d_fmt_flags, st );
+    b->d_fmt_slots = b->d_fmt_out = nullptr;
+    b->d_fmt_lens = nullptr;
+    b->d_fmt_bsum = nullptr;
+    b->d_fmt_eoff = nullptr;
+    b->d_fmt_flags = nullptr;
+    b->fmt_cap_entries = 0;
+    PB_CUDA( cudaMallocAsync( reinterpret_cast<void**>( &b->d_fmt_slots ), (size_t)cap_entries * pb::kFmtSlot, st ) );
+    PB_CUDA( cudaMallocAsync( reinterpret_cast<void**>( &b->d_fmt_out ), (size_t)cap_entries * pb::kFmtSlot, st ) );
+    PB_CUDA( cudaMallocAsync( reinterpret_cast<void**>( &b->d_fmt_lens ), (size_t)cap_entries, st ) );
+    PB_CUDA( cudaMallocAsync( reinterpret_cast<void**>( &b->d_fmt_bsum ), sizeof( unsigned long long ) * ( (size_t)( cap_entries / pb::kFmtPerBlock ) + 2 ), st ) );
+    PB_CUDA( cudaMallocAsync( reinterpret_cast<void**>( &b->d_fmt_eoff ), sizeof( long long ) * 2 * ( (size_t)b->count + 1 ), st ) );
+    PB_CUDA( cudaMallocAsync( reinterpret_cast<void**>( &b->d_fmt_flags ), sizeof( int ) * (size_t)b->count, st ) );
+    b->fmt_cap_entries = cap_entries;
+  }
+  PB_CUDA( cudaMemsetAsync( b->d_fmt_flags + first, 0, sizeof( int ) * count, st ) );
+  size_t written = 0;
+  std::vector<long long> eoff, boff;
+  int k0 = first;
+  const int kend = first + count;
+  while ( k0 < kend ) {
+    int k1 = k0;
+    long long entries = 0;
+    while ( k1 < kend && ( k1 == k0 || entries + (long long)b->n[k1] * b->n[k1] <= b->fmt_cap_entries ) ) {
+      entries += (long long)b->n[k1] * b->n[k1];
+      ++k1;
+    }
+    const int cnt = k1 - k0;
+    eoff.assign( cnt + 1, 0 );
+    for ( int q = 0; q < cnt; ++q ) eoff[q + 1] = eoff[q] + (long long)b->n[k0 + q] * b->n[k0 + q];
+    if ( entries > 0 ) {
+      PB_CUDA( cudaMemcpyAsync( b->d_fmt_eoff, eoff.data(), sizeof( long long ) * ( cnt + 1 ), cudaMemcpyHostToDevice, st ) );
+      pb::FmtArgs fa;
+      fa.n = b->d_n + k0;
+      fa.a_off = b->d_a_off + k0;
+      fa.w_off = b->d_w_off + k0;
+      fa.e_off = b->d_fmt_eoff;
+      fa.count = cnt;
+      fa.vecs = vecs;
+      fa.wi = b->d_wi;
+      fa.max2 = b->d_max2;
+      fa.info = b->d_info + k0;
+      fa.threshold = threshold;
+      fa.slots = b->d_fmt_slots;
+      fa.lens = b->d_fmt_lens;
+      fa.needs_host = b->d_fmt_flags + k0;
+      const long long nblocks = ( entries + pb::kFmtPerBlock - 1 ) / pb::kFmtPerBlock;
+      long long* d_boff = b->d_fmt_eoff + ( b->count + 1 );
+      pb::fmt_lines_kernel<<<(unsigned)( ( entries + pb::kFmtThreads - 1 ) / pb::kFmtThreads ), pb::kFmtThreads, 0, st>>>( fa, entries );
+      pb::fmt_blocksum_kernel<<<(unsigned)nblocks, pb::kFmtThreads, 0, st>>>( b->d_fmt_lens, entries, b->d_fmt_bsum );
+      pb::fmt_scan_kernel<<<1, 1024, 0, st>>>( b->d_fmt_bsum, nblocks );
+      pb::fmt_bodyoff_kernel<<<( cnt + 1 + 127 ) / 128, 128, 0, st>>>( fa, entries, nblocks, b->d_fmt_bsum, d_boff );
+      pb::fmt_compact_kernel<<<(unsigned)nblocks, pb::kFmtThreads, 0, st>>>( fa, entries, b->d_fmt_bsum, b->d_fmt_out );
+      PB_CUDA( cudaGetLastError() );
+      boff.assign( cnt + 1, 0 );
+      PB_CUDA( cudaMemcpyAsync( boff.data(), d_boff, sizeof( long long ) * ( cnt + 1 ), cudaMemcpyDeviceToHost, st ) );
+      PB_CUDA( cudaStreamSynchronize( st ) );
+      const size_t bytes = (size_t)boff[cnt];
+      if ( text == nullptr ) {
+        // the compacted text stays on the device for paladin_gpu_batch_fetch_text: only possible for a single group
+        if ( k0 != first || k1 != kend ) return fail( PALADIN_GPU_EINVAL, "range too large to keep the formatted text on the device (48 Mi components at most)" );
+      } else {
+        if ( written + bytes > cap ) return fail( PALADIN_GPU_EINVAL, "text buffer too small for the formatted vectors (48 bytes per component always suffice)" );
+        if ( bytes ) PB_CUDA( cudaMemcpyAsync( text + written, b->d_fmt_out, bytes, cudaMemcpyDeviceToHost, st ) );
+      }
+      for ( int q = 0; q < cnt; ++q ) body_off[k0 - first + q + 1] = (int64_t)( written + (size_t)boff[q + 1] );
+      PB_CUDA( cudaStreamSynchronize( st ) );
+      written += bytes;
+    } else {
+      for ( int q = 0; q < cnt; ++q ) body_off[k0 - first + q + 1] = (int64_t)written;
+    }
+    k0 = k1;
+  }
+  PB_CUDA( cudaMemcpyAsync( needs_host, b->d_fmt_flags + first, sizeof( int ) * count, cudaMemcpyDeviceToHost, st ) );
+  PB_CUDA( cudaStreamSynchronize( st ) );
+  b->fmt_text_bytes = text == nullptr ? written : 0;
+  return PALADIN_GPU_OK;
+}
+
+int paladin_gpu_batch_fetch_text( paladin_gpu_batch* b, size_t offset, size_t bytes, char* dst ) {
+  if ( !b || ( bytes > 0 && !dst ) ) return fail( PALADIN_GPU_EINVAL, "bad arguments" );
+  if ( offset + bytes > b->fmt_text_bytes ) return fail( PALADIN_GPU_EINVAL, "range outside the formatted text kept on the device" );
+  if ( bytes == 0 ) return PALADIN_GPU_OK;
+  PB_CUDA( cudaSetDevice( b->device ) );
+  // (a copy of its own: several writer threads fetch their files side by side; the legacy-blocking semantics of cudaMemcpy
+  // do not apply to the batch's non-blocking stream, whose work has been synchronised by the format call)
+  PB_CUDA( cudaMemcpy( dst, b->d_fmt_out + offset, bytes, cudaMemcpyDeviceToHost ) );
   return PALADIN_GPU_OK;
 }
 

@@ -586,6 +586,113 @@ print("OK", i, len(got))
 
 
 # ---------------------------------------------------------------------------------------------------
+# (b2) the text ends on the device: MatrixMarket entry lines -> COO, eigenvector files <- vectors
+# ---------------------------------------------------------------------------------------------------
+def _entry_text(path_or_bytes):
+    """(n, nnz, body bytes) of a MatrixMarket file: everything after the size line, as the file has it."""
+    raw = open(path_or_bytes, "rb").read() if isinstance(path_or_bytes, str) else path_or_bytes
+    pos = raw.index(b"\n") + 1                      # banner
+    while raw[pos:pos + 1] == b"%":
+        pos = raw.index(b"\n", pos) + 1
+    end = raw.index(b"\n", pos)
+    n, _, nnz = (int(x) for x in raw[pos:end].split())
+    return n, nnz, raw[end + 1:]
+
+
+def test_text_parse_on_device_is_bit_exact(pg, tmp_path):
+    """paladin_gpu_batch_upload_text against the host reader (which is pinned to the reference reader's dense dumps): golden
+    fixtures, the benchmark's own "%d %d %.17g" format, short spellings, and spellings the device hands to the C library
+    (hex floats, inf / nan, 25-digit mantissas, exponents out of range, leading '+', leading blanks)."""
+    from paladin_b200 import host as ph
+    files = sorted(glob.glob(os.path.join(GOLD, "ref_run", "*.matrix")) + glob.glob(os.path.join(GOLD, "ref_parser", "*.matrix")) +
+                   glob.glob(os.path.join(GOLD, "ref_ctest", "*", "*.matrix")))
+    rng = np.random.default_rng(17)
+    for q, n in enumerate([3, 64, 200, 513]):
+        ii, jj, vv = po.random_dense_coo(n, [31, q])
+        p = tmp_path / ("dense%d.matrix" % n)
+        p.write_bytes(po.mm_text(n, ii, jj, vv)[:-1] if q % 2 == 0 else po.mm_text(n, ii, jj, vv))   # with and without the last newline
+        files.append(str(p))
+    # odd spellings: every one is a legal field for atof
+    odd = ["0x1.8p3", "inf", "-inf", "nan", "1234567890123456789012345", "1e400", "-1e-400", "+2.5", " 3.25", "1.", ".5", "-.5e-3", "0", "-0",
+           "0.0000000000000000000000001234", "4.9406564584124654e-324", "2.2250738585072011e-308", "1.7976931348623157e308", "1e22", "1e23",
+           "9007199254740993", "9007199254740992.5", "0.30000000000000004", "123456789012345678", "1E5", "1e+5", "1e-05"]
+    lines = ["%d %d %s" % (k % 7 + 1, k // 7 + 1, w) for k, w in enumerate(odd)]
+    p = tmp_path / "odd.matrix"
+    p.write_bytes(("%%MatrixMarket matrix coordinate real general\n7 7 %d\n" % len(lines) + "\n".join(lines)).encode())
+    files.append(str(p))
+    metas = [_entry_text(f) for f in files]
+    n = np.array([m[0] for m in metas], dtype=np.int32)
+    off = np.concatenate([[0], np.cumsum([m[1] for m in metas])]).astype(np.int64)
+    text = b"".join(m[2] for m in metas)
+    toff = np.concatenate([[0], np.cumsum([len(m[2]) for m in metas])]).astype(np.int64)
+    b = pg.Batch(n, off, jobvr="N")
+    need = b.upload_text(text, toff)
+    gi, gj, gv = b.get_coo()
+    b.destroy()
+    assert not need.any(), [f for f, x in zip(files, need) if x]
+    for k, f in enumerate(files):
+        nk, nnz, hi, hj, hv = ph.parse_mm(f)
+        assert nk == n[k] and nnz == metas[k][1]
+        s = slice(off[k], off[k + 1])
+        assert np.array_equal(gi[s], hi) and np.array_equal(gj[s], hj), f
+        assert gv[s].tobytes() == hv.tobytes(), (f, np.nonzero(gv[s].view(np.uint64) != hv.view(np.uint64))[0][:5])
+
+
+def test_text_parse_hands_irregular_files_to_the_host_reader(pg):
+    """Lines the reference's FIELD reader would not see as lines (a missing blank, an empty line) and over-long fields mark
+    the matrix for the host reader; the other matrices of the batch are parsed on the device."""
+    good = b"1 1 1.5\n2 2 -2.5\n"
+    cases = [good, b"1 1 1.5\n22 2.5\n", good, b"1 1 1.5\n\n2 2 2.5\n", b"123456 1 1.5\n2 2 2.5\n", b"1 1 1.5\n", good]
+    n = np.full(len(cases), 2, dtype=np.int32)
+    off = np.arange(len(cases) + 1, dtype=np.int64) * 2
+    toff = np.concatenate([[0], np.cumsum([len(c) for c in cases])]).astype(np.int64)
+    b = pg.Batch(n, off, jobvr="N")
+    need = b.upload_text(b"".join(cases), toff)
+    gi, gj, gv = b.get_coo()
+    b.destroy()
+    assert need.tolist() == [0, 1, 0, 1, 1, 1, 0]
+    for k in (0, 2, 6):
+        assert gi[2 * k:2 * k + 2].tolist() == [1, 2] and gv[2 * k:2 * k + 2].tolist() == [1.5, -2.5]
+
+
+@pytest.mark.parametrize("threshold", [1e-3, 0.3, 0.0])
+def test_vector_files_formatted_on_device_are_byte_exact(pg, threshold):
+    """paladin_gpu_batch_format_vectors against the host writer (pinned to the reference's .exact files): same bytes for the
+    bodies of .rightvecs / .leftvecs, same kept counts, every size class, conjugate pairs and real eigenvalues."""
+    from paladin_b200 import host as ph
+    sizes = [1, 2, 5, 33, 64, 100, 300, 600]
+    mats = _random_mats(sizes, 58)
+    # plus the reference's own 2x2 / identity cases (exact ties and signed zeros in the output)
+    for pth in CTEST:
+        nk, nnz, ii, jj, vv = po.read_mm(pth)
+        mats.append((nk, ii, jj, vv))
+    n, off, ii, jj, vv = _concat(mats)
+    b = pg.Batch(n, off, jobvl="V", jobvr="V")
+    b.upload(ii, jj, vv)
+    b.scatter()
+    b.solve()
+    got = {side: b.format_vectors(side, threshold) for side in ("R", "L")}
+    wr, wi, vr, info = b.download()
+    vl = b.vl
+    b.destroy()
+    assert not info.any()
+    wo, vo = 0, 0
+    for k, m in enumerate(mats):
+        nk = m[0]
+        for side, packed, which in (("R", vr, 1), ("L", vl, 2)):
+            V = packed[vo:vo + nk * nk].reshape((nk, nk), order="F")
+            want = ph.format_output(wr[wo:wo + nk], wi[wo:wo + nk], V, which, threshold)
+            bodies, kept, need = got[side]
+            if need[k]:
+                continue   # the device refused a rounding: the executable formats this matrix on the host
+            head = b"%%MatrixMarket matrix coordinate complex general\n" + ("%d %d %d\n" % (nk, nk, kept[k])).encode()
+            assert head + bodies[k] == want, (nk, side)
+        wo += nk
+        vo += nk * nk
+    assert sum(int(x.sum()) for _, _, x in got.values()) <= 2   # refusals are rare events, not the normal path
+
+
+# ---------------------------------------------------------------------------------------------------
 # (c) the reference's own golden files through the GPU path
 # ---------------------------------------------------------------------------------------------------
 CTEST = sorted(glob.glob(os.path.join(GOLD, "ref_ctest", "*", "*.matrix")))
