@@ -168,6 +168,55 @@ __global__ void __launch_bounds__( 32 ) geev_warp_kernel( BatchView bv, const in
   if ( lane == 0 ) bv.info[id] = info;
 }
 
+// the same with a small CTA (2 or 4 warps) per matrix: the shared-memory footprint of a matrix caps the warp-per-matrix kernel
+// at 6 warps per SM for n = 64 (33 KB each); more warps on the SAME matrix raise the occupancy without raising the footprint
+// (PALADIN_GPU_SMALL_WARPS)
+__global__ void __launch_bounds__( 128 ) geev_smallcta_kernel( BatchView bv, const int* ids, int nmax, int lds ) {
+  extern __shared__ double smem[];
+  __shared__ double red[64];
+  const int id = ids[blockIdx.x];
+  const int n = bv.n[id];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const size_t msz = (size_t)lds * nmax;
+  double* As = smem;
+  double* p = As + msz;
+  double* Vs = p;
+  if ( bv.wantvr ) p += msz;
+  double* Ls = p;
+  if ( bv.wantvl ) p += msz;
+  double* dw = p;
+  int* iw = reinterpret_cast<int*>( dw + 5 * nmax );
+  const double* Ag = bv.A + bv.a_off[id];
+  const int nn = n * n;
+  for ( int q = tid; q < nn; q += nt ) {
+    const int c = q / n, r = q - c * n;
+    As[r + c * lds] = Ag[q];
+  }
+  __syncthreads();
+  pb::CtaGroup g{ red };
+  double* wr = bv.wr + bv.w_off[id];
+  double* wi = bv.wi + bv.w_off[id];
+  const int info = pb::geev_group( g, n, As, lds, wr, wi, bv.wantvl != 0, Ls, lds, bv.wantvr != 0, Vs, lds, dw, iw );
+  __syncthreads();
+  if ( info == 0 ) {
+    if ( bv.wantvr ) {
+      double* Vg = bv.V + bv.a_off[id];
+      for ( int q = tid; q < nn; q += nt ) {
+        const int c = q / n, r = q - c * n;
+        Vg[q] = Vs[r + c * lds];
+      }
+    }
+    if ( bv.wantvl ) {
+      double* Lg = bv.VL + bv.a_off[id];
+      for ( int q = tid; q < nn; q += nt ) {
+        const int c = q / n, r = q - c * n;
+        Lg[q] = Ls[r + c * lds];
+      }
+    }
+  }
+  if ( tid == 0 ) bv.info[id] = info;
+}
+
 // ---- size-generic path: one CTA per matrix, in place in global memory ----------------------------
 __global__ void __launch_bounds__( kGenericThreads ) geev_cta_kernel( BatchView bv, const int* ids ) {
   __shared__ double red[64];
@@ -331,14 +380,13 @@ __global__ void __launch_bounds__( pb::kBhThreads, ( MAXCH == 16 ? 2 : 1 ) ) mid
   extern __shared__ __align__( 128 ) double smem[];
   __shared__ double red[64];
   __shared__ long long lstats[kNumTicks];
-  __shared__ __align__( 8 ) uint64_t bars[2];
+  __shared__ __align__( 8 ) uint64_t bars[pb::kBhMaxStages];
   const int id = a.ids[blockIdx.x];
   const int n = a.bv.n[id];
   pb::CtaGroup g{ red };
   stats_begin( g, a.stats, lstats );
   if ( threadIdx.x == 0 ) {
-    pb::bh_mbar_init( &bars[0], 1 );
-    pb::bh_mbar_init( &bars[1], 1 );
+    for ( int q = 0; q < pb::kBhMaxStages; ++q ) pb::bh_mbar_init( &bars[q], 1 );
     asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" );
   }
   __syncthreads();
@@ -749,6 +797,7 @@ int set_kernel_attributes( DeviceCtx& c ) {
   if ( c.attrs_set ) return PALADIN_GPU_OK;
   const int o = c.max_smem_optin;
   PB_CUDA( raise_smem_limit( geev_warp_kernel, o ) );
+  PB_CUDA( raise_smem_limit( geev_smallcta_kernel, o ) );
   PB_CUDA( raise_smem_limit( mid_prep_kernel<0>, o ) );
   PB_CUDA( raise_smem_limit( mid_prep_kernel<16>, o ) );
   PB_CUDA( raise_smem_limit( mid_prep_kernel<32>, o ) );
@@ -1412,7 +1461,9 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
       const size_t smem = warp_smem_bytes( g.nmax, ( wantvr ? 1 : 0 ) + ( wantvl ? 1 : 0 ) );
       if ( smem <= (size_t)c.max_smem_optin ) {
         stage_begin( b, PALADIN_GPU_STAGE_SMALL, st );
-        geev_warp_kernel<<<cnt, 32, smem, st>>>( bv, ids, g.nmax, g.nmax | 1 );
+        static const int small_warps = std::getenv( "PALADIN_GPU_SMALL_WARPS" ) ? std::max( 1, std::min( 4, std::atoi( std::getenv( "PALADIN_GPU_SMALL_WARPS" ) ) ) ) : 1;
+        if ( small_warps > 1 && g.nmax >= 32 ) geev_smallcta_kernel<<<cnt, 32 * small_warps, smem, st>>>( bv, ids, g.nmax, g.nmax | 1 );
+        else geev_warp_kernel<<<cnt, 32, smem, st>>>( bv, ids, g.nmax, g.nmax | 1 );
         stage_end( b, PALADIN_GPU_STAGE_SMALL, st, 1 );
         PB_CUDA( cudaGetLastError() );
         continue;

@@ -32,14 +32,16 @@ namespace pb {
 
 constexpr int kTickHessUpdate = 7;  // phase-profile slot: Y top rows + trailing updates (the panels are counted as kTickHess)
 constexpr int kBhNB = 32;        // panel width
-constexpr int kBhTC = 8;         // columns per update tile (one DMMA n-tile)
+constexpr int kBhTC = 16;        // columns per update tile (two DMMA n-tiles)
+constexpr int kBhMaxStages = 8;  // row blocks of a tile that can be resident at once
 constexpr int kBhBoxRows = 256;  // rows per TMA box (box = kBhBoxRows x 1 column of doubles)
 constexpr int kBhThreads = kHessThreads;
 constexpr int kBhWarps = kBhThreads / 32;
 constexpr int kBhLdT = kBhNB + 1;  // T(q, p) at Ts[q * kBhLdT + p]
 
-// rows of a staged tile column (a multiple of the TMA box)
-__host__ __device__ inline int bh_tile_ld( int n ) { return ( ( n + kBhBoxRows - 1 ) / kBhBoxRows ) * kBhBoxRows; }
+// an update tile is staged in ROW BLOCKS of kBhBoxRows rows x kBhTC columns (one TMA box per column): doubles per stage
+constexpr int kBhStageDoubles = kBhBoxRows * kBhTC;
+__host__ __device__ inline int bh_row_blocks( int n ) { return ( n + kBhBoxRows - 1 ) / kBhBoxRows; }
 // number of panels of a reduction with n_refl reflector columns
 __host__ __device__ inline int bh_num_panels( int n ) { return n > 2 ? ( n - 2 + kBhNB - 1 ) / kBhNB : 0; }
 // global scratch per matrix (doubles): Y (ldy x NB), VT (ldy x NB), T of every panel (NB x NB each); ldy = n rounded up to even
@@ -47,11 +49,16 @@ __host__ __device__ inline size_t bh_scratch_doubles( int n ) {
   const size_t ldy = (size_t)( ( n + 1 ) & ~1 );
   return 2 * ldy * kBhNB + (size_t)bh_num_panels( n ) * kBhNB * kBhNB + 16;
 }
+// stages of the tile ring: every row block of the tallest tile resident when that fits (then nothing is re-read), two otherwise
+__host__ __device__ inline int bh_stages( int n ) {
+  const int nrb = bh_row_blocks( n );
+  return nrb <= 4 ? ( nrb < 2 ? 2 : nrb ) : 2;
+}
 // shared memory (doubles): vs, bs (2 n) | ws, wt, w2s, vrow (4 x 32) | red (64) | Ts (32 x 33) |
-//   union { ypart: 8 n ; tiles: 2 stages x 8 columns x ld + Wp: 8 warps x 256 + Wt: 256 }
+//   union { ypart: 8 x min(n, 1024) ; stages x (256 x 16) + Ws: 32 x 16 + Wt: 32 x 16 }
 __host__ __device__ inline size_t bh_smem_doubles( int n ) {
-  const size_t u1 = (size_t)kBhWarps * n;
-  const size_t u2 = (size_t)2 * kBhTC * bh_tile_ld( n ) + (size_t)kBhWarps * kBhNB * kBhTC + (size_t)kBhNB * kBhTC;
+  const size_t u1 = (size_t)kBhWarps * ( n < 1024 ? n : 1024 );
+  const size_t u2 = (size_t)bh_stages( n ) * kBhStageDoubles + 2 * (size_t)kBhNB * kBhTC;
   return 2 * (size_t)n + 4 * kBhNB + 64 + (size_t)kBhNB * kBhLdT + ( u1 > u2 ? u1 : u2 ) + 32;
 }
 
@@ -105,9 +112,9 @@ __device__ __forceinline__ double bh_v( const double* Av, int ldv, int k, int ih
 // per-CTA working set
 struct BhSmem {
   double *vs, *bs, *ws, *wt, *w2s, *vrow, *red, *Ts, *un;  // un: union of ypart / (tiles, Wp, Wt)
-  uint64_t* bars;                                          // 2 mbarriers (static shared memory of the kernel)
-  uint32_t phase;                                          // parity bits of the two barriers
-  int ldt;                                                 // rows of a staged tile column
+  uint64_t* bars;                                          // kBhMaxStages mbarriers (static shared memory of the kernel)
+  uint32_t phase;                                          // parity bits of the barriers
+  int nstages;                                             // stages of the tile ring
 };
 __device__ __forceinline__ BhSmem bh_carve( double* sm, int n, uint64_t* bars ) {
   BhSmem s;
@@ -125,7 +132,7 @@ __device__ __forceinline__ BhSmem bh_carve( double* sm, int n, uint64_t* bars ) 
   s.un = p;
   s.bars = bars;
   s.phase = 0;
-  s.ldt = bh_tile_ld( n );
+  s.nstages = bh_stages( n );
   return s;
 }
 
@@ -410,187 +417,215 @@ __device__ inline void bh_ytop( int ihi, int k, int ib, const double* A, int lda
   __syncthreads();
 }
 
-// ---- tile pass: columns [c_begin, c_end) of the target M in tiles of kBhTC, staged by TMA -----------------------------------
+// ---- tile pass: columns [c_begin, c_end) of the target M in tiles of kBhTC columns, staged by TMA in row blocks ------------------
 //   R update (r_rows > 0):  M(0:r_rows, cc) -= Y(0:r_rows, 0:ib) V(cc, 0:ib)^T          for cc <= r_col_hi
 //   L update (do_l):        M(k+1:ihi, cc)  <- (I - V op(T) V^T) M(k+1:ihi, cc)          op(T) = T^T (TRANS_T) or T
 //   rows [st_lo, st_hi) of every tile column are written back.
+// A tile is worked on in row blocks of kBhBoxRows rows (one TMA box per column and block, sh.nstages blocks on chip):
+//   sweep A  per block: R update (DMMA, C fragments in shared memory, Y fragments from L2), then the block's share of
+//            W = V^T M (every warp owns one 8 x 8 tile of the 32 x 16 result and walks all rows: no reduction);
+//   then     Wt = -op(T) W;
+//   sweep B  per block: M -= V Wt (DMMA), write back.
+// When the tile's blocks all fit the ring (n <= 4 kBhBoxRows) they stay resident between the sweeps; otherwise sweep A
+// writes its blocks back and sweep B streams them again (they come from L2).
 // V lives below the subdiagonal of Av (panel start k, ib columns). tmap describes M (box kBhBoxRows x 1); without a tensor
-// map (odd leading dimension) the tile is staged by plain loads.
+// map (odd leading dimension) the blocks are staged by plain loads.
 template <bool TRANS_T>
 __device__ void bh_tile_pass( int n, int ihi, int k, int ib, double* M, int ldm, const CUtensorMap* tmap, const double* Av, int ldv,
                               const double* Y, int ldy, int r_rows, int r_col_hi, bool do_l, int c_begin, int c_end, int st_lo, int st_hi,
                               BhSmem& sh ) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;
-  const int ldt = sh.ldt;
-  const int nbox = ldt / kBhBoxRows;
-  double* tiles = sh.un;                                            // [2][kBhTC][ldt]
-  double* Wp = tiles + (size_t)2 * kBhTC * ldt;                     // [kBhWarps][kBhNB][kBhTC]
-  double* Wt = Wp + (size_t)kBhWarps * kBhNB * kBhTC;               // [kBhNB][kBhTC]
+  const int NS = sh.nstages;
+  double* ring = sh.un;                                      // [NS][kBhTC][kBhBoxRows]
+  double* Ws = ring + (size_t)NS * kBhStageDoubles;           // [kBhNB][kBhTC]
+  double* Wt = Ws + kBhNB * kBhTC;                            // [kBhNB][kBhTC]
   const int ntiles = ( c_end - c_begin + kBhTC - 1 ) / kBhTC;
   if ( ntiles <= 0 ) return;
+  // row blocks the pass touches: R rows [0, r_rows), L rows [k+1, ihi], stored rows [st_lo, st_hi)
+  const int row_lo = imin( st_lo, imin( r_rows > 0 ? 0 : n, do_l ? k + 1 : n ) );
+  const int row_hi = imax( st_hi - 1, imax( r_rows - 1, do_l ? ihi : -1 ) );
+  const int rb0 = row_lo / kBhBoxRows, rb1 = row_hi / kBhBoxRows;
+  const int nA = rb1 - rb0 + 1;
+  const bool resident = nA <= NS;
+  const int lb0 = do_l ? ( k + 1 ) / kBhBoxRows : 0, lb1 = do_l ? ihi / kBhBoxRows : -1;  // blocks of sweep B
+  const int nB = ( do_l && !resident ) ? lb1 - lb0 + 1 : 0;
+  const int nseq = nA + nB;  // loads per tile, in this order: sweep A blocks, then (streaming mode) sweep B blocks
   // global data this CTA wrote through the generic proxy is about to be read by the async proxy (TMA)
   bh_fence_proxy_async();
   __syncthreads();
-  auto issue = [&]( int t ) {  // thread 0 only
-    const int stage = t & 1;
-    double* dst = tiles + (size_t)stage * kBhTC * ldt;
-    bh_mbar_expect_tx( &sh.bars[stage], (uint32_t)( kBhTC * ldt * sizeof( double ) ) );
-    for ( int q = 0; q < kBhTC; ++q )
-      for ( int b = 0; b < nbox; ++b ) bh_tma_load_box( dst + (size_t)q * ldt + b * kBhBoxRows, tmap, b * kBhBoxRows, c_begin + t * kBhTC + q, &sh.bars[stage] );
+  auto block_of = [&]( int q ) { return q < nA ? rb0 + q : lb0 + ( q - nA ); };
+  auto issue = [&]( int cc0, int q ) {  // thread 0 only: load q of the tile that starts at column cc0
+    const int stage = q % NS;
+    double* dst = ring + (size_t)stage * kBhStageDoubles;
+    const int row0 = block_of( q ) * kBhBoxRows;
+    bh_mbar_expect_tx( &sh.bars[stage], (uint32_t)( kBhStageDoubles * sizeof( double ) ) );
+    for ( int c = 0; c < kBhTC; ++c ) bh_tma_load_box( dst + (size_t)c * kBhBoxRows, tmap, row0, cc0 + c, &sh.bars[stage] );
   };
-  if ( tmap != nullptr && tid == 0 ) {
-    issue( 0 );
-    if ( ntiles > 1 ) issue( 1 );
-  }
-  for ( int t = 0; t < ntiles; ++t ) {
-    const int stage = t & 1;
-    double* St = tiles + (size_t)stage * kBhTC * ldt;
-    const int cc0 = c_begin + t * kBhTC;
+  // block q of the current tile is on chip after this
+  auto acquire = [&]( int cc0, int q ) -> double* {
+    const int stage = q % NS;
+    double* St = ring + (size_t)stage * kBhStageDoubles;
     if ( tmap != nullptr ) {
       bh_mbar_wait( &sh.bars[stage], ( sh.phase >> stage ) & 1u );
       sh.phase ^= 1u << stage;
     } else {
-      for ( int q = tid; q < kBhTC * n; q += kBhThreads ) {
-        const int col = q / n, r = q - col * n;
-        St[(size_t)col * ldt + r] = ( cc0 + col < c_end ) ? M[r + (size_t)( cc0 + col ) * ldm] : 0.0;
+      const int row0 = block_of( q ) * kBhBoxRows;
+      __syncthreads();
+      for ( int e = tid; e < kBhStageDoubles; e += kBhThreads ) {
+        const int c = e / kBhBoxRows, r = row0 + ( e - c * kBhBoxRows );
+        St[e] = ( cc0 + c < n && r < n ) ? M[r + (size_t)( cc0 + c ) * ldm] : 0.0;
       }
       __syncthreads();
     }
-    // ---- R update ----
-    if ( r_rows > 0 && cc0 <= r_col_hi ) {
-      double bv[8];
-      {
-        const int cc = cc0 + gid;
-        const bool cok = cc < c_end && cc <= r_col_hi;
-#pragma unroll
-        for ( int s = 0; s < 8; ++s ) {
-          const int p = 4 * s + tig;
-          bv[s] = ( cok && p < ib ) ? -bh_v( Av, ldv, k, ihi, cc, p ) : 0.0;
-        }
-      }
-      const int nrt = ( r_rows + 7 ) >> 3;
-      // (the fragments of the next row tile are requested before the current one is multiplied: L2 latency, not DMMA, bounds this loop)
-      auto load_y = [&]( int rt, double* a ) {
-        const int r = 8 * rt + gid;
-        const bool rok = r < r_rows;
-        const double* yr = Y + imin( r, r_rows - 1 );
-#pragma unroll
-        for ( int s = 0; s < 8; ++s ) {
-          const int p = 4 * s + tig;
-          a[s] = ( rok && p < ib ) ? yr[(size_t)p * ldy] : 0.0;
-        }
-      };
-      double a[8], an[8];
-      if ( warp < nrt ) load_y( warp, a );
-      for ( int rt = warp; rt < nrt; rt += kBhWarps ) {
-        if ( rt + kBhWarps < nrt ) load_y( rt + kBhWarps, an );
-        double* cp = St + (size_t)( 2 * tig ) * ldt + 8 * rt + gid;
-        double c0 = cp[0], c1 = cp[ldt];
-#pragma unroll
-        for ( int s = 0; s < 8; ++s ) bh_dmma( c0, c1, a[s], bv[s] );
-        cp[0] = c0;
-        cp[ldt] = c1;
-#pragma unroll
-        for ( int s = 0; s < 8; ++s ) a[s] = an[s];
-      }
-      __syncthreads();
+    return St;
+  };
+  // rows [lo, hi) of a block back to global memory, then the stage is free for load q + NS
+  auto store_rows = [&]( const double* St, int row0, int cc0, int lo, int hi ) {
+    lo = imax( lo, row0 );
+    hi = imin( hi, row0 + kBhBoxRows );
+    const int nr = hi - lo;
+    if ( nr <= 0 ) return;
+    for ( int e = tid; e < kBhTC * nr; e += kBhThreads ) {
+      const int c = e / nr, r = lo + ( e - c * nr );
+      if ( cc0 + c < c_end ) M[r + (size_t)( cc0 + c ) * ldm] = St[(size_t)c * kBhBoxRows + ( r - row0 )];
     }
-    // ---- L update ----
-    if ( do_l ) {
-      // W(p, t) = sum_r V(r, p) St(r, t), rows k+1..ihi in groups of 4 dealt to the warps
-      double acc[4][2];
-#pragma unroll
-      for ( int mt = 0; mt < 4; ++mt ) acc[mt][0] = acc[mt][1] = 0.0;
-      const int g0 = ( k + 1 ) >> 2, g1 = ihi >> 2;
-      for ( int g = g0 + warp; g <= g1; g += 2 * kBhWarps ) {
-        double av[2][4], bb[2];
-#pragma unroll
-        for ( int h = 0; h < 2; ++h ) {
-          const int gg = g + h * kBhWarps;
-          const int r = 4 * imin( gg, g1 ) + tig;
-          bb[h] = ( gg <= g1 ) ? St[(size_t)gid * ldt + r] : 0.0;
-#pragma unroll
-          for ( int mt = 0; mt < 4; ++mt ) {
-            const int p = 8 * mt + gid;
-            av[h][mt] = ( p < ib && gg <= g1 ) ? bh_v( Av, ldv, k, ihi, r, p ) : 0.0;
-          }
-        }
-#pragma unroll
-        for ( int h = 0; h < 2; ++h )
-#pragma unroll
-          for ( int mt = 0; mt < 4; ++mt ) bh_dmma( acc[mt][0], acc[mt][1], av[h][mt], bb[h] );
-      }
-#pragma unroll
-      for ( int mt = 0; mt < 4; ++mt ) {
-        double* wp = Wp + ( (size_t)warp * kBhNB + 8 * mt + gid ) * kBhTC + 2 * tig;
-        wp[0] = acc[mt][0];
-        wp[1] = acc[mt][1];
-      }
-      __syncthreads();
-      {
-        // Wt = op(T) * (sum over warps): thread (p, t)
-        const int p = tid >> 3, tc = tid & 7;
-        double s = 0.0;
-        if ( TRANS_T ) {
-          for ( int q = 0; q <= p; ++q ) {
-            double w = 0.0;
-#pragma unroll
-            for ( int ww = 0; ww < kBhWarps; ++ww ) w += Wp[( (size_t)ww * kBhNB + q ) * kBhTC + tc];
-            s += sh.Ts[q * kBhLdT + p] * w;
-          }
-        } else {
-          for ( int q = p; q < ib; ++q ) {
-            double w = 0.0;
-#pragma unroll
-            for ( int ww = 0; ww < kBhWarps; ++ww ) w += Wp[( (size_t)ww * kBhNB + q ) * kBhTC + tc];
-            s += sh.Ts[p * kBhLdT + q] * w;
-          }
-        }
-        Wt[p * kBhTC + tc] = ( p < ib ) ? -s : 0.0;
-      }
-      __syncthreads();
-      {
-        double bw[8];
-#pragma unroll
-        for ( int s = 0; s < 8; ++s ) bw[s] = Wt[( 4 * s + tig ) * kBhTC + gid];
-        const int rt0 = ( k + 1 ) >> 3, rt1 = ihi >> 3;
-        auto load_v = [&]( int rt, double* a ) {
-          const int r = 8 * rt + gid;
-#pragma unroll
-          for ( int s = 0; s < 8; ++s ) {
-            const int p = 4 * s + tig;
-            a[s] = ( p < ib ) ? bh_v( Av, ldv, k, ihi, r, p ) : 0.0;
-          }
-        };
-        double a[8], an[8];
-        if ( rt0 + warp <= rt1 ) load_v( rt0 + warp, a );
-        for ( int rt = rt0 + warp; rt <= rt1; rt += kBhWarps ) {
-          if ( rt + kBhWarps <= rt1 ) load_v( rt + kBhWarps, an );
-          double* cp = St + (size_t)( 2 * tig ) * ldt + 8 * rt + gid;
-          double c0 = cp[0], c1 = cp[ldt];
-#pragma unroll
-          for ( int s = 0; s < 8; ++s ) bh_dmma( c0, c1, a[s], bw[s] );
-          cp[0] = c0;
-          cp[ldt] = c1;
-#pragma unroll
-          for ( int s = 0; s < 8; ++s ) a[s] = an[s];
-        }
-      }
-      __syncthreads();
-    }
-    // ---- write back ----
-    {
-      const int nr = st_hi - st_lo;
-      for ( int q = tid; q < kBhTC * nr; q += kBhThreads ) {
-        const int col = q / nr, r = st_lo + ( q - col * nr );
-        if ( cc0 + col < c_end ) M[r + (size_t)( cc0 + col ) * ldm] = St[(size_t)col * ldt + r];
-      }
-    }
-    // the stage is free again once every thread has read it: generic accesses to the buffer before the async write
+  };
+  auto release = [&]( int cc0, int q ) {
     bh_fence_proxy_async();
     __syncthreads();
-    if ( tmap != nullptr && tid == 0 && t + 2 < ntiles ) issue( t + 2 );
+    if ( tmap != nullptr && tid == 0 && q + NS < nseq ) issue( cc0, q + NS );
+  };
+  // M(rows of the block) -= A B with A = rows x 32 fragments from L2 (Y or V), B = 32 x 16 in registers (two n-tiles)
+  auto rank_update = [&]( double* St, int row0, int r_first, int r_last, const double ( &bfr )[2][8], bool from_y ) {
+    const int t0 = imax( r_first, row0 ) >> 3, t1 = imin( r_last, row0 + kBhBoxRows - 1 ) >> 3;  // 8-row tiles (global numbering)
+    auto load_a = [&]( int rt, double* a ) {
+      const int r = 8 * rt + gid;
+#pragma unroll
+      for ( int s2 = 0; s2 < 8; ++s2 ) {
+        const int p = 4 * s2 + tig;
+        if ( from_y ) a[s2] = ( r <= r_last && p < ib ) ? Y[imin( r, r_last ) + (size_t)p * ldy] : 0.0;
+        else a[s2] = ( p < ib ) ? bh_v( Av, ldv, k, ihi, r, p ) : 0.0;
+      }
+    };
+    for ( int rt = t0 + warp; rt <= t1; rt += kBhWarps ) {
+      double a[8];
+      load_a( rt, a );
+      double* cp = St + (size_t)( 2 * tig ) * kBhBoxRows + ( 8 * rt + gid - row0 );
+      double c00 = cp[0], c01 = cp[kBhBoxRows], c10 = cp[8 * kBhBoxRows], c11 = cp[9 * kBhBoxRows];
+#pragma unroll
+      for ( int s2 = 0; s2 < 8; ++s2 ) {
+        bh_dmma( c00, c01, a[s2], bfr[0][s2] );
+        bh_dmma( c10, c11, a[s2], bfr[1][s2] );
+      }
+      cp[0] = c00;
+      cp[kBhBoxRows] = c01;
+      cp[8 * kBhBoxRows] = c10;
+      cp[9 * kBhBoxRows] = c11;
+    }
+  };
+  if ( tmap != nullptr && tid == 0 )
+    for ( int q = 0; q < imin( NS, nseq ); ++q ) issue( c_begin, q );
+  for ( int t = 0; t < ntiles; ++t ) {
+    const int cc0 = c_begin + t * kBhTC;
+    const bool do_r = r_rows > 0 && cc0 <= r_col_hi;
+    double bf[2][8];  // B fragments: -V(cc, :) during sweep A, Wt during sweep B
+    if ( do_r ) {
+#pragma unroll
+      for ( int nt = 0; nt < 2; ++nt ) {
+        const int cc = cc0 + 8 * nt + gid;
+        const bool cok = cc < c_end && cc <= r_col_hi;
+#pragma unroll
+        for ( int s2 = 0; s2 < 8; ++s2 ) {
+          const int p = 4 * s2 + tig;
+          bf[nt][s2] = ( cok && p < ib ) ? -bh_v( Av, ldv, k, ihi, cc, p ) : 0.0;
+        }
+      }
+    }
+    // W(p, c): warp w owns the 8 x 8 tile (mt = w & 3, nt = w >> 2), four interleaved accumulator pairs over the rows
+    const int wmt = warp & 3, wnt = warp >> 2;
+    double wacc[2][2];
+#pragma unroll
+    for ( int h = 0; h < 2; ++h ) wacc[h][0] = wacc[h][1] = 0.0;
+    // ---- sweep A ----
+    for ( int q = 0; q < nA; ++q ) {
+      const int row0 = ( rb0 + q ) * kBhBoxRows;
+      double* St = acquire( cc0, q );
+      if ( do_r && row0 < r_rows ) {
+        rank_update( St, row0, 0, r_rows - 1, bf, true );
+        __syncthreads();
+      }
+      if ( do_l ) {
+        const int g0 = imax( k + 1, row0 ) >> 2, g1 = imin( ihi, row0 + kBhBoxRows - 1 ) >> 2;  // groups of 4 rows
+        const int p = 8 * wmt + gid;
+        for ( int g = g0; g <= g1; g += 2 ) {
+          double av[2], bb[2];
+#pragma unroll
+          for ( int h = 0; h < 2; ++h ) {
+            const int gg = g + h;
+            const int r = 4 * imin( gg, g1 ) + tig;
+            const bool ok = gg <= g1;
+            bb[h] = ok ? St[(size_t)( 8 * wnt + gid ) * kBhBoxRows + ( r - row0 )] : 0.0;
+            av[h] = ( ok && p < ib ) ? bh_v( Av, ldv, k, ihi, r, p ) : 0.0;
+          }
+#pragma unroll
+          for ( int h = 0; h < 2; ++h ) bh_dmma( wacc[h][0], wacc[h][1], av[h], bb[h] );
+        }
+      }
+      if ( !resident ) {
+        if ( do_r ) store_rows( St, row0, cc0, imax( st_lo, 0 ), imin( st_hi, r_rows ) );
+        release( cc0, q );
+      }
+    }
+    if ( do_l ) {
+      {
+        double* wp = Ws + ( 8 * wmt + gid ) * kBhTC + 8 * wnt + 2 * tig;
+        wp[0] = wacc[0][0] + wacc[1][0];
+        wp[1] = wacc[0][1] + wacc[1][1];
+      }
+      __syncthreads();
+      for ( int e = tid; e < kBhNB * kBhTC; e += kBhThreads ) {
+        const int p = e / kBhTC, c = e - p * kBhTC;
+        double acc = 0.0;
+        if ( TRANS_T ) {
+          for ( int q2 = 0; q2 <= p; ++q2 ) acc += sh.Ts[q2 * kBhLdT + p] * Ws[q2 * kBhTC + c];
+        } else {
+          for ( int q2 = p; q2 < ib; ++q2 ) acc += sh.Ts[p * kBhLdT + q2] * Ws[q2 * kBhTC + c];
+        }
+        Wt[e] = ( p < ib ) ? -acc : 0.0;
+      }
+      __syncthreads();
+#pragma unroll
+      for ( int nt = 0; nt < 2; ++nt )
+#pragma unroll
+        for ( int s2 = 0; s2 < 8; ++s2 ) bf[nt][s2] = Wt[( 4 * s2 + tig ) * kBhTC + 8 * nt + gid];
+      // ---- sweep B ----
+      for ( int blk = lb0; blk <= lb1; ++blk ) {
+        const int row0 = blk * kBhBoxRows;
+        const int q = resident ? blk - rb0 : nA + ( blk - lb0 );
+        double* St = resident ? ring + (size_t)( q % NS ) * kBhStageDoubles : acquire( cc0, q );
+        rank_update( St, row0, k + 1, ihi, bf, false );
+        if ( !resident ) {
+          __syncthreads();
+          store_rows( St, row0, cc0, imax( st_lo, k + 1 ), imin( st_hi, ihi + 1 ) );
+          release( cc0, q );
+        }
+      }
+    }
+    if ( resident ) {
+      __syncthreads();
+      for ( int q = 0; q < nA; ++q ) store_rows( ring + (size_t)( q % NS ) * kBhStageDoubles, ( rb0 + q ) * kBhBoxRows, cc0, st_lo, st_hi );
+      bh_fence_proxy_async();
+      __syncthreads();
+    }
+    // the loads of the next tile
+    if ( tmap != nullptr && tid == 0 && t + 1 < ntiles ) {
+      if ( resident ) {
+        for ( int q = 0; q < nseq; ++q ) issue( cc0 + kBhTC, q );
+      } else {
+        for ( int q = 0; q < imin( NS, nseq ); ++q ) issue( cc0 + kBhTC, q );
+      }
+    }
   }
 }
 
