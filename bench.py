@@ -804,7 +804,7 @@ def main():
     ap.add_argument("--ref-per-rank", type=int, default=0, help="matrices per host core in the reference sample (0: 8 / 1 / 200 for 512v / 3072v / 64n)")
     ap.add_argument("--mixed-m", type=int, default=2048, help="matrices of the mixed batch (fixed total, strong scaling)")
     ap.add_argument("--ref-mixed-stride", type=int, default=64, help="the reference sample of the mixed batch takes every k-th matrix")
-    ap.add_argument("--exe-matrices", type=int, default=3552, help="matrices of the text-in/text-out executable leg (0 = skip)")
+    ap.add_argument("--exe-matrices", type=int, default=7104, help="matrices of the text-in/text-out executable leg (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="e2e: the step's matrices go through the C-ABI as this many batches, one host thread each")

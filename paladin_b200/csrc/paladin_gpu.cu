@@ -434,6 +434,72 @@ __global__ void __launch_bounds__( pb::kBhThreads, ( MAXCH == 16 ? 2 : 1 ) ) mid
 }
 
 
+// ---- stage 1, blocked, n > 1024: one matrix per thread-block cluster of S CTAs (S = 1 ... 16 by how many large matrices the
+// launch holds), pb_bhess.cuh::bhc_* -------------------------------------------------------------------------------------------
+inline size_t bcprep_smem_bytes( int nmax ) { return sizeof( double ) * pb::bh_smem_doubles( nmax ); }
+
+__global__ void __launch_bounds__( pb::kBhThreads, 1 ) big_prep_blocked_kernel( MidArgs a, int csize ) {
+  extern __shared__ __align__( 128 ) double smem[];
+  __shared__ double red[64];
+  __shared__ long long lstats[kNumTicks];
+  __shared__ __align__( 8 ) uint64_t bars[pb::kBhMaxStages];
+  pb::BhPart pt;
+  pt.size = csize;
+  pt.rank = csize > 1 ? (int)cooperative_groups::this_cluster().block_rank() : 0;
+  const int id = a.ids[blockIdx.x / csize];
+  const int n = a.bv.n[id];
+  pb::CtaGroup g{ red };
+  stats_begin( g, pt.rank == 0 ? a.stats : nullptr, lstats );
+  if ( threadIdx.x == 0 ) {
+    for ( int q = 0; q < pb::kBhMaxStages; ++q ) pb::bh_mbar_init( &bars[q], 1 );
+    asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" );
+  }
+  __syncthreads();
+  double *A, *V, *wr, *wi, *dw;
+  int* iw;
+  mid_pointers( a.bv, id, n, A, V, wr, wi, dw, iw );
+  double* tau = dw;
+  double* scale = dw + n;
+  if ( pt.rank == 0 ) {
+    // scale check + balancing: one CTA per matrix (a few passes over it)
+    pb::GeevScaling sc;
+    int ilo = 0, ihi = n - 1, info = 0;
+    if ( !pb::geev_prologue( g, n, A, n, sc, &ilo, &ihi, scale, iw, smem ) ) {
+      info = PALADIN_GPU_INFO_NONFINITE;
+      sc.scalea = false;
+      sc.anrm = 0.0;
+      sc.cscale = 1.0;
+    }
+    if ( threadIdx.x == 0 ) {
+      MidMeta m;
+      m.ilo = ilo;
+      m.ihi = ihi;
+      m.info = info;
+      m.scalea = sc.scalea ? 1 : 0;
+      m.anrm = sc.anrm;
+      m.cscale = sc.cscale;
+      a.meta[id] = m;
+      a.bv.info[id] = info;
+    }
+    __threadfence();
+  }
+  pb::bh_part_sync( pt );
+  g.tick( pb::kTickBalance );
+  const int4 mi = __ldcg( reinterpret_cast<const int4*>( &a.meta[id] ) );
+  const int ilo = mi.x, ihi = mi.y, info = mi.z;
+  if ( info == 0 ) {
+    pb::BhSmem sh = pb::bh_carve( smem, n, bars );
+    const bool tma = a.hess_tma != 0 && a.tmap_ok[id] != 0;
+    double* scratch = a.hwork + a.h_off[id];
+    pb::bhc_gehrd( g, n, ilo, ihi, A, n, tau, scratch, tma ? a.tmaps + 2 * (size_t)id : nullptr, sh, pt );
+    if ( a.bv.wantvr || a.bv.wantvl ) pb::bhc_form_q( n, ilo, ihi, A, n, V, n, scratch, tma ? a.tmaps + 2 * (size_t)id + 1 : nullptr, sh, pt );
+    g.tick( pb::kTickOrghr );
+    if ( pt.rank == 0 ) pb::geev_isolated_eigenvalues( g, n, ilo, ihi, A, n, wr, wi );
+  }
+  stats_end( pt.rank == 0 ? a.stats : nullptr, lstats );
+}
+
+
 // ---- stage 1 for large matrices (kMidMaxFusedN < n <= kMidMaxBigN): groups of S cooperating CTAs, one matrix per group
 // at a time (pb_coop.cuh); cooperative launch, one CTA per SM ------------------------------------------------------------
 constexpr int kCoopMaxGroups = 37;
@@ -804,6 +870,8 @@ int set_kernel_attributes( DeviceCtx& c ) {
   PB_CUDA( raise_smem_limit( mid_prep_blocked_kernel<16>, o ) );
   PB_CUDA( raise_smem_limit( mid_prep_blocked_kernel<32>, o ) );
   PB_CUDA( raise_smem_limit( big_prep_kernel, o ) );
+  PB_CUDA( raise_smem_limit( big_prep_blocked_kernel, o ) );
+  PB_CUDA( cudaFuncSetAttribute( big_prep_blocked_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1 ) );
   PB_CUDA( raise_smem_limit( mid_qr_kernel<false>, o ) );
   PB_CUDA( raise_smem_limit( mid_qr_kernel<true>, o ) );
   PB_CUDA( cudaFuncSetAttribute( mid_qr_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1 ) );
@@ -1199,7 +1267,7 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
     // and of the Schur-vector array (box = 256 rows x 1 column of doubles; needs an even leading dimension)
     std::vector<int64_t> h_off( count + 1, 0 );
     for ( int k = 0; k < count; ++k )
-      h_off[k + 1] = h_off[k] + ( ( n[k] > kSmallMax && n[k] <= kMidMaxFusedN ) ? (int64_t)( ( pb::bh_scratch_doubles( n[k] ) + 1 ) & ~(size_t)1 ) : 0 );
+      h_off[k + 1] = h_off[k] + ( ( n[k] > kSmallMax && n[k] <= kMidMaxBigN ) ? (int64_t)( ( ( n[k] <= kMidMaxFusedN ? pb::bh_scratch_doubles( n[k] ) : pb::bhc_scratch_doubles( n[k], 16 ) ) + 1 ) & ~(size_t)1 ) : 0 );
     if ( h_off[count] > 0 ) {
       A( dev_alloc( &b->d_hwork, (size_t)h_off[count] ) );
       A( dev_alloc( &b->d_h_off, count + 1 ) );
@@ -1211,7 +1279,7 @@ int paladin_gpu_batch_create( int device, int count, const int* n, const int64_t
         std::memset( maps.data(), 0, sizeof( CUtensorMap ) * maps.size() );
         double* qbase = jobvr == 'V' ? b->d_V : ( jobvl == 'V' ? b->d_VL : nullptr );
         for ( int k = 0; k < count; ++k ) {
-          if ( !( n[k] > kSmallMax && n[k] <= kMidMaxFusedN ) || ( n[k] & 1 ) ) continue;
+          if ( !( n[k] > kSmallMax && n[k] <= kMidMaxBigN ) || ( n[k] & 1 ) ) continue;
           bool good = encode_matrix_map( &maps[2 * (size_t)k], b->d_A + b->a_off[k], n[k] );
           if ( good && qbase ) good = encode_matrix_map( &maps[2 * (size_t)k + 1], qbase + b->a_off[k], n[k] );
           ok[k] = good ? 1 : 0;
@@ -1524,7 +1592,40 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
         int nhuge = 0;  // [0, nhuge): beyond the streaming kernels (n > kMidMaxBigN)
         for ( int q = 0; q < nbig; ++q )
           if ( b->n[gid[q]] > kMidMaxBigN ) nhuge = q + 1;
-        if ( b->coop_S > 0 && nbig > nhuge ) {
+        // n > 1024: blocked reduction, a cluster of S CTAs per matrix (S by how many large matrices there are: the GPU's SMs
+        // divided among them, a power of two up to 16; PALADIN_GPU_BHESS_CLUSTER forces it, PALADIN_GPU_HESS=fused selects
+        // the unblocked cooperative groups instead)
+        bool big_done = false;
+        // (measured on B200: the cluster-shared blocked reduction is correct for every order up to 4608 but its thin panel
+        // steps and tile fragments are latency-bound -- 8 x 3072^2: 1091 ms against 486 ms, mixed batch of 512: 8.0 s against
+        // 2.8 s for the unblocked cooperative groups -- so it only runs on request: PALADIN_GPU_HESS=blocked_big)
+        if ( hess_blocked && env_hess == "blocked_big" && nbig > nhuge ) {
+          static const int env_bc = std::getenv( "PALADIN_GPU_BHESS_CLUSTER" ) ? std::atoi( std::getenv( "PALADIN_GPU_BHESS_CLUSTER" ) ) : 0;
+          const int nmat = nbig - nhuge;
+          int S = 1;
+          while ( S < 16 && 2 * S * nmat <= c.sm_count ) S *= 2;
+          if ( env_bc > 0 ) S = std::min( 16, env_bc );
+          MidArgs mc = ma;
+          mc.ids = ids + nhuge;
+          mc.count = nmat;
+          const size_t sb = bcprep_smem_bytes( b->n[gid[nhuge]] );
+          cudaLaunchConfig_t cfg = {};
+          cfg.gridDim = dim3( nmat * S );
+          cfg.blockDim = dim3( pb::kBhThreads );
+          cfg.dynamicSmemBytes = sb;
+          cfg.stream = st;
+          cudaLaunchAttribute attr[1];
+          attr[0].id = cudaLaunchAttributeClusterDimension;
+          attr[0].val.clusterDim.x = S;
+          attr[0].val.clusterDim.y = 1;
+          attr[0].val.clusterDim.z = 1;
+          cfg.attrs = attr;
+          cfg.numAttrs = S > 1 ? 1 : 0;
+          PB_CUDA( cudaLaunchKernelEx( &cfg, big_prep_blocked_kernel, mc, S ) );
+          ++launches;
+          big_done = true;
+        }
+        if ( !big_done && b->coop_S > 0 && nbig > nhuge ) {
           // large matrices: groups of cooperating CTAs, one matrix per group at a time. The size-sorted list is cut into
           // classes: all SMs on one matrix above n = 2048, two groups down to 1400, four groups below.
           static const int env_groups = std::getenv( "PALADIN_GPU_COOP_GROUPS" ) ? std::max( 1, std::atoi( std::getenv( "PALADIN_GPU_COOP_GROUPS" ) ) ) : 0;
@@ -1568,7 +1669,7 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
             q0 = q1;
           }
         }
-        const int n0 = ( b->coop_S > 0 ) ? nhuge : nbig;  // what is left for the one-CTA streaming / unblocked kernel
+        const int n0 = ( b->coop_S > 0 || big_done ) ? nhuge : nbig;  // what is left for the one-CTA streaming / unblocked kernel
         if ( n0 > 0 ) {
           MidArgs m0 = ma;
           const size_t sbig = sizeof( double ) * pb::hess_big_smem_doubles( std::min( g.nmax, kMidMaxBigN ) );

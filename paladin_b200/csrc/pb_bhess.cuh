@@ -26,6 +26,7 @@
 
 #if defined( __CUDACC__ )
 
+#include <cooperative_groups.h>
 #include <cuda.h>  // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint, nothing links libcuda)
 
 namespace pb {
@@ -105,8 +106,17 @@ __device__ __forceinline__ void bh_dmma( double& c0, double& c1, double a, doubl
 // V(r, p) of the panel that starts at column k: unit lower trapezoidal, stored below the subdiagonal of Av
 __device__ __forceinline__ double bh_v( const double* Av, int ldv, int k, int ihi, int r, int p ) {
   const int c = k + p;
-  if ( r > c + 1 && r <= ihi ) return Av[r + (size_t)c * ldv];
+  if ( r > c + 1 && r <= ihi ) return __ldcg( Av + r + (size_t)c * ldv );
   return r == c + 1 ? 1.0 : 0.0;
+}
+
+// the CTAs that share one matrix (a thread-block cluster for n > 1024; {0, 1} = one CTA per matrix)
+struct BhPart {
+  int rank = 0, size = 1;
+};
+__device__ __forceinline__ void bh_part_sync( const BhPart& pt ) {
+  if ( pt.size > 1 ) cooperative_groups::this_cluster().sync();
+  else __syncthreads();
 }
 
 // per-CTA working set
@@ -144,7 +154,7 @@ __device__ __forceinline__ BhSmem bh_carve( double* sm, int n, uint64_t* bars ) 
 constexpr int kBhPfDist = 4;
 template <int CH, int NC>
 __device__ __forceinline__ void bh_gemv_cols( const double* A, int lda, int rb, int rlast, int c_first, int c_last, const double* vs,
-                                              double* ypart_w, int r_first ) {
+                                              double* ypart_w, int r_first, BhPart pt = BhPart() ) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   double acc[CH];
 #pragma unroll
@@ -152,9 +162,10 @@ __device__ __forceinline__ void bh_gemv_cols( const double* A, int lda, int rb, 
   const int span = rlast - rb;  // clamp for the (masked) rows past the block
   const bool pf = ( lda & 1 ) == 0 && lane == 0;
   const uint32_t pf_bytes = (uint32_t)( ( ( span + 2 ) & ~1 ) * sizeof( double ) );
-  for ( int cc0 = c_first + warp * NC; cc0 <= c_last; cc0 += kBhWarps * NC ) {
+  const int stride = pt.size * kBhWarps * NC;
+  for ( int cc0 = c_first + ( pt.rank * kBhWarps + warp ) * NC; cc0 <= c_last; cc0 += stride ) {
     if ( pf ) {
-      const int cp = cc0 + kBhPfDist * kBhWarps * NC;
+      const int cp = cc0 + kBhPfDist * stride;
 #pragma unroll
       for ( int q = 0; q < NC; ++q )
         if ( cp + q <= c_last ) bh_prefetch_l2( A + (size_t)( cp + q ) * lda + rb, pf_bytes );
@@ -176,7 +187,7 @@ __device__ __forceinline__ void bh_gemv_cols( const double* A, int lda, int rb, 
   if ( pf ) {
     // the next column step starts one column further right
     for ( int it = 0; it < kBhPfDist; ++it ) {
-      const int cp = c_first + 1 + ( it * kBhWarps + warp ) * NC;
+      const int cp = c_first + 1 + ( ( it * pt.size + pt.rank ) * kBhWarps + warp ) * NC;
 #pragma unroll
       for ( int q = 0; q < NC; ++q )
         if ( cp + q <= c_last ) bh_prefetch_l2( A + (size_t)( cp + q ) * lda + rb, pf_bytes );
@@ -198,7 +209,7 @@ __device__ __forceinline__ double bh_dot_chunks( const double* col, const double
   const int span = rlast - rb;
   double a[CH];
 #pragma unroll
-  for ( int u = 0; u < CH; ++u ) a[u] = col[rb + imin( lane + 32 * u, span )];
+  for ( int u = 0; u < CH; ++u ) a[u] = __ldcg( col + rb + imin( lane + 32 * u, span ) );
   double s = 0.0;
 #pragma unroll
   for ( int u = 0; u < CH; ++u ) {
@@ -357,10 +368,12 @@ __device__ void bh_panel( int n, int ihi, int k, int ib, double* A, int lda, dou
 }
 
 // ---- VT = V T (rows k+1..ihi) to global memory; T of the panel to its slot of the scratch ----------------------------------
-__device__ inline void bh_vt( int ihi, int k, int ib, const double* A, int lda, double* VT, int ldy, double* Tsave, const BhSmem& sh ) {
+__device__ inline void bh_vt( int ihi, int k, int ib, const double* A, int lda, double* VT, int ldy, double* Tsave, const BhSmem& sh,
+                              BhPart pt = BhPart() ) {
   const int tid = threadIdx.x;
-  for ( int q = tid; q < kBhNB * kBhNB; q += kBhThreads ) Tsave[q] = sh.Ts[( q >> 5 ) * kBhLdT + ( q & 31 )];
-  for ( int r = k + 1 + tid; r <= ihi; r += kBhThreads ) {
+  if ( pt.rank == 0 )
+    for ( int q = tid; q < kBhNB * kBhNB; q += kBhThreads ) Tsave[q] = sh.Ts[( q >> 5 ) * kBhLdT + ( q & 31 )];
+  for ( int r = k + 1 + pt.rank * kBhThreads + tid; r <= ihi; r += kBhThreads * pt.size ) {
     double v[kBhNB];
 #pragma unroll
     for ( int q = 0; q < kBhNB; ++q ) v[q] = ( q < ib ) ? bh_v( A, lda, k, ihi, r, q ) : 0.0;
@@ -371,15 +384,15 @@ __device__ inline void bh_vt( int ihi, int k, int ib, const double* A, int lda, 
       VT[r + (size_t)p * ldy] = s;
     }
   }
-  __syncthreads();
+  bh_part_sync( pt );
 }
 
 // ---- Y(0:k, 0:ib) = A(0:k, k+1:ihi) VT(k+1:ihi, 0:ib)   (DMMA, fragments from global memory) -------------------------------
-__device__ inline void bh_ytop( int ihi, int k, int ib, const double* A, int lda, const double* VT, double* Y, int ldy ) {
+__device__ inline void bh_ytop( int ihi, int k, int ib, const double* A, int lda, const double* VT, double* Y, int ldy, BhPart pt = BhPart() ) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gid = lane >> 2, tig = lane & 3;
   const int ntile = ( k + 1 + 7 ) >> 3;
-  for ( int rt = warp; rt < ntile; rt += kBhWarps ) {
+  for ( int rt = pt.rank * kBhWarps + warp; rt < ntile; rt += kBhWarps * pt.size ) {
     const int r = 8 * rt + gid;
     const bool rok = r <= k;
     const double* arow = A + imin( r, k );
@@ -397,7 +410,7 @@ __device__ inline void bh_ytop( int ihi, int k, int ib, const double* A, int lda
 #pragma unroll
         for ( int nt = 0; nt < 4; ++nt ) {
           const int p = 8 * nt + gid;
-          b[u][nt] = ( cok && p < ib ) ? VT[ccl + (size_t)p * ldy] : 0.0;
+          b[u][nt] = ( cok && p < ib ) ? __ldcg( VT + ccl + (size_t)p * ldy ) : 0.0;
         }
       }
 #pragma unroll
@@ -414,7 +427,7 @@ __device__ inline void bh_ytop( int ihi, int k, int ib, const double* A, int lda
       }
     }
   }
-  __syncthreads();
+  bh_part_sync( pt );
 }
 
 // ---- tile pass: columns [c_begin, c_end) of the target M in tiles of kBhTC columns, staged by TMA in row blocks ------------------
@@ -433,7 +446,7 @@ __device__ inline void bh_ytop( int ihi, int k, int ib, const double* A, int lda
 template <bool TRANS_T>
 __device__ void bh_tile_pass( int n, int ihi, int k, int ib, double* M, int ldm, const CUtensorMap* tmap, const double* Av, int ldv,
                               const double* Y, int ldy, int r_rows, int r_col_hi, bool do_l, int c_begin, int c_end, int st_lo, int st_hi,
-                              BhSmem& sh ) {
+                              BhSmem& sh, BhPart pt = BhPart() ) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, tig = lane & 3;
   const int NS = sh.nstages;
@@ -491,10 +504,12 @@ __device__ void bh_tile_pass( int n, int ihi, int k, int ib, double* M, int ldm,
       if ( cc0 + c < c_end ) M[r + (size_t)( cc0 + c ) * ldm] = St[(size_t)c * kBhBoxRows + ( r - row0 )];
     }
   };
+  // (sweep B re-reads what sweep A stored: its loads are never requested before sweep A has released its last block)
   auto release = [&]( int cc0, int q ) {
     bh_fence_proxy_async();
     __syncthreads();
-    if ( tmap != nullptr && tid == 0 && q + NS < nseq ) issue( cc0, q + NS );
+    const int lim = q < nA ? nA : nseq;
+    if ( tmap != nullptr && tid == 0 && q + NS < lim ) issue( cc0, q + NS );
   };
   // M(rows of the block) -= A B with A = rows x 32 fragments from L2 (Y or V), B = 32 x 16 in registers (two n-tiles)
   auto rank_update = [&]( double* St, int row0, int r_first, int r_last, const double ( &bfr )[2][8], bool from_y ) {
@@ -504,7 +519,7 @@ __device__ void bh_tile_pass( int n, int ihi, int k, int ib, double* M, int ldm,
 #pragma unroll
       for ( int s2 = 0; s2 < 8; ++s2 ) {
         const int p = 4 * s2 + tig;
-        if ( from_y ) a[s2] = ( r <= r_last && p < ib ) ? Y[imin( r, r_last ) + (size_t)p * ldy] : 0.0;
+        if ( from_y ) a[s2] = ( r <= r_last && p < ib ) ? __ldcg( Y + imin( r, r_last ) + (size_t)p * ldy ) : 0.0;
         else a[s2] = ( p < ib ) ? bh_v( Av, ldv, k, ihi, r, p ) : 0.0;
       }
     };
@@ -524,9 +539,9 @@ __device__ void bh_tile_pass( int n, int ihi, int k, int ib, double* M, int ldm,
       cp[9 * kBhBoxRows] = c11;
     }
   };
-  if ( tmap != nullptr && tid == 0 )
-    for ( int q = 0; q < imin( NS, nseq ); ++q ) issue( c_begin, q );
-  for ( int t = 0; t < ntiles; ++t ) {
+  if ( tmap != nullptr && tid == 0 && pt.rank < ntiles )
+    for ( int q = 0; q < imin( NS, nA ); ++q ) issue( c_begin + pt.rank * kBhTC, q );
+  for ( int t = pt.rank; t < ntiles; t += pt.size ) {
     const int cc0 = c_begin + t * kBhTC;
     const bool do_r = r_rows > 0 && cc0 <= r_col_hi;
     double bf[2][8];  // B fragments: -V(cc, :) during sweep A, Wt during sweep B
@@ -600,6 +615,8 @@ __device__ void bh_tile_pass( int n, int ihi, int k, int ib, double* M, int ldm,
 #pragma unroll
         for ( int s2 = 0; s2 < 8; ++s2 ) bf[nt][s2] = Wt[( 4 * s2 + tig ) * kBhTC + 8 * nt + gid];
       // ---- sweep B ----
+      if ( !resident && tmap != nullptr && tid == 0 )
+        for ( int q = nA; q < imin( nA + NS, nseq ); ++q ) issue( cc0, q );
       for ( int blk = lb0; blk <= lb1; ++blk ) {
         const int row0 = blk * kBhBoxRows;
         const int q = resident ? blk - rb0 : nA + ( blk - lb0 );
@@ -619,11 +636,11 @@ __device__ void bh_tile_pass( int n, int ihi, int k, int ib, double* M, int ldm,
       __syncthreads();
     }
     // the loads of the next tile
-    if ( tmap != nullptr && tid == 0 && t + 1 < ntiles ) {
+    if ( tmap != nullptr && tid == 0 && t + pt.size < ntiles ) {
       if ( resident ) {
-        for ( int q = 0; q < nseq; ++q ) issue( cc0 + kBhTC, q );
+        for ( int q = 0; q < nseq; ++q ) issue( cc0 + pt.size * kBhTC, q );
       } else {
-        for ( int q = 0; q < imin( NS, nseq ); ++q ) issue( cc0 + kBhTC, q );
+        for ( int q = 0; q < imin( NS, nA ); ++q ) issue( cc0 + pt.size * kBhTC, q );
       }
     }
   }
@@ -675,6 +692,221 @@ __device__ inline void bh_form_q( int n, int ilo, int ihi, const double* A, int 
     for ( int q = tid; q < kBhNB * kBhNB; q += kBhThreads ) sh.Ts[( q >> 5 ) * kBhLdT + ( q & 31 )] = Tp[q];
     __syncthreads();
     bh_tile_pass<false>( n, ihi, k, ib, Q, ldq, tmapQ, A, lda, nullptr, 0, 0, -1, true, k + 1, ihi + 1, k + 1, ihi + 1, sh );
+  }
+}
+
+// =====================================================================================================================
+// n > 1024: the same blocked reduction with ONE MATRIX SHARED BY A THREAD-BLOCK CLUSTER of S CTAs (S = 1 when the batch
+// holds enough large matrices to fill the GPU with one CTA each, up to 16 when it holds a few).
+//   panel: every CTA runs the thin O(n * 32) steps redundantly (bit-identical: same data, same order), the streamed
+//          product y = A(k+1:ihi, c+1:ihi) v is split by COLUMNS over the cluster (rows in segments of 1024 = 32 register
+//          chunks), the partial sums meet in global memory (L2), and every CTA adds them up in the same order;
+//          rank 0 alone writes column c of A, tau and Y(:, j). Two cluster barriers per column.
+//   trailing update / Y top rows / V T / explicit Q: tiles (or rows) dealt round-robin to the CTAs, a cluster barrier
+//          between passes; update tiles are streamed in row blocks (two stages on chip).
+// Everything another CTA may have written is read through L2 (ld.global.cg / TMA).
+// =====================================================================================================================
+constexpr int kBhSeg = 1024;  // rows per segment of the streamed product (32 chunks of 32 rows in registers)
+
+// extra global scratch of the cluster path: S partial products of n rows (behind the bh_scratch_doubles block)
+__host__ __device__ inline size_t bhc_scratch_doubles( int n, int smax ) {
+  return bh_scratch_doubles( n ) + (size_t)smax * ( ( n + 1 ) & ~1 ) + 16;
+}
+
+__device__ inline void bhc_panel( int n, int ihi, int k, int ib, double* A, int lda, double* tau, double* Y, int ldy, double* gpart, BhSmem& sh,
+                                  const BhPart& pt ) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* ypart = sh.un;  // [kBhWarps][kBhSeg]
+  for ( int q = tid; q < kBhNB * kBhLdT; q += kBhThreads ) sh.Ts[q] = 0.0;
+  for ( int j = 0; j < ib; ++j ) {
+    const int c = k + j;
+    // (a) b = A(k+1:ihi, c) - Y(k+1:ihi, 0:j) V(c, 0:j)^T
+    if ( tid < kBhNB ) sh.vrow[tid] = ( tid < j ) ? bh_v( A, lda, k, ihi, c, tid ) : 0.0;
+    __syncthreads();
+    for ( int r = k + 1 + tid; r <= ihi; r += kBhThreads ) {
+      double x = __ldcg( A + r + (size_t)c * lda );
+      const double* yr = Y + r;
+#pragma unroll 8
+      for ( int jj = 0; jj < j; ++jj ) x -= __ldcg( yr + (size_t)jj * ldy ) * sh.vrow[jj];
+      sh.bs[r] = x;
+    }
+    __syncthreads();
+    if ( j > 0 ) {
+      // (b) b <- (I - V T^T V^T) b
+      for ( int jj = warp; jj < j; jj += kBhWarps ) {
+        const int cj = k + jj;
+        double s = sh.bs[cj + 1];
+        for ( int r0 = cj + 2; r0 <= ihi; r0 += kBhSeg - 32 ) s += bh_dot<32>( A + (size_t)cj * lda, sh.bs, r0, imin( ihi, r0 + kBhSeg - 33 ) );  // (31 rows of alignment slack)
+        if ( lane == 0 ) sh.ws[jj] = s;
+      }
+      __syncthreads();
+      if ( tid < j ) {
+        double s = 0.0;
+        for ( int q = 0; q <= tid; ++q ) s += sh.Ts[q * kBhLdT + tid] * sh.ws[q];
+        sh.wt[tid] = s;
+      }
+      __syncthreads();
+      for ( int r = k + 1 + tid; r <= ihi; r += kBhThreads ) {
+        const int d = r - k - 1;
+        const int jl = imin( j, d );
+        double x = sh.bs[r];
+        const double* vr = A + r + (size_t)k * lda;
+#pragma unroll 8
+        for ( int jj = 0; jj < jl; ++jj ) x -= __ldcg( vr + (size_t)jj * lda ) * sh.wt[jj];
+        if ( d < j ) x -= sh.wt[d];
+        sh.bs[r] = x;
+      }
+      __syncthreads();
+    }
+    // (c) reflector from b(c+1:ihi)   (LAPACK dlarfg)
+    double tj = 0.0, beta, sc = 0.0;
+    {
+      const double alpha = sh.bs[c + 1];
+      double mx = 0.0;
+      for ( int r = c + 2 + tid; r <= ihi; r += kBhThreads ) mx = fmax( mx, fabs( sh.bs[r] ) );
+      mx = cta_max( mx, sh.red );
+      beta = alpha;
+      if ( mx != 0.0 ) {
+        double ss = 0.0;
+        for ( int r = c + 2 + tid; r <= ihi; r += kBhThreads ) {
+          const double x = sh.bs[r] / mx;
+          ss += x * x;
+        }
+        double xnorm = mx * sqrt( cta_sum( ss, sh.red ) );
+        double al = alpha;
+        beta = -dsign( dlapy2( al, xnorm ), al );
+        const double safmin = kSafmin / kEps;
+        int knt = 0;
+        double pre = 1.0;
+        if ( fabs( beta ) < safmin ) {
+          const double rsafmn = 1.0 / safmin;
+          do {
+            ++knt;
+            pre *= rsafmn;
+            xnorm *= rsafmn;
+            beta *= rsafmn;
+            al *= rsafmn;
+          } while ( fabs( beta ) < safmin && knt < 20 );
+          beta = -dsign( dlapy2( al, xnorm ), al );
+        }
+        tj = ( beta - al ) / beta;
+        sc = pre / ( al - beta );
+        for ( int q = 0; q < knt; ++q ) beta *= safmin;
+      }
+    }
+    __syncthreads();
+    // v to shared memory only: column c of A is written (by rank 0) after the cluster has finished reading it
+    for ( int r = tid; r < n; r += kBhThreads ) {
+      double v = 0.0;
+      if ( r == c + 1 ) v = 1.0;
+      else if ( r >= c + 2 && r <= ihi ) v = sh.bs[r] * sc;
+      sh.vs[r] = v;
+    }
+    __syncthreads();
+    // (d) this CTA's share of y = A(k+1:ihi, c+1:ihi) v, a segment of rows at a time, to gpart[rank]; w2 = V^T v
+    {
+      const int rb = ( k + 1 ) & ~31;
+      double* gp = gpart + (size_t)pt.rank * ldy;
+      for ( int r0 = rb; r0 <= ihi; r0 += kBhSeg ) {
+        const int r1 = imin( ihi, r0 + kBhSeg - 1 );
+        const int nch = ( r1 - r0 ) / 32 + 1;
+        double* yw = ypart + (size_t)warp * kBhSeg - r0;  // indexed by the global row
+        if ( nch > 24 ) bh_gemv_cols<32, 1>( A, lda, r0, r1, c + 1, ihi, sh.vs, yw, k + 1, pt );
+        else if ( nch > 16 ) bh_gemv_cols<24, 1>( A, lda, r0, r1, c + 1, ihi, sh.vs, yw, k + 1, pt );
+        else if ( nch > 8 ) bh_gemv_cols<16, 1>( A, lda, r0, r1, c + 1, ihi, sh.vs, yw, k + 1, pt );
+        else if ( nch > 4 ) bh_gemv_cols<8, 2>( A, lda, r0, r1, c + 1, ihi, sh.vs, yw, k + 1, pt );
+        else bh_gemv_cols<4, 4>( A, lda, r0, r1, c + 1, ihi, sh.vs, yw, k + 1, pt );
+        __syncthreads();
+        for ( int r = imax( r0, k + 1 ) + tid; r <= r1; r += kBhThreads ) {
+          double y = 0.0;
+#pragma unroll
+          for ( int w = 0; w < kBhWarps; ++w ) y += ypart[(size_t)w * kBhSeg + ( r - r0 )];
+          __stcg( gp + r, y );
+        }
+        __syncthreads();
+      }
+      for ( int jj = warp; jj < j; jj += kBhWarps ) {
+        double s = 0.0;
+        for ( int r0 = c + 1; r0 <= ihi; r0 += kBhSeg - 32 ) s += bh_dot<32>( A + (size_t)( k + jj ) * lda, sh.vs, r0, imin( ihi, r0 + kBhSeg - 33 ) );
+        if ( lane == 0 ) sh.w2s[jj] = s;
+      }
+    }
+    bh_part_sync( pt );  // every share of y is in L2; nobody reads column c of A any more
+    // (e) Y(:, j) = tau (y - Y(:, 0:j) w2) (every CTA the same sum, rank 0 stores) ; column c of A, tau ; T(:, j)
+    for ( int r = k + 1 + tid; r <= ihi; r += kBhThreads ) {
+      double y = 0.0;
+      for ( int s2 = 0; s2 < pt.size; ++s2 ) y += __ldcg( gpart + (size_t)s2 * ldy + r );
+      const double* yr = Y + r;
+#pragma unroll 8
+      for ( int jj = 0; jj < j; ++jj ) y -= __ldcg( yr + (size_t)jj * ldy ) * sh.w2s[jj];
+      if ( pt.rank == 0 ) __stcg( Y + r + (size_t)j * ldy, tj * y );
+    }
+    if ( pt.rank == 0 ) {
+      for ( int r = k + 1 + tid; r <= ihi; r += kBhThreads ) {
+        double x;
+        if ( r <= c ) x = sh.bs[r];
+        else if ( r == c + 1 ) x = beta;
+        else x = sh.vs[r];
+        __stcg( A + r + (size_t)c * lda, x );
+      }
+      if ( tid == 0 ) tau[c] = tj;
+    }
+    if ( tid < j ) {
+      double s = 0.0;
+      for ( int p = tid; p < j; ++p ) s += sh.Ts[tid * kBhLdT + p] * sh.w2s[p];
+      sh.ws[tid] = -tj * s;
+    }
+    __syncthreads();
+    if ( tid < j ) sh.Ts[tid * kBhLdT + j] = sh.ws[tid];
+    if ( tid == 0 ) sh.Ts[j * kBhLdT + j] = tj;
+    bh_part_sync( pt );  // column c, Y(:, j) visible to the cluster
+  }
+}
+
+__device__ inline void bhc_gehrd( const CtaGroup& g, int n, int ilo, int ihi, double* A, int lda, double* tau, double* scratch,
+                                  const CUtensorMap* tmapA, BhSmem& sh, const BhPart& pt ) {
+  const int tid = threadIdx.x;
+  const int ldy = ( n + 1 ) & ~1;
+  double* Y = scratch;
+  double* VT = Y + (size_t)ldy * kBhNB;
+  double* Tall = VT + (size_t)ldy * kBhNB;
+  double* gpart = scratch + bh_scratch_doubles( n );
+  if ( pt.rank == 0 )
+    for ( int j = tid; j < n; j += kBhThreads ) tau[j] = 0.0;
+  bh_part_sync( pt );
+  int pidx = 0;
+  for ( int k = ilo; k <= ihi - 2; k += kBhNB, ++pidx ) {
+    const int ib = imin( kBhNB, ihi - 2 - k + 1 );
+    bhc_panel( n, ihi, k, ib, A, lda, tau, Y, ldy, gpart, sh, pt );
+    g.tick( kTickHess );
+    bh_vt( ihi, k, ib, A, lda, VT, ldy, Tall + (size_t)pidx * kBhNB * kBhNB, sh, pt );
+    bh_ytop( ihi, k, ib, A, lda, VT, Y, ldy, pt );
+    bh_tile_pass<true>( n, ihi, k, ib, A, lda, tmapA, A, lda, Y, ldy, k + 1, k + ib - 1, false, k + 1, k + ib, 0, k + 1, sh, pt );
+    bh_tile_pass<true>( n, ihi, k, ib, A, lda, tmapA, A, lda, Y, ldy, ihi + 1, ihi, true, k + ib, n, 0, ihi + 1, sh, pt );
+    bh_part_sync( pt );
+    g.tick( kTickHessUpdate );
+  }
+}
+
+__device__ inline void bhc_form_q( int n, int ilo, int ihi, const double* A, int lda, double* Q, int ldq, const double* scratch,
+                                   const CUtensorMap* tmapQ, BhSmem& sh, const BhPart& pt ) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ldy = ( n + 1 ) & ~1;
+  const double* Tall = scratch + (size_t)2 * ldy * kBhNB;
+  for ( int c = pt.rank * kBhWarps + warp; c < n; c += kBhWarps * pt.size )
+    for ( int r = lane; r < n; r += 32 ) Q[r + (size_t)c * ldq] = ( r == c ) ? 1.0 : 0.0;
+  bh_part_sync( pt );
+  const int nrefl = ihi - 2 - ilo + 1;
+  if ( nrefl <= 0 ) return;
+  const int npan = ( nrefl + kBhNB - 1 ) / kBhNB;
+  for ( int pidx = npan - 1; pidx >= 0; --pidx ) {
+    const int k = ilo + pidx * kBhNB;
+    const int ib = imin( kBhNB, ihi - 2 - k + 1 );
+    const double* Tp = Tall + (size_t)pidx * kBhNB * kBhNB;
+    for ( int q = tid; q < kBhNB * kBhNB; q += kBhThreads ) sh.Ts[( q >> 5 ) * kBhLdT + ( q & 31 )] = __ldcg( Tp + q );
+    __syncthreads();
+    bh_tile_pass<false>( n, ihi, k, ib, Q, ldq, tmapQ, A, lda, nullptr, 0, 0, -1, true, k + 1, ihi + 1, k + 1, ihi + 1, sh, pt );
+    bh_part_sync( pt );
   }
 }
 

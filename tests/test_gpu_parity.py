@@ -248,7 +248,9 @@ def test_large_matrices_cooperative_path(pg, jobvr, sizes):
                                  {"PALADIN_GPU_COOP_GROUPS": "4"}, {"PALADIN_GPU_COOP_GROUPS": "16", "PALADIN_GPU_AED": "48"},
                                  {"PALADIN_GPU_NO_COOP": "1", "PALADIN_GPU_CLUSTER": "1", "PALADIN_GPU_AED": "0"},
                                  {"PALADIN_GPU_AED_MOVES": "1000", "PALADIN_GPU_BIGVEC_MIN_N": "4000"},
-                                 {"PALADIN_GPU_HESS": "fused"}, {"PALADIN_GPU_HESS": "notma"}])
+                                 {"PALADIN_GPU_HESS": "fused"}, {"PALADIN_GPU_HESS": "notma"},
+                                 {"PALADIN_GPU_HESS": "blocked_big"}, {"PALADIN_GPU_HESS": "blocked_big", "PALADIN_GPU_BHESS_CLUSTER": "1"},
+                                 {"PALADIN_GPU_HESS": "blocked_big", "PALADIN_GPU_BHESS_CLUSTER": "8"}])
 def test_tuning_overrides_keep_parity(env):
     """Every cluster size, cooperative group count and AED variant the launcher can choose (forced through the tuning
     environment variables, which are read once per process) gives the same spectra within tolerance."""
@@ -478,7 +480,8 @@ def test_blocked_hessenberg_factorisation(pg):
     """Stage 1 alone (PALADIN_GPU_DEBUG_STOP_AFTER_PREP): the blocked reduction (dlahr2 panels, DMMA / TMA-staged trailing
     updates) leaves H upper Hessenberg with Q^T A Q = H and Q orthogonal, for orders on both sides of every tile / box /
     chunk boundary, odd orders (tiles staged without TMA) and a matrix whose balancing isolates eigenvalues."""
-    sizes = [65, 66, 96, 130, 200, 255, 256, 258, 300, 511, 512, 514, 600, 768, 1000, 1024]
+    # (n > 1024: the cluster-shared variant, update tiles streamed in row blocks; 1537 is odd: staged without TMA)
+    sizes = [65, 66, 96, 130, 200, 255, 256, 258, 300, 511, 512, 514, 600, 768, 1000, 1024, 1026, 1300, 1537, 2050]
     mats = _random_mats(sizes, 93)
     n, off, ii, jj, vv = _concat(mats)
     os.environ["PALADIN_GPU_DEBUG_STOP_AFTER_PREP"] = "1"
