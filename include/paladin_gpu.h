@@ -194,7 +194,7 @@ int paladin_gpu_batch_timer_start( paladin_gpu_batch* b );
 int paladin_gpu_batch_timer_stop( paladin_gpu_batch* b, float* ms );
 
 /* Phase profile of the most recent CTA-per-matrix solve: SM cycles summed over all CTAs, 16 slots
- * (0 balance, 1 Hessenberg panels, 2 form Q, 3 QR remainder, 4 eigenvectors of T, 5 un-balance + normalise, 6 back-transform
+ * (0 balance, 1 Hessenberg panels, 2 form Q, 3 QR remainder (fused kernel; in the multishift kernel: the share of slot 14 that follows the window's own QR iteration), 4 eigenvectors of T, 5 un-balance + normalise, 6 back-transform
  *  GEMM, 7 Hessenberg trailing updates, 8 deflation scans, 9 shift computation, 10 in-window bulge chasing, 11 strip updates by
  *  recorded reflectors, 12 small-block solves, 13 strip updates by small U, 14 early-deflation window, 15 its off-window update).
  * Diagnostic only. */

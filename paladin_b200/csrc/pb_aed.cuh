@@ -378,7 +378,7 @@ struct AedStopHook {
 // work: >= 2 jw doubles visible to the group.
 template <class G>
 PB_D void aed_window( const G& g, int jw, int max_moves, double* T, int ldt, double* V, int ldv, double s, double* sr, double* si,
-                      double* work, int* out ) {
+                      double* work, int* out, long long* t_qr_done = nullptr ) {
   const int t = g.tid(), nt = g.size();
   const double smlnum = kSafmin * ( (double)jw / kUlp );
   int ns = jw;    // T(0:ns, 0:ns) is the part not (yet) deflated
@@ -396,6 +396,9 @@ PB_D void aed_window( const G& g, int jw, int max_moves, double* T, int ldt, dou
     infqr = lahqr<G, true>( g, true, true, jw, 0, jw - 1, T, ldt, sr, si, 0, jw - 1, V, ldv );
   }
   g.sync();
+#if defined( __CUDA_ARCH__ )
+  if ( t_qr_done != nullptr ) *t_qr_done = clock64();  // (phase profile: what follows is the spike test / re-reduction)
+#endif
   if ( infqr != 0 ) {
     if ( t == 0 ) {
       out[0] = 0;

@@ -99,6 +99,7 @@ PB_D int warp_isum( int x ) {
 // one warp; every lane receives bit-identical reduction results (xor butterflies)
 struct WarpGroup {
   static constexpr bool kIsCta = false;
+  static constexpr int kLanes = 1;  // one lane per thread: lane-explicit code (pb_small.cuh::francis_sweep_lanes) applies
   PB_D int tid() const { return threadIdx.x & 31; }
   PB_D int size() const { return 32; }
   PB_D void sync() const { __syncwarp(); }
@@ -417,6 +418,56 @@ PB_HD void larfg3_fast( int n, double& a0, double& a1, double& a2, double& t1 ) 
   a1 *= rs;
   a2 *= rs;
   a0 = beta;
+}
+
+// Branch-free reflector for the register-resident Francis sweep (pb_small.cuh::francis_sweep_lanes): the step loop must
+// stay one basic block so that the updates of the previous step are scheduled into the latency of this chain. The
+// entries are scaled by the power of two that brings the largest one into [1, 2) -- no over/underflow of the squares
+// whatever the input, no rescaling loop --, the reciprocal square root and the reciprocal start from the hardware
+// approximations (MUFU.RSQ64H / MUFU.RCP64H, 2^-23) and are refined in registers (one third-order / two second-order
+// steps: full precision up to the last rounding, no special-case paths: the arguments are in [1, 12] and [1, 6]).
+// A column below 2^-1022 in magnitude is treated as zero; x with |x|^2 underflowing against a0^2 (ratio below 1e-154) gives
+// tau = 0 exactly as dlarfg does for x = 0. Same contract as larfg3_fast.
+PB_HD void larfg3_bf( int n, double& a0, double& a1, double& a2, double& t1 ) {
+#if defined( __CUDA_ARCH__ )
+  a2 = n < 3 ? 0.0 : a2;
+  a1 = n < 2 ? 0.0 : a1;
+  const double mx = fmax( fabs( a0 ), fmax( fabs( a1 ), fabs( a2 ) ) );
+  const int ex = imin( __double2hiint( mx ) & 0x7ff00000, 0x7fd00000 );  // (clamped: the scale itself must stay normal)
+  const double sc = __hiloint2double( 0x7fe00000 - ex, 0 );  // 2^(1023 - E): mx * sc in [1, 2)
+  const double si = __hiloint2double( ex, 0 );               // 2^(E - 1023)  (0 for a zero or subnormal column)
+  const double x0 = a0 * sc, x1 = a1 * sc, x2 = a2 * sc;
+  const double xn2 = x1 * x1 + x2 * x2;
+  const double nn = x0 * x0 + xn2;  // in [1, 12]
+  double y;
+  asm( "rsqrt.approx.ftz.f64 %0, %1;" : "=d"( y ) : "d"( nn ) );
+  {
+    const double e = fma( -nn * y, y, 1.0 );
+    y = fma( y * e, fma( e, 0.375, 0.5 ), y );
+  }
+  double nrm = nn * y;
+  nrm = fma( fma( -nrm, nrm, nn ), 0.5 * y, nrm );  // sqrt(nn), last-bit correction
+  const double aa = fabs( x0 );
+  const double den = aa + nrm;  // in [1, 6]
+  double r;
+  asm( "rcp.approx.ftz.f64 %0, %1;" : "=d"( r ) : "d"( den ) );
+  {
+    double e = fma( -den, r, 1.0 );
+    r = fma( r, fma( e, e, e ), r );
+    e = fma( -den, r, 1.0 );
+    r = fma( r, e, r );
+  }
+  const bool refl = xn2 > 0.0;
+  const double rs = a0 >= 0.0 ? r : -r;
+  const double bt = a0 >= 0.0 ? -nrm : nrm;
+  t1 = refl ? fma( aa, y, 1.0 ) : 0.0;
+  a1 = refl ? x1 * rs : 0.0;
+  a2 = refl ? x2 * rs : 0.0;
+  a0 = refl ? bt * si : a0;
+#else
+  larfg3_fast( n, a0, a1, a2, t1 );
+  if ( n < 3 ) a2 = 0.0;
+#endif
 }
 
 // dlartg (LAPACK 3.10+ la_lartg semantics for the unscaled range): r has the sign of f

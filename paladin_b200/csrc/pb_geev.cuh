@@ -63,7 +63,8 @@ struct QrLahqr {
   template <class G>
   PB_D int operator()( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, double* H, int ldh, double* wr,
                        double* wi, double* Z, int ldz ) const {
-    return lahqr( g, wantt, wantz, n, ilo, ihi, H, ldh, wr, wi, 0, n - 1, Z, ldz );
+    // (a single warp runs the register-resident sweep, whose step loop wants the branch-free reflector)
+    return lahqr<G, ( GroupLanes<G>::value > 0 )>( g, wantt, wantz, n, ilo, ihi, H, ldh, wr, wi, 0, n - 1, Z, ldz );
   }
 };
 

@@ -873,8 +873,8 @@ PB_D void ms_chase_chain( const G& g, bool wantt, bool wantz, int n, int l, int 
 #if defined( __CUDACC__ )
 // kept out of line: the window code has its own register allocation and stack frame, the sweep code around it keeps its own
 __device__ __noinline__ void aed_window_warps( double* red, int jw, int max_moves, double* T, int ldt, double* V, int ldv, double s,
-                                               double* sr, double* si, double* work, int* out ) {
-  aed_window( small_group<kSmallWarps>( red ), jw, max_moves, T, ldt, V, ldv, s, sr, si, work, out );
+                                               double* sr, double* si, double* work, int* out, long long* t_qr_done ) {
+  aed_window( small_group<kSmallWarps>( red ), jw, max_moves, T, ldt, V, ldv, s, sr, si, work, out, t_qr_done );
 }
 #endif
 
@@ -915,10 +915,11 @@ PB_D void ms_aed( const G& g, bool wantt, bool wantz, int n, int ktop, int kbot,
   double* ei = wk.tile + jw;
   bool warp_done = false;
   int spec_inf = 0;
+  long long t_qr_done = 0;
 #if defined( __CUDACC__ )
   if constexpr ( G::kIsCta ) {
     // a window of <= 48 rows keeps a few warps busy at best: they run it behind their own named barrier
-    if ( ( threadIdx.x >> 5 ) < kSmallWarps ) aed_window_warps( g.red, jw, cfg.aed_moves, wk.Hw, ldw, wk.U, ldw, s, er, ei, wk.tile + 2 * jw, out );
+    if ( ( threadIdx.x >> 5 ) < kSmallWarps ) aed_window_warps( g.red, jw, cfg.aed_moves, wk.Hw, ldw, wk.U, ldw, s, er, ei, wk.tile + 2 * jw, out, &t_qr_done );
     else if ( spec_ns > 0 && ( threadIdx.x >> 5 ) == kSmallWarps ) {
       // the warp next to them: eigenvalues of the speculative shift block, side by side with the window
       const int r = lahqr<WarpGroup, true>( WarpGroup(), false, false, spec_ns, 0, spec_ns - 1, S2, ldw, sr2, si2, 0, spec_ns - 1, (double*)nullptr, 1 );
@@ -937,6 +938,12 @@ PB_D void ms_aed( const G& g, bool wantt, bool wantz, int n, int ktop, int kbot,
   const int ns = out[0], infqr = out[1], changed = out[2];
   PB_CHECK_UNIFORM( g, ns * 4 + changed, "aed result" );
   g.tick( kTickMsAed );
+#if defined( __CUDACC__ )
+  if constexpr ( G::kIsCta ) {
+    // slot 3 (unused by this kernel otherwise): the part of the window phase that follows its QR iteration
+    if ( g.stats != nullptr && threadIdx.x == 0 && t_qr_done != 0 ) g.stats[3] += g.last - t_qr_done;
+  }
+#endif
   if ( spec_out != nullptr ) *spec_out = 0;
   if ( infqr != 0 ) {  // the window's own QR iteration failed: nothing was written back, no shifts from here
     *nd_out = 0;

@@ -397,6 +397,221 @@ PB_D void orghr( const G& g, int n, int ilo, int ihi, const double* A, int lda, 
 }
 
 // ------------------------------------------------------------------------------------------------
+// One Francis double-shift sweep on ONE WARP with the data a step depends on held in registers.
+//
+// LAPACK's loop (the generic code in lahqr below) is one dependent chain per bulge position k: bulge column from memory ->
+// reflector -> row update -> barrier -> column update -> barrier -> next bulge column: 1,300 (eigenvalues only) to 1,900
+// (Schur form + vectors) cycles per step on a B200 warp whatever the order (32..64), of which the reflector is 280 and
+// the rest is branches, address arithmetic and shared-memory round trips (tools/mb_lahqr.cu). Here
+//   * every lane tracks the 4 x 3 diagonal block the bulge lives in (rows k..k+3, columns k..k+2, and the bulge column) in
+//     registers, redundantly and bit-identically, so reflector k+1 follows from reflector k by register arithmetic alone;
+//   * lane j owns COLUMN j for the row updates right of the block (rows k, k+1 carried in registers from step to step:
+//     one load, one store per step), lane r owns ROW r for the column updates above the block and row r of Z (likewise);
+//     the block's own entries never go through memory: they enter it from the owning lane by a shuffle (column k+3) and
+//     leave it to the lane that owns row k in registers;
+//   * these updates run ONE STEP BEHIND the reflectors (the updates of step k-1 are independent of the generation of
+//     reflector k and are issued next to it), and nothing written in a step is read in the same step: one __syncwarp per step.
+// The matrix goes through exactly LAPACK's sequence of reflections; only the association of the (exactly orthogonal)
+// products differs, i.e. rounding. Requires i2 <= 32 SLOTS - 1 and ihiz <= 32 SLOTS - 1.
+//
+// Lane-explicit code: NL = 1 on the device (this thread is lane g.tid()), NL = 32 in the host emulation (tests/hostsim:
+// one thread walks the 32 lanes phase by phase, which is what the warp does in lockstep).
+// ------------------------------------------------------------------------------------------------
+template <class G, class = void>
+struct GroupLanes {
+  static constexpr int value = 0;
+};
+template <class G>
+struct GroupLanes<G, decltype( (void)G::kLanes )> {
+  static constexpr int value = G::kLanes;
+};
+
+template <class G, int SLOTS, bool WANTZ, bool FASTREFL>
+PB_D void francis_sweep_lanes( const G& g, int l, int i, int m, double v0, double v1, double v2, int i1, int i2, double* H, int ldh,
+                               int iloz, int ihiz, double* Z, int ldz ) {
+  constexpr int NL = GroupLanes<G>::value;
+  static_assert( NL == 1 || NL == 32, "one lane per thread, or all 32 on one host thread" );
+#define PB_FOR_LANES for ( int li = 0; li < NL; ++li )
+#define PB_LANE ( NL == 1 ? g.tid() : li )
+  auto hg = [&]( int r, int c ) -> double { return ( r <= i && c <= i ) ? PB_H( r, c ) : 0.0; };
+  // ---- tracked block (uniform) ----
+  double b0 = v0, b1 = v1, b2 = v2;
+  double c00 = hg( m, m ), c01 = hg( m, m + 1 ), c02 = hg( m, m + 2 );
+  double c10 = hg( m + 1, m ), c11 = hg( m + 1, m + 1 ), c12 = hg( m + 1, m + 2 );
+  double c20 = hg( m + 2, m ), c21 = hg( m + 2, m + 1 ), c22 = hg( m + 2, m + 2 );
+  double c30 = hg( m + 3, m ), c31 = hg( m + 3, m + 1 ), c32 = hg( m + 3, m + 2 );
+  // ---- per-lane carried entries: x = H(k, j), H(k+1, j) of the lane's column j; y = H(r, k), H(r, k+1) of the lane's
+  // row r; z likewise for Z (k = the next step to be applied to memory) ----
+  double x0[NL][SLOTS], x1[NL][SLOTS], y0[NL][SLOTS], y1[NL][SLOTS], z0[NL][SLOTS], z1[NL][SLOTS];
+  PB_FOR_LANES {
+#pragma unroll
+    for ( int s = 0; s < SLOTS; ++s ) {
+      const int idx = PB_LANE + 32 * s;
+      const bool xa = idx >= m && idx <= i2;
+      x0[li][s] = xa ? PB_H( m, idx ) : 0.0;
+      x1[li][s] = xa ? PB_H( m + 1, idx ) : 0.0;
+      const bool ya = idx >= i1 && idx <= m - 1;
+      y0[li][s] = ya ? PB_H( idx, m ) : 0.0;
+      y1[li][s] = ya ? PB_H( idx, m + 1 ) : 0.0;
+      if ( WANTZ ) {
+        const bool za = idx >= iloz && idx <= ihiz;
+        z0[li][s] = za ? PB_Z( idx, m ) : 0.0;
+        z1[li][s] = za ? PB_Z( idx, m + 1 ) : 0.0;
+      }
+    }
+  }
+  // entry of the lane that owns column c (uniform result)
+  auto from_owner = [&]( const double ( &a )[NL][SLOTS], int c ) -> double {
+    const int s = c >> 5;
+#if defined( __CUDA_ARCH__ )
+    double v = a[0][0];
+    if ( SLOTS > 1 && s == 1 ) v = a[0][SLOTS - 1];
+    return __shfl_sync( 0xffffffffu, v, c & 31 );
+#else
+    return a[NL == 1 ? 0 : ( c & 31 )][s < SLOTS ? s : 0];
+#endif
+  };
+  // pending step (reflector generated, stored matrix not yet updated) and the finished top row of its block
+  int p = m, pnr = 0;
+  double pw2 = 0.0, pw3 = 0.0, pt1 = 0.0, pbeta = 0.0, pf00 = 0.0, pf01 = 0.0, pf02 = 0.0, qf01 = 0.0, qf02 = 0.0;
+  // reflector of step k from the tracked bulge column, then step k on the tracked block (column k+3 joins it)
+  auto step = [&]( int k ) {
+    const int nr = imin( 3, i - k + 1 );
+    double a0 = b0, a1 = b1, a2 = b2, t1;
+    if ( FASTREFL ) larfg3_bf( nr, a0, a1, a2, t1 );
+    else dlarfg3( nr, a0, a1, a2, t1 );
+    if ( nr < 3 ) a2 = 0.0;
+    const bool din = k + 3 <= i;
+    double d0 = from_owner( x0, k + 3 ), d1 = from_owner( x1, k + 3 );
+    d0 = din ? d0 : 0.0;
+    d1 = din ? d1 : 0.0;
+    double d2 = hg( k + 2, k + 3 );
+    const double d3 = hg( k + 3, k + 3 ), d4 = hg( k + 4, k + 3 );
+    const double w2 = a1, w3 = a2, t2 = t1 * w2, t3 = t1 * w3;
+    double s = c00 + w2 * c10 + w3 * c20;
+    c00 -= s * t1;
+    c10 -= s * t2;
+    c20 -= s * t3;
+    s = c01 + w2 * c11 + w3 * c21;
+    c01 -= s * t1;
+    c11 -= s * t2;
+    c21 -= s * t3;
+    s = c02 + w2 * c12 + w3 * c22;
+    c02 -= s * t1;
+    c12 -= s * t2;
+    c22 -= s * t3;
+    s = d0 + w2 * d1 + w3 * d2;
+    d1 -= s * t2;
+    d2 -= s * t3;
+    s = c00 + w2 * c01 + w3 * c02;
+    qf01 = pf01;
+    qf02 = pf02;
+    pf00 = c00 - s * t1;
+    pf01 = c01 - s * t2;
+    pf02 = c02 - s * t3;
+    s = c10 + w2 * c11 + w3 * c12;
+    c10 -= s * t1;
+    c11 -= s * t2;
+    c12 -= s * t3;
+    s = c20 + w2 * c21 + w3 * c22;
+    c20 -= s * t1;
+    c21 -= s * t2;
+    c22 -= s * t3;
+    s = c30 + w2 * c31 + w3 * c32;
+    c30 -= s * t1;
+    c31 -= s * t2;
+    c32 -= s * t3;
+    b0 = c10;
+    b1 = c20;
+    b2 = c30;
+    c00 = c11; c01 = c12; c02 = d1;
+    c10 = c21; c11 = c22; c12 = d2;
+    c20 = c31; c21 = c32; c22 = d3;
+    c30 = 0.0; c31 = 0.0; c32 = d4;
+    p = k;
+    pnr = nr;
+    pw2 = w2;
+    pw3 = w3;
+    pt1 = t1;
+    pbeta = a0;
+  };
+  // the updates of step P (parameters W2, W3, T1; QF = top-row entries of the block of step P-1) on the stored matrix
+  auto apply = [&]( int P, double W2, double W3, double T1, double BETA, double F00, double QF1, double QF2 ) {
+    const double T2 = T1 * W2, T3 = T1 * W3;
+    const bool third = P + 2 <= i;
+    PB_FOR_LANES {
+#pragma unroll
+      for ( int s = 0; s < SLOTS; ++s ) {
+        const int idx = PB_LANE + 32 * s;
+        {  // rows P..P+2 of column idx
+          const bool act = idx <= i2 && ( idx >= P + 3 || idx > i );
+          const double e0 = x0[li][s], e1 = x1[li][s];
+          const double e2 = ( act && third ) ? PB_H( P + 2, idx ) : 0.0;
+          const double sum = e0 + W2 * e1 + W3 * e2;
+          if ( act ) PB_H( P, idx ) = e0 - sum * T1;
+          x0[li][s] = e1 - sum * T2;
+          x1[li][s] = e2 - sum * T3;
+        }
+        {  // columns P..P+2 of row idx (row P-1 joins with the entries the tracked block finished one step earlier)
+          const bool act = idx >= i1 && idx <= P - 1;
+          const bool join = P > m && idx == P - 1;
+          const double e0 = join ? QF1 : y0[li][s], e1 = join ? QF2 : y1[li][s];
+          const double e2 = ( act && third ) ? PB_H( idx, P + 2 ) : 0.0;
+          const double sum = e0 + W2 * e1 + W3 * e2;
+          if ( act ) PB_H( idx, P ) = e0 - sum * T1;
+          y0[li][s] = e1 - sum * T2;
+          y1[li][s] = e2 - sum * T3;
+        }
+        if ( WANTZ ) {
+          const bool act = idx >= iloz && idx <= ihiz;
+          const double e0 = z0[li][s], e1 = z1[li][s];
+          const double e2 = ( act && third ) ? PB_Z( idx, P + 2 ) : 0.0;
+          const double sum = e0 + W2 * e1 + W3 * e2;
+          if ( act ) PB_Z( idx, P ) = e0 - sum * T1;
+          z0[li][s] = e1 - sum * T2;
+          z1[li][s] = e2 - sum * T3;
+        }
+      }
+    }
+    if ( g.tid() == 0 ) {
+      PB_H( P, P ) = F00;
+      if ( P > m ) PB_H( P, P - 1 ) = BETA;
+    }
+  };
+  // ---- first step: nothing pending yet ----
+  step( m );
+  if ( g.tid() == 0 && m > l ) PB_H( m, m - 1 ) = PB_H( m, m - 1 ) * ( 1.0 - pt1 );
+  for ( int k = m + 1; k <= i - 1; ++k ) {
+    const int P = p;
+    const double W2 = pw2, W3 = pw3, T1 = pt1, BETA = pbeta, F00 = pf00, QF1 = qf01, QF2 = qf02;
+    apply( P, W2, W3, T1, BETA, F00, QF1, QF2 );
+    step( k );
+    g.sync();
+  }
+  apply( p, pw2, pw3, pt1, pbeta, pf00, qf01, qf02 );
+  // ---- what is still in registers after the last step (p = i-1, a 2 x 2 reflection) ----
+  PB_FOR_LANES {
+#pragma unroll
+    for ( int s = 0; s < SLOTS; ++s ) {
+      const int idx = PB_LANE + 32 * s;
+      if ( idx > i && idx <= i2 ) PB_H( i, idx ) = x0[li][s];
+      if ( idx >= i1 && idx <= i - 2 ) PB_H( idx, i ) = y0[li][s];
+      if ( WANTZ ) {
+        if ( idx >= iloz && idx <= ihiz ) PB_Z( idx, i ) = z0[li][s];
+      }
+    }
+  }
+  if ( g.tid() == 0 ) {
+    PB_H( i - 1, i ) = pf01;
+    PB_H( i, i - 1 ) = b0;
+    PB_H( i, i ) = c00;
+  }
+  g.sync();
+#undef PB_FOR_LANES
+#undef PB_LANE
+}
+
+// ------------------------------------------------------------------------------------------------
 // lahqr. H upper Hessenberg in rows/cols ilo..ihi of an n x n array. With wantt the full Schur form
 // is produced (updates extend over 0..n-1), otherwise only eigenvalues. With wantz the same
 // transformations are accumulated into rows iloz..ihiz of Z.
@@ -578,6 +793,32 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
       }
       g.sync();  // every thread has finished reading H for the shift vector before the sweep writes
       // ---- double-shift QR sweep ----
+#ifndef PB_LAHQR_NO_LANES
+      if constexpr ( GroupLanes<G>::value > 0 ) {
+        // one warp, everything the updates touch within 64 columns / rows: the register-resident sweep
+        const int top = wantz ? imax( i2, ihiz ) : i2;
+        if ( top < 64 ) {
+#ifdef PB_AED_COUNT
+          for ( int k = m; k <= i - 1; ++k ) PB_AED_COUNT( wantt ? 1 : 2 );
+          PB_AED_COUNT( 3 );
+#endif
+#ifdef PB_SWEEP_PROFILE
+          PB_SWEEP_PROFILE( 0 );
+#endif
+          if ( top < 32 ) {
+            if ( wantz ) francis_sweep_lanes<G, 1, true, FASTREFL>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz );
+            else francis_sweep_lanes<G, 1, false, FASTREFL>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz );
+          } else {
+            if ( wantz ) francis_sweep_lanes<G, 2, true, FASTREFL>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz );
+            else francis_sweep_lanes<G, 2, false, FASTREFL>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz );
+          }
+#ifdef PB_SWEEP_PROFILE
+          PB_SWEEP_PROFILE( 1 );
+#endif
+          continue;
+        }
+      }
+#endif
       for ( int k = m; k <= i - 1; ++k ) {
 #ifdef PB_AED_COUNT
         PB_AED_COUNT( wantt ? 1 : 2 );

@@ -227,6 +227,21 @@ int ht_geev_lr( int nt, int n, double* A, double* wr, double* wi, int wantvl, do
   } );
 }
 
+// the lane-explicit warp code (pb_small.cuh::francis_sweep_lanes) with one host thread walking the 32 lanes
+struct HostWarpGroup : pb::HostGroup {
+  static constexpr int kLanes = 32;
+};
+int hs_geev_warp( int n, double* A, double* wr, double* wi, int wantvr, double* V ) {
+  HostWarpGroup g;
+  std::vector<double> dw( 5 * n + 5 );
+  std::vector<int> iw( 2 * n + 2 );
+  return pb::geev_group( g, n, A, n, wr, wi, false, (double*)nullptr, n, wantvr != 0, V, n, dw.data(), iw.data() );
+}
+int hs_lahqr_warp( int wantt, int wantz, int n, int ilo, int ihi, double* H, double* wr, double* wi, double* Z ) {
+  HostWarpGroup g;
+  return pb::lahqr<HostWarpGroup, true>( g, wantt != 0, wantz != 0, n, ilo, ihi, H, n, wr, wi, 0, n - 1, Z, n );
+}
+
 int hs_geev( int n, double* A, double* wr, double* wi, int wantvr, double* V ) {
   pb::HostGroup g;
   std::vector<double> dw( 5 * n + 5 );

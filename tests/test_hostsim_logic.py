@@ -63,6 +63,54 @@ def test_geev_pipeline_matches_lapack(hs, n):
         assert infoe == 0 and po.match_eigenvalues((wre + 1j * wie) / s, w0) <= 1e-9 * nrm
 
 
+@pytest.mark.parametrize("n", [2, 3, 4, 5, 8, 17, 31, 32, 33, 40, 48, 63, 64])
+def test_warp_register_sweep_matches_lapack(hs, n):
+    """The lane-explicit Francis sweep of a single warp (pb_small.cuh::francis_sweep_lanes), 32 lanes walked by
+    one host thread: whole pipeline against dgeev (same eigenvalue order as dlahqr), and lahqr alone on
+    sub-blocks ilo..ihi with and without the Schur form: Z' H Z = T, T quasi-triangular, Z orthogonal."""
+    rng = np.random.default_rng([11, n])
+    for q, (A, s) in enumerate(_cases(rng, n)):
+        A2 = np.array(A, order="F")
+        wr, wi, V = np.zeros(n), np.zeros(n), np.zeros((n, n), order="F")
+        assert hs.hs_geev_warp(n, dp(A2), dp(wr), dp(wi), 1, dp(V)) == 0
+        wr0, wi0, _, VR0, info0 = ls.dgeev(A)
+        As, w, w0 = A / s, (wr + 1j * wi) / s, (wr0 + 1j * wi0) / s
+        nrm = max(1.0, np.linalg.norm(As, 2))
+        if q == 0:
+            assert np.abs(w - w0).max() <= 1e-11 * nrm
+        assert po.match_eigenvalues(w, w0) <= 1e-9 * nrm
+        assert po.backward_error(As, wr / s, wi / s, V) <= 100
+        A2 = np.array(A, order="F")
+        wre, wie = np.zeros(n), np.zeros(n)
+        assert hs.hs_geev_warp(n, dp(A2), dp(wre), dp(wie), 0, dp(V)) == 0
+        assert po.match_eigenvalues((wre + 1j * wie) / s, w0) <= 1e-9 * nrm
+    for trial in range(6):
+        H0 = np.triu(rng.standard_normal((n, n)), -1)
+        ilo = int(rng.integers(0, max(1, n // 3)))
+        ihi = int(rng.integers(max(ilo, n - 1 - n // 3), n))
+        if trial == 0:
+            ilo, ihi = 0, n - 1
+        # isolate the active block the way dgebal / an earlier deflation would
+        H0[ilo:, :ilo] = 0
+        H0[ihi + 1:, :ihi + 1] = 0
+        H0[np.tril_indices(n, -1)] *= (np.abs(np.subtract.outer(np.arange(n), np.arange(n))[np.tril_indices(n, -1)]) == 1)
+        for wantt in (0, 1):
+            H = np.array(H0, order="F")
+            Z = np.eye(n, order="F")
+            wr, wi = np.zeros(n), np.zeros(n)
+            assert hs.hs_lahqr_warp(wantt, wantt, n, ilo, ihi, dp(H), dp(wr), dp(wi), dp(Z)) == 0
+            w = (wr + 1j * wi)[ilo:ihi + 1]
+            w0 = np.linalg.eigvals(H0[ilo:ihi + 1, ilo:ihi + 1])
+            nrm = max(1.0, np.linalg.norm(H0, 2))
+            assert po.match_eigenvalues(w, w0) <= 1e-9 * nrm
+            if wantt:
+                assert np.abs(Z.T @ Z - np.eye(n)).max() <= 1e-13 * n
+                assert np.abs(Z.T @ H0 @ Z - H).max() <= 1e-13 * n * nrm
+                assert np.abs(np.tril(H, -2)).max() == 0.0
+                sub = np.abs(np.diag(H, -1))[ilo:ihi]  # subdiagonal of the active block
+                assert not np.any((sub[:-1] != 0) & (sub[1:] != 0))  # 2 x 2 blocks do not touch
+
+
 def _hessenberg_case(n, seed, sparse=False):
     rng = np.random.default_rng([seed, n])
     A = rng.standard_normal((n, n))
