@@ -376,7 +376,10 @@ __global__ void __launch_bounds__( pb::kHessThreads, ( MAXCH == 16 ? 2 : 1 ) ) m
 inline size_t bprep_smem_bytes( int nmax ) { return sizeof( double ) * pb::bh_smem_doubles( nmax ); }
 
 template <int MAXCH>
-__global__ void __launch_bounds__( pb::kBhThreads, ( MAXCH == 16 ? 2 : 1 ) ) mid_prep_blocked_kernel( MidArgs a ) {
+#ifndef PB_BH_OCC
+#define PB_BH_OCC 2
+#endif
+__global__ void __launch_bounds__( pb::kBhThreads, ( MAXCH == 16 ? PB_BH_OCC : 1 ) ) mid_prep_blocked_kernel( MidArgs a ) {
   extern __shared__ __align__( 128 ) double smem[];
   __shared__ double red[64];
   __shared__ long long lstats[kNumTicks];

@@ -35,7 +35,14 @@ constexpr int kTickHessUpdate = 7;  // phase-profile slot: Y top rows + trailing
 constexpr int kBhNB = 32;        // panel width
 constexpr int kBhTC = 16;        // columns per update tile (two DMMA n-tiles)
 constexpr int kBhMaxStages = 8;  // row blocks of a tile that can be resident at once
-constexpr int kBhBoxRows = 256;  // rows per TMA box (box = kBhBoxRows x 1 column of doubles)
+#ifndef PB_BH_BOXROWS
+#define PB_BH_BOXROWS 256
+#endif
+#ifndef PB_BH_MAXRES
+#define PB_BH_MAXRES 4
+#endif
+constexpr int kBhBoxRows = PB_BH_BOXROWS;  // rows per TMA box (box = kBhBoxRows x 1 column of doubles)
+constexpr int kBhMaxResident = PB_BH_MAXRES;  // a tile whose row blocks number at most this many stays on chip between its two sweeps
 constexpr int kBhThreads = kHessThreads;
 constexpr int kBhWarps = kBhThreads / 32;
 constexpr int kBhLdT = kBhNB + 1;  // T(q, p) at Ts[q * kBhLdT + p]
@@ -53,7 +60,7 @@ __host__ __device__ inline size_t bh_scratch_doubles( int n ) {
 // stages of the tile ring: every row block of the tallest tile resident when that fits (then nothing is re-read), two otherwise
 __host__ __device__ inline int bh_stages( int n ) {
   const int nrb = bh_row_blocks( n );
-  return nrb <= 4 ? ( nrb < 2 ? 2 : nrb ) : 2;
+  return nrb <= kBhMaxResident ? ( nrb < 2 ? 2 : nrb ) : 2;
 }
 // shared memory (doubles): vs, bs (2 n) | ws, wt, w2s, vrow (4 x 32) | red (64) | Ts (32 x 33) |
 //   union { ypart: 8 x min(n, 1024) ; stages x (256 x 16) + Ws: 32 x 16 + Wt: 32 x 16 }
