@@ -217,6 +217,19 @@ __global__ void __launch_bounds__( 128 ) geev_smallcta_kernel( BatchView bv, con
   if ( tid == 0 ) bv.info[id] = info;
 }
 
+// ---- n <= 64, eigenvalues only, in two launches ---------------------------------------------------------------------
+// The one-launch kernel above keeps the full matrix in shared memory from the balancing to the last QR sweep: 33 KB per
+// matrix at n = 64, i.e. 6 warps per SM for an iteration that is one dependent chain per warp. Only the reduction needs the
+// full matrix. Stage 1 (small_hess_kernel, one warp per matrix as before) ends with the Hessenberg matrix back in A and
+// ilo / ihi / the scaling in the per-matrix meta record; stage 2 (small_qr_pair_kernel) runs the iteration with TWO
+// Hessenberg matrices in one nmax x (nmax + 3) array, one warp each: matrix 0 at (r, c + 3), matrix 1 transposed at (c, r) --
+// an upper Hessenberg matrix has no entry with r > c + 1, so the first occupies cells with col - row >= 2 and the second
+// cells with col - row <= 1 -- which doubles the warps in flight (12 per SM at n = 64). The register-resident sweep never
+// stores a bulge, so neither matrix ever touches the other's cells (pb::lahqr, hrs / band_only).
+struct MidMeta;  // (defined with the mid-size path below)
+__global__ void __launch_bounds__( 32 ) small_hess_kernel( BatchView bv, const int* ids, MidMeta* meta, int nmax, int lds );
+__global__ void __launch_bounds__( 64 ) small_qr_pair_kernel( BatchView bv, const int* ids, int count, const MidMeta* meta, int nmax, int lds );
+
 // ---- size-generic path: one CTA per matrix, in place in global memory ----------------------------
 __global__ void __launch_bounds__( kGenericThreads ) geev_cta_kernel( BatchView bv, const int* ids ) {
   __shared__ double red[64];
@@ -252,6 +265,86 @@ struct MidMeta {
   int ilo, ihi, info, scalea;
   double anrm, cscale;
 };
+
+__global__ void __launch_bounds__( 32 ) small_hess_kernel( BatchView bv, const int* ids, MidMeta* meta, int nmax, int lds ) {
+  extern __shared__ double smem[];
+  const int id = ids[blockIdx.x];
+  const int n = bv.n[id];
+  const int lane = threadIdx.x;
+  double* As = smem;
+  double* dw = As + (size_t)lds * nmax;
+  int* iw = reinterpret_cast<int*>( dw + 5 * nmax );
+  double* Ag = bv.A + bv.a_off[id];
+  const int nn = n * n;
+  for ( int q = lane; q < nn; q += 32 ) {
+    const int c = q / n, r = q - c * n;
+    As[r + c * lds] = Ag[q];
+  }
+  __syncwarp();
+  pb::WarpGroup g;
+  double* wr = bv.wr + bv.w_off[id];
+  double* wi = bv.wi + bv.w_off[id];
+  MidMeta m;
+  m.ilo = 0;
+  m.ihi = n - 1;
+  m.info = 0;
+  m.scalea = 0;
+  m.anrm = 0.0;
+  m.cscale = 1.0;
+  if ( n > 0 ) {
+    pb::GeevScaling sc;
+    if ( !pb::geev_prologue( g, n, As, lds, sc, &m.ilo, &m.ihi, dw + nmax, iw ) ) {
+      m.info = PALADIN_GPU_INFO_NONFINITE;
+    } else {
+      m.scalea = sc.scalea ? 1 : 0;
+      m.anrm = sc.anrm;
+      m.cscale = sc.cscale;
+      pb::gehd2( g, n, m.ilo, m.ihi, As, lds, dw, dw + 2 * nmax );
+      __syncwarp();
+      pb::geev_isolated_eigenvalues( g, n, m.ilo, m.ihi, As, lds, wr, wi );
+      for ( int q = lane; q < nn; q += 32 ) {
+        const int c = q / n, r = q - c * n;
+        if ( r <= c + 1 ) Ag[q] = As[r + c * lds];
+      }
+    }
+  }
+  if ( lane == 0 ) {
+    meta[id] = m;
+    if ( m.info != 0 ) bv.info[id] = m.info;
+  }
+}
+
+__global__ void __launch_bounds__( 64 ) small_qr_pair_kernel( BatchView bv, const int* ids, int count, const MidMeta* meta, int nmax, int lds ) {
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int k = 2 * blockIdx.x + warp;
+  if ( k >= count ) return;  // (the warps of a pair never meet at a barrier)
+  const int id = ids[k];
+  const int n = bv.n[id];
+  const MidMeta m = meta[id];
+  if ( m.info != 0 || n == 0 ) {
+    if ( lane == 0 && m.info == 0 ) bv.info[id] = 0;
+    return;
+  }
+  // warp 0: H(r, c) at cell (r, c + 3); warp 1: H(r, c) at cell (c, r)   (cell (row, col) at smem[row + col * lds])
+  double* H = warp == 0 ? smem + 3 * (size_t)lds : smem;
+  const int hrs = warp == 0 ? 1 : lds, ldh = warp == 0 ? lds : 1;
+  const double* Ag = bv.A + bv.a_off[id];
+  const int nn = n * n;
+  for ( int q = lane; q < nn; q += 32 ) {
+    const int c = q / n, r = q - c * n;
+    if ( r <= c + 1 ) H[(size_t)r * hrs + (size_t)c * ldh] = Ag[q];
+  }
+  __syncwarp();
+  pb::WarpGroup g;
+  double* wr = bv.wr + bv.w_off[id];
+  double* wi = bv.wi + bv.w_off[id];
+  const int info = pb::lahqr<pb::WarpGroup, true>( g, false, false, n, m.ilo, m.ihi, H, ldh, wr, wi, 0, n - 1, (double*)nullptr, 1, pb::LahqrNoHook(), hrs, true );
+  __syncwarp();
+  pb::GeevScaling sc{ m.scalea != 0, m.anrm, m.cscale };
+  pb::geev_unscale( g, n, sc, info, m.ilo, wr, wi );
+  if ( lane == 0 ) bv.info[id] = info;
+}
 
 struct MidArgs {
   BatchView bv;
@@ -866,6 +959,8 @@ int set_kernel_attributes( DeviceCtx& c ) {
   if ( c.attrs_set ) return PALADIN_GPU_OK;
   const int o = c.max_smem_optin;
   PB_CUDA( raise_smem_limit( geev_warp_kernel, o ) );
+  PB_CUDA( raise_smem_limit( small_hess_kernel, o ) );
+  PB_CUDA( raise_smem_limit( small_qr_pair_kernel, o ) );
   PB_CUDA( raise_smem_limit( geev_smallcta_kernel, o ) );
   PB_CUDA( raise_smem_limit( mid_prep_kernel<0>, o ) );
   PB_CUDA( raise_smem_limit( mid_prep_kernel<16>, o ) );
@@ -1533,9 +1628,18 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
       if ( smem <= (size_t)c.max_smem_optin ) {
         stage_begin( b, PALADIN_GPU_STAGE_SMALL, st );
         static const int small_warps = std::getenv( "PALADIN_GPU_SMALL_WARPS" ) ? std::max( 1, std::min( 4, std::atoi( std::getenv( "PALADIN_GPU_SMALL_WARPS" ) ) ) ) : 1;
+        // eigenvalues only: reduction and iteration as two launches, the iteration with two matrices per shared array
+        // (PALADIN_GPU_SMALL_SPLIT=0: the one-launch kernel)
+        static const bool small_split = !( std::getenv( "PALADIN_GPU_SMALL_SPLIT" ) && std::atoi( std::getenv( "PALADIN_GPU_SMALL_SPLIT" ) ) == 0 );
+        int nl = 1;
         if ( small_warps > 1 && g.nmax >= 32 ) geev_smallcta_kernel<<<cnt, 32 * small_warps, smem, st>>>( bv, ids, g.nmax, g.nmax | 1 );
-        else geev_warp_kernel<<<cnt, 32, smem, st>>>( bv, ids, g.nmax, g.nmax | 1 );
-        stage_end( b, PALADIN_GPU_STAGE_SMALL, st, 1 );
+        else if ( small_split && !wantvr && !wantvl && g.nmax >= 8 ) {
+          const int lds = g.nmax | 1;
+          small_hess_kernel<<<cnt, 32, smem, st>>>( bv, ids, b->d_meta, g.nmax, lds );
+          small_qr_pair_kernel<<<( cnt + 1 ) / 2, 64, sizeof( double ) * (size_t)lds * ( g.nmax + 3 ), st>>>( bv, ids, cnt, b->d_meta, g.nmax, lds );
+          nl = 2;
+        } else geev_warp_kernel<<<cnt, 32, smem, st>>>( bv, ids, g.nmax, g.nmax | 1 );
+        stage_end( b, PALADIN_GPU_STAGE_SMALL, st, nl );
         PB_CUDA( cudaGetLastError() );
         continue;
       }

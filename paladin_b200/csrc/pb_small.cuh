@@ -396,6 +396,9 @@ PB_D void orghr( const G& g, int n, int ilo, int ihi, const double* A, int lda, 
   }
 }
 
+// H(i, j) with separate row and column strides (hrs = 1 everywhere except where two matrices share one array, see lahqr)
+#define PB_HH( i, j ) H[(size_t)( i ) * hrs + (size_t)( j ) * ldh]
+
 // ------------------------------------------------------------------------------------------------
 // One Francis double-shift sweep on ONE WARP with the data a step depends on held in registers.
 //
@@ -428,12 +431,13 @@ struct GroupLanes<G, decltype( (void)G::kLanes )> {
 
 template <class G, int SLOTS, bool WANTZ, bool FASTREFL>
 PB_D void francis_sweep_lanes( const G& g, int l, int i, int m, double v0, double v1, double v2, int i1, int i2, double* H, int ldh,
-                               int iloz, int ihiz, double* Z, int ldz ) {
+                               int iloz, int ihiz, double* Z, int ldz, int hrs = 1 ) {
   constexpr int NL = GroupLanes<G>::value;
   static_assert( NL == 1 || NL == 32, "one lane per thread, or all 32 on one host thread" );
 #define PB_FOR_LANES for ( int li = 0; li < NL; ++li )
 #define PB_LANE ( NL == 1 ? g.tid() : li )
-  auto hg = [&]( int r, int c ) -> double { return ( r <= i && c <= i ) ? PB_H( r, c ) : 0.0; };
+  // (entries below the first subdiagonal are zero at the start of a sweep and never stored by it: not even read)
+  auto hg = [&]( int r, int c ) -> double { return ( r <= i && c <= i && r <= c + 1 ) ? PB_HH( r, c ) : 0.0; };
   // ---- tracked block (uniform) ----
   double b0 = v0, b1 = v1, b2 = v2;
   double c00 = hg( m, m ), c01 = hg( m, m + 1 ), c02 = hg( m, m + 2 );
@@ -448,11 +452,11 @@ PB_D void francis_sweep_lanes( const G& g, int l, int i, int m, double v0, doubl
     for ( int s = 0; s < SLOTS; ++s ) {
       const int idx = PB_LANE + 32 * s;
       const bool xa = idx >= m && idx <= i2;
-      x0[li][s] = xa ? PB_H( m, idx ) : 0.0;
-      x1[li][s] = xa ? PB_H( m + 1, idx ) : 0.0;
+      x0[li][s] = xa ? PB_HH( m, idx ) : 0.0;
+      x1[li][s] = xa ? PB_HH( m + 1, idx ) : 0.0;
       const bool ya = idx >= i1 && idx <= m - 1;
-      y0[li][s] = ya ? PB_H( idx, m ) : 0.0;
-      y1[li][s] = ya ? PB_H( idx, m + 1 ) : 0.0;
+      y0[li][s] = ya ? PB_HH( idx, m ) : 0.0;
+      y1[li][s] = ya ? PB_HH( idx, m + 1 ) : 0.0;
       if ( WANTZ ) {
         const bool za = idx >= iloz && idx <= ihiz;
         z0[li][s] = za ? PB_Z( idx, m ) : 0.0;
@@ -546,9 +550,9 @@ PB_D void francis_sweep_lanes( const G& g, int l, int i, int m, double v0, doubl
         {  // rows P..P+2 of column idx
           const bool act = idx <= i2 && ( idx >= P + 3 || idx > i );
           const double e0 = x0[li][s], e1 = x1[li][s];
-          const double e2 = ( act && third ) ? PB_H( P + 2, idx ) : 0.0;
+          const double e2 = ( act && third ) ? PB_HH( P + 2, idx ) : 0.0;
           const double sum = e0 + W2 * e1 + W3 * e2;
-          if ( act ) PB_H( P, idx ) = e0 - sum * T1;
+          if ( act ) PB_HH( P, idx ) = e0 - sum * T1;
           x0[li][s] = e1 - sum * T2;
           x1[li][s] = e2 - sum * T3;
         }
@@ -556,9 +560,9 @@ PB_D void francis_sweep_lanes( const G& g, int l, int i, int m, double v0, doubl
           const bool act = idx >= i1 && idx <= P - 1;
           const bool join = P > m && idx == P - 1;
           const double e0 = join ? QF1 : y0[li][s], e1 = join ? QF2 : y1[li][s];
-          const double e2 = ( act && third ) ? PB_H( idx, P + 2 ) : 0.0;
+          const double e2 = ( act && third ) ? PB_HH( idx, P + 2 ) : 0.0;
           const double sum = e0 + W2 * e1 + W3 * e2;
-          if ( act ) PB_H( idx, P ) = e0 - sum * T1;
+          if ( act ) PB_HH( idx, P ) = e0 - sum * T1;
           y0[li][s] = e1 - sum * T2;
           y1[li][s] = e2 - sum * T3;
         }
@@ -574,13 +578,13 @@ PB_D void francis_sweep_lanes( const G& g, int l, int i, int m, double v0, doubl
       }
     }
     if ( g.tid() == 0 ) {
-      PB_H( P, P ) = F00;
-      if ( P > m ) PB_H( P, P - 1 ) = BETA;
+      PB_HH( P, P ) = F00;
+      if ( P > m ) PB_HH( P, P - 1 ) = BETA;
     }
   };
   // ---- first step: nothing pending yet ----
   step( m );
-  if ( g.tid() == 0 && m > l ) PB_H( m, m - 1 ) = PB_H( m, m - 1 ) * ( 1.0 - pt1 );
+  if ( g.tid() == 0 && m > l ) PB_HH( m, m - 1 ) = PB_HH( m, m - 1 ) * ( 1.0 - pt1 );
   for ( int k = m + 1; k <= i - 1; ++k ) {
     const int P = p;
     const double W2 = pw2, W3 = pw3, T1 = pt1, BETA = pbeta, F00 = pf00, QF1 = qf01, QF2 = qf02;
@@ -594,17 +598,17 @@ PB_D void francis_sweep_lanes( const G& g, int l, int i, int m, double v0, doubl
 #pragma unroll
     for ( int s = 0; s < SLOTS; ++s ) {
       const int idx = PB_LANE + 32 * s;
-      if ( idx > i && idx <= i2 ) PB_H( i, idx ) = x0[li][s];
-      if ( idx >= i1 && idx <= i - 2 ) PB_H( idx, i ) = y0[li][s];
+      if ( idx > i && idx <= i2 ) PB_HH( i, idx ) = x0[li][s];
+      if ( idx >= i1 && idx <= i - 2 ) PB_HH( idx, i ) = y0[li][s];
       if ( WANTZ ) {
         if ( idx >= iloz && idx <= ihiz ) PB_Z( idx, i ) = z0[li][s];
       }
     }
   }
   if ( g.tid() == 0 ) {
-    PB_H( i - 1, i ) = pf01;
-    PB_H( i, i - 1 ) = b0;
-    PB_H( i, i ) = c00;
+    PB_HH( i - 1, i ) = pf01;
+    PB_HH( i, i - 1 ) = b0;
+    PB_HH( i, i ) = c00;
   }
   g.sync();
 #undef PB_FOR_LANES
@@ -627,8 +631,12 @@ struct LahqrNoHook {
   PB_HD bool operator()( int, int ) const { return false; }
 };
 template <class G, bool FASTREFL = false, class HOOK = LahqrNoHook>
+// hrs / band_only: H(i, j) at H[i * hrs + j * ldh], and only the entries with i <= j + 1 exist (two Hessenberg matrices share
+// one array, the second one transposed: the values-only n <= 64 kernel, paladin_gpu.cu::small_qr_pair_kernel). Needs the
+// register-resident sweep (a single warp, wantt == false): it is the one that never stores a bulge.
 PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, double* H, int ldh,
-                double* wr, double* wi, int iloz, int ihiz, double* Z, int ldz, const HOOK& hook = HOOK() ) {
+                double* wr, double* wi, int iloz, int ihiz, double* Z, int ldz, const HOOK& hook = HOOK(), int hrs = 1,
+                bool band_only = false ) {
   const int t = g.tid(), nt = g.size();
   // the Schur-vector loops start half a group away from the column loops they follow: in a group wider than the
   // block both run side by side
@@ -636,18 +644,20 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
   if ( n == 0 || ihi < ilo ) return 0;
   if ( ilo == ihi ) {
     if ( t == 0 ) {
-      wr[ilo] = PB_H( ilo, ilo );
+      wr[ilo] = PB_HH( ilo, ilo );
       wi[ilo] = 0.0;
     }
     g.sync();
     return 0;
   }
   // clear out the trash below the subdiagonal
-  for ( int j = ilo + t; j <= ihi - 3; j += nt ) {
-    PB_H( j + 2, j ) = 0.0;
-    PB_H( j + 3, j ) = 0.0;
+  if ( !band_only ) {
+    for ( int j = ilo + t; j <= ihi - 3; j += nt ) {
+      PB_HH( j + 2, j ) = 0.0;
+      PB_HH( j + 3, j ) = 0.0;
+    }
+    if ( t == 0 && ilo <= ihi - 2 ) PB_HH( ihi, ihi - 2 ) = 0.0;
   }
-  if ( t == 0 && ilo <= ihi - 2 ) PB_H( ihi, ihi - 2 ) = 0.0;
   g.sync();
 
   const int nh = ihi - ilo + 1;
@@ -666,21 +676,21 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
       // ---- look for a single small subdiagonal element (largest k in l+1..i that qualifies) ----
       int kfound = l;
       for ( int k = i - t; k > l; k -= nt ) {
-        const double hkk1 = fabs( PB_H( k, k - 1 ) );
+        const double hkk1 = fabs( PB_HH( k, k - 1 ) );
         bool small = false;
         if ( hkk1 <= smlnum ) {
           small = true;
         } else {
-          double tst = fabs( PB_H( k - 1, k - 1 ) ) + fabs( PB_H( k, k ) );
+          double tst = fabs( PB_HH( k - 1, k - 1 ) ) + fabs( PB_HH( k, k ) );
           if ( tst == 0.0 ) {
-            if ( k - 2 >= ilo ) tst += fabs( PB_H( k - 1, k - 2 ) );
-            if ( k + 1 <= ihi ) tst += fabs( PB_H( k + 1, k ) );
+            if ( k - 2 >= ilo ) tst += fabs( PB_HH( k - 1, k - 2 ) );
+            if ( k + 1 <= ihi ) tst += fabs( PB_HH( k + 1, k ) );
           }
           if ( hkk1 <= kUlp * tst ) {
-            const double hk1k = fabs( PB_H( k - 1, k ) );
+            const double hk1k = fabs( PB_HH( k - 1, k ) );
             const double ab = dmax( hkk1, hk1k ), ba = dmin( hkk1, hk1k );
-            const double dd = fabs( PB_H( k - 1, k - 1 ) - PB_H( k, k ) );
-            const double aa = dmax( fabs( PB_H( k, k ) ), dd ), bb = dmin( fabs( PB_H( k, k ) ), dd );
+            const double dd = fabs( PB_HH( k - 1, k - 1 ) - PB_HH( k, k ) );
+            const double aa = dmax( fabs( PB_HH( k, k ) ), dd ), bb = dmin( fabs( PB_HH( k, k ) ), dd );
             const double s = aa + ab;
             if ( ba * ( ab / s ) <= dmax( smlnum, kUlp * ( bb * ( aa / s ) ) ) ) small = true;
           }
@@ -692,7 +702,7 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
       }
       l = g.imax_( kfound );
       if ( l > ilo ) {
-        if ( t == 0 ) PB_H( l, l - 1 ) = 0.0;
+        if ( t == 0 ) PB_HH( l, l - 1 ) = 0.0;
       }
       g.sync();
       if ( l >= i - 1 ) {
@@ -706,22 +716,22 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
       }
       double h11, h21, h12, h22;
       if ( kdefl % ( 2 * kexsh ) == 0 ) {
-        const double s = fabs( PB_H( i, i - 1 ) ) + fabs( PB_H( i - 1, i - 2 ) );
-        h11 = dat1 * s + PB_H( i, i );
+        const double s = fabs( PB_HH( i, i - 1 ) ) + fabs( PB_HH( i - 1, i - 2 ) );
+        h11 = dat1 * s + PB_HH( i, i );
         h12 = dat2 * s;
         h21 = s;
         h22 = h11;
       } else if ( kdefl % kexsh == 0 ) {
-        const double s = fabs( PB_H( l + 1, l ) ) + fabs( PB_H( l + 2, l + 1 ) );
-        h11 = dat1 * s + PB_H( l, l );
+        const double s = fabs( PB_HH( l + 1, l ) ) + fabs( PB_HH( l + 2, l + 1 ) );
+        h11 = dat1 * s + PB_HH( l, l );
         h12 = dat2 * s;
         h21 = s;
         h22 = h11;
       } else {
-        h11 = PB_H( i - 1, i - 1 );
-        h21 = PB_H( i, i - 1 );
-        h12 = PB_H( i - 1, i );
-        h22 = PB_H( i, i );
+        h11 = PB_HH( i - 1, i - 1 );
+        h21 = PB_HH( i, i - 1 );
+        h12 = PB_HH( i - 1, i );
+        h22 = PB_HH( i, i );
       }
       double rt1r, rt1i, rt2r, rt2i;
       {
@@ -758,20 +768,20 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
       // ---- look for two consecutive small subdiagonal elements (largest m in l..i-2) ----
       int mfound = l;
       for ( int m = i - 2 - t; m > l; m -= nt ) {
-        double h21s = fabs( PB_H( m + 1, m ) );
-        double s = fabs( PB_H( m, m ) - rt2r ) + fabs( rt2i ) + h21s;
-        h21s = PB_H( m + 1, m ) / s;
-        double v0 = h21s * PB_H( m, m + 1 ) + ( PB_H( m, m ) - rt1r ) * ( ( PB_H( m, m ) - rt2r ) / s ) -
+        double h21s = fabs( PB_HH( m + 1, m ) );
+        double s = fabs( PB_HH( m, m ) - rt2r ) + fabs( rt2i ) + h21s;
+        h21s = PB_HH( m + 1, m ) / s;
+        double v0 = h21s * PB_HH( m, m + 1 ) + ( PB_HH( m, m ) - rt1r ) * ( ( PB_HH( m, m ) - rt2r ) / s ) -
                     rt1i * ( rt2i / s );
-        double v1 = h21s * ( PB_H( m, m ) + PB_H( m + 1, m + 1 ) - rt1r - rt2r );
-        double v2 = h21s * PB_H( m + 2, m + 1 );
+        double v1 = h21s * ( PB_HH( m, m ) + PB_HH( m + 1, m + 1 ) - rt1r - rt2r );
+        double v2 = h21s * PB_HH( m + 2, m + 1 );
         s = fabs( v0 ) + fabs( v1 ) + fabs( v2 );
         v0 /= s;
         v1 /= s;
         v2 /= s;
-        const double h00 = fabs( PB_H( m - 1, m - 1 ) ), h11a = fabs( PB_H( m, m ) ),
-                     h22a = fabs( PB_H( m + 1, m + 1 ) );
-        if ( fabs( PB_H( m, m - 1 ) ) * ( fabs( v1 ) + fabs( v2 ) ) <= kUlp * fabs( v0 ) * ( h00 + h11a + h22a ) ) {
+        const double h00 = fabs( PB_HH( m - 1, m - 1 ) ), h11a = fabs( PB_HH( m, m ) ),
+                     h22a = fabs( PB_HH( m + 1, m + 1 ) );
+        if ( fabs( PB_HH( m, m - 1 ) ) * ( fabs( v1 ) + fabs( v2 ) ) <= kUlp * fabs( v0 ) * ( h00 + h11a + h22a ) ) {
           mfound = m;
           break;
         }
@@ -779,13 +789,13 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
       const int m = g.imax_( mfound );
       double v0, v1, v2;
       {
-        double h21s = fabs( PB_H( m + 1, m ) );
-        double s = fabs( PB_H( m, m ) - rt2r ) + fabs( rt2i ) + h21s;
-        h21s = PB_H( m + 1, m ) / s;
-        v0 = h21s * PB_H( m, m + 1 ) + ( PB_H( m, m ) - rt1r ) * ( ( PB_H( m, m ) - rt2r ) / s ) -
+        double h21s = fabs( PB_HH( m + 1, m ) );
+        double s = fabs( PB_HH( m, m ) - rt2r ) + fabs( rt2i ) + h21s;
+        h21s = PB_HH( m + 1, m ) / s;
+        v0 = h21s * PB_HH( m, m + 1 ) + ( PB_HH( m, m ) - rt1r ) * ( ( PB_HH( m, m ) - rt2r ) / s ) -
              rt1i * ( rt2i / s );
-        v1 = h21s * ( PB_H( m, m ) + PB_H( m + 1, m + 1 ) - rt1r - rt2r );
-        v2 = h21s * PB_H( m + 2, m + 1 );
+        v1 = h21s * ( PB_HH( m, m ) + PB_HH( m + 1, m + 1 ) - rt1r - rt2r );
+        v2 = h21s * PB_HH( m + 2, m + 1 );
         s = fabs( v0 ) + fabs( v1 ) + fabs( v2 );
         v0 /= s;
         v1 /= s;
@@ -806,11 +816,11 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
           PB_SWEEP_PROFILE( 0 );
 #endif
           if ( top < 32 ) {
-            if ( wantz ) francis_sweep_lanes<G, 1, true, FASTREFL>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz );
-            else francis_sweep_lanes<G, 1, false, FASTREFL>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz );
+            if ( wantz ) francis_sweep_lanes<G, 1, true, FASTREFL>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz, hrs );
+            else francis_sweep_lanes<G, 1, false, FASTREFL>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz, hrs );
           } else {
-            if ( wantz ) francis_sweep_lanes<G, 2, true, FASTREFL>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz );
-            else francis_sweep_lanes<G, 2, false, FASTREFL>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz );
+            if ( wantz ) francis_sweep_lanes<G, 2, true, FASTREFL>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz, hrs );
+            else francis_sweep_lanes<G, 2, false, FASTREFL>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz, hrs );
           }
 #ifdef PB_SWEEP_PROFILE
           PB_SWEEP_PROFILE( 1 );
@@ -827,9 +837,9 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
         const int nr = imin( 3, i - k + 1 );
         double a0, a1, a2 = 0.0, t1;
         if ( k > m ) {
-          a0 = PB_H( k, k - 1 );
-          a1 = PB_H( k + 1, k - 1 );
-          if ( nr == 3 ) a2 = PB_H( k + 2, k - 1 );
+          a0 = PB_HH( k, k - 1 );
+          a1 = PB_HH( k + 1, k - 1 );
+          if ( nr == 3 ) a2 = PB_HH( k + 2, k - 1 );
         } else {
           a0 = v0;
           a1 = v1;
@@ -843,29 +853,29 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
 #define PB_FIX_BULGE_COLUMN()                                \
   if ( t == 0 ) {                                            \
     if ( k > m ) {                                           \
-      PB_H( k, k - 1 ) = a0;                                 \
-      PB_H( k + 1, k - 1 ) = 0.0;                            \
-      if ( k < i - 1 ) PB_H( k + 2, k - 1 ) = 0.0;           \
+      PB_HH( k, k - 1 ) = a0;                                 \
+      PB_HH( k + 1, k - 1 ) = 0.0;                            \
+      if ( k < i - 1 ) PB_HH( k + 2, k - 1 ) = 0.0;           \
     } else if ( m > l ) {                                    \
-      PB_H( k, k - 1 ) = PB_H( k, k - 1 ) * ( 1.0 - t1 );    \
+      PB_HH( k, k - 1 ) = PB_HH( k, k - 1 ) * ( 1.0 - t1 );    \
     }                                                        \
   }
         if ( nr == 3 ) {
           const double w3 = a2, t3 = t1 * w3;
           for ( int j = k + t; j <= i2; j += nt ) {
-            const double sum = PB_H( k, j ) + w2 * PB_H( k + 1, j ) + w3 * PB_H( k + 2, j );
-            PB_H( k, j ) -= sum * t1;
-            PB_H( k + 1, j ) -= sum * t2;
-            PB_H( k + 2, j ) -= sum * t3;
+            const double sum = PB_HH( k, j ) + w2 * PB_HH( k + 1, j ) + w3 * PB_HH( k + 2, j );
+            PB_HH( k, j ) -= sum * t1;
+            PB_HH( k + 1, j ) -= sum * t2;
+            PB_HH( k + 2, j ) -= sum * t3;
           }
           g.sync();
           PB_FIX_BULGE_COLUMN();
           const int jend = imin( k + 3, i );
           for ( int j = i1 + t; j <= jend; j += nt ) {
-            const double sum = PB_H( j, k ) + w2 * PB_H( j, k + 1 ) + w3 * PB_H( j, k + 2 );
-            PB_H( j, k ) -= sum * t1;
-            PB_H( j, k + 1 ) -= sum * t2;
-            PB_H( j, k + 2 ) -= sum * t3;
+            const double sum = PB_HH( j, k ) + w2 * PB_HH( j, k + 1 ) + w3 * PB_HH( j, k + 2 );
+            PB_HH( j, k ) -= sum * t1;
+            PB_HH( j, k + 1 ) -= sum * t2;
+            PB_HH( j, k + 2 ) -= sum * t3;
           }
           if ( wantz ) {
             for ( int j = iloz + tz; j <= ihiz; j += nt ) {
@@ -877,16 +887,16 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
           }
         } else if ( nr == 2 ) {
           for ( int j = k + t; j <= i2; j += nt ) {
-            const double sum = PB_H( k, j ) + w2 * PB_H( k + 1, j );
-            PB_H( k, j ) -= sum * t1;
-            PB_H( k + 1, j ) -= sum * t2;
+            const double sum = PB_HH( k, j ) + w2 * PB_HH( k + 1, j );
+            PB_HH( k, j ) -= sum * t1;
+            PB_HH( k + 1, j ) -= sum * t2;
           }
           g.sync();
           PB_FIX_BULGE_COLUMN();
           for ( int j = i1 + t; j <= i; j += nt ) {
-            const double sum = PB_H( j, k ) + w2 * PB_H( j, k + 1 );
-            PB_H( j, k ) -= sum * t1;
-            PB_H( j, k + 1 ) -= sum * t2;
+            const double sum = PB_HH( j, k ) + w2 * PB_HH( j, k + 1 );
+            PB_HH( j, k ) -= sum * t1;
+            PB_HH( j, k + 1 ) -= sum * t2;
           }
           if ( wantz ) {
             for ( int j = iloz + tz; j <= ihiz; j += nt ) {
@@ -904,19 +914,19 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
 
     if ( l == i ) {
       if ( t == 0 ) {
-        wr[i] = PB_H( i, i );
+        wr[i] = PB_HH( i, i );
         wi[i] = 0.0;
       }
     } else if ( l == i - 1 ) {
-      double a = PB_H( i - 1, i - 1 ), b = PB_H( i - 1, i ), c = PB_H( i, i - 1 ), d = PB_H( i, i );
+      double a = PB_HH( i - 1, i - 1 ), b = PB_HH( i - 1, i ), c = PB_HH( i, i - 1 ), d = PB_HH( i, i );
       double r1r, r1i, r2r, r2i, cs, sn;
       dlanv2( a, b, c, d, r1r, r1i, r2r, r2i, cs, sn );
       g.sync();
       if ( t == 0 ) {
-        PB_H( i - 1, i - 1 ) = a;
-        PB_H( i - 1, i ) = b;
-        PB_H( i, i - 1 ) = c;
-        PB_H( i, i ) = d;
+        PB_HH( i - 1, i - 1 ) = a;
+        PB_HH( i - 1, i ) = b;
+        PB_HH( i, i - 1 ) = c;
+        PB_HH( i, i ) = d;
         wr[i - 1] = r1r;
         wi[i - 1] = r1i;
         wr[i] = r2r;
@@ -924,14 +934,14 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
       }
       if ( wantt ) {
         for ( int j = i + 1 + t; j <= i2; j += nt ) {
-          const double x = PB_H( i - 1, j ), y = PB_H( i, j );
-          PB_H( i - 1, j ) = cs * x + sn * y;
-          PB_H( i, j ) = cs * y - sn * x;
+          const double x = PB_HH( i - 1, j ), y = PB_HH( i, j );
+          PB_HH( i - 1, j ) = cs * x + sn * y;
+          PB_HH( i, j ) = cs * y - sn * x;
         }
         for ( int j = i1 + t; j < i - 1; j += nt ) {
-          const double x = PB_H( j, i - 1 ), y = PB_H( j, i );
-          PB_H( j, i - 1 ) = cs * x + sn * y;
-          PB_H( j, i ) = cs * y - sn * x;
+          const double x = PB_HH( j, i - 1 ), y = PB_HH( j, i );
+          PB_HH( j, i - 1 ) = cs * x + sn * y;
+          PB_HH( j, i ) = cs * y - sn * x;
         }
       }
       if ( wantz ) {

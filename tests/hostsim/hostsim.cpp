@@ -242,6 +242,24 @@ int hs_lahqr_warp( int wantt, int wantz, int n, int ilo, int ihi, double* H, dou
   return pb::lahqr<HostWarpGroup, true>( g, wantt != 0, wantz != 0, n, ilo, ihi, H, n, wr, wi, 0, n - 1, Z, n );
 }
 
+// two upper Hessenberg matrices in one n x (n + 3) array (paladin_gpu.cu::small_qr_pair_kernel): matrix 0 at cell (r, c + 3),
+// matrix 1 transposed at cell (c, r); eigenvalues only, first matrix 0 to the end, then matrix 1 (whose cells must have survived)
+int hs_lahqr_pair( int n, const double* H0, const double* H1, double* wr0, double* wi0, double* wr1, double* wi1 ) {
+  HostWarpGroup g;
+  const int lds = n | 1;
+  std::vector<double> S( (size_t)lds * ( n + 3 ), 1e300 );  // (a cell nobody owns must never be read: poison)
+  for ( int c = 0; c < n; ++c )
+    for ( int r = 0; r < n && r <= c + 1; ++r ) {
+      S[r + (size_t)( c + 3 ) * lds] = H0[r + (size_t)c * n];
+      S[c + (size_t)r * lds] = H1[r + (size_t)c * n];
+    }
+  const int i0 = pb::lahqr<HostWarpGroup, true>( g, false, false, n, 0, n - 1, S.data() + 3 * (size_t)lds, lds, wr0, wi0, 0, n - 1, (double*)nullptr, 1,
+                                                 pb::LahqrNoHook(), 1, true );
+  const int i1 = pb::lahqr<HostWarpGroup, true>( g, false, false, n, 0, n - 1, S.data(), 1, wr1, wi1, 0, n - 1, (double*)nullptr, 1, pb::LahqrNoHook(), lds,
+                                                 true );
+  return i0 * 1000 + i1;
+}
+
 int hs_geev( int n, double* A, double* wr, double* wi, int wantvr, double* V ) {
   pb::HostGroup g;
   std::vector<double> dw( 5 * n + 5 );

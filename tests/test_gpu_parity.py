@@ -278,6 +278,50 @@ print("OK")
     assert "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
 
 
+def test_small_values_only_two_launch_path(pg):
+    """n <= 64 without vectors runs as two launches (reduction; iteration with two Hessenberg matrices per shared array,
+    the second transposed): ragged sizes in one bucket, an odd count (a lone warp in the last pair), n = 1 / 2, a
+    non-finite matrix next to a healthy one; eigenvalues against the oracle, and the same values in the same order as
+    the one-launch kernel (PALADIN_GPU_SMALL_SPLIT=0)."""
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r)
+import paladin_b200 as pg
+from oracle import paladin_oracle as po
+sizes = [64, 64, 63, 50, 64, 33, 40, 64, 17, 9, 8, 5, 2, 1, 64, 48, 64]
+mats = [(n,) + po.random_dense_coo(n, [71, q]) for q, n in enumerate(sizes)]
+bad = 3
+mats[bad][3][5] = np.inf
+n = np.array([m[0] for m in mats], dtype=np.int32)
+off = np.concatenate([[0], np.cumsum([len(m[3]) for m in mats])]).astype(np.int64)
+res, info = pg.geev_batch(n, off, np.concatenate([m[1] for m in mats]), np.concatenate([m[2] for m in mats]),
+                          np.concatenate([m[3] for m in mats]), jobvr="N")
+assert info[bad] == -4 and not np.delete(info, bad).any(), info
+out = []
+for q, (m, (wr, wi, _)) in enumerate(zip(mats, res)):
+    if q == bad:
+        continue
+    A = po.dense_matrix(*m)
+    wr0, wi0, _, _, _ = po.dgeev(A, right=False)
+    assert po.match_eigenvalues(po.eigenvalues(wr, wi), po.eigenvalues(wr0, wi0)) <= 1e-9 * max(1.0, np.linalg.norm(A, 2))
+    assert np.abs((wr + 1j * wi) - (wr0 + 1j * wi0)).max() <= 1e-10 * max(1.0, np.linalg.norm(A, 2))  # dlahqr's order
+    out.append(np.concatenate([wr, wi]))
+np.save(sys.argv[1], np.concatenate(out))
+print("OK")
+""" % ROOT
+    import subprocess
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        got = []
+        for split in ("1", "0"):
+            f = os.path.join(d, "w%s.npy" % split)
+            r = subprocess.run([sys.executable, "-c", code, f], capture_output=True, text=True,
+                               env=dict(os.environ, PALADIN_GPU_SMALL_SPLIT=split), timeout=600)
+            assert "OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+            got.append(np.load(f))
+        assert np.abs(got[0] - got[1]).max() <= 1e-10 * max(1.0, np.abs(got[1]).max())
+
+
 def test_bench_sized_step_properties(pg):
     """One bench-sized step of BASELINE.json configs[2] (592 distinct dense N(0,1) 512 x 512 matrices, default_rng([3, k]),
     eigenvalues + right eigenvectors) checked through size-independent properties: info == 0, sum of eigenvalues = trace,

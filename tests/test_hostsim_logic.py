@@ -111,6 +111,19 @@ def test_warp_register_sweep_matches_lapack(hs, n):
                 assert not np.any((sub[:-1] != 0) & (sub[1:] != 0))  # 2 x 2 blocks do not touch
 
 
+@pytest.mark.parametrize("n", [2, 3, 5, 16, 33, 64])
+def test_two_hessenberg_matrices_share_one_array(hs, n):
+    """The values-only n <= 64 kernel iterates on two Hessenberg matrices stored in one array (the second transposed,
+    pb::lahqr hrs / band_only): neither run may read or write a cell of the other (poisoned cells outside both)."""
+    rng = np.random.default_rng([21, n])
+    H0 = np.asfortranarray(np.triu(rng.standard_normal((n, n)), -1))
+    H1 = np.asfortranarray(np.triu(rng.standard_normal((n, n)), -1))
+    w = [np.zeros(n) for _ in range(4)]
+    assert hs.hs_lahqr_pair(n, dp(H0), dp(H1), dp(w[0]), dp(w[1]), dp(w[2]), dp(w[3])) == 0
+    for H, wr, wi in ((H0, w[0], w[1]), (H1, w[2], w[3])):
+        assert po.match_eigenvalues(wr + 1j * wi, np.linalg.eigvals(H)) <= 1e-9 * max(1.0, np.linalg.norm(H, 2))
+
+
 def _hessenberg_case(n, seed, sparse=False):
     rng = np.random.default_rng([seed, n])
     A = rng.standard_normal((n, n))
