@@ -376,7 +376,9 @@ def run_uniform(cx, args, wl, n, job, B, distinct, seed, steps, warmup, full):
     # K steps, like the batches of the paladin-gpu executable.
     halves = []
     if full and B >= 2:
-        nchunk = max(2, min(args.e2e_chunks, B))
+        # (large matrices: a batch of fewer than 16 gets clusters of 16 CTAs per matrix and leader-bound QR phases that do not
+        # overlap; keep at least 16 per batch)
+        nchunk = max(2, min(args.e2e_chunks, B if n <= 1024 else B // 16))
         cuts = [B * q // nchunk for q in range(nchunk + 1)]
         for lo, hi in zip(cuts[:-1], cuts[1:]):
             hb = pg.Batch(nvec[lo:hi], off[lo:hi + 1] - off[lo], jobvr=job, device=dev)
