@@ -695,6 +695,18 @@ inline int host_main( int argc, char* argv[] ) {
     std::cerr << "paladin-gpu: no usable sm_100 device (there is no CPU fallback)\n";
     return 3;
   }
+  // the CUDA contexts (and the library's per-device state) come up while the listing pre-pass reads the size lines
+  std::thread warm;
+  if ( o.dump_partition.empty() )
+    warm = std::thread( [pods] {
+      for ( int r = 0; r < pods; ++r ) paladin_gpu_init( r );
+    } );
+  struct Joiner {
+    std::thread& t;
+    ~Joiner() {
+      if ( t.joinable() ) t.join();
+    }
+  } warm_joiner{ warm };
   const int total = count_nonempty_lines( o.listing );
   std::cout << "\nCommand line parsed!" << '\n';
   std::cout << "GPUs (pods)        : " << pods << '\n';
@@ -703,6 +715,7 @@ inline int host_main( int argc, char* argv[] ) {
   std::cout << "Load measure type  : " << measure_type_description( o.measure ) << '\n';
   std::cout << "Timing repeats     : " << o.repeats << '\n' << '\n';
   const Plan plan = make_plan( o, pods );
+  if ( warm.joinable() ) warm.join();
   if ( !o.dump_partition.empty() ) {
     std::ofstream out( o.dump_partition );
     for ( std::size_t s = 0; s < plan.paths.size(); ++s ) out << s << " " << plan.colour[s] << " " << plan.paths[s] << '\n';
