@@ -1811,9 +1811,14 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
         int nqbig = 0;
         for ( int q = 0; q < cnt; ++q )
           if ( b->n[gid[q]] > kMidMaxFusedN ) nqbig = q + 1;
-        // cluster size per size class of the sorted list (n > 2048: 16, > 1400: 8, else 4 CTAs), halved together until the
-        // clusters fit the 2 x SM-count resident CTAs (one and a half times: the tail of a class may queue); every class
-        // is its own launch on its own stream, the remaining matrices (one CTA each) run next to them
+        // cluster size per size class of the sorted list (n > 2048: 16 for up to four matrices, else 8; > 1400: 8; else 4
+        // CTAs), halved together until the clusters fit one and a half times the 2 x SM-count resident CTAs (the tail of a
+        // class may queue; with a tighter limit the largest class of a mixed batch loses its clusters of 8: 62 against 74
+        // matrices/s on 256 mixed matrices); every class is its own launch on its own stream, the remaining matrices (one
+        // CTA each) run next to them. The iteration is bound by its leader CTA:
+        // measured on 3072^2 (QR stage, ms): 2 matrices 1015 / 1059 with clusters of 16 / 8, 4: 1019 / 1073, 8: 1158 / 1088,
+        // 16: 2154 / 1396 (/ 1821 with 4), 32: 1483 with 8, 48: 2762 with 8, 64: 2745 with 4 -- a cluster of 16 only pays
+        // while it has the SMs to itself
         const int slots = 3 * c.sm_count;
         struct QrClass { int first, count, csize; };
         QrClass cls[3] = { { 0, 0, 16 }, { 0, 0, 8 }, { 0, 0, 4 } };
@@ -1823,6 +1828,7 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
           if ( k.count == 0 ) k.first = q;
           k.count += 1;
         }
+        if ( cls[0].count > 4 ) cls[0].csize = 8;
         static const int env_cluster = std::getenv( "PALADIN_GPU_CLUSTER" ) ? std::atoi( std::getenv( "PALADIN_GPU_CLUSTER" ) ) : 0;
         for ( ;; ) {
           int demand = 0;
