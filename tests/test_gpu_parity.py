@@ -569,6 +569,16 @@ def test_n3072_full_decomposition(pg):
         _check_eigs(po.dense_matrix(*m), wr, wi, VR, inf, True, label="n=3072 matrix %d" % q)
 
 
+def test_order_above_the_cooperative_limit(pg):
+    """n > 4608: 6 n + 64 doubles no longer fit one SM's shared memory, so the reduction falls back on the unblocked one-CTA
+    code (pb_small.cuh::gehd2) while the QR iteration keeps its cluster; eigenvalues only (the reduction alone takes tens
+    of seconds on one SM), plain 1e-9 bar against LAPACK."""
+    mats = _random_mats([4640], 9)
+    res, info = pg.geev_batch(*_concat(mats), jobvr="N")
+    for q, (m, (wr, wi, VR), inf) in enumerate(zip(mats, res, info)):
+        _check_eigs(po.dense_matrix(*m), wr, wi, VR, inf, False, label="n=4640 matrix %d" % q)
+
+
 def test_mixed_batch_up_to_3072_matches_oracle(pg):
     """BASELINE.json configs[3]: sizes log-uniform over the whole range 32...3072 (both ends forced), densities 1-100 %,
     shuffled COO order; every size class of the launcher in one batch."""
