@@ -369,8 +369,10 @@ def run_uniform(cx, args, wl, n, job, B, distinct, seed, steps, warmup, full):
         batch.scatter()
         batch.solve()
 
-    # e2e: the step's matrices go through the C-ABI as --e2e-chunks batches (default 8 x 74 matrices: four of them fill
-    # the 296 CTA slots of the QR kernel) driven by one host thread each; every batch owns a stream, so the copies of one
+    # e2e: the step's matrices go through the C-ABI as --e2e-chunks batches (default 16 x 37 matrices when the rank has 16
+    # host cores to itself, else 8 x 74: measured 1368-1377/s with 16, 1301-1322/s with 8, 1345/s with 4, 1002/s with 24 on
+    # one B200 and 16 cores -- the finer the batches, the shorter the pipeline's fill and drain inside the K timed steps,
+    # until the kernels get too small) driven by one host thread each; every batch owns a stream, so the copies of one
     # batch run under the kernels of the others. Over K steps each thread streams its share K times (upload, scatter,
     # solve, download per step, results of every step land in host memory); the threads are joined once, at the end of the
     # K steps, like the batches of the paladin-gpu executable.
@@ -378,7 +380,10 @@ def run_uniform(cx, args, wl, n, job, B, distinct, seed, steps, warmup, full):
     if full and B >= 2:
         # (large matrices: a batch of fewer than 16 gets clusters of 16 CTAs per matrix and leader-bound QR phases that do not
         # overlap; keep at least 16 per batch)
-        nchunk = max(2, min(args.e2e_chunks, B if n <= 1024 else B // 16))
+        want = args.e2e_chunks
+        if want <= 0:
+            want = 16 if (os.cpu_count() or 1) // max(1, cx.world) >= 16 else 8
+        nchunk = max(2, min(want, B if n <= 1024 else B // 16))
         cuts = [B * q // nchunk for q in range(nchunk + 1)]
         for lo, hi in zip(cuts[:-1], cuts[1:]):
             hb = pg.Batch(nvec[lo:hi], off[lo:hi + 1] - off[lo], jobvr=job, device=dev)
@@ -811,7 +816,7 @@ def main():
     ap.add_argument("--exe-matrices", type=int, default=7104, help="matrices of the text-in/text-out executable leg (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-secondary", action="store_true")
-    ap.add_argument("--e2e-chunks", type=int, default=8, help="e2e: the step's matrices go through the C-ABI as this many batches, one host thread each")
+    ap.add_argument("--e2e-chunks", type=int, default=-1, help="e2e: the step's matrices go through the C-ABI as this many batches, one host thread each (<= 0: 16 with 16 host cores per rank, else 8)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
