@@ -106,7 +106,10 @@ __device__ __forceinline__ void strip_apply_line_regular( double ( &x )[kStripW 
 // 3*NB + kStripPF positions in registers: position 24+PF+1+t is fetched while macro-step t runs and position 1+t is
 // stored right after it. Positions 0 and W-1 are never touched by a steady-state window and are neither loaded
 // nor stored. LD(p) / ST(p, v) access position p of the thread's line.
-constexpr int kStripPF = 10;
+#ifndef PB_STRIP_PF
+#define PB_STRIP_PF 10
+#endif
+constexpr int kStripPF = PB_STRIP_PF;
 
 template <class LD, class ST>
 __device__ __forceinline__ void strip_regular_stream( LD ld, ST st, const double* refl ) {
