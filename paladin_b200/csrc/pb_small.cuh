@@ -812,7 +812,7 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
           for ( int k = m; k <= i - 1; ++k ) PB_AED_COUNT( wantt ? 1 : 2 );
           PB_AED_COUNT( 3 );
 #endif
-#ifdef PB_SWEEP_PROFILE
+#ifdef PB_SWEEP_PROFILE  // (defined by tools/mb_lahqr.cu only: cycles inside the sweeps vs. the scans / shifts around them)
           PB_SWEEP_PROFILE( 0 );
 #endif
           if ( top < 32 ) {
