@@ -339,7 +339,7 @@ __global__ void __launch_bounds__( 64 ) small_qr_pair_kernel( BatchView bv, cons
   pb::WarpGroup g;
   double* wr = bv.wr + bv.w_off[id];
   double* wi = bv.wi + bv.w_off[id];
-  const int info = pb::lahqr<pb::WarpGroup, true>( g, false, false, n, m.ilo, m.ihi, H, ldh, wr, wi, 0, n - 1, (double*)nullptr, 1, pb::LahqrNoHook(), hrs, true );
+  const int info = pb::lahqr<pb::WarpGroup, true, pb::LahqrNoHook, true>( g, false, false, n, m.ilo, m.ihi, H, ldh, wr, wi, 0, n - 1, (double*)nullptr, 1, pb::LahqrNoHook(), hrs, true );
   __syncwarp();
   pb::GeevScaling sc{ m.scalea != 0, m.anrm, m.cscale };
   pb::geev_unscale( g, n, sc, info, m.ilo, wr, wi );

@@ -429,7 +429,16 @@ struct GroupLanes<G, decltype( (void)G::kLanes )> {
   static constexpr int value = G::kLanes;
 };
 
-template <class G, int SLOTS, bool WANTZ, bool FASTREFL>
+struct SweepStepGuarded {
+  static constexpr bool value = false;
+};
+struct SweepStepInside {
+  static constexpr bool value = true;
+};
+// SPLIT: the steps whose block lies strictly inside the active part (k <= i - 4) run in a loop of their own without the
+// end-of-block guards (about a sixth of the instructions of a step; worth it where the sweep is bound by issue slots: the
+// values-only n <= 64 kernel at twelve warps per SM)
+template <class G, int SLOTS, bool WANTZ, bool FASTREFL, bool SPLIT = false>
 PB_D void francis_sweep_lanes( const G& g, int l, int i, int m, double v0, double v1, double v2, int i1, int i2, double* H, int ldh,
                                int iloz, int ihiz, double* Z, int ldz, int hrs = 1 ) {
   constexpr int NL = GroupLanes<G>::value;
@@ -479,18 +488,19 @@ PB_D void francis_sweep_lanes( const G& g, int l, int i, int m, double v0, doubl
   int p = m, pnr = 0;
   double pw2 = 0.0, pw3 = 0.0, pt1 = 0.0, pbeta = 0.0, pf00 = 0.0, pf01 = 0.0, pf02 = 0.0, qf01 = 0.0, qf02 = 0.0;
   // reflector of step k from the tracked bulge column, then step k on the tracked block (column k+3 joins it)
-  auto step = [&]( int k ) {
-    const int nr = imin( 3, i - k + 1 );
+  auto step = [&]( auto inside, int k ) {
+    constexpr bool kInside = decltype( inside )::value;  // k + 4 <= i: nothing of the block or of column k+3 is outside
+    const int nr = kInside ? 3 : imin( 3, i - k + 1 );
     double a0 = b0, a1 = b1, a2 = b2, t1;
     if ( FASTREFL ) larfg3_bf( nr, a0, a1, a2, t1 );
     else dlarfg3( nr, a0, a1, a2, t1 );
     if ( nr < 3 ) a2 = 0.0;
-    const bool din = k + 3 <= i;
+    const bool din = kInside || k + 3 <= i;
     double d0 = from_owner( x0, k + 3 ), d1 = from_owner( x1, k + 3 );
     d0 = din ? d0 : 0.0;
     d1 = din ? d1 : 0.0;
-    double d2 = hg( k + 2, k + 3 );
-    const double d3 = hg( k + 3, k + 3 ), d4 = hg( k + 4, k + 3 );
+    double d2 = kInside ? PB_HH( k + 2, k + 3 ) : hg( k + 2, k + 3 );
+    const double d3 = kInside ? PB_HH( k + 3, k + 3 ) : hg( k + 3, k + 3 ), d4 = kInside ? PB_HH( k + 4, k + 3 ) : hg( k + 4, k + 3 );
     const double w2 = a1, w3 = a2, t2 = t1 * w2, t3 = t1 * w3;
     double s = c00 + w2 * c10 + w3 * c20;
     c00 -= s * t1;
@@ -540,9 +550,9 @@ PB_D void francis_sweep_lanes( const G& g, int l, int i, int m, double v0, doubl
     pbeta = a0;
   };
   // the updates of step P (parameters W2, W3, T1; QF = top-row entries of the block of step P-1) on the stored matrix
-  auto apply = [&]( int P, double W2, double W3, double T1, double BETA, double F00, double QF1, double QF2 ) {
+  auto apply = [&]( auto inside, int P, double W2, double W3, double T1, double BETA, double F00, double QF1, double QF2 ) {
     const double T2 = T1 * W2, T3 = T1 * W3;
-    const bool third = P + 2 <= i;
+    const bool third = decltype( inside )::value || P + 2 <= i;
     PB_FOR_LANES {
 #pragma unroll
       for ( int s = 0; s < SLOTS; ++s ) {
@@ -583,16 +593,28 @@ PB_D void francis_sweep_lanes( const G& g, int l, int i, int m, double v0, doubl
     }
   };
   // ---- first step: nothing pending yet ----
-  step( m );
+  using Guarded = SweepStepGuarded;
+  using Inside = SweepStepInside;
+  step( Guarded(), m );
   if ( g.tid() == 0 && m > l ) PB_HH( m, m - 1 ) = PB_HH( m, m - 1 ) * ( 1.0 - pt1 );
-  for ( int k = m + 1; k <= i - 1; ++k ) {
+  int k = m + 1;
+  if constexpr ( SPLIT ) {
+    for ( ; k <= i - 4; ++k ) {
+      const int P = p;
+      const double W2 = pw2, W3 = pw3, T1 = pt1, BETA = pbeta, F00 = pf00, QF1 = qf01, QF2 = qf02;
+      apply( Inside(), P, W2, W3, T1, BETA, F00, QF1, QF2 );
+      step( Inside(), k );
+      g.sync();
+    }
+  }
+  for ( ; k <= i - 1; ++k ) {
     const int P = p;
     const double W2 = pw2, W3 = pw3, T1 = pt1, BETA = pbeta, F00 = pf00, QF1 = qf01, QF2 = qf02;
-    apply( P, W2, W3, T1, BETA, F00, QF1, QF2 );
-    step( k );
+    apply( Guarded(), P, W2, W3, T1, BETA, F00, QF1, QF2 );
+    step( Guarded(), k );
     g.sync();
   }
-  apply( p, pw2, pw3, pt1, pbeta, pf00, qf01, qf02 );
+  apply( Guarded(), p, pw2, pw3, pt1, pbeta, pf00, qf01, qf02 );
   // ---- what is still in registers after the last step (p = i-1, a 2 x 2 reflection) ----
   PB_FOR_LANES {
 #pragma unroll
@@ -630,7 +652,7 @@ struct LahqrNoHook {
   static constexpr bool kActive = false;
   PB_HD bool operator()( int, int ) const { return false; }
 };
-template <class G, bool FASTREFL = false, class HOOK = LahqrNoHook>
+template <class G, bool FASTREFL = false, class HOOK = LahqrNoHook, bool SPLIT = false>
 // hrs / band_only: H(i, j) at H[i * hrs + j * ldh], and only the entries with i <= j + 1 exist (two Hessenberg matrices share
 // one array, the second one transposed: the values-only n <= 64 kernel, paladin_gpu.cu::small_qr_pair_kernel). Needs the
 // register-resident sweep (a single warp, wantt == false): it is the one that never stores a bulge.
@@ -816,11 +838,11 @@ PB_D int lahqr( const G& g, bool wantt, bool wantz, int n, int ilo, int ihi, dou
           PB_SWEEP_PROFILE( 0 );
 #endif
           if ( top < 32 ) {
-            if ( wantz ) francis_sweep_lanes<G, 1, true, FASTREFL>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz, hrs );
-            else francis_sweep_lanes<G, 1, false, FASTREFL>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz, hrs );
+            if ( wantz ) francis_sweep_lanes<G, 1, true, FASTREFL, SPLIT>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz, hrs );
+            else francis_sweep_lanes<G, 1, false, FASTREFL, SPLIT>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz, hrs );
           } else {
-            if ( wantz ) francis_sweep_lanes<G, 2, true, FASTREFL>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz, hrs );
-            else francis_sweep_lanes<G, 2, false, FASTREFL>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz, hrs );
+            if ( wantz ) francis_sweep_lanes<G, 2, true, FASTREFL, SPLIT>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz, hrs );
+            else francis_sweep_lanes<G, 2, false, FASTREFL, SPLIT>( g, l, i, m, v0, v1, v2, i1, i2, H, ldh, iloz, ihiz, Z, ldz, hrs );
           }
 #ifdef PB_SWEEP_PROFILE
           PB_SWEEP_PROFILE( 1 );

@@ -253,9 +253,9 @@ int hs_lahqr_pair( int n, const double* H0, const double* H1, double* wr0, doubl
       S[r + (size_t)( c + 3 ) * lds] = H0[r + (size_t)c * n];
       S[c + (size_t)r * lds] = H1[r + (size_t)c * n];
     }
-  const int i0 = pb::lahqr<HostWarpGroup, true>( g, false, false, n, 0, n - 1, S.data() + 3 * (size_t)lds, lds, wr0, wi0, 0, n - 1, (double*)nullptr, 1,
+  const int i0 = pb::lahqr<HostWarpGroup, true, pb::LahqrNoHook, true>( g, false, false, n, 0, n - 1, S.data() + 3 * (size_t)lds, lds, wr0, wi0, 0, n - 1, (double*)nullptr, 1,
                                                  pb::LahqrNoHook(), 1, true );
-  const int i1 = pb::lahqr<HostWarpGroup, true>( g, false, false, n, 0, n - 1, S.data(), 1, wr1, wi1, 0, n - 1, (double*)nullptr, 1, pb::LahqrNoHook(), lds,
+  const int i1 = pb::lahqr<HostWarpGroup, true, pb::LahqrNoHook, true>( g, false, false, n, 0, n - 1, S.data(), 1, wr1, wi1, 0, n - 1, (double*)nullptr, 1, pb::LahqrNoHook(), lds,
                                                  true );
   return i0 * 1000 + i1;
 }
