@@ -227,7 +227,11 @@ __global__ void __launch_bounds__( 128 ) geev_smallcta_kernel( BatchView bv, con
 // cells with col - row <= 1 -- which doubles the warps in flight (12 per SM at n = 64). The register-resident sweep never
 // stores a bulge, so neither matrix ever touches the other's cells (pb::lahqr, hrs / band_only).
 struct MidMeta;  // (defined with the mid-size path below)
-__global__ void __launch_bounds__( 32 ) small_hess_kernel( BatchView bv, const int* ids, MidMeta* meta, int nmax, int lds );
+#ifndef PB_SMALL_HESS_THREADS
+#define PB_SMALL_HESS_THREADS 64
+#endif
+constexpr int kSmallHessThreads = PB_SMALL_HESS_THREADS;
+__global__ void __launch_bounds__( kSmallHessThreads ) small_hess_kernel( BatchView bv, const int* ids, MidMeta* meta, int nmax, int lds );
 __global__ void __launch_bounds__( 64 ) small_qr_pair_kernel( BatchView bv, const int* ids, int count, const MidMeta* meta, int nmax, int lds );
 
 // ---- size-generic path: one CTA per matrix, in place in global memory ----------------------------
@@ -266,22 +270,26 @@ struct MidMeta {
   double anrm, cscale;
 };
 
-__global__ void __launch_bounds__( 32 ) small_hess_kernel( BatchView bv, const int* ids, MidMeta* meta, int nmax, int lds ) {
+// (kSmallHessThreads threads per matrix: the reduction's row / column updates are 64 wide at n = 64, and the shared-memory
+// footprint -- the limit on matrices per SM -- does not grow with the threads)
+__global__ void __launch_bounds__( kSmallHessThreads ) small_hess_kernel( BatchView bv, const int* ids, MidMeta* meta, int nmax, int lds ) {
   extern __shared__ double smem[];
+  __shared__ double red[64];
   const int id = ids[blockIdx.x];
   const int n = bv.n[id];
   const int lane = threadIdx.x;
+  constexpr int kT = kSmallHessThreads;
   double* As = smem;
   double* dw = As + (size_t)lds * nmax;
   int* iw = reinterpret_cast<int*>( dw + 5 * nmax );
   double* Ag = bv.A + bv.a_off[id];
   const int nn = n * n;
-  for ( int q = lane; q < nn; q += 32 ) {
+  for ( int q = lane; q < nn; q += kT ) {
     const int c = q / n, r = q - c * n;
     As[r + c * lds] = Ag[q];
   }
-  __syncwarp();
-  pb::WarpGroup g;
+  __syncthreads();
+  pb::CtaGroup g{ red };
   double* wr = bv.wr + bv.w_off[id];
   double* wi = bv.wi + bv.w_off[id];
   MidMeta m;
@@ -300,9 +308,9 @@ __global__ void __launch_bounds__( 32 ) small_hess_kernel( BatchView bv, const i
       m.anrm = sc.anrm;
       m.cscale = sc.cscale;
       pb::gehd2( g, n, m.ilo, m.ihi, As, lds, dw, dw + 2 * nmax );
-      __syncwarp();
+      __syncthreads();
       pb::geev_isolated_eigenvalues( g, n, m.ilo, m.ihi, As, lds, wr, wi );
-      for ( int q = lane; q < nn; q += 32 ) {
+      for ( int q = lane; q < nn; q += kT ) {
         const int c = q / n, r = q - c * n;
         if ( r <= c + 1 ) Ag[q] = As[r + c * lds];
       }
@@ -1635,7 +1643,7 @@ int paladin_gpu_batch_solve( paladin_gpu_batch* b ) {
         if ( small_warps > 1 && g.nmax >= 32 ) geev_smallcta_kernel<<<cnt, 32 * small_warps, smem, st>>>( bv, ids, g.nmax, g.nmax | 1 );
         else if ( small_split && !wantvr && !wantvl && g.nmax >= 8 ) {
           const int lds = g.nmax | 1;
-          small_hess_kernel<<<cnt, 32, smem, st>>>( bv, ids, b->d_meta, g.nmax, lds );
+          small_hess_kernel<<<cnt, kSmallHessThreads, smem, st>>>( bv, ids, b->d_meta, g.nmax, lds );
           small_qr_pair_kernel<<<( cnt + 1 ) / 2, 64, sizeof( double ) * (size_t)lds * ( g.nmax + 3 ), st>>>( bv, ids, cnt, b->d_meta, g.nmax, lds );
           nl = 2;
         } else geev_warp_kernel<<<cnt, 32, smem, st>>>( bv, ids, g.nmax, g.nmax | 1 );
